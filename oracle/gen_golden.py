@@ -1,0 +1,443 @@
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Run in the build container, where
+/root/reference exists:
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+The reference's own tests hold no filter-level golden vectors, so parity is
+pinned by outputs of the reference itself on seeded inputs.  Every file records the inputs
+(measurements, model parameters, the reference's quadrature points and weights) next to the
+outputs (filtered / predictive / smoothed moments, simulated trajectories, BQ weights, scores),
+so that both the numpy oracle (oracle/ssm_oracle.py) and the CUDA path can be checked against
+them without the reference being present.
+
+Reference entry points exercised (file:line relative to /root/reference/ssmtoybox):
+  ssinf.py:66-147   forward_pass / backward_pass
+  ssinf.py:254-344  Gaussian time / measurement / smoothing updates
+  ssinf.py:634-736  Studentian updates
+  mtran.py:105-149  SigmaPointTransform.apply
+  bq/bqmtran.py:60-109, 394-415   BQTransform.apply, TPQ covariance
+  bq/bqmod.py:495-523, 893-992    GP / BS quadrature weights
+  bq/bqkern.py:329-424            RBFGauss kernel and its expectations
+  ssmod.py:168-244, 1011-1039     simulators
+  utils.py:18-148                 scores
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+warnings.simplefilter('ignore')
+ref_shim.install()
+
+import scipy  # noqa: E402
+from ssmtoybox import ssinf, ssmod, mtran, utils  # noqa: E402
+from ssmtoybox.bq import bqmtran, bqmod, bqkern  # noqa: E402
+from ssmtoybox.utils import GaussRV, StudentRV  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+VERSIONS = {'numpy': np.__version__, 'scipy': scipy.__version__,
+            'reference': 'jacobnzw/SSMToybox v0.1.1a0 (/root/reference)'}
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class InjectedRV(utils.RandomVariable):
+    """Random variable that replays given samples (pattern of research/tpq/tpq_base.py:13-31)."""
+
+    def __init__(self, base, samples):
+        self.base, self.samples = base, list(samples)
+        self.dim = base.dim
+        for a in ('mean', 'cov', 'scale', 'dof'):
+            if hasattr(base, a):
+                setattr(self, a, getattr(base, a))
+
+    def sample(self, size):
+        return self.samples.pop(0)
+
+    def get_stats(self):
+        return self.base.get_stats()
+
+
+def transform_dict(tf, prefix):
+    """Flatten a reference moment transform into arrays."""
+    d = {}
+    if isinstance(tf, bqmtran.BQTransform):
+        kind = {bqmod.GaussianProcessModel: 'gp', bqmod.BayesSardModel: 'bs',
+                bqmod.StudentTProcessModel: 'tp'}[type(tf.model)]
+        d['kind'] = kind
+        d['points'] = tf.model.points
+        d['wm'], d['Wc'], d['Wcc'] = tf.wm, tf.Wc, tf.Wcc
+        d['model_var'] = np.asarray(tf.model.model_var, dtype=float)
+        d['integral_var'] = np.asarray(tf.model.integral_var, dtype=float)
+        d['kern_par'] = tf.model.kernel.par
+        d['dim_out'] = np.asarray(tf.I_out.shape[0])
+        if kind == 'tp':
+            d['iK'] = tf.model.iK
+            d['nu'] = np.asarray(float(tf.model.nu))
+        if kind == 'bs':
+            d['mulind'] = np.asarray(tf.model.mulind)
+    else:
+        d['kind'] = 'sp'
+        d['points'] = tf.unit_sp
+        d['wm'], d['Wc'] = tf.wm, tf.Wc
+    return {prefix + k: np.asarray(v) for k, v in d.items()}
+
+
+def model_dict(dyn, obs):
+    d = {'dyn_name': type(dyn).__name__, 'obs_name': type(obs).__name__}
+    d['dyn_dt'] = float(getattr(dyn, 'dt', 0.0))
+    d['G'] = dyn.noise_gain
+    d['state_index'] = np.asarray(obs.state_index if obs.state_index is not None else [], dtype=np.int64)
+    d['radar_loc'] = np.asarray(getattr(obs, 'radar_loc', [0.0, 0.0]), dtype=float)
+    st = dyn.init_rv.get_stats()
+    d['m0'], d['P0'] = st[0], st[1]
+    d['q_mean'], d['q_cov'] = dyn.noise_rv.get_stats()[:2]
+    d['r_mean'], d['r_cov'] = obs.noise_rv.get_stats()[:2]
+    if len(st) == 3:
+        d['x0_dof'] = float(st[2])
+        d['q_dof'] = float(dyn.noise_rv.dof)
+        d['r_dof'] = float(obs.noise_rv.dof)
+    return {k: np.asarray(v) for k, v in d.items()}
+
+
+def run_filter(alg, y, smooth=True):
+    """Run forward (and backward) pass per trajectory exactly like research/gpq/icinco_demo.py:120-124.
+    Exceptions are recorded per trajectory (status = failing step k, 1-based; 0 = ok)."""
+    dy, N, M = y.shape
+    dx = alg.mod_dyn.dim_state
+    out = {
+        'fi_mean': np.full((dx, N, M), np.nan), 'fi_cov': np.full((dx, dx, N, M), np.nan),
+        'pr_mean': np.full((dx, N + 1, M), np.nan), 'pr_cov': np.full((dx, dx, N + 1, M), np.nan),
+        'pr_xx_cov': np.full((dx, dx, N + 1, M), np.nan),
+        'sm_mean': np.full((dx, N, M), np.nan), 'sm_cov': np.full((dx, dx, N, M), np.nan),
+        'status': np.zeros(M, dtype=np.int64),
+    }
+    exc = []
+    for i in range(M):
+        try:
+            m, P = alg.forward_pass(y[..., i])
+            out['fi_mean'][..., i], out['fi_cov'][..., i] = m, P
+            out['pr_mean'][..., i], out['pr_cov'][..., i] = alg.pr_mean, alg.pr_cov
+            out['pr_xx_cov'][..., i] = alg.pr_xx_cov
+            if smooth and not isinstance(alg, ssinf.StudentianInference):
+                ms, Ps = alg.backward_pass()
+                out['sm_mean'][..., i], out['sm_cov'][..., i] = ms, Ps
+            exc.append('')
+        except (np.linalg.LinAlgError, ValueError) as e:
+            # find the step: first all-zero column of fi_mean after slot 0 (arrays are zero-initialised)
+            fi = alg.fi_mean
+            k = 1
+            while k <= N and np.any(fi[:, k] != 0):
+                k += 1
+            out['status'][i] = k
+            out['fi_mean'][:, :k - 1, i] = fi[:, 1:k]
+            out['fi_cov'][:, :, :k - 1, i] = alg.fi_cov[:, :, 1:k]
+            exc.append(type(e).__name__ + ': ' + str(e)[:60])
+        alg.reset()
+    out['exceptions'] = np.asarray(json.dumps(exc))
+    return out
+
+
+def save(name, **arrays):
+    arrays['versions'] = np.asarray(json.dumps(VERSIONS))
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('{:32s} {:8.1f} kB'.format(name, os.path.getsize(path) / 1e3))
+
+
+def filter_case(name, alg, x, y, smooth=True, extra=None):
+    d = {'x': x, 'y': y}
+    d.update(model_dict(alg.mod_dyn, alg.mod_obs))
+    d.update(transform_dict(alg.tf_dyn, 'dyn_'))
+    d.update(transform_dict(alg.tf_obs, 'obs_'))
+    d['alg_name'] = np.asarray(type(alg).__name__)
+    if isinstance(alg, ssinf.StudentianInference):
+        d['dof'] = np.asarray(float(alg.dof))
+        d['fixed_dof'] = np.asarray(int(alg.fixed_dof))
+    d.update(run_filter(alg, y, smooth))
+    if extra:
+        d.update(extra)
+    save(name, **d)
+    return d
+
+
+# ----------------------------------------------------------------------------------------------
+# state-space model fixtures
+# ----------------------------------------------------------------------------------------------
+def ungm(steps, mc):
+    x0 = GaussRV(1, cov=np.atleast_2d(5.0))
+    q = GaussRV(1, cov=np.atleast_2d(10.0))
+    dyn = ssmod.UNGMTransition(x0, q)
+    obs = ssmod.UNGMMeasurement(GaussRV(1), 1)
+    x = dyn.simulate_discrete(steps, mc_sims=mc)
+    y = obs.simulate_measurements(x)
+    return dyn, obs, x, y
+
+
+def pendulum(steps, mc):
+    x0 = GaussRV(2, mean=np.array([1.5, 0]), cov=0.01 * np.eye(2))
+    dt = 0.01
+    q = GaussRV(2, cov=0.01 * np.array([[(dt ** 3) / 3, (dt ** 2) / 2], [(dt ** 2) / 2, dt]]))
+    r = GaussRV(1, cov=np.array([[0.1]]))
+    dyn = ssmod.Pendulum2DTransition(x0, q, dt=dt)
+    obs = ssmod.Pendulum2DMeasurement(r, dyn.dim_state)
+    x = dyn.simulate_discrete(steps, mc_sims=mc)
+    y = obs.simulate_measurements(x)
+    return dyn, obs, x, y
+
+
+def reentry(steps, mc):
+    """research/bsq/bsq_tracking.py:230-261 (truth by Euler-Maruyama at dt=0.05, sub-sampled ::2)."""
+    tau, disc_tau = 0.05, 0.1
+    m0 = np.array([6500, 350, -1.8, -6.8, 0.7])
+    sysm = ssmod.ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0])),
+                                            GaussRV(3, cov=np.diag([2.4e-5, 2.4e-5, 0])))
+    obs = ssmod.Radar2DMeasurement(GaussRV(2, cov=np.diag([1e-6, 0.17e-6])), 5, radar_loc=np.array([6374, 0.0]))
+    x = sysm.simulate_continuous(duration=steps * disc_tau, dt=tau, mc_sims=mc)
+    y = obs.simulate_measurements(x)
+    x, y = x[:, ::2, ...], y[:, ::2, ...]
+    m0 = np.array([6500, 350, -1.1, -6.1, 0.7])
+    dyn = ssmod.ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 1])),
+                                           GaussRV(3, cov=np.diag([2.4e-5, 2.4e-5, 1e-6])), dt=disc_tau)
+    return dyn, obs, x[:, :steps], y[:, :steps]
+
+
+def coordinated_turn(steps, mc, student=False, dt=0.1):
+    """Dynamics of tests/test_ssinf.py:65-78 with the radar of research/tpq/synthetic.py:2126."""
+    m0 = np.array([1000, 300, 1000, 0, np.deg2rad(-3.0)])
+    P0 = np.diag([100, 10, 100, 10, 0.1])
+    rho_1, rho_2 = 0.1, 1.75e-4
+    A = np.array([[dt ** 3 / 3, dt ** 2 / 2], [dt ** 2 / 2, dt]])
+    Q = np.zeros((5, 5))
+    Q[:2, :2], Q[2:4, 2:4], Q[4, 4] = rho_1 * A, rho_1 * A, rho_2 * dt
+    R = np.diag([100, 10e-6])
+    # data always come from the Gaussian model (simulate_discrete cannot sample StudentRV with a
+    # tuple size, utils.py:380-382), heavy tails are injected as outliers below
+    dyn_g = ssmod.CoordinatedTurnTransition(GaussRV(5, m0, P0), GaussRV(5, cov=Q), dt=dt)
+    obs_g = ssmod.Radar2DMeasurement(GaussRV(2, cov=R), 5, state_index=[0, 2])
+    x = dyn_g.simulate_discrete(steps, mc_sims=mc)
+    y = obs_g.simulate_measurements(x)
+    # 5 % outliers with 50x covariance (research/tpq/synthetic.py:2126-2137)
+    out = np.random.rand(steps, mc) < 0.05
+    y = y + out[None] * (np.sqrt(49.0) * np.sqrt(np.diag(R))[:, None, None] * np.random.randn(2, steps, mc))
+    if not student:
+        return dyn_g, obs_g, x, y
+    nu = 6.0
+    sc = (nu - 2) / nu
+    dyn_s = ssmod.CoordinatedTurnTransition(StudentRV(5, m0, sc * P0, nu), StudentRV(5, scale=sc * Q, dof=nu), dt=dt)
+    obs_s = ssmod.Radar2DMeasurement(StudentRV(2, scale=sc * R, dof=nu), 5, state_index=[0, 2])
+    return dyn_s, obs_s, x, y
+
+
+MUL_UT = lambda d: np.hstack((np.zeros((d, 1)), np.eye(d), 2 * np.eye(d))).astype(int)  # noqa: E731
+
+
+# ----------------------------------------------------------------------------------------------
+# golden sets
+# ----------------------------------------------------------------------------------------------
+def gen_filters():
+    # C1: UNGM, UKF, 500 steps (research/gpq/icinco_demo.py:81-125)
+    np.random.seed(42)
+    dyn, obs, x, y = ungm(500, 6)
+    filter_case('c1_ungm_ukf', ssinf.UnscentedKalman(dyn, obs), x, y)
+    filter_case('c1_ungm_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :2], y[..., :2])
+    filter_case('c1_ungm_ghkf5', ssinf.GaussHermiteKalman(dyn, obs, deg=5), x[..., :2], y[..., :2])
+    kp = np.array([[1.0, 3.0]])
+    filter_case('c1_ungm_gpq_ut', ssinf.GaussianProcessKalman(dyn, obs, kp, kp, points='ut'), x[..., :3], y[..., :3])
+    kp = np.array([[1.0, 0.1]])
+    filter_case('c1_ungm_gpq_gh10', ssinf.GaussianProcessKalman(dyn, obs, kp, kp, points='gh',
+                                                                point_hyp={'degree': 10}), x[..., :2], y[..., :2])
+    kp = np.array([[1.0, 3.0]])
+    filter_case('c1_ungm_tpq_ut', ssinf.StudentProcessKalman(dyn, obs, kp, kp), x[..., :3], y[..., :3])
+    filter_case('c1_ungm_bsq_ut', ssinf.BayesSardKalman(dyn, obs, kp, kp, MUL_UT(1), MUL_UT(1)), x[..., :3], y[..., :3])
+
+    # C2: UNGM GPQ length-scale sweep (research/gpq/icinco_demo.py:166-196), with reset() between
+    # trajectories (the script forgets it; the batched API mirrors the reset behaviour)
+    for iel, el in enumerate([1e-3, 3e-3, 1e-2, 3e-2, 1e-1, 3e-1, 1, 3, 1e1, 3e1, 1e2]):
+        kp = np.array([[1.0, el]])
+        alg = ssinf.GaussianProcessKalman(dyn, obs, kp, kp, points='ut', point_hyp={'kappa': 0.0})
+        filter_case('c2_ungm_gpq_el{:02d}'.format(iel), alg, x[..., :2], y[..., :2], smooth=False)
+
+    # C5a: pendulum (tests/test_ssinf.py:42-51)
+    np.random.seed(7)
+    dyn, obs, x, y = pendulum(300, 3)
+    filter_case('c5_pend_ukf', ssinf.UnscentedKalman(dyn, obs), x, y)
+    kp = np.array([[1.0, 1.0, 1.0]])
+    filter_case('c5_pend_gpq', ssinf.GaussianProcessKalman(dyn, obs, kp, kp), x, y)
+    filter_case('c5_pend_tpq', ssinf.StudentProcessKalman(dyn, obs, kp, kp), x, y)
+    filter_case('c5_pend_bsq', ssinf.BayesSardKalman(dyn, obs, kp, kp, MUL_UT(2), MUL_UT(2)), x, y)
+    filter_case('c5_pend_ghkf3', ssinf.GaussHermiteKalman(dyn, obs, deg=3), x[..., :2], y[..., :2])
+
+    # C3: reentry GPQ + RTS (research/gpq/gpq_tracking.py:41-44, research/bsq/bsq_tracking.py:230-261)
+    np.random.seed(0)
+    dyn, obs, x, y = reentry(500, 3)
+    hdyn = np.array([[1.0, 25, 25, 25, 25, 25]])
+    hobs = np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
+    filter_case('c3_reentry_gpq', ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut'), x, y)
+    filter_case('c3_reentry_ukf', ssinf.UnscentedKalman(dyn, obs), x[..., :2], y[..., :2])
+    filter_case('c3_reentry_ukf_b0', ssinf.UnscentedKalman(dyn, obs, beta=0.0), x[..., :1], y[..., :1])
+    filter_case('c3_reentry_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :1], y[..., :1])
+    # BSQ with model variance assigned from outside (research/bsq/bsq_tracking.py:266-281)
+    par_dyn = np.array([[1.0, 1, 1, 1, 1, 1]])
+    par_obs = np.array([[1.0, 0.9, 0.9, 1e4, 1e4, 1e4]])
+    alg = ssinf.BayesSardKalman(dyn, obs, par_dyn, par_obs, MUL_UT(5), MUL_UT(5), points='ut')
+    alg.tf_dyn.model.model_var = 2e-6 * np.eye(5)
+    alg.tf_obs.model.model_var = 0 * np.eye(2)
+    filter_case('c3_reentry_bsq', alg, x[..., :2], y[..., :2])
+    # failure semantics: GPQ with unit length-scales is not PD on this model
+    one = np.array([[1.0, 1, 1, 1, 1, 1]])
+    filter_case('c3_reentry_gpq_fail', ssinf.GaussianProcessKalman(dyn, obs, one, one), x[:, :60, :2], y[:, :60, :2])
+
+    # C4: coordinated turn + radar, heavy tails: TPQKF (Gaussian SSM) vs Student-t UKF (Student SSM)
+    np.random.seed(3)
+    dyn, obs, x, y = coordinated_turn(200, 4)
+    par_dyn = np.array([[1.0, 1, 1, 1, 1, 1]])
+    par_obs = np.array([[1.0, 1, 1e2, 1, 1e2, 1e2]])
+    filter_case('c4_ct_tpq', ssinf.StudentProcessKalman(dyn, obs, par_dyn, par_obs), x, y)
+    filter_case('c4_ct_gpq', ssinf.GaussianProcessKalman(dyn, obs, par_dyn, par_obs), x[..., :2], y[..., :2])
+    filter_case('c4_ct_ukf', ssinf.UnscentedKalman(dyn, obs), x[..., :2], y[..., :2])
+    filter_case('c4_ct_bsq', ssinf.BayesSardKalman(dyn, obs, np.ones((1, 6)), np.ones((1, 6)), MUL_UT(5), MUL_UT(5)),
+                x[..., :2], y[..., :2])
+    np.random.seed(3)
+    dyn_s, obs_s, x, y = coordinated_turn(200, 4, student=True)
+    filter_case('c4_ct_fsstudent', ssinf.FullySymmetricStudent(dyn_s, obs_s, kappa=None, dof=6.0), x, y, smooth=False)
+    filter_case('c4_ct_fsstudent_incdof', ssinf.FullySymmetricStudent(dyn_s, obs_s, dof=6.0, fixed_dof=False),
+                x[..., :2], y[..., :2], smooth=False)
+    filter_case('c4_ct_fsstudent_deg5', ssinf.FullySymmetricStudent(dyn_s, obs_s, degree=5, dof=6.0),
+                x[..., :1], y[..., :1], smooth=False)
+
+
+def gen_weights():
+    """BQ weights and kernel expectations (bqmod.py:495-523, 893-992; bqkern.py:329-424)."""
+    cases = []
+    for dim, pts, php, par in [
+        (1, 'ut', None, [1.0, 3.0]), (1, 'ut', {'kappa': 0.0}, [1.0, 1e-3]), (1, 'ut', {'kappa': 0.0}, [1.0, 1e2]),
+        (1, 'sr', None, [1.0, 0.3]), (1, 'gh', {'degree': 5}, [1.0, 0.3]), (1, 'gh', {'degree': 20}, [1.0, 0.1]),
+        (2, 'ut', None, [1.0, 1.0, 1.0]), (2, 'ut', None, [2.5, 3.0, 0.7]), (2, 'gh', {'degree': 3}, [1.0, 2.0, 2.0]),
+        (5, 'ut', None, [1.0, 25, 25, 25, 25, 25]), (5, 'ut', None, [1.0, 25, 25, 1e4, 1e4, 1e4]),
+        (5, 'ut', None, [1.0, 1, 1, 1, 1, 1]), (5, 'sr', None, [1.0, 3, 3, 3, 3, 3]),
+        (5, 'fs', {'degree': 3, 'kappa': None, 'dof': 6.0}, [1.0, 2, 2, 2, 2, 2]),
+    ]:
+        cases.append((dim, pts, php, np.array([par])))
+    d = {'n': np.asarray(len(cases))}
+    for i, (dim, pts, php, par) in enumerate(cases):
+        p = 'w{:02d}_'.format(i)
+        gp = bqmod.GaussianProcessModel(dim, par, 'rbf', pts, php)
+        wm, Wc, Wcc, emv, ivar = gp.bq_weights(par)
+        x = gp.points
+        d.update({p + 'dim': dim, p + 'pts': pts, p + 'php': json.dumps(php), p + 'par': par, p + 'points': x,
+                  p + 'K': gp.kernel.eval(par, x), p + 'iK': gp.iK, p + 'q': gp.q, p + 'Q': gp.Q,
+                  p + 'R': gp.kernel.exp_x_xkx(par, x), p + 'kbar': gp.kernel.exp_xy_kxy(par),
+                  p + 'gp_wm': wm, p + 'gp_Wc': Wc, p + 'gp_Wcc': Wcc, p + 'gp_emv': emv, p + 'gp_ivar': ivar})
+        # Bayes-Sard with UT multi-index (pi-unisolvent special case only when N == 2D+1)
+        if pts in ('ut', 'fs'):
+            mi = MUL_UT(dim)
+            bs = bqmod.BayesSardModel(dim, par, mi, pts, php)
+            wm, Wc, Wcc, emv, ivar = bs.bq_weights(par, mi)
+            d.update({p + 'bs_mulind': mi, p + 'bs_wm': wm, p + 'bs_Wc': Wc, p + 'bs_Wcc': Wcc,
+                      p + 'bs_emv': emv, p + 'bs_ivar': ivar})
+        # Bayes-Sard general case (fewer basis functions than points): total degree <= 1
+        mi = np.hstack((np.zeros((dim, 1)), np.eye(dim))).astype(int)
+        if mi.shape[1] < x.shape[1]:
+            bs = bqmod.BayesSardModel(dim, par, mi, pts, php)
+            wm, Wc, Wcc, emv, ivar = bs.bq_weights(par, mi)
+            d.update({p + 'bsg_mulind': mi, p + 'bsg_wm': wm, p + 'bsg_Wc': Wc, p + 'bsg_Wcc': Wcc,
+                      p + 'bsg_emv': emv, p + 'bsg_ivar': ivar})
+    save('weights', **{k: np.asarray(v) for k, v in d.items()})
+
+    # classical point sets and weights (mtran.py:166-520)
+    d = {}
+    for dim in (1, 2, 5):
+        d['ut{}_pts'.format(dim)] = mtran.UnscentedTransform.unit_sigma_points(dim)
+        d['ut{}_wm'.format(dim)], d['ut{}_wc'.format(dim)] = mtran.UnscentedTransform.weights(dim)
+        d['ut{}k0_pts'.format(dim)] = mtran.UnscentedTransform.unit_sigma_points(dim, kappa=0.0)
+        d['ut{}k2a_wm'.format(dim)], d['ut{}k2a_wc'.format(dim)] = mtran.UnscentedTransform.weights(dim, 2.0, 0.5, 1.0)
+        d['ut{}k2a_pts'.format(dim)] = mtran.UnscentedTransform.unit_sigma_points(dim, 2.0, 0.5)
+        d['sr{}_pts'.format(dim)] = mtran.SphericalRadialTransform.unit_sigma_points(dim)
+        d['sr{}_wm'.format(dim)] = mtran.SphericalRadialTransform.weights(dim)
+        for deg in (3, 5):
+            d['fs{}d{}_pts'.format(dim, deg)] = mtran.FullySymmetricStudentTransform.unit_sigma_points(dim, deg, None, 6.0)
+            d['fs{}d{}_wm'.format(dim, deg)] = mtran.FullySymmetricStudentTransform.weights(dim, deg, None, 6.0)
+    for dim, deg in ((1, 3), (1, 5), (1, 20), (2, 3), (2, 5), (5, 3)):
+        d['gh{}d{}_pts'.format(dim, deg)] = mtran.GaussHermiteTransform.unit_sigma_points(dim, deg)
+        d['gh{}d{}_wm'.format(dim, deg)] = mtran.GaussHermiteTransform.weights(dim, deg)
+    save('pointsets', **d)
+
+
+def gen_simulation():
+    """Simulators with injected noise (ssmod.py:168-244, 1011-1039)."""
+    rng = np.random.RandomState(11)
+    d = {}
+    steps, mc = 40, 3
+    for name, mk in (('ungm', ungm), ('pend', pendulum), ('reentry', reentry), ('ct', coordinated_turn)):
+        np.random.seed(5)
+        dyn, obs, _, _ = mk(4, 1)
+        dx, dq, dr = dyn.dim_state, dyn.dim_noise, obs.dim_noise
+        x0 = dyn.init_rv.mean[:, None] + rng.randn(dx, mc) * 0.1
+        q = rng.randn(dq, steps, mc) * np.sqrt(np.diag(dyn.noise_rv.cov))[:, None, None]
+        r = rng.randn(dr, steps, mc) * np.sqrt(np.diag(obs.noise_rv.cov))[:, None, None]
+        dyn.init_rv = InjectedRV(dyn.init_rv, [x0])
+        dyn.noise_rv = InjectedRV(dyn.noise_rv, [q])
+        obs.noise_rv = InjectedRV(obs.noise_rv, [r])
+        x = dyn.simulate_discrete(steps, mc_sims=mc)
+        y = obs.simulate_measurements(x)
+        d.update({name + '_x0': x0, name + '_q': q, name + '_r': r, name + '_x': x, name + '_y': y})
+        d.update({name + '_' + k: v for k, v in model_dict(dyn, obs).items()})
+        if name == 'reentry':
+            # Euler-Maruyama (ssmod.py:201-244): q has steps+1 slices, result drops x0
+            dt = 0.05
+            qc = rng.randn(dq, steps + 1, mc) * np.sqrt(np.diag(dyn.noise_rv.cov))[:, None, None]
+            dyn.init_rv.samples, dyn.noise_rv.samples = [x0], [qc]
+            xc = dyn.simulate_continuous(duration=steps * dt, dt=dt, mc_sims=mc)
+            d.update({'reentry_qc': qc, 'reentry_xc': xc, 'reentry_dtc': np.asarray(dt)})
+    save('simulation', **d)
+
+
+def gen_scores():
+    """Scores (utils.py:18-148) aggregated like research/gpq/icinco_demo.py:17-52 (no bootstrap)."""
+    sys.path.insert(0, os.path.join(ref_shim.REFERENCE_PATH, 'research', 'gpq'))
+    for m in ('tqdm',):
+        try:
+            __import__(m)
+        except ImportError:
+            import types
+            sys.modules[m] = types.ModuleType(m)
+            sys.modules[m].trange = range
+    import icinco_demo
+    d = {}
+    for name in ('c1_ungm_ukf', 'c5_pend_gpq', 'c3_reentry_gpq'):
+        g = np.load(os.path.join(OUT, name + '.npz'))
+        x = g['x']
+        mf, Pf, ms, Ps = g['fi_mean'][..., None], g['fi_cov'][..., None], g['sm_mean'][..., None], g['sm_cov'][..., None]
+        sc = icinco_demo.evaluate_performance(x, mf, Pf, ms, Ps, bootstrap_variance=False)
+        for k, v in zip(('rmse_f', 'nci_f', 'nll_f', 'rmse_s', 'nci_s', 'nll_s'), sc):
+            d[name + '_' + k] = np.asarray(v)
+        # per-step building blocks
+        dx, N, M = x.shape
+        mse = np.stack([utils.mse_matrix(x[:, k, :], mf[:, k, :, 0]) for k in range(N)], axis=-1)
+        nll = np.array([[utils.neg_log_likelihood(x[:, k, s], mf[:, k, s, 0], Pf[:, :, k, s, 0]) for s in range(M)]
+                        for k in range(N)])
+        lcr = np.array([[utils.log_cred_ratio(x[:, k, s], mf[:, k, s, 0], Pf[:, :, k, s, 0], mse[..., k])
+                         for s in range(M)] for k in range(N)])
+        d.update({name + '_mse': mse, name + '_nll': nll, name + '_lcr': lcr})
+        # tracking-style RMSE (research/bsq/bsq_tracking.py:330-337)
+        se = utils.squared_error(x, mf[..., 0])
+        d[name + '_rmse_vs_time'] = np.sqrt(se.sum(axis=0)).mean(axis=1)
+    save('scores', **d)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    gen_filters()
+    gen_weights()
+    gen_simulation()
+    gen_scores()

@@ -1,0 +1,65 @@
+"""Compatibility shim that makes the UNMODIFIED reference (/root/reference, jacobnzw/SSMToybox
+v0.1.1a0) importable under the container's numpy 2.x / scipy 1.18 / no-matplotlib stack.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (ssmtoybox_b200/) may import this
+module; it is used by oracle/gen_golden.py (run in the build container, where /root/reference
+exists) to generate the golden vectors committed under tests/golden/.  /root/reference does
+not exist on the GPU box, so nothing that runs there imports this file.
+
+What is patched:
+  * matplotlib is absent and bq/bqmod.py:3 imports it at module top -> stub modules;
+  * removed numpy aliases np.int / np.float / np.asscalar / np.alltrue (utils.py:463-469,182);
+  * scipy.log10 removed (utils.py:120);
+  * scipy.special.factorial2(-1) must be 1 (reference relies on it in bqmod.py:656-661,694,727;
+    scipy >= 1.11 returns 0).
+"""
+import sys
+import types
+
+import numpy as np
+import scipy
+import scipy.special
+
+REFERENCE_PATH = '/root/reference'
+
+
+def install():
+    """Install the shim and put the reference on sys.path. Idempotent."""
+    if getattr(install, '_done', False):
+        return
+    # 1. matplotlib stubs
+    for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.gridspec', 'matplotlib.lines'):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    mpl = sys.modules['matplotlib']
+    for sub in ('pyplot', 'gridspec', 'lines'):
+        if not hasattr(mpl, sub):
+            setattr(mpl, sub, sys.modules['matplotlib.' + sub])
+    # 2. numpy aliases
+    for alias, target in (('int', int), ('float', float), ('bool', bool)):
+        if alias not in np.__dict__:
+            setattr(np, alias, target)
+    if not hasattr(np, 'asscalar'):
+        np.asscalar = lambda a: np.asarray(a).item()
+    if not hasattr(np, 'alltrue'):
+        np.alltrue = np.all
+    # 3. scipy.log10
+    if not hasattr(scipy, 'log10'):
+        scipy.log10 = np.log10
+    # 4. factorial2(-1) == 1 (and (-1)!! for array input is not needed by the reference)
+    _f2 = scipy.special.factorial2
+
+    def factorial2(n, exact=False, **kw):
+        if np.isscalar(n) and n == -1:
+            return 1 if exact else 1.0
+        return _f2(n, exact=exact, **kw)
+
+    if not getattr(_f2, '_shimmed', False):
+        factorial2._shimmed = True
+        scipy.special.factorial2 = factorial2
+    if REFERENCE_PATH not in sys.path:
+        sys.path.insert(0, REFERENCE_PATH)
+    install._done = True
