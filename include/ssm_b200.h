@@ -1,0 +1,224 @@
+/*
+ * ssm_b200.h -- C ABI of the B200-native (sm_100a) Monte-Carlo sigma-point / Bayesian-quadrature
+ * Kalman filtering library behind the SSMToybox Python API.
+ *
+ * The reference (jacobnzw/SSMToybox, pure Python) has no FFI; the entry points below are what a
+ * binding for its hot path would call.  Each one names the reference interface it replaces
+ * (file:line relative to /root/reference/ssmtoybox/).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Descriptor structs and the small arrays they point to live in
+ *    HOST memory and are copied at call time; all bulk buffers are DEVICE pointers to fp64 data
+ *    allocated by the caller.  The library never allocates persistent memory and never frees
+ *    caller memory.
+ *  - Bulk layout is structure-of-arrays  [component][time step][trajectory]  with the trajectory
+ *    index fastest and a caller-supplied leading dimension ld >= n_traj (elements), i.e. element
+ *    (c, k, t) of an array with C components and N steps lives at  (c * N + k) * ld + t.
+ *    Matrices are flattened row-major into the component index (c = row * dim + col).
+ *    This is exactly a C-contiguous numpy array of shape (dim, N, M) / (dim, dim, N, M) -- the
+ *    shapes the reference's research drivers assemble (research/gpq/icinco_demo.py:115-123).
+ *  - Every call is asynchronous on the given CUDA stream (cudaStream_t passed as void*; NULL =
+ *    default stream) and re-entrant; there is no global mutable state.
+ *  - Return value: 0 on success, negative SSM_E_* on invalid arguments / unsupported
+ *    configurations / CUDA errors (ssm_last_error() gives a thread-local message).  Numerical
+ *    failures of individual trajectories are NOT errors: they are reported in status[traj]
+ *    (0 = ok, otherwise (k << 8) | code, k = 1-based time step, code = SSM_FAIL_*), the
+ *    trajectory is frozen and its remaining outputs are filled with NaN.  The reference raises
+ *    numpy.linalg.LinAlgError / ValueError at the same places (mtran.py:139, bq/bqmtran.py:98,
+ *    ssinf.py:321, 342).
+ */
+#ifndef SSM_B200_H
+#define SSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSM_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define SSM_OK             0
+#define SSM_E_INVALID     -1   /* bad argument (null pointer, size, dimension mismatch)           */
+#define SSM_E_UNSUPPORTED -2   /* model / transform combination without a device implementation  */
+#define SSM_E_CUDA        -3   /* CUDA runtime error, see ssm_last_error()                        */
+
+/* ---- per-trajectory numerical failure codes (low byte of status[]) ------------------------- */
+#define SSM_FAIL_CHOL_DYN        1  /* input covariance of the dynamics transform not PD  (mtran.py:139, bqmtran.py:98) */
+#define SSM_FAIL_CHOL_OBS        2  /* input covariance of the measurement transform not PD                           */
+#define SSM_FAIL_CHOL_GAIN       3  /* measurement covariance not PD in cho_factor        (ssinf.py:321, 724)         */
+#define SSM_FAIL_NONFINITE_GAIN  4  /* inf/NaN reaching cho_factor/cho_solve (scipy ValueError, ssinf.py:321)        */
+#define SSM_FAIL_CHOL_SMOOTH     5  /* predictive covariance not PD in the smoother       (ssinf.py:342)              */
+
+/* ---- model ids (ssmod.py) ------------------------------------------------------------------ */
+#define SSM_DYN_UNGM      1  /* UNGMTransition.dyn_fcn              ssmod.py:268-269  par: -                      */
+#define SSM_DYN_PENDULUM  2  /* Pendulum2DTransition.dyn_fcn        ssmod.py:357-358  par[0] = dt                 */
+#define SSM_DYN_REENTRY   3  /* ReentryVehicle2DTransition.dyn_fcn  ssmod.py:530-564  par[0] = dt                 */
+#define SSM_DYN_COORDTURN 4  /* CoordinatedTurnTransition.dyn_fcn   ssmod.py:675-690  par[0] = dt                 */
+#define SSM_OBS_UNGM      1  /* UNGMMeasurement.meas_fcn            ssmod.py:1060-1061                            */
+#define SSM_OBS_PENDULUM  2  /* Pendulum2DMeasurement.meas_fcn      ssmod.py:1114-1115                            */
+#define SSM_OBS_RADAR     3  /* Radar2DMeasurement.meas_fcn         ssmod.py:1227-1252 par[0..1] = radar_loc      */
+
+/* ---- moment-transform kinds ---------------------------------------------------------------- */
+#define SSM_TF_SP 1  /* sigma-point rule, centred form, diagonal Wc   SigmaPointTransform.apply mtran.py:105-149   */
+#define SSM_TF_BQ 2  /* GPQ / BSQ, un-centred form, dense Wc + model variance  BQTransform.apply bqmtran.py:60-223 */
+#define SSM_TF_TP 3  /* TPQ: BQ + data-dependent variance  StudentTProcessTransform._covariance bqmtran.py:394-415 */
+
+/* ---- filter families ----------------------------------------------------------------------- */
+#define SSM_FAMILY_GAUSS   1  /* GaussianInference   ssinf.py:215-344 */
+#define SSM_FAMILY_STUDENT 2  /* StudentianInference ssinf.py:555-740 */
+
+/* One moment transform: unit points and quadrature weights (host arrays, row-major).
+ * Replaces the attributes the reference's transform objects carry (mtran.py:226-232,
+ * bqmtran.py:55-58, 306-310): unit_sp / model.points, wm, Wc, Wcc, model.model_var, model.iK. */
+typedef struct ssm_transform {
+    int32_t kind;            /* SSM_TF_*                                                        */
+    int32_t dim_in;          /* D                                                               */
+    int32_t dim_out;         /* E                                                               */
+    int32_t n_pts;           /* N                                                               */
+    const double *points;    /* (D, N) unit sigma points                                        */
+    const double *wm;        /* (N)                                                             */
+    const double *Wc;        /* (N, N); SSM_TF_SP reads the diagonal only                       */
+    const double *Wcc;       /* (D, N); BQ / TP only                                            */
+    const double *model_var; /* BQ: (E, E) matrix ADDED to the covariance (already multiplied by
+                                I_out, bqmtran.py:198); TP: 1 value, the GP model variance      */
+    const double *iK;        /* (N, N) inverse kernel matrix; TP only (bqmod.py:1155-1158)      */
+    double nu;               /* TP degrees of freedom (always the model default 4.0) */
+    int32_t tp_full_matrix;  /* TP: 1 = add the full E x E matrix (I_out is 1x1, ssinf.py:550)  */
+    int32_t reserved;
+} ssm_transform;
+
+/* A filter lowered to plain data.  Replaces the object graph filter -> transform -> model ->
+ * kernel of ssinf.py:233-247 (GaussianInference.__init__) / :589-624 (StudentianInference). */
+typedef struct ssm_desc {
+    int32_t dyn_model, obs_model;   /* SSM_DYN_*, SSM_OBS_*                                      */
+    int32_t dx, dy;                 /* state / measurement dimension                             */
+    double dyn_par[8], obs_par[8];  /* model parameters, see the model ids                       */
+    int32_t n_state_index;          /* 0 = measurement uses the leading state components         */
+    int32_t state_index[8];         /* MeasurementModel.state_index, ssmod.py:905                */
+    int32_t family;                 /* SSM_FAMILY_*                                              */
+    int32_t reserved;
+    const double *m0;               /* (dx)      initial mean          ssinf.py:239             */
+    const double *P0;               /* (dx, dx)  initial covariance (Student: scale matrix)     */
+    const double *GQG;              /* (dx, dx)  G Q G^T               ssinf.py:279             */
+    const double *R;                /* (dy, dy)  measurement noise cov ssinf.py:291             */
+    /* Student family only (ssinf.py:589-624) */
+    double dof, x0_dof, q_dof, r_dof;
+    int32_t fixed_dof;
+    int32_t reserved2;
+    ssm_transform tf_dyn, tf_obs;
+} ssm_desc;
+
+/* ---- library info -------------------------------------------------------------------------- */
+int ssm_abi_version(void);
+const char *ssm_last_error(void);
+
+/* ---- K2: fused forward pass -----------------------------------------------------------------
+ * Replaces StateSpaceInference.forward_pass (ssinf.py:66-118) with _time_update (:254-295 /
+ * :634-698), _measurement_update (:297-323 / :700-736), MomentTransform.apply and the model
+ * functions, for n_traj independent trajectories at once.
+ *   y          (dy, n_steps, ld)            measurements
+ *   fi_mean    (dx, n_steps, ld)            filtered means, steps 1..N        (nullable)
+ *   fi_cov     (dx*dx, n_steps, ld)         filtered covariances               (nullable)
+ *   pr_mean    (dx, n_steps, ld)            predictive means                   (nullable)
+ *   pr_cov     (dx*dx, n_steps, ld)         predictive covariances             (nullable)
+ *   pr_xx_cov  (dx*dx, n_steps, ld)         Cov(x_k, x_{k-1}) (E x D)          (nullable)
+ *   init_mean  (dx, ld), init_cov (dx*dx, ld)  per-trajectory initial moments; NULL = (m0, P0)
+ *              for every trajectory (the reference after reset(), ssinf.py:249-252)
+ *   last_mean / last_cov (dx, ld)/(dx*dx, ld)  moments after the last step (nullable); Student
+ *              family: last_cov receives the filtered SCALE matrix x_smat_fi (ssinf.py:733)
+ *   t_offset   (ld) int32 per-trajectory shift of the time index, nullable
+ *   k0         time index of the first step (the reference passes time = k - 1, ssinf.py:104)
+ *   status     (ld) int32, see above
+ */
+int ssm_filter(const ssm_desc *desc, const double *y,
+               double *fi_mean, double *fi_cov,
+               double *pr_mean, double *pr_cov, double *pr_xx_cov,
+               const double *init_mean, const double *init_cov,
+               double *last_mean, double *last_cov,
+               const int32_t *t_offset, int32_t k0,
+               int32_t *status, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* ---- K3: RTS smoother -----------------------------------------------------------------------
+ * Replaces StateSpaceInference.backward_pass + GaussianInference._smoothing_update
+ * (ssinf.py:120-147, 325-344), including the reference's index range (slots N and N-1 are never
+ * smoothed).  Arrays as produced by ssm_filter (n_steps slots = steps 1..N).
+ */
+int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov,
+               const double *pr_mean, const double *pr_cov, const double *pr_xx_cov,
+               double *sm_mean, double *sm_cov, int32_t *status,
+               int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* ---- K1: batched simulation -----------------------------------------------------------------
+ * Replaces TransitionModel.simulate_discrete / simulate_continuous (ssmod.py:168-244),
+ * MeasurementModel.simulate_measurements (ssmod.py:1011-1039) and the samplers
+ * GaussRV.sample / StudentRV.sample (utils.py:618-619, 670-671).
+ * Noise source: either injected arrays (x0, q, r device pointers; parity mode) or Philox4x32-10
+ * keyed by (seed, global trajectory index) with Box-Muller normals coloured by the host-supplied
+ * factors (rng->*_factor, A A^T = cov).
+ */
+typedef struct ssm_rng {
+    uint64_t seed;
+    int64_t traj_offset;        /* global index of trajectory 0 (sharding-invariant draws)       */
+    const double *x0_mean;      /* (dx)                                                          */
+    const double *x0_factor;    /* (dx, dx)  x0 = mean + F z                                     */
+    const double *q_factor;     /* (dq, dq)                                                      */
+    const double *r_factor;     /* (dy, dy)                                                      */
+    double x0_dof, q_dof, r_dof; /* > 0: Student-t draws  n / sqrt(gamma(nu/2, 2/nu))  (utils.py:349-382); 0: Gaussian */
+    int32_t dq;
+    int32_t reserved;
+} ssm_rng;
+
+#define SSM_SIM_DISCRETE   1
+#define SSM_SIM_CONTINUOUS 2  /* Euler-Maruyama with dt_cont; output drops x0 (ssmod.py:244)     */
+
+int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mode, double dt_cont, int32_t sub,
+                 const double *x0_inj, const double *q_inj, const double *r_inj,
+                 double *x, double *y,
+                 int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* ---- K5: batched Bayesian-quadrature weights ------------------------------------------------
+ * Replaces GaussianProcessModel.bq_weights (bq/bqmod.py:495-523) with RBFGauss.eval /
+ * eval_inv_dot / exp_x_kx / exp_x_xkx / exp_x_kxkx / exp_xy_kxy (bq/bqkern.py:96-120, 329-424)
+ * and BayesSardModel.bq_weights (bq/bqmod.py:893-992, incl. utils.vandermonde :478-502 and the
+ * polynomial expectations :635-797) for n_par kernel-parameter vectors at once (one CTA each).
+ *   par      (n_par, D+1) host   [alpha, l_1..l_D]
+ *   points   (D, N) host         unit sigma points (shared by the whole batch)
+ *   mulind   (D, Q) host int32   Bayes-Sard multi-indices, NULL = plain GP weights
+ * Outputs are DEVICE arrays: wm (n_par, N), Wc (n_par, N, N), Wcc (n_par, D, N),
+ * iK (n_par, N, N), scal (n_par, 2) = [model_var, integral_var]; info (n_par) int32 != 0 when a
+ * Cholesky factorisation failed.
+ */
+int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const double *par, const double *points,
+                   const int32_t *mulind, int32_t n_basis,
+                   double *wm, double *Wc, double *Wcc, double *iK, double *scal, int32_t *info,
+                   void *stream);
+
+/* ---- K6: error statistics -------------------------------------------------------------------
+ * Replaces utils.squared_error / mse_matrix / neg_log_likelihood / log_cred_ratio
+ * (utils.py:18-148) and the reductions of research/gpq/icinco_demo.py:17-52.
+ * Phase 1 accumulates, per time step k, over the trajectories with status == 0:
+ *   stats[k, :] = [ sum SE (dx) | sum dx dx^T (dx*dx) | sum NLL | sum sqrt(sum_d SE) | count ]
+ * (row length ssm_scores_width(dx)); rmse_acc (dx, ld) receives per-trajectory time-sums of SE.
+ * The packed stats rows are what the multi-GPU path all-reduces (NCCL, one call).
+ * Phase 2 takes the global per-step MSE matrices (dx*dx, n_steps) and accumulates the log
+ * credibility ratio: lcr[k] = sum_traj 10 (log10 d'P^-1 d - log10 d'MSE^-1 d).
+ */
+int32_t ssm_scores_width(int32_t dx);
+int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const double *cov,
+                      const int32_t *status, double *stats, double *rmse_acc,
+                      int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+int ssm_scores_phase2(int32_t dx, const double *x, const double *mean, const double *cov,
+                      const int32_t *status, const double *mse, double *lcr,
+                      int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* ---- FP64 FMA micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no fp64 figure) --
+ * Launches a dependent-chain-free DFMA loop; returns the number of FLOPs it executes in *flops.
+ * The caller times it with CUDA events. */
+int ssm_fp64_peak_kernel(int32_t n_blocks, int32_t n_iters, double *sink, double *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSM_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of the C-ABI CUDA library (include/ssm_b200.h).
+
+The library is the only compute back-end of this package: there is no CPU fallback.  Importing
+this module fails loudly when libssmb200.so has not been built (python -m ssmtoybox_b200.build,
+or __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libssmb200.so')
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+# constants of include/ssm_b200.h
+SSM_OK, SSM_E_INVALID, SSM_E_UNSUPPORTED, SSM_E_CUDA = 0, -1, -2, -3
+FAIL_CHOL_DYN, FAIL_CHOL_OBS, FAIL_CHOL_GAIN, FAIL_NONFINITE_GAIN, FAIL_CHOL_SMOOTH = 1, 2, 3, 4, 5
+DYN_IDS = {'UNGMTransition': 1, 'Pendulum2DTransition': 2, 'ReentryVehicle2DTransition': 3,
+           'CoordinatedTurnTransition': 4}
+OBS_IDS = {'UNGMMeasurement': 1, 'Pendulum2DMeasurement': 2, 'Radar2DMeasurement': 3}
+TF_SP, TF_BQ, TF_TP = 1, 2, 3
+FAMILY_GAUSS, FAMILY_STUDENT = 1, 2
+SIM_DISCRETE, SIM_CONTINUOUS = 1, 2
+
+
+class SsmTransform(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('dim_in', C.c_int32), ('dim_out', C.c_int32), ('n_pts', C.c_int32),
+                ('points', c_double_p), ('wm', c_double_p), ('Wc', c_double_p), ('Wcc', c_double_p),
+                ('model_var', c_double_p), ('iK', c_double_p), ('nu', C.c_double),
+                ('tp_full_matrix', C.c_int32), ('reserved', C.c_int32)]
+
+
+class SsmDesc(C.Structure):
+    _fields_ = [('dyn_model', C.c_int32), ('obs_model', C.c_int32), ('dx', C.c_int32), ('dy', C.c_int32),
+                ('dyn_par', C.c_double * 8), ('obs_par', C.c_double * 8),
+                ('n_state_index', C.c_int32), ('state_index', C.c_int32 * 8),
+                ('family', C.c_int32), ('reserved', C.c_int32),
+                ('m0', c_double_p), ('P0', c_double_p), ('GQG', c_double_p), ('R', c_double_p),
+                ('dof', C.c_double), ('x0_dof', C.c_double), ('q_dof', C.c_double), ('r_dof', C.c_double),
+                ('fixed_dof', C.c_int32), ('reserved2', C.c_int32),
+                ('tf_dyn', SsmTransform), ('tf_obs', SsmTransform)]
+
+
+class SsmRng(C.Structure):
+    _fields_ = [('seed', C.c_uint64), ('traj_offset', C.c_int64),
+                ('x0_mean', c_double_p), ('x0_factor', c_double_p), ('q_factor', c_double_p), ('r_factor', c_double_p),
+                ('x0_dof', C.c_double), ('q_dof', C.c_double), ('r_dof', C.c_double),
+                ('dq', C.c_int32), ('reserved', C.c_int32)]
+
+
+class SsmError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'ssmtoybox_b200: CUDA library {} not found. Build it with `python -m ssmtoybox_b200.build` '
+            '(nvcc, sm_100a). There is no CPU fallback.'.format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.ssm_abi_version.restype = C.c_int
+    lib.ssm_last_error.restype = C.c_char_p
+    lib.ssm_filter.restype = C.c_int
+    lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
+    lib.ssm_smooth.restype = C.c_int
+    lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+    lib.ssm_fp64_peak_kernel.restype = C.c_int
+    lib.ssm_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]
+    if hasattr(lib, 'ssm_simulate'):
+        lib.ssm_simulate.restype = C.c_int
+        lib.ssm_simulate.argtypes = [C.POINTER(SsmDesc), C.POINTER(SsmRng), i32, dbl, i32, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+    if hasattr(lib, 'ssm_bq_weights'):
+        lib.ssm_bq_weights.restype = C.c_int
+        lib.ssm_bq_weights.argtypes = [i32, i32, i32, c_double_p, c_double_p, c_int32_p, i32, vp, vp, vp, vp, vp, vp, vp]
+    if hasattr(lib, 'ssm_scores_phase1'):
+        lib.ssm_scores_width.restype = i32
+        lib.ssm_scores_width.argtypes = [i32]
+        lib.ssm_scores_phase1.restype = C.c_int
+        lib.ssm_scores_phase1.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+        lib.ssm_scores_phase2.restype = C.c_int
+        lib.ssm_scores_phase2.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != SSM_OK:
+        msg = lib.ssm_last_error().decode('utf-8', 'replace')
+        if rc == SSM_E_UNSUPPORTED:
+            raise NotImplementedError('{}: {}'.format(what, msg))
+        if rc == SSM_E_INVALID:
+            raise ValueError('{}: {}'.format(what, msg))
+        raise SsmError('{}: {} (rc={})'.format(what, msg, rc))

@@ -1,0 +1,70 @@
+// extern "C" entry points (include/ssm_b200.h): argument validation and model dispatch.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "ssm_filter.cuh"
+
+namespace ssm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int filter_ungm(const FilterLaunch &L);
+int filter_pendulum(const FilterLaunch &L);
+int filter_reentry(const FilterLaunch &L);
+int filter_coordturn(const FilterLaunch &L);
+
+static bool tf_valid(const ssm_transform &t) {
+    if (t.n_pts < 1 || !t.points || !t.wm || !t.Wc) return false;
+    if (t.kind != SSM_TF_SP && t.kind != SSM_TF_BQ && t.kind != SSM_TF_TP) return false;
+    if (t.kind != SSM_TF_SP && !t.Wcc) return false;
+    if (t.kind == SSM_TF_TP && (!t.iK || !t.model_var)) return false;
+    return true;
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+extern "C" int ssm_abi_version(void) { return SSM_ABI_VERSION; }
+extern "C" const char *ssm_last_error(void) { return g_err; }
+
+extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                          double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                          double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    if (!desc || !y || !status) { set_error("ssm_filter: desc, y and status must not be NULL"); return SSM_E_INVALID; }
+    if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_filter: bad sizes (n_traj=%lld n_steps=%d ld=%lld)", (long long)n_traj, n_steps, (long long)ld); return SSM_E_INVALID; }
+    if (!desc->m0 || !desc->P0 || !desc->GQG || !desc->R) { set_error("ssm_filter: m0, P0, GQG, R must not be NULL"); return SSM_E_INVALID; }
+    if ((init_mean == nullptr) != (init_cov == nullptr)) { set_error("ssm_filter: init_mean and init_cov go together"); return SSM_E_INVALID; }
+    if (!tf_valid(desc->tf_dyn) || !tf_valid(desc->tf_obs)) { set_error("ssm_filter: incomplete transform description"); return SSM_E_INVALID; }
+    if (desc->family != SSM_FAMILY_GAUSS && desc->family != SSM_FAMILY_STUDENT) { set_error("ssm_filter: unknown family %d", desc->family); return SSM_E_INVALID; }
+    if (n_traj == 0 || n_steps == 0) return SSM_OK;
+    FilterLaunch L;
+    L.desc = desc;
+    L.stream = (cudaStream_t)stream;
+    L.buf = FilterBuffers{y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
+                          t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0};
+    const int dm = desc->dyn_model, om = desc->obs_model;
+    const int nsi = desc->n_state_index;
+    const int32_t *si = desc->state_index;
+    int rc = SSM_E_UNSUPPORTED;
+    if (dm == SSM_DYN_UNGM && om == SSM_OBS_UNGM && desc->dx == 1 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = filter_ungm(L);
+    else if (dm == SSM_DYN_PENDULUM && om == SSM_OBS_PENDULUM && desc->dx == 2 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = filter_pendulum(L);
+    else if (dm == SSM_DYN_REENTRY && om == SSM_OBS_RADAR && desc->dx == 5 && desc->dy == 2 && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = filter_reentry(L);
+    else if (dm == SSM_DYN_COORDTURN && om == SSM_OBS_RADAR && desc->dx == 5 && desc->dy == 2 && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = filter_coordturn(L);
+    else
+        set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
+    if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}

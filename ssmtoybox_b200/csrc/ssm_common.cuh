@@ -1,0 +1,86 @@
+// Shared device helpers: packed-symmetric small matrices held in registers, Cholesky and
+// triangular solves, streaming loads/stores of the [component][step][trajectory] layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ssm_b200.h"
+
+#define SSM_DEV __device__ __forceinline__
+
+namespace ssm {
+
+// index into a packed lower-triangular array, r >= c
+SSM_DEV constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }
+SSM_DEV constexpr int sym(int r, int c) { return r >= c ? tri(r, c) : tri(c, r); }
+template <int D>
+struct TriSize {
+    static constexpr int value = D * (D + 1) / 2;
+};
+
+// streaming (evict-first) global accesses: every bulk array is touched exactly once per pass
+SSM_DEV double ld_stream(const double *p) { return __ldcs(p); }
+SSM_DEV void st_stream(double *p, double v) { __stcs(p, v); }
+
+SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// Lower Cholesky factor of a symmetric matrix given by its packed lower triangle.
+// Mirrors LAPACK dpotrf('L') as called by numpy.linalg.cholesky (mtran.py:139, bqmtran.py:98):
+// only the lower triangle is read, a pivot <= 0 or NaN is a failure.  Returns false on failure.
+template <int D>
+SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSize<D>::value]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s = A[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[tri(j, k)], L[tri(j, k)], s);
+        ok = ok && (s > 0.0);
+        const double d = sqrt(s);
+        const double inv = 1.0 / d;
+        L[tri(j, j)] = d;
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) {
+            double t = A[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[tri(i, k)], L[tri(j, k)], t);
+            L[tri(i, j)] = t * inv;
+        }
+    }
+    return ok;
+}
+
+// X = (S^-1 C)^T for SPD S (packed lower, E x E) and C (E x D): the reference's
+// cho_solve(cho_factor(S), C).T (ssinf.py:321, 342).  K is D x E.  Returns false if S is not PD.
+template <int E, int D>
+SSM_DEV bool spd_gain(const double (&S)[TriSize<E>::value], const double (&C)[E][D], double (&K)[D][E],
+                      double (&Ls)[TriSize<E>::value]) {
+    const bool ok = chol_lower<E>(S, Ls);
+    double inv[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) inv[i] = 1.0 / Ls[tri(i, i)];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double z[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {  // forward substitution L z = C[:, d]
+            double t = C[i][d];
+#pragma unroll
+            for (int k = 0; k < i; ++k) t = fma(-Ls[tri(i, k)], z[k], t);
+            z[i] = t * inv[i];
+        }
+#pragma unroll
+        for (int i = E - 1; i >= 0; --i) {  // back substitution L^T x = z
+            double t = z[i];
+#pragma unroll
+            for (int k = i + 1; k < E; ++k) t = fma(-Ls[tri(k, i)], K[d][k], t);
+            K[d][i] = t * inv[i];
+        }
+    }
+    return ok;
+}
+
+SSM_DEV bool finite_d(double v) { return isfinite(v); }
+
+}  // namespace ssm

@@ -1,0 +1,596 @@
+// K2: fused forward pass.  One thread owns one trajectory for the whole time loop; the filter
+// state (mean, packed covariance), the Cholesky factor, the sigma points and the function
+// evaluations live in registers; quadrature weights are read from the kernel-parameter constant
+// bank (fast path) so every DFMA takes its weight operand straight from c[0][..]; measurements are
+// read and moments written with coalesced streaming accesses over the trajectory axis.
+//
+// Replaces, per trajectory and time step (file:line in /root/reference/ssmtoybox):
+//   StateSpaceInference.forward_pass            ssinf.py:66-118
+//   GaussianInference._time_update / _measurement_update      ssinf.py:254-323
+//   StudentianInference._time_update / _measurement_update    ssinf.py:634-736
+//   SigmaPointTransform.apply                   mtran.py:105-149
+//   BQTransform.apply (+ _mean/_covariance/_cross_covariance)  bq/bqmtran.py:60-223
+//   StudentTProcessTransform._covariance        bq/bqmtran.py:394-415 (bq/bqmod.py:1132-1160)
+#pragma once
+#include "ssm_models.cuh"
+
+namespace ssm {
+
+enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
+constexpr int GEN_CAP = 64;  // capacity of the runtime-N (generic point set) path
+
+// ------------------------------------------------------------------------------------------------
+// transform parameters, fast path: everything by value inside the kernel parameter block
+// ------------------------------------------------------------------------------------------------
+template <int D, int E, int NCAP, int KIND, int PTS>
+struct TfConst {
+    static constexpr int NW = (KIND == SSM_TF_SP) ? 1 : NCAP;
+    static constexpr int NK = (KIND == SSM_TF_TP) ? NCAP : 1;
+    static constexpr int DU = (PTS == PTS_GENERIC) ? D : 1;
+    static constexpr int DC = (KIND == SSM_TF_SP) ? 1 : D;
+    int n;
+    int tp_full;
+    double c;  // axis point scale
+    double tp_a, tp_b;  // nu - 2, 1 / (nu - 2 + N)
+    double wm_[NCAP];
+    double wc_[NCAP];
+    double Wc_[NW][NCAP];
+    double Wcc_[DC][NCAP];
+    double mv_[E][E];
+    double iK_[NK][NCAP];
+    double U_[DU][NCAP];
+    SSM_DEV double wm(int i) const { return wm_[i]; }
+    SSM_DEV double wc(int i) const { return wc_[i]; }
+    SSM_DEV double Wc(int i, int j) const { return Wc_[i][j]; }
+    SSM_DEV double Wcc(int d, int i) const { return Wcc_[d][i]; }
+    SSM_DEV double mv(int a, int b) const { return mv_[a][b]; }
+    SSM_DEV double iK(int i, int j) const { return iK_[i][j]; }
+    SSM_DEV double U(int d, int i) const { return U_[d][i]; }
+};
+
+// generic path: weights in global memory (uniform addresses -> one broadcast transaction per warp)
+template <int D, int E>
+struct TfGlobal {
+    int n;
+    int tp_full;
+    double c;
+    double tp_a, tp_b;
+    const double *wm_, *wc_, *Wc_, *Wcc_, *iK_, *U_;
+    double mv_[E][E];
+    SSM_DEV double wm(int i) const { return __ldg(wm_ + i); }
+    SSM_DEV double wc(int i) const { return __ldg(wc_ + i); }
+    SSM_DEV double Wc(int i, int j) const { return __ldg(Wc_ + i * n + j); }
+    SSM_DEV double Wcc(int d, int i) const { return __ldg(Wcc_ + d * n + i); }
+    SSM_DEV double mv(int a, int b) const { return mv_[a][b]; }
+    SSM_DEV double iK(int i, int j) const { return __ldg(iK_ + i * n + j); }
+    SSM_DEV double U(int d, int i) const { return __ldg(U_ + d * n + i); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// sigma point i from mean m and Cholesky factor L:  x = m + L u_i   (mtran.py:139, bqmtran.py:101)
+// Axis sets (UT / SR / fully-symmetric degree 3): u_i = +-c e_j, so x = m +- c L[:, j]; rows above j
+// are structurally equal to m, which lets the compiler share model sub-expressions between points.
+// The product and the sum are rounded separately, like numpy's  mean + L.dot(U).
+// ------------------------------------------------------------------------------------------------
+template <int D, int PTS, class Tf>
+SSM_DEV void sigma_point(const Tf &tf, int i, const double (&m)[D], const double (&L)[TriSize<D>::value], double (&x)[D]) {
+    if (PTS == PTS_GENERIC) {
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j <= r; ++j) s = fma(L[tri(r, j)], tf.U(j, i), s);
+            x[r] = __dadd_rn(m[r], s);
+        }
+    } else {
+        const int base = (PTS == PTS_AXIS_C) ? 1 : 0;
+        if (PTS == PTS_AXIS_C && i == 0) {
+#pragma unroll
+            for (int r = 0; r < D; ++r) x[r] = m[r];
+            return;
+        }
+        const int j = (i - base) % D;
+        const double cs = ((i - base) < D) ? tf.c : -tf.c;
+#pragma unroll
+        for (int r = 0; r < D; ++r) x[r] = (r >= j) ? __dadd_rn(m[r], __dmul_rn(cs, L[tri(r, j)])) : m[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one moment transform.  F(x, out) evaluates the (noise-free) model function.
+// Outputs: mf (E), Cf packed lower (E), Cfx (E x D) when want_cross.  Returns false when the input
+// covariance is not positive definite.
+// ------------------------------------------------------------------------------------------------
+template <int D, int E, int PTS, int NPTS, int KIND, class Tf, class F>
+SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (&P)[TriSize<D>::value], F f,
+                              double (&mf)[E], double (&Cf)[TriSize<E>::value], double (&Cfx)[E][D],
+                              const bool want_cross) {
+    constexpr int NCAP = (NPTS > 0) ? NPTS : GEN_CAP;
+    const int n = (NPTS > 0) ? NPTS : tf.n;
+    double L[TriSize<D>::value];
+    const bool ok = chol_lower<D>(P, L);
+
+    double fx[E][NCAP];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        double x[D], o[E];
+        sigma_point<D, PTS>(tf, i, m, L, x);
+        f(x, o);
+#pragma unroll
+        for (int a = 0; a < E; ++a) fx[a][i] = o[a];
+    }
+    // mean_f = fx . wm                                          mtran.py:143, bqmtran.py:175
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) s = fma(fx[a][i], tf.wm(i), s);
+        mf[a] = s;
+    }
+#pragma unroll
+    for (int a = 0; a < TriSize<E>::value; ++a) Cf[a] = 0.0;
+
+    if (KIND == SSM_TF_SP) {
+        // centred form with diagonal weights                    mtran.py:145-148
+#pragma unroll
+        for (int a = 0; a < E; ++a)
+#pragma unroll
+            for (int i = 0; i < n; ++i) fx[a][i] -= mf[a];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const double w = tf.wc(i);
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const double t = fx[a][i] * w;
+#pragma unroll
+                for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(t, fx[b][i], Cf[tri(a, b)]);
+            }
+        }
+        if (want_cross) {
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int r = 0; r < D; ++r) Cfx[a][r] = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                if (PTS == PTS_AXIS_C && i == 0) continue;  // x_0 - m == 0
+                const double w = tf.wc(i);
+                double x[D];
+                sigma_point<D, PTS>(tf, i, m, L, x);
+                const int j0 = (PTS == PTS_GENERIC) ? 0 : (i - (PTS == PTS_AXIS_C ? 1 : 0)) % D;
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    if (r < j0) continue;  // structurally zero
+                    const double dxr = x[r] - m[r];  // (x - mean), mtran.py:148
+#pragma unroll
+                    for (int a = 0; a < E; ++a) Cfx[a][r] = fma(fx[a][i] * w, dxr, Cfx[a][r]);
+                }
+            }
+        }
+    } else {
+        // un-centred form with dense weights                    bqmtran.py:198-199, 223
+        if (want_cross) {
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                double T[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < n; ++i) s = fma(fx[a][i], tf.Wcc(d, i), s);
+                    T[d] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < D; ++r) {  // (T L^T)[a][r] = sum_{d<=r} T[d] L[r][d]
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d <= r; ++d) s = fma(T[d], L[tri(r, d)], s);
+                    Cfx[a][r] = s;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < E; ++a) {
+            double row[NCAP];
+#pragma unroll
+            for (int j = 0; j < n; ++j) row[j] = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const double v = fx[a][i];
+#pragma unroll
+                for (int j = 0; j < n; ++j) row[j] = fma(v, tf.Wc(i, j), row[j]);
+            }
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < n; ++j) s = fma(row[j], fx[b][j], s);
+                Cf[tri(a, b)] = s - mf[a] * mf[b];
+            }
+        }
+        if (KIND == SSM_TF_TP) {
+            // data-dependent model variance  mv (nu - 2 + fx iK fx^T) / (nu - 2 + N)   bqmod.py:1155-1160
+            const double mv0 = tf.mv(0, 0);
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                double row[NCAP];
+#pragma unroll
+                for (int j = 0; j < n; ++j) row[j] = 0.0;
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const double v = fx[a][i];
+#pragma unroll
+                    for (int j = 0; j < n; ++j) row[j] = fma(v, tf.iK(i, j), row[j]);
+                }
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    if (!tf.tp_full && b != a) continue;
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < n; ++j) s = fma(row[j], fx[b][j], s);
+                    Cf[tri(a, b)] += ((tf.tp_a + s) * tf.tp_b) * mv0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) Cf[tri(a, b)] += tf.mv(a, b);
+        }
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct FilterBuffers {
+    const double *y;
+    double *fi_mean, *fi_cov, *pr_mean, *pr_cov, *pr_xx;
+    const double *init_mean, *init_cov;
+    double *last_mean, *last_cov;
+    const int32_t *t_offset;
+    int32_t *status;
+    long long n_traj, ld;
+    int n_steps, k0;
+};
+
+template <int DX, int DY, class TfD, class TfO>
+struct FilterPar {
+    TfD tf_dyn;
+    TfO tf_obs;
+    double dyn_par[4], obs_par[4];
+    double m0[DX];
+    double P0[TriSize<DX>::value];
+    double GQG[TriSize<DX>::value];
+    double R[TriSize<DY>::value];
+    double dof, x0_dof, q_dof, r_dof, s0;  // Student family
+    int fixed_dof;
+    FilterBuffers b;
+};
+
+template <int C>
+SSM_DEV void store_vec(double *base, long long n_steps, long long ld, int k, long long t, const double (&v)[C]) {
+    if (!base) return;
+#pragma unroll
+    for (int c = 0; c < C; ++c) st_stream(base + ((long long)c * n_steps + k) * ld + t, v[c]);
+}
+template <int D>
+SSM_DEV void store_sym(double *base, long long n_steps, long long ld, int k, long long t, const double (&P)[TriSize<D>::value]) {
+    if (!base) return;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) st_stream(base + ((long long)(r * D + c) * n_steps + k) * ld + t, P[sym(r, c)]);
+}
+template <int E, int D>
+SSM_DEV void store_mat(double *base, long long n_steps, long long ld, int k, long long t, const double (&M)[E][D]) {
+    if (!base) return;
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) st_stream(base + ((long long)(r * D + c) * n_steps + k) * ld + t, M[r][c]);
+}
+SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, int k_from, long long t) {
+    if (!base) return;
+    for (int c = 0; c < comps; ++c)
+        for (int k = k_from; k < n_steps; ++k) base[((long long)c * n_steps + k) * ld + t] = qnan();
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, class Par, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_constant__ Par p) {
+    constexpr int DX = Dyn::DX, DY = Obs::DY;
+    constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
+    const FilterBuffers &b = p.b;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.n_traj) return;
+    const int N = b.n_steps;
+    const long long ld = b.ld;
+
+    double m[DX], P[TX];  // filtered mean and covariance (Student family: scale matrix x_smat_fi)
+    if (b.init_mean) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) m[a] = b.init_mean[(long long)a * ld + t];
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) P[tri(r, c)] = b.init_cov[(long long)(r * DX + c) * ld + t];
+    } else {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) m[a] = p.m0[a];
+#pragma unroll
+        for (int a = 0; a < TX; ++a) P[a] = (FAMILY == SSM_FAMILY_STUDENT) ? p.s0 * p.P0[a] : p.P0[a];
+    }
+    const double tbase = (double)(b.k0 + (b.t_offset ? b.t_offset[t] : 0));
+
+    double ynext[DY];
+#pragma unroll
+    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N) * ld + t);
+
+    int fail = 0, kfail = 0;
+    for (int k = 0; k < N; ++k) {
+        double yk[DY];
+#pragma unroll
+        for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
+        if (k + 1 < N) {
+#pragma unroll
+            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N + k + 1) * ld + t);
+        }
+        const double time = tbase + (double)k;  // the reference passes time = k - 1, k 1-based (ssinf.py:104)
+
+        double scale = 1.0;
+        if (FAMILY == SSM_FAMILY_STUDENT) {  // ssinf.py:650-660
+            double dof_pr = p.dof;
+            if (p.fixed_dof) dof_pr = fmin(fmin(p.x0_dof + (double)k * DY, p.q_dof), p.r_dof);
+            scale = (dof_pr - 2.0) / dof_pr;
+        }
+
+        // ---- time update: predictive state moments (ssinf.py:276-279 / 669-676) ----------------
+        double mp[DX], Pp[TX], Cxx[DX][DX];
+        const bool want_xx = b.pr_xx != nullptr;
+        bool ok = moment_transform<DX, DX, PTS, NPTS, KIND>(
+            p.tf_dyn, m, P,
+            [&](const double (&x)[DX], double (&o)[DX]) {
+                const double q0[Dyn::DQ] = {};
+                Dyn::template f<false>(p.dyn_par, x, q0, time, o);
+            },
+            mp, Pp, Cxx, want_xx);
+        if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; break; }
+        if (FAMILY == SSM_FAMILY_STUDENT) {
+            if (b.pr_cov) {
+                double Cp[TX];
+#pragma unroll
+                for (int a = 0; a < TX; ++a) Cp[a] = Pp[a] + p.GQG[a];  // x_cov_pr, ssinf.py:675
+                store_sym<DX>(b.pr_cov, N, ld, k, t, Cp);
+            }
+#pragma unroll
+            for (int a = 0; a < TX; ++a) Pp[a] = fma(scale, Pp[a], p.s0 * p.GQG[a]);  // x_smat_pr, ssinf.py:672, 676
+        } else {
+#pragma unroll
+            for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:279
+            store_sym<DX>(b.pr_cov, N, ld, k, t, Pp);
+        }
+        store_vec<DX>(b.pr_mean, N, ld, k, t, mp);
+        if (want_xx) store_mat<DX, DX>(b.pr_xx, N, ld, k, t, Cxx);
+
+        // ---- predictive measurement moments (ssinf.py:287-291 / 684-693) ------------------------
+        double my[DY], Sy[TY], Syx[DY][DX];
+        ok = moment_transform<DX, DY, PTS, NPTS, KIND>(
+            p.tf_obs, mp, Pp,
+            [&](const double (&x)[DX], double (&o)[DY]) {
+                const double r0[DY] = {};
+                Obs::template h<false>(p.obs_par, x, r0, time, o);
+            },
+            my, Sy, Syx, true);
+        if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; break; }
+        if (FAMILY == SSM_FAMILY_STUDENT) {
+#pragma unroll
+            for (int a = 0; a < TY; ++a) Sy[a] = fma(scale, Sy[a], p.s0 * p.R[a]);
+#pragma unroll
+            for (int a = 0; a < DY; ++a)
+#pragma unroll
+                for (int d = 0; d < DX; ++d) Syx[a][d] *= scale;
+        } else {
+#pragma unroll
+            for (int a = 0; a < TY; ++a) Sy[a] += p.R[a];
+        }
+
+        // ---- measurement update (ssinf.py:321-323 / 724-736) -----------------------------------
+        bool fin = true;
+#pragma unroll
+        for (int a = 0; a < TY; ++a) fin = fin && finite_d(Sy[a]);
+#pragma unroll
+        for (int a = 0; a < DY; ++a)
+#pragma unroll
+            for (int d = 0; d < DX; ++d) fin = fin && finite_d(Syx[a][d]);
+        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; break; }
+        double K[DX][DY], Ls[TY];
+        ok = spd_gain<DY, DX>(Sy, Syx, K, Ls);
+        if (!ok) { fail = SSM_FAIL_CHOL_GAIN; kfail = k; break; }
+        double e[DY];
+#pragma unroll
+        for (int a = 0; a < DY; ++a) e[a] = yk[a] - my[a];
+#pragma unroll
+        for (int d = 0; d < DX; ++d) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DY; ++a) s = fma(K[d][a], e[a], s);
+            m[d] = mp[d] + s;
+        }
+        {
+            double KS[DX][DY];  // gain . Sy
+#pragma unroll
+            for (int d = 0; d < DX; ++d)
+#pragma unroll
+                for (int a = 0; a < DY; ++a) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DY; ++c) s = fma(K[d][c], Sy[sym(c, a)], s);
+                    KS[d][a] = s;
+                }
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int a = 0; a < DY; ++a) s = fma(KS[r][a], K[c][a], s);
+                    P[tri(r, c)] = Pp[tri(r, c)] - s;
+                }
+        }
+        store_vec<DX>(b.fi_mean, N, ld, k, t, m);
+        store_sym<DX>(b.fi_cov, N, ld, k, t, P);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
+        if (FAMILY == SSM_FAMILY_STUDENT) {
+            // delta = chol(Sy)^-1 e ; x_smat_fi = (dof + delta'delta) / (dof + dy) x_cov_fi   ssinf.py:731-733
+            double dd = 0.0, z[DY];
+#pragma unroll
+            for (int i = 0; i < DY; ++i) {
+                double s = e[i];
+#pragma unroll
+                for (int c = 0; c < i; ++c) s = fma(-Ls[tri(i, c)], z[c], s);
+                z[i] = s / Ls[tri(i, i)];
+                dd = fma(z[i], z[i], dd);
+            }
+            const double sc = (p.dof + dd) / (p.dof + (double)DY);
+#pragma unroll
+            for (int a = 0; a < TX; ++a) P[a] *= sc;
+        }
+    }
+
+    if (fail) {
+        fill_nan(b.fi_mean, DX, N, ld, kfail, t);
+        fill_nan(b.fi_cov, DX * DX, N, ld, kfail, t);
+        fill_nan(b.pr_mean, DX, N, ld, kfail, t);
+        fill_nan(b.pr_cov, DX * DX, N, ld, kfail, t);
+        fill_nan(b.pr_xx, DX * DX, N, ld, kfail, t);
+#pragma unroll
+        for (int a = 0; a < DX; ++a) m[a] = qnan();
+#pragma unroll
+        for (int a = 0; a < TX; ++a) P[a] = qnan();
+    }
+    if (b.last_mean) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) b.last_mean[(long long)a * ld + t] = m[a];
+    }
+    if (b.last_cov) {
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) b.last_cov[(long long)(r * DX + c) * ld + t] = P[sym(r, c)];
+    }
+    b.status[t] = fail ? (((kfail + 1) << 8) | fail) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: lowering of ssm_desc into the parameter block and launch
+// ------------------------------------------------------------------------------------------------
+struct HostTfInfo {
+    int pts;      // PTS_*
+    double c;     // axis scale
+};
+
+// classify a unit point set: [0 | cI | -cI], [cI | -cI] or generic
+inline HostTfInfo classify_points(const ssm_transform &tf) {
+    const int D = tf.dim_in, N = tf.n_pts;
+    HostTfInfo r{PTS_GENERIC, 0.0};
+    auto U = [&](int d, int i) { return tf.points[d * N + i]; };
+    for (int base = 0; base <= 1; ++base) {
+        if (N != 2 * D + base) continue;
+        const double c = U(0, base);
+        bool ok = c > 0.0;
+        for (int d = 0; d < D && ok; ++d)
+            for (int i = 0; i < N && ok; ++i) {
+                double want = 0.0;
+                if (i >= base && i - base < D && i - base == d) want = c;
+                if (i - base >= D && i - base - D == d) want = -c;
+                ok = (U(d, i) == want);
+            }
+        if (ok) { r.pts = base ? PTS_AXIS_C : PTS_AXIS; r.c = c; return r; }
+    }
+    return r;
+}
+
+template <int D>
+inline void pack_lower(const double *full, double *packed) {
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c <= r; ++c) packed[r * (r + 1) / 2 + c] = full[r * D + c];
+}
+
+template <class Tf>
+inline void fill_tf_common(Tf &o, const ssm_transform &tf, const HostTfInfo &info) {
+    o.n = tf.n_pts;
+    o.tp_full = tf.tp_full_matrix;
+    o.c = info.c;
+    o.tp_a = tf.nu - 2.0;
+    o.tp_b = 1.0 / (tf.nu - 2.0 + (double)tf.n_pts);
+    const int E = tf.dim_out;
+    for (int a = 0; a < E; ++a)
+        for (int b = 0; b < E; ++b) o.mv_[a][b] = 0.0;
+    if (tf.kind == SSM_TF_BQ && tf.model_var)
+        for (int a = 0; a < E; ++a)
+            for (int b = 0; b < E; ++b) o.mv_[a][b] = tf.model_var[a * E + b];
+    if (tf.kind == SSM_TF_TP && tf.model_var) o.mv_[0][0] = tf.model_var[0];
+}
+
+template <int D, int E, int NCAP, int KIND, int PTS>
+inline void fill_tf(TfConst<D, E, NCAP, KIND, PTS> &o, const ssm_transform &tf, const HostTfInfo &info) {
+    memset(&o, 0, sizeof(o));
+    fill_tf_common(o, tf, info);
+    const int N = tf.n_pts;
+    for (int i = 0; i < N; ++i) {
+        o.wm_[i] = tf.wm[i];
+        o.wc_[i] = tf.Wc[i * N + i];
+    }
+    if (KIND != SSM_TF_SP) {
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) o.Wc_[i % o.NW][j] = tf.Wc[i * N + j];
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < N; ++i) o.Wcc_[d % o.DC][i] = tf.Wcc[d * N + i];
+    }
+    if (KIND == SSM_TF_TP)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) o.iK_[i % o.NK][j] = tf.iK[i * N + j];
+    if (PTS == PTS_GENERIC)
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < N; ++i) o.U_[d % o.DU][i] = tf.points[d * N + i];
+}
+
+struct FilterLaunch {
+    const ssm_desc *desc;
+    FilterBuffers buf;
+    cudaStream_t stream;
+};
+
+// fast path launcher (all weights in the parameter block)
+template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, int THREADS, int MINB>
+int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo &io) {
+    constexpr int DX = Dyn::DX, DY = Obs::DY;
+    using TfD = TfConst<DX, DX, NPTS, KIND, PTS>;
+    using TfO = TfConst<DX, DY, NPTS, KIND, PTS>;
+    using Par = FilterPar<DX, DY, TfD, TfO>;
+    static_assert(sizeof(Par) <= 32000, "kernel parameter block too large");
+    const ssm_desc &d = *L.desc;
+    Par *pp = new Par;
+    Par &p = *pp;
+    memset(pp, 0, sizeof(Par));
+    fill_tf(p.tf_dyn, d.tf_dyn, id);
+    fill_tf(p.tf_obs, d.tf_obs, io);
+    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d.dyn_par[i]; p.obs_par[i] = d.obs_par[i]; }
+    for (int i = 0; i < DX; ++i) p.m0[i] = d.m0[i];
+    pack_lower<DX>(d.P0, p.P0);
+    pack_lower<DX>(d.GQG, p.GQG);
+    pack_lower<DY>(d.R, p.R);
+    p.dof = d.dof; p.x0_dof = d.x0_dof; p.q_dof = d.q_dof; p.r_dof = d.r_dof;
+    p.s0 = (d.family == SSM_FAMILY_STUDENT) ? (d.dof - 2.0) / d.dof : 1.0;
+    p.fixed_dof = d.fixed_dof;
+    p.b = L.buf;
+    const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
+    filter_kernel<Dyn, Obs, PTS, NPTS, KIND, FAMILY, Par, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
+    delete pp;
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+}  // namespace ssm

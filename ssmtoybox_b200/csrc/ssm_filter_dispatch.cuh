@@ -1,0 +1,131 @@
+// Host-side dispatch of one (dynamics, measurement) model pair over point-set type, transform kind
+// and filter family.  Each model pair is compiled in its own translation unit (ssm_filter_*.cu) so
+// the instantiations build in parallel.
+#pragma once
+#include <string.h>
+
+#include "ssm_filter.cuh"
+
+namespace ssm {
+
+void set_error(const char *fmt, ...);
+
+template <class Dyn, class Obs, int PTS, int KIND, int FAMILY, int THREADS, int MINB>
+int dispatch_npts(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo &io) {
+    constexpr int D = Dyn::DX;
+    constexpr int N = (PTS == PTS_AXIS_C) ? 2 * D + 1 : 2 * D;
+    return launch_filter_const<Dyn, Obs, PTS, N, KIND, FAMILY, THREADS, MINB>(L, id, io);
+}
+
+template <class Dyn, class Obs, int THREADS, int MINB>
+int launch_filter_generic(const FilterLaunch &L, int kind, int family);
+
+template <class Dyn, class Obs, int THREADS, int MINB>
+int dispatch_filter_model(const FilterLaunch &L) {
+    const ssm_desc &d = *L.desc;
+    const ssm_transform &a = d.tf_dyn, &b = d.tf_obs;
+    if (a.dim_in != Dyn::DX || a.dim_out != Dyn::DX || b.dim_in != Dyn::DX || b.dim_out != Obs::DY) {
+        set_error("transform dimensions do not match the model (additive noise: dim_in = dim_state)");
+        return SSM_E_INVALID;
+    }
+    if (a.kind != b.kind) { set_error("dynamics and measurement transforms must be of the same kind"); return SSM_E_UNSUPPORTED; }
+    const HostTfInfo id = classify_points(a), io = classify_points(b);
+    const int kind = a.kind, fam = d.family;
+    if (fam == SSM_FAMILY_STUDENT && kind != SSM_TF_SP) {
+        set_error("Student family is implemented for sigma-point transforms only");
+        return SSM_E_UNSUPPORTED;
+    }
+    const bool same = id.pts == io.pts && a.n_pts == b.n_pts;
+    if (!same || id.pts == PTS_GENERIC) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
+#define SSM_CASE(P, K, F)                                                        \
+    if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, MINB>(L, id, io);
+    SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS, SSM_TF_SP, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS, SSM_TF_BQ, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS, SSM_TF_TP, SSM_FAMILY_GAUSS)
+    SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_STUDENT)
+    SSM_CASE(PTS_AXIS, SSM_TF_SP, SSM_FAMILY_STUDENT)
+#undef SSM_CASE
+    set_error("unsupported transform kind %d / family %d", kind, fam);
+    return SSM_E_UNSUPPORTED;
+}
+
+// ---- generic point sets: runtime N <= GEN_CAP, weights staged in device memory ------------------
+template <int D, int E>
+inline int fill_tf_global(TfGlobal<D, E> &o, const ssm_transform &tf, const HostTfInfo &info, double *dev, double *host,
+                          size_t &off) {
+    fill_tf_common(o, tf, info);
+    const int N = tf.n_pts;
+    auto put = [&](const double *src, size_t cnt, const double *&dst) {
+        if (src) memcpy(host + off, src, cnt * sizeof(double));
+        else memset(host + off, 0, cnt * sizeof(double));
+        dst = dev + off;
+        off += cnt;
+    };
+    put(tf.wm, N, o.wm_);
+    {   // diagonal of Wc
+        for (int i = 0; i < N; ++i) host[off + i] = tf.Wc[i * N + i];
+        o.wc_ = dev + off;
+        off += N;
+    }
+    put(tf.Wc, (size_t)N * N, o.Wc_);
+    put(tf.kind != SSM_TF_SP ? tf.Wcc : nullptr, (size_t)D * N, o.Wcc_);
+    put(tf.kind == SSM_TF_TP ? tf.iK : nullptr, (size_t)N * N, o.iK_);
+    put(tf.points, (size_t)D * N, o.U_);
+    return SSM_OK;
+}
+
+template <class Dyn, class Obs, int KIND, int FAMILY, int THREADS, int MINB>
+int launch_filter_global(const FilterLaunch &L) {
+    constexpr int DX = Dyn::DX, DY = Obs::DY;
+    using TfD = TfGlobal<DX, DX>;
+    using TfO = TfGlobal<DX, DY>;
+    using Par = FilterPar<DX, DY, TfD, TfO>;
+    const ssm_desc &d = *L.desc;
+    const int Na = d.tf_dyn.n_pts, Nb = d.tf_obs.n_pts;
+    if (Na > GEN_CAP || Nb > GEN_CAP || Na < 1 || Nb < 1) {
+        set_error("generic point sets support at most %d points (got %d / %d)", GEN_CAP, Na, Nb);
+        return SSM_E_UNSUPPORTED;
+    }
+    const size_t cnt = (size_t)(2 * Na + 2 * Na * Na + 2 * DX * Na) + (size_t)(2 * Nb + 2 * Nb * Nb + 2 * DX * Nb);
+    double *host = (double *)malloc(cnt * sizeof(double));
+    double *dev = nullptr;
+    if (cudaMallocAsync(&dev, cnt * sizeof(double), L.stream) != cudaSuccess) { free(host); set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
+    Par p;
+    memset(&p, 0, sizeof(p));
+    size_t off = 0;
+    HostTfInfo gi{PTS_GENERIC, 0.0};
+    fill_tf_global(p.tf_dyn, d.tf_dyn, gi, dev, host, off);
+    fill_tf_global(p.tf_obs, d.tf_obs, gi, dev, host, off);
+    // pageable-source async copy: staged before the call returns, so `host` can be freed below
+    cudaMemcpyAsync(dev, host, off * sizeof(double), cudaMemcpyHostToDevice, L.stream);
+    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d.dyn_par[i]; p.obs_par[i] = d.obs_par[i]; }
+    for (int i = 0; i < DX; ++i) p.m0[i] = d.m0[i];
+    pack_lower<DX>(d.P0, p.P0);
+    pack_lower<DX>(d.GQG, p.GQG);
+    pack_lower<DY>(d.R, p.R);
+    p.dof = d.dof; p.x0_dof = d.x0_dof; p.q_dof = d.q_dof; p.r_dof = d.r_dof;
+    p.s0 = (d.family == SSM_FAMILY_STUDENT) ? (d.dof - 2.0) / d.dof : 1.0;
+    p.fixed_dof = d.fixed_dof;
+    p.b = L.buf;
+    const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
+    filter_kernel<Dyn, Obs, PTS_GENERIC, 0, KIND, FAMILY, Par, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dev, L.stream);
+    free(host);
+    return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+template <class Dyn, class Obs, int THREADS, int MINB>
+int launch_filter_generic(const FilterLaunch &L, int kind, int family) {
+    if (family == SSM_FAMILY_STUDENT) return launch_filter_global<Dyn, Obs, SSM_TF_SP, SSM_FAMILY_STUDENT, THREADS, MINB>(L);
+    if (kind == SSM_TF_SP) return launch_filter_global<Dyn, Obs, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB>(L);
+    if (kind == SSM_TF_BQ) return launch_filter_global<Dyn, Obs, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB>(L);
+    if (kind == SSM_TF_TP) return launch_filter_global<Dyn, Obs, SSM_TF_TP, SSM_FAMILY_GAUSS, THREADS, MINB>(L);
+    set_error("unsupported transform kind %d", kind);
+    return SSM_E_UNSUPPORTED;
+}
+
+}  // namespace ssm

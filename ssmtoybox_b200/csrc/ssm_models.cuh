@@ -1,0 +1,147 @@
+// State-space model functions (device).  Each restates one dyn_fcn / meas_fcn of the reference's
+// ssmod.py for additive noise; the noise vector q / r is passed explicitly so the same code
+// serves the filter (zero noise, TransitionModel.dyn_eval ssmod.py:129-166,
+// MeasurementModel.meas_eval ssmod.py:960-1009) and the simulators (ssmod.py:168-244, 1011-1039).
+#pragma once
+#include "ssm_common.cuh"
+
+namespace ssm {
+
+// ---- UNGMTransition.dyn_fcn, ssmod.py:268-269 -------------------------------------------------
+struct DynUngm {
+    static constexpr int DX = 1, DQ = 1, ID = SSM_DYN_UNGM;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
+        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + 8.0 * cos(1.2 * t);
+        if (NOISE) o[0] += q[0];
+    }
+    SSM_DEV static void fc(const double *, const double (&)[1], const double (&)[1], double, double (&o)[1]) { o[0] = 0.0; }
+};
+
+// ---- Pendulum2DTransition.dyn_fcn, ssmod.py:357-358; par[0] = dt, g = 9.81 (ssmod.py:351) ------
+struct DynPendulum {
+    static constexpr int DX = 2, DQ = 2, ID = SSM_DYN_PENDULUM;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[2], const double (&q)[2], double, double (&o)[2]) {
+        const double dt = par[0];
+        o[0] = x[0] + x[1] * dt;
+        if (NOISE) o[0] += q[0];
+        o[1] = x[1] - 9.81 * dt * sin(x[0]);
+        if (NOISE) o[1] += q[1];
+    }
+    SSM_DEV static void fc(const double *, const double (&)[2], const double (&)[2], double, double (&o)[2]) { o[0] = o[1] = 0.0; }
+};
+
+// ---- ReentryVehicle2DTransition, ssmod.py:521-584; par[0] = dt ---------------------------------
+// constants ssmod.py:523-526; the 3-dimensional noise enters components 2..4 (G = [0; I3], :527)
+struct DynReentry {
+    static constexpr int DX = 5, DQ = 3, ID = SSM_DYN_REENTRY;
+    static constexpr bool HAS_CONT = true;
+    SSM_DEV static void forces(const double (&x)[5], double &D, double &G) {
+        const double R0 = 6374.0, H0 = 13.406, Gm0 = 3.9860e5, b0 = -0.59783;
+        const double b = b0 * exp(x[4]);
+        const double R = sqrt(x[0] * x[0] + x[1] * x[1]);
+        const double V = sqrt(x[2] * x[2] + x[3] * x[3]);
+        D = b * exp((R0 - R) / H0) * V;
+        G = -Gm0 / (R * R * R);
+    }
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[3], double, double (&o)[5]) {
+        const double dt = par[0];
+        double D, G;
+        forces(x, D, G);
+        o[0] = x[0] + dt * x[2];
+        o[1] = x[1] + dt * x[3];
+        o[2] = x[2] + dt * (D * x[2] + G * x[0]);
+        if (NOISE) o[2] += q[0];
+        o[3] = x[3] + dt * (D * x[3] + G * x[1]);
+        if (NOISE) o[3] += q[1];
+        o[4] = x[4];
+        if (NOISE) o[4] += q[2];
+    }
+    // dyn_fcn_cont, ssmod.py:569-584
+    SSM_DEV static void fc(const double *, const double (&x)[5], const double (&q)[3], double, double (&o)[5]) {
+        double D, G;
+        forces(x, D, G);
+        o[0] = x[2];
+        o[1] = x[3];
+        o[2] = D * x[2] + G * x[0] + q[0];
+        o[3] = D * x[3] + G * x[1] + q[1];
+        o[4] = q[2];
+    }
+};
+
+// ---- CoordinatedTurnTransition.dyn_fcn, ssmod.py:675-690; par[0] = dt --------------------------
+// No omega == 0 guard: sin(0)/0 = NaN, and because the reference multiplies the
+// full 5x5 matrix, the NaN entries c, d contaminate rows 0 and 2 only (0 * NaN terms do not occur
+// in rows 1, 3, 4: their c/d coefficients are structural zeros of mdyn but numpy still multiplies
+// 0 * x, which is finite).  Rows 0 and 2 become NaN, exactly as below.
+struct DynCoordTurn {
+    static constexpr int DX = 5, DQ = 5, ID = SSM_DYN_COORDTURN;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[5], double, double (&o)[5]) {
+        const double dt = par[0];
+        const double om = x[4];
+        double a, b;
+        sincos(om * dt, &a, &b);
+        const double c = a / om;
+        const double d = (1.0 - b) / om;
+        o[0] = x[0] + c * x[1] - d * x[3];
+        if (NOISE) o[0] += q[0];
+        o[1] = b * x[1] - a * x[3];
+        if (NOISE) o[1] += q[1];
+        o[2] = d * x[1] + x[2] + c * x[3];
+        if (NOISE) o[2] += q[2];
+        o[3] = a * x[1] + b * x[3];
+        if (NOISE) o[3] += q[3];
+        o[4] = x[4];
+        if (NOISE) o[4] += q[4];
+    }
+    SSM_DEV static void fc(const double *, const double (&)[5], const double (&)[5], double, double (&o)[5]) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o[i] = 0.0;
+    }
+};
+
+// ---- UNGMMeasurement.meas_fcn, ssmod.py:1060-1061 ----------------------------------------------
+template <int DXS, int I0>
+struct ObsUngm {
+    static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_UNGM;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
+        o[0] = 0.05 * x[I0] * x[I0];
+        if (NOISE) o[0] += r[0];
+    }
+};
+
+// ---- Pendulum2DMeasurement.meas_fcn, ssmod.py:1114-1115 ----------------------------------------
+template <int DXS, int I0>
+struct ObsPendulum {
+    static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_PENDULUM;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
+        o[0] = sin(x[I0]);
+        if (NOISE) o[0] += r[0];
+    }
+};
+
+// ---- Radar2DMeasurement.meas_fcn, ssmod.py:1227-1252; par[0..1] = radar_loc --------------------
+// I0, I1 = state_index (compile-time so that sigma points sharing both coordinates share the
+// sqrt / atan2 through common-subexpression elimination)
+template <int DXS, int I0, int I1>
+struct ObsRadar {
+    static constexpr int DX = DXS, DY = 2, ID = SSM_OBS_RADAR;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[2], double, double (&o)[2]) {
+        const double ex = x[I0] - par[0], ey = x[I1] - par[1];
+        o[0] = sqrt(ex * ex + ey * ey);
+        if (NOISE) o[0] += r[0];
+        o[1] = atan2(ey, ex);
+        if (NOISE) o[1] += r[1];
+    }
+};
+
+}  // namespace ssm

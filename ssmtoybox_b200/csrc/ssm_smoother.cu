@@ -1,0 +1,173 @@
+// K3: Rauch-Tung-Striebel smoother, one thread per trajectory, reverse time loop over the arrays
+// stored by the forward pass.  Pure small-matrix algebra on five streamed arrays: HBM-bound.
+// Replaces StateSpaceInference.backward_pass (ssinf.py:120-147) and
+// GaussianInference._smoothing_update (ssinf.py:325-344).
+#include "ssm_common.cuh"
+
+namespace ssm {
+
+void set_error(const char *fmt, ...);
+
+template <int DX>
+__global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
+                                                       const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
+                                                       const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
+                                                       double *__restrict__ sm_cov, int32_t *__restrict__ status,
+                                                       long long n_traj, int N, long long ld) {
+    constexpr int TX = TriSize<DX>::value;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_traj) return;
+    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    if (status[t] != 0) {  // the forward pass failed: nothing to smooth
+        for (int k = 0; k < N; ++k) {
+            for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
+            for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
+        }
+        return;
+    }
+    // The reference iterates k = N-2 .. 1 over arrays with N+1 slots (slot 0 = initial moments):
+    // slots N and N-1 (indices N-1, N-2 here) keep their filtered values, and the recursion starts
+    // from the filtered moments of slot N (ssinf.py:117, 137).
+    double ms[DX], Ps[TX];
+    for (int k = N - 1; k >= 0 && k >= N - 2; --k) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) {
+            const double v = ld_stream(fi_mean + at(a, k));
+            if (k == N - 1) ms[a] = v;
+            st_stream(sm_mean + at(a, k), v);
+        }
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) {
+                const double v = ld_stream(fi_cov + at(r * DX + c, k));
+                if (k == N - 1 && c <= r) Ps[tri(r, c)] = v;
+                st_stream(sm_cov + at(r * DX + c, k), v);
+            }
+    }
+    int fail = 0, kfail = 0;
+    for (int k = N - 3; k >= 0; --k) {
+        double mp[DX], Pp[TX], Pxx[DX][DX], mf[DX], Pf[TX];
+#pragma unroll
+        for (int a = 0; a < DX; ++a) {
+            mp[a] = ld_stream(pr_mean + at(a, k + 1));
+            mf[a] = ld_stream(fi_mean + at(a, k));
+        }
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) {
+                Pxx[r][c] = ld_stream(pr_xx + at(r * DX + c, k + 1));
+                if (c <= r) {
+                    Pp[tri(r, c)] = ld_stream(pr_cov + at(r * DX + c, k + 1));
+                    Pf[tri(r, c)] = ld_stream(fi_cov + at(r * DX + c, k));
+                }
+            }
+        // D = (Pp^-1 Pxx)^T                                                       ssinf.py:342
+        double Dg[DX][DX], Ls[TX];
+        if (!spd_gain<DX, DX>(Pp, Pxx, Dg, Ls)) { fail = SSM_FAIL_CHOL_SMOOTH; kfail = k; break; }
+        // m_s = m_f + D (m_s+ - m_p)                                              ssinf.py:343
+        double dm[DX];
+#pragma unroll
+        for (int a = 0; a < DX; ++a) dm[a] = ms[a] - mp[a];
+#pragma unroll
+        for (int a = 0; a < DX; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < DX; ++c) s = fma(Dg[a][c], dm[c], s);
+            ms[a] = mf[a] + s;
+        }
+        // P_s = P_f + D (P_s+ - P_p) D^T                                          ssinf.py:344
+        double dP[TX], T[DX][DX];
+#pragma unroll
+        for (int a = 0; a < TX; ++a) dP[a] = Ps[a] - Pp[a];
+#pragma unroll
+        for (int a = 0; a < DX; ++a)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int e = 0; e < DX; ++e) s = fma(Dg[a][e], dP[sym(e, c)], s);
+                T[a][c] = s;
+            }
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int e = 0; e < DX; ++e) s = fma(T[r][e], Dg[c][e], s);
+                Ps[tri(r, c)] = Pf[tri(r, c)] + s;
+            }
+#pragma unroll
+        for (int a = 0; a < DX; ++a) st_stream(sm_mean + at(a, k), ms[a]);
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) st_stream(sm_cov + at(r * DX + c, k), Ps[sym(r, c)]);
+    }
+    if (fail) {
+        for (int k = kfail; k >= 0; --k) {
+            for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
+            for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
+        }
+        status[t] = ((kfail + 1) << 8) | fail;
+    }
+}
+
+template <int DX>
+static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
+                           const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, long long n_traj, int N,
+                           long long ld, cudaStream_t s) {
+    const long long blocks = (n_traj + 127) / 128;
+    smoother_kernel<DX><<<(unsigned)blocks, 128, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status,
+                                                         n_traj, N, ld);
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                          const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
+                          int32_t *status, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    if (!fi_mean || !fi_cov || !pr_mean || !pr_cov || !pr_xx_cov || !sm_mean || !sm_cov || !status) {
+        set_error("ssm_smooth: NULL buffer");
+        return SSM_E_INVALID;
+    }
+    if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_smooth: bad sizes"); return SSM_E_INVALID; }
+    if (n_traj == 0 || n_steps == 0) return SSM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    switch (dx) {
+        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
+        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
+        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
+        default: set_error("ssm_smooth: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+    }
+    if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}
+
+// ---- FP64 FMA micro-benchmark: 8 independent DFMA chains per thread -----------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int n_iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < n_iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+extern "C" int ssm_fp64_peak_kernel(int32_t n_blocks, int32_t n_iters, double *sink, double *flops, void *stream) {
+    if (n_blocks <= 0 || n_iters <= 0 || !sink) { set_error("ssm_fp64_peak_kernel: bad arguments"); return SSM_E_INVALID; }
+    fp64_peak_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(sink, n_iters);
+    if (flops) *flops = 2.0 * 64.0 * (double)n_iters * 256.0 * (double)n_blocks;
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
