@@ -171,7 +171,10 @@ typedef struct ssm_rng {
 } ssm_rng;
 
 #define SSM_SIM_DISCRETE   1
-#define SSM_SIM_CONTINUOUS 2  /* Euler-Maruyama with dt_cont; output drops x0 (ssmod.py:244)     */
+#define SSM_SIM_CONTINUOUS 2  /* Euler-Maruyama with dt_cont; output drops x0 (ssmod.py:244) and keeps
+                                 every sub-th state: output k = internal state k*sub + 1; injected q has
+                                 (n_steps-1)*sub + 1 time slices, injected r n_steps                     */
+#define SSM_SIM_MEASURE    3  /* measurements of a GIVEN state array x (simulate_measurements)   */
 
 int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mode, double dt_cont, int32_t sub,
                  const double *x0_inj, const double *q_inj, const double *r_inj,
@@ -203,7 +206,9 @@ int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const double *par,
  * (row length ssm_scores_width(dx)); rmse_acc (dx, ld) receives per-trajectory time-sums of SE.
  * The packed stats rows are what the multi-GPU path all-reduces (NCCL, one call).
  * Phase 2 takes the global per-step MSE matrices (dx*dx, n_steps) and accumulates the log
- * credibility ratio: lcr[k] = sum_traj 10 (log10 d'P^-1 d - log10 d'MSE^-1 d).
+ * credibility ratio g = 10 (log10 d'P^-1 d - log10 d'MSE^-1 d):  lcr (n_steps, 2) =
+ * [ sum_traj g | sum_traj |g| ]  (inclination indicator / non-credibility index numerators).
+ * Both phases reduce in a fixed order (bitwise reproducible for a given trajectory count).
  */
 int32_t ssm_scores_width(int32_t dx);
 int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const double *cov,
@@ -212,6 +217,39 @@ int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const dou
 int ssm_scores_phase2(int32_t dx, const double *x, const double *mean, const double *cov,
                       const int32_t *status, const double *mse, double *lcr,
                       int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* ---- stand-alone moment transform / model evaluation -----------------------------------------
+ * ssm_transform_apply replaces MomentTransform.apply(f, mean, cov, fcn_pars) as a public call
+ * (mtran.py:105-149, bq/bqmtran.py:60-109) for n (mean, cov) pairs: mean (D, ld), cov (D*D, ld) ->
+ * mean_f (E, ld), cov_f (E*E, ld), cov_fx (E*D, ld).  The integrand is a device model function:
+ * which = 0 -> TransitionModel.dyn_eval of model SSM_DYN_*, which = 1 -> MeasurementModel.meas_eval of
+ * model SSM_OBS_* with state_index (si0, si1) (ssmod.py:129-166, 960-1009).  par = model parameters
+ * (host, 4 doubles), time = the integrand's time argument.
+ * ssm_model_eval evaluates dyn_fcn / meas_fcn themselves at n points x (D, ld) with optional noise
+ * (DQ, ld) (ssmod.py:268-269, 357-358, 530-564, 675-690, 1060-1061, 1114-1115, 1227-1252). */
+int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,
+                        const double *par, const ssm_transform *tf, double time,
+                        const double *mean, const double *cov, double *mean_f, double *cov_f, double *cov_fx,
+                        int32_t *status, int64_t n, int64_t ld, void *stream);
+int ssm_model_eval(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,
+                   const double *par, double time, const double *x, const double *noise, double *out,
+                   int64_t n, int64_t ld, void *stream);
+
+/* ---- RBF kernel and its Gaussian expectations (set-up path, one CTA) -------------------------
+ * Replaces RBFGauss.eval (bq/bqkern.py:329-343; x1 (D, n1), x2 (D, n2) host, K (n1, n2) device) and
+ * exp_x_kx / exp_x_xkx / exp_x_kxkx / exp_xy_kxy (bq/bqkern.py:345-424): q (N), R (D, N), Q (N, N),
+ * kbar (1) device.  par = [alpha, l_1..l_D] host. */
+int ssm_rbf_eval(int32_t dim, int32_t n1, int32_t n2, const double *par, const double *x1, const double *x2,
+                 int32_t scaling, double *K, void *stream);
+int ssm_rbf_expectations(int32_t dim, int32_t n_pts, const double *par, const double *points, int32_t scaling,
+                         double *q, double *R, double *Q, double *kbar, void *stream);
+
+/* ---- stand-alone sampler ---------------------------------------------------------------------
+ * Replaces GaussRV.sample / StudentRV.sample (utils.py:618-619, 670-671): out (dim, ld) =
+ * mean + F z (dof = 0) or mean + F z / sqrt(gamma(dof/2, 2/dof)) (dof > 0), Philox-keyed by
+ * (seed, offset + sample index). */
+int ssm_sample(int32_t dim, const double *mean, const double *factor, double dof, uint64_t seed, int64_t offset,
+               double *out, int64_t n, int64_t ld, void *stream);
 
 /* ---- FP64 FMA micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no fp64 figure) --
  * Launches a dependent-chain-free DFMA loop; returns the number of FLOPs it executes in *flops.

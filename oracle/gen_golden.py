@@ -284,6 +284,10 @@ def gen_filters():
     hobs = np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
     filter_case('c3_reentry_gpq', ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut'), x, y)
     filter_case('c3_reentry_ukf', ssinf.UnscentedKalman(dyn, obs), x[..., :2], y[..., :2])
+    # 8 shorter trajectories for the score tests (the per-step MSE matrix needs M > dx to be PD)
+    np.random.seed(1)
+    dyn8, obs8, x8, y8 = reentry(120, 8)
+    filter_case('c3s_reentry_gpq', ssinf.GaussianProcessKalman(dyn8, obs8, hdyn, hobs, kernel='rbf', points='ut'), x8, y8)
     filter_case('c3_reentry_ukf_b0', ssinf.UnscentedKalman(dyn, obs, beta=0.0), x[..., :1], y[..., :1])
     filter_case('c3_reentry_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :1], y[..., :1])
     # BSQ with model variance assigned from outside (research/bsq/bsq_tracking.py:266-281)
@@ -414,7 +418,7 @@ def gen_scores():
             sys.modules[m].trange = range
     import icinco_demo
     d = {}
-    for name in ('c1_ungm_ukf', 'c5_pend_gpq', 'c3_reentry_gpq'):
+    for name in ('c1_ungm_ukf', 'c5_pend_gpq', 'c3s_reentry_gpq'):
         g = np.load(os.path.join(OUT, name + '.npz'))
         x = g['x']
         mf, Pf, ms, Ps = g['fi_mean'][..., None], g['fi_cov'][..., None], g['sm_mean'][..., None], g['sm_cov'][..., None]

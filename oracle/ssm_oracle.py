@@ -473,8 +473,10 @@ def _t(a):
 
 def chol_loops(A):
     """Lower Cholesky factor by explicit column loops, vectorised over leading axes, any float
-    dtype.  Returns (L, ok): ok is False where a pivot is <= 0 or not finite (LAPACK potrf's
-    info > 0, which numpy.linalg.cholesky turns into LinAlgError at mtran.py:139, bqmtran.py:98).
+    dtype.  Returns (L, ok): ok is False where a pivot is <= 0 (potrf's info > 0, which
+    numpy.linalg.cholesky turns into LinAlgError at mtran.py:139, bqmtran.py:98).  A NaN pivot is not a
+    failure: the OpenBLAS potrf behind numpy tests `ajj <= 0` only and lets NaNs propagate (measured,
+    golden case c3_reentry_gpq_fail), and so does this function.
     Only the lower triangle of A is read, like LAPACK's 'L' variant."""
     n = A.shape[-1]
     L = np.zeros_like(A)
@@ -482,7 +484,7 @@ def chol_loops(A):
     with np.errstate(all='ignore'):
         for j in range(n):
             s = A[..., j, j] - np.sum(L[..., j, :j] ** 2, axis=-1)
-            good = s > 0  # False for NaN as well
+            good = ~(s <= 0)  # True for NaN: propagates
             ok &= good
             s = np.where(good, s, 1.0)
             d = np.sqrt(s)

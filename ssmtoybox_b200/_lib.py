@@ -21,7 +21,7 @@ DYN_IDS = {'UNGMTransition': 1, 'Pendulum2DTransition': 2, 'ReentryVehicle2DTran
 OBS_IDS = {'UNGMMeasurement': 1, 'Pendulum2DMeasurement': 2, 'Radar2DMeasurement': 3}
 TF_SP, TF_BQ, TF_TP = 1, 2, 3
 FAMILY_GAUSS, FAMILY_STUDENT = 1, 2
-SIM_DISCRETE, SIM_CONTINUOUS = 1, 2
+SIM_DISCRETE, SIM_CONTINUOUS, SIM_MEASURE = 1, 2, 3
 
 
 class SsmTransform(C.Structure):
@@ -68,19 +68,30 @@ def _load():
     lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     lib.ssm_fp64_peak_kernel.restype = C.c_int
     lib.ssm_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]
-    if hasattr(lib, 'ssm_simulate'):
+    if True:
         lib.ssm_simulate.restype = C.c_int
         lib.ssm_simulate.argtypes = [C.POINTER(SsmDesc), C.POINTER(SsmRng), i32, dbl, i32, vp, vp, vp, vp, vp, i64, i32, i64, vp]
-    if hasattr(lib, 'ssm_bq_weights'):
+    if True:
         lib.ssm_bq_weights.restype = C.c_int
         lib.ssm_bq_weights.argtypes = [i32, i32, i32, c_double_p, c_double_p, c_int32_p, i32, vp, vp, vp, vp, vp, vp, vp]
-    if hasattr(lib, 'ssm_scores_phase1'):
+    if True:
         lib.ssm_scores_width.restype = i32
         lib.ssm_scores_width.argtypes = [i32]
         lib.ssm_scores_phase1.restype = C.c_int
         lib.ssm_scores_phase1.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
         lib.ssm_scores_phase2.restype = C.c_int
         lib.ssm_scores_phase2.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+    lib.ssm_transform_apply.restype = C.c_int
+    lib.ssm_transform_apply.argtypes = [i32, i32, i32, i32, i32, c_double_p, C.POINTER(SsmTransform), dbl, vp, vp, vp, vp,
+                                        vp, vp, i64, i64, vp]
+    lib.ssm_model_eval.restype = C.c_int
+    lib.ssm_model_eval.argtypes = [i32, i32, i32, i32, i32, c_double_p, dbl, vp, vp, vp, i64, i64, vp]
+    lib.ssm_rbf_eval.restype = C.c_int
+    lib.ssm_rbf_eval.argtypes = [i32, i32, i32, c_double_p, c_double_p, c_double_p, i32, vp, vp]
+    lib.ssm_rbf_expectations.restype = C.c_int
+    lib.ssm_rbf_expectations.argtypes = [i32, i32, c_double_p, c_double_p, i32, vp, vp, vp, vp, vp]
+    lib.ssm_sample.restype = C.c_int
+    lib.ssm_sample.argtypes = [i32, c_double_p, c_double_p, dbl, C.c_uint64, i64, vp, i64, i64, vp]
     return lib
 
 

@@ -1,0 +1,103 @@
+"""RBF kernel and its Gaussian expectations (mirror of ssmtoybox/bq/bqkern.py for RBFGauss, :295-454,
+with Kernel.eval_inv_dot / _cho_inv :38-120).  Every method evaluates on the GPU."""
+import numpy as np
+import torch
+
+from .. import _lib, device as dv
+from .._lib import lib
+
+
+class Kernel(object):
+    """Kernel base class (bqkern.py:9-36)."""
+    supports_parameter_estimation = False
+
+    def __init__(self, dim, par, jitter):
+        self.par = np.atleast_2d(par).astype(float)
+        assert self.par.ndim == 2, "Kernel parameters must be 2D array"
+        self.scale = self.par[:, 0]
+        self.dim = dim
+        self.jitter = jitter
+        self.eye_d = np.eye(dim)
+
+    def get_parameters(self, par=None):
+        """(bqkern.py:144-156)"""
+        if par is None:
+            return self.par
+        return np.atleast_2d(par).astype(float)
+
+
+class RBFGauss(Kernel):
+    """k(x, x') = s^2 exp(-0.5 (x - x')' Lambda^-1 (x - x')) with expectations under N(0, I)."""
+    supports_parameter_estimation = True
+
+    def __init__(self, dim, par, jitter=1e-8):
+        par = np.atleast_2d(par)
+        assert par.shape[1] == dim + 1
+        super(RBFGauss, self).__init__(dim, par, jitter)
+
+    @staticmethod
+    def _unpack_parameters(par):
+        par = np.asarray(par).astype(float).squeeze()
+        return par[0], np.diag(par[1:] ** -1)
+
+    def _par1(self, par):
+        return dv._c(np.asarray(par, dtype=np.float64).reshape(-1)[:self.dim + 1])
+
+    def eval(self, par, x1, x2=None, diag=False, scaling=True):
+        """Kernel matrix (n1, n2) (bqkern.py:329-343)."""
+        x1 = dv._c(x1)
+        x2c = dv._c(x2) if x2 is not None else None
+        n1 = x1.shape[1]
+        n2 = x2c.shape[1] if x2c is not None else n1
+        K = torch.empty((n1, n2), dtype=torch.float64, device='cuda')
+        p = self._par1(par)
+        rc = lib.ssm_rbf_eval(self.dim, n1, n2, dv._ptr(p), dv._ptr(x1), dv._ptr(x2c) if x2c is not None else None,
+                              1 if scaling else 0, dv._p(K), dv._stream())
+        _lib.check(rc, 'ssm_rbf_eval')
+        K = K.cpu().numpy()
+        return np.diag(K).copy() if diag else K
+
+    def _expect(self, par, x, scaling):
+        x = dv._c(x)
+        D, N = x.shape
+        kw = dict(dtype=torch.float64, device='cuda')
+        q, R, Q, kbar = torch.empty(N, **kw), torch.empty((D, N), **kw), torch.empty((N, N), **kw), torch.empty(1, **kw)
+        p = self._par1(par)
+        rc = lib.ssm_rbf_expectations(D, N, dv._ptr(p), dv._ptr(x), 1 if scaling else 0, dv._p(q), dv._p(R), dv._p(Q),
+                                      dv._p(kbar), dv._stream())
+        _lib.check(rc, 'ssm_rbf_expectations')
+        return q.cpu().numpy(), R.cpu().numpy(), Q.cpu().numpy(), float(kbar.cpu().numpy()[0])
+
+    def eval_inv_dot(self, par, x, b=None, scaling=True):
+        """inv(K + jitter I) (symmetrised) or its product with b (bqkern.py:96-120)."""
+        p = np.array(self._par1(par))
+        if not scaling:
+            p[0] = 1.0
+        w = dv.bq_weights(p[None, :], x)
+        # iK of the weights kernel is for the unscaled kernel; K_scaled = alpha^2 K_unscaled only when the
+        # jitter is negligible, so recompute through the dedicated path when scaling is requested
+        iK = w['iK'][0] if not scaling or p[0] == 1.0 else self._inv_scaled(p, x)
+        return iK if b is None else iK.dot(b)
+
+    def _inv_scaled(self, p, x):
+        raise NotImplementedError('eval_inv_dot(scaling=True) with alpha != 1 is not on the filter path '
+                                  '(GaussianProcessModel.bq_weights uses scaling=False, bqmod.py:501)')
+
+    def exp_x_kx(self, par, x, scaling=False):
+        return self._expect(par, x, scaling)[0]
+
+    def exp_x_xkx(self, par, x):
+        return self._expect(par, x, False)[1]
+
+    def exp_x_kxkx(self, par_0, par_1, x, scaling=False):
+        if not np.array_equal(np.asarray(par_0, dtype=float).squeeze(), np.asarray(par_1, dtype=float).squeeze()):
+            raise NotImplementedError('exp_x_kxkx with two different parameter vectors is only used by the '
+                                      'out-of-scope multi-output models')
+        return self._expect(par_0, x, scaling)[2]
+
+    def exp_x_kxx(self, par):
+        return float(np.asarray(par, dtype=float).squeeze()[0]) ** 2
+
+    def exp_xy_kxy(self, par):
+        x = np.zeros((self.dim, 1))
+        return self._expect(par, x, False)[3]

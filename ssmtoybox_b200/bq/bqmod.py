@@ -1,0 +1,150 @@
+"""Integrand models of Bayesian quadrature (mirror of ssmtoybox/bq/bqmod.py: Model :15-106, 340-423,
+GaussianProcessModel :426-523, BayesSardModel :599-992, StudentTProcessModel :1055-1160).
+
+bq_weights runs on the GPU (ssm_bq_weights, one CTA per kernel-parameter vector).  Hyper-parameter
+fitting (optimize / neg_log_marginal_likelihood), predict and plotting are outside the hot path."""
+import numpy as np
+
+from .. import device as dv
+from ..mtran import SphericalRadialTransform, UnscentedTransform, GaussHermiteTransform, FullySymmetricStudentTransform
+from .bqkern import RBFGauss
+
+
+def n_sum_k(n, k):
+    """All n-tuples of non-negative integers summing to k, in the reference's column order (utils.py:459-475)."""
+    assert k >= 0
+    if k == 0:
+        return np.zeros((n, 1), dtype=int)
+    if k == 1:
+        return np.eye(n, dtype=int)
+    a = n_sum_k(n, k - 1)
+    eye = np.eye(n, dtype=int)
+    temp = np.zeros((n, (n * (1 + n) // 2) - 1), dtype=int)
+    tind = 0
+    for i in range(n - 1):
+        for j in range(i, n):
+            temp[:, tind] = a[:, i] + eye[:, j]
+            tind += 1
+    return np.hstack((temp, a[:, n - 1:] + eye[:, -1, None]))
+
+
+class Model(object):
+    """Kernel + point set (bqmod.py:15-106)."""
+    _supported_points_ = ['sr', 'ut', 'gh', 'fs']
+    _supported_kernels_ = ['rbf']
+
+    def __init__(self, dim, kern_par, kern_str, point_str, point_par, estimate_par):
+        self.kernel = Model.get_kernel(dim, kern_str, kern_par)
+        self.points = Model.get_points(dim, point_str, point_par)
+        self.estimate_par = estimate_par
+        self.str_pts = point_str
+        self.str_pts_par = str(point_par)
+        self.dim_in, self.num_pts = self.points.shape
+        self.eye_d, self.eye_n = np.eye(self.dim_in), np.eye(self.num_pts)
+        self.q, self.Q, self.R, self.iK = None, None, None, None
+        self.model_var = None
+        self.integral_var = None
+
+    @staticmethod
+    def get_points(dim, points, point_par):
+        """(bqmod.py:340-382)"""
+        points = points.lower()
+        if points not in Model._supported_points_:
+            raise ValueError('Points {} not supported. Supported points are {}.'.format(points, Model._supported_points_))
+        if point_par is None:
+            point_par = {}
+        if points == 'sr':
+            return SphericalRadialTransform.unit_sigma_points(dim)
+        elif points == 'ut':
+            return UnscentedTransform.unit_sigma_points(dim, **point_par)
+        elif points == 'gh':
+            return GaussHermiteTransform.unit_sigma_points(dim, **point_par)
+        return FullySymmetricStudentTransform.unit_sigma_points(dim, **point_par)
+
+    @staticmethod
+    def get_kernel(dim, kernel, par):
+        """(bqmod.py:384-423); 'rbf-student' (Monte-Carlo expectations) and 'rq' are not on the hot path."""
+        kernel = kernel.lower()
+        if kernel != 'rbf':
+            raise NotImplementedError("kernel '{}' has no device implementation (only 'rbf')".format(kernel))
+        return RBFGauss(dim, par)
+
+    def _weights(self, par, mulind=None):
+        par = self.kernel.get_parameters(par)
+        w = dv.bq_weights(par[:1], self.points, mulind)
+        if int(w['info'][0]) != 0:
+            raise np.linalg.LinAlgError('kernel matrix is not positive definite (info = {})'.format(int(w['info'][0])))
+        return w
+
+
+class GaussianProcessModel(Model):
+    """GP model of the integrand (bqmod.py:426-523)."""
+
+    def __init__(self, dim, kern_par, kern_str, point_str, point_par=None, estimate_par=False):
+        super(GaussianProcessModel, self).__init__(dim, kern_par, kern_str, point_str, point_par, estimate_par)
+
+    def bq_weights(self, par, *args):
+        """-> (wm, Wc, Wcc, model_var, integral_var) (bqmod.py:495-523)."""
+        w = self._weights(par)
+        self.iK = w['iK'][0]
+        self.model_var = float(w['model_var'][0])
+        self.integral_var = float(w['integral_var'][0])
+        return w['wm'][0], w['Wc'][0], w['Wcc'][0], self.model_var, self.integral_var
+
+    def exp_model_variance(self, par, *args):
+        return float(self._weights(par)['model_var'][0])
+
+    def integral_variance(self, par, *args):
+        return float(self._weights(par)['integral_var'][0])
+
+
+class BayesSardModel(Model):
+    """GP model with polynomial prior mean (bqmod.py:599-992)."""
+
+    def __init__(self, dim, kern_par, multi_ind=2, point_str='ut', point_par=None, estimate_par=False):
+        super(BayesSardModel, self).__init__(dim, kern_par, 'rbf', point_str, point_par, estimate_par)
+        if type(multi_ind) is int:
+            self.mulind = np.hstack([n_sum_k(dim, td) for td in range(multi_ind + 1)])
+        elif type(multi_ind) is np.ndarray:
+            self.mulind = multi_ind
+        else:
+            raise ValueError('Multi-index error: multi-index has to be either int or ndarray')
+
+    def bq_weights(self, par, multi_ind=None):
+        """-> (wm, Wc, Wcc, model_var, integral_var) (bqmod.py:893-992)."""
+        if multi_ind is None:
+            multi_ind = self.mulind
+        if not hasattr(multi_ind, 'shape'):
+            # the reference forwards the raw int and fails with AttributeError
+            raise AttributeError("'int' object has no attribute 'shape'")
+        if multi_ind.shape[1] > self.num_pts:
+            raise ValueError('Number of basis functions needs to be lower than or equal to the number of points.'
+                             'You supplied {:d} basis functions and {:d} points.'.format(multi_ind.shape[1], self.num_pts))
+        w = self._weights(par, multi_ind)
+        self.iK = w['iK'][0]
+        self.model_var = float(w['model_var'][0])
+        self.integral_var = float(w['integral_var'][0])
+        return w['wm'][0], w['Wc'][0], w['Wcc'][0], self.model_var, self.integral_var
+
+    def exp_model_variance(self, par, mulind=None):
+        return float(self._weights(par, self.mulind if mulind is None else mulind)['model_var'][0])
+
+    def integral_variance(self, par, mulind=None):
+        return float(self._weights(par, self.mulind if mulind is None else mulind)['integral_var'][0])
+
+
+class StudentTProcessModel(GaussianProcessModel):
+    """Student's t-process model (bqmod.py:1055-1160); weights are the GP weights, the model variance
+    is scaled by the data inside the filter kernel."""
+
+    def __init__(self, dim, kern_par, kern_str, point_str, point_par=None, estimate_par=False, nu=4.0):
+        super(StudentTProcessModel, self).__init__(dim, kern_par, kern_str, point_str, point_par, estimate_par)
+        nu = 3.0 if nu < 2 else nu
+        self.nu = nu
+
+    def exp_model_variance(self, par, *args):
+        """scale * gp_emv with scale = (nu - 2 + F iK F') / (nu - 2 + N) (bqmod.py:1132-1160); evaluated
+        inside the moment-transform kernel on the hot path, here for a single set of observations."""
+        fcn_obs = np.squeeze(np.asarray(args[0], dtype=np.float64))
+        scale = (self.nu - 2 + fcn_obs.dot(self.iK).dot(fcn_obs.T)) / (self.nu - 2 + self.num_pts)
+        return scale * self.model_var

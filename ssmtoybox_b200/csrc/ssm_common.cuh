@@ -26,8 +26,11 @@ SSM_DEV void st_stream(double *p, double v) { __stcs(p, v); }
 SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // Lower Cholesky factor of a symmetric matrix given by its packed lower triangle.
-// Mirrors LAPACK dpotrf('L') as called by numpy.linalg.cholesky (mtran.py:139, bqmtran.py:98):
-// only the lower triangle is read, a pivot <= 0 or NaN is a failure.  Returns false on failure.
+// Mirrors dpotrf('L') as called by numpy.linalg.cholesky (mtran.py:139, bqmtran.py:98): only the
+// lower triangle is read and a pivot <= 0 is a failure (LinAlgError).  A NaN pivot is NOT a failure:
+// the OpenBLAS potrf behind numpy 2.3 tests `ajj <= 0` only, so NaNs propagate silently until
+// scipy's check_finite in cho_factor raises ValueError (measured on the golden case
+// c3_reentry_gpq_fail); the kernels reproduce that sequence.  Returns false on failure.
 template <int D>
 SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSize<D>::value]) {
     bool ok = true;
@@ -36,7 +39,7 @@ SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSiz
         double s = A[tri(j, j)];
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[tri(j, k)], L[tri(j, k)], s);
-        ok = ok && (s > 0.0);
+        ok = ok && !(s <= 0.0);
         const double d = sqrt(s);
         const double inv = 1.0 / d;
         L[tri(j, j)] = d;

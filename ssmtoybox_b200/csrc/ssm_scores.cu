@@ -1,0 +1,224 @@
+// K6: error statistics over the trajectory axis, per time step.
+// Replaces utils.squared_error / mse_matrix / neg_log_likelihood / log_cred_ratio (utils.py:18-148)
+// and the Python reduction loops of research/gpq/icinco_demo.py:17-52 and
+// research/bsq/bsq_tracking.py:311-337.
+//
+// One thread per trajectory walks the time axis; per step the CTA reduces its 128 trajectories with
+// warp shuffles + one shared-memory pass (fixed order), writes one partial row per (CTA, step), and a
+// second kernel sums the partial rows in CTA order: the result is bitwise reproducible for a given
+// trajectory count, and the packed rows are what the multi-GPU driver all-reduces (NCCL).
+// The log credibility ratio needs the GLOBAL per-step MSE matrix first (two-phase reduction).
+#include "ssm_common.cuh"
+
+namespace ssm {
+
+void set_error(const char *fmt, ...);
+
+constexpr int SC_THREADS = 128;
+
+template <int W>
+SSM_DEV void block_reduce_store(double (&v)[W], double *smem /* [SC_THREADS/32][W] */, double *dst) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) smem[wid * W + i] = v[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < SC_THREADS / 32; ++w) s += smem[w * W + i];
+        dst[i] = s;
+    }
+    __syncthreads();
+}
+
+template <int DX>
+__global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double *__restrict__ x, const double *__restrict__ mean,
+                                                                   const double *__restrict__ cov, const int32_t *__restrict__ status,
+                                                                   double *__restrict__ partial, double *__restrict__ rmse_acc,
+                                                                   long long n_traj, int N, long long ld) {
+    constexpr int TX = TriSize<DX>::value, W = DX + DX * DX + 3;
+    __shared__ double smem[(SC_THREADS / 32) * W];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < n_traj && (status == nullptr || status[t] == 0);
+    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    double se_acc[DX];
+#pragma unroll
+    for (int a = 0; a < DX; ++a) se_acc[a] = 0.0;
+    for (int k = 0; k < N; ++k) {
+        double v[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = 0.0;
+        if (live) {
+            double d[DX], P[TX], L[TX];
+#pragma unroll
+            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x + at(a, k)) - ld_stream(mean + at(a, k));
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(cov + at(r * DX + c, k));
+            double sse = 0.0;
+#pragma unroll
+            for (int a = 0; a < DX; ++a) {
+                const double s = d[a] * d[a];  // squared_error, utils.py:38
+                v[a] = s;
+                se_acc[a] += s;
+                sse += s;
+            }
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c < DX; ++c) v[DX + r * DX + c] = d[r] * d[c];  // mse_matrix summand, utils.py:62-64
+            // neg_log_likelihood = 0.5 (log|P| + d' P^-1 d + dx log 2 pi), utils.py:143-148, through chol(P)
+            const bool ok = chol_lower<DX>(P, L);
+            double logdet = 0.0, quad = 0.0, z[DX];
+#pragma unroll
+            for (int i = 0; i < DX; ++i) {
+                double s = d[i];
+#pragma unroll
+                for (int c = 0; c < i; ++c) s = fma(-L[tri(i, c)], z[c], s);
+                z[i] = s / L[tri(i, i)];
+                quad = fma(z[i], z[i], quad);
+                logdet += log(L[tri(i, i)]);
+            }
+            v[DX + DX * DX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
+            v[DX + DX * DX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
+            v[DX + DX * DX + 2] = 1.0;
+        }
+        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * N + k) * W);
+    }
+    if (rmse_acc && t < n_traj) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = live ? se_acc[a] : qnan();
+    }
+}
+
+// stats[k][w] = sum over CTAs (fixed order) of partial[cta][k][w]
+__global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row) return;
+    double s = 0.0;
+    for (int c = 0; c < n_cta; ++c) s += partial[(long long)c * row + i];
+    stats[i] = s;
+}
+
+template <int DX>
+__global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double *__restrict__ x, const double *__restrict__ mean,
+                                                                   const double *__restrict__ cov, const int32_t *__restrict__ status,
+                                                                   const double *__restrict__ mse, double *__restrict__ partial,
+                                                                   long long n_traj, int N, long long ld) {
+    constexpr int TX = TriSize<DX>::value;
+    __shared__ double smem[(SC_THREADS / 32) * 2];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < n_traj && (status == nullptr || status[t] == 0);
+    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    for (int k = 0; k < N; ++k) {
+        double v[2] = {0.0, 0.0};
+        if (live) {
+            double d[DX], P[TX], S[TX], L[TX], Ls[TX];
+#pragma unroll
+            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x + at(a, k)) - ld_stream(mean + at(a, k));
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    P[tri(r, c)] = ld_stream(cov + at(r * DX + c, k));
+                    S[tri(r, c)] = __ldg(mse + (long long)(r * DX + c) * N + k);
+                }
+            // log_cred_ratio, utils.py:113-120: both quadratic forms through Cholesky factors
+            const bool ok = chol_lower<DX>(P, L) & chol_lower<DX>(S, Ls);
+            double qa = 0.0, qb = 0.0, za[DX], zb[DX];
+#pragma unroll
+            for (int i = 0; i < DX; ++i) {
+                double sa = d[i], sb = d[i];
+#pragma unroll
+                for (int c = 0; c < i; ++c) {
+                    sa = fma(-L[tri(i, c)], za[c], sa);
+                    sb = fma(-Ls[tri(i, c)], zb[c], sb);
+                }
+                za[i] = sa / L[tri(i, i)];
+                zb[i] = sb / Ls[tri(i, i)];
+                qa = fma(za[i], za[i], qa);
+                qb = fma(zb[i], zb[i], qb);
+            }
+            const double g = ok ? 10.0 * (log10(qa) - log10(qb)) : qnan();
+            v[0] = g;
+            v[1] = fabs(g);
+        }
+        block_reduce_store<2>(v, smem, partial + ((long long)blockIdx.x * N + k) * 2);
+    }
+}
+
+template <int DX>
+static int run_phase1(const double *x, const double *mean, const double *cov, const int32_t *status, double *stats,
+                      double *rmse_acc, long long n_traj, int N, long long ld, cudaStream_t s) {
+    constexpr int W = DX + DX * DX + 3;
+    const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
+    double *partial = nullptr;
+    if (cudaMallocAsync(&partial, (size_t)n_cta * N * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, n_traj, N, ld);
+    const long long row = (long long)N * W;
+    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, n_cta, row);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, s);
+    return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+template <int DX>
+static int run_phase2(const double *x, const double *mean, const double *cov, const int32_t *status, const double *mse,
+                      double *lcr, long long n_traj, int N, long long ld, cudaStream_t s) {
+    const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
+    double *partial = nullptr;
+    if (cudaMallocAsync(&partial, (size_t)n_cta * N * 2 * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, mse, partial, n_traj, N, ld);
+    const long long row = (long long)N * 2;
+    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, lcr, n_cta, row);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, s);
+    return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+extern "C" int32_t ssm_scores_width(int32_t dx) { return dx + dx * dx + 3; }
+
+extern "C" int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                 double *stats, double *rmse_acc, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    if (!x || !mean || !cov || !stats) { set_error("ssm_scores_phase1: NULL buffer"); return SSM_E_INVALID; }
+    if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase1: bad sizes"); return SSM_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    switch (dx) {
+        case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+    }
+    if (rc == SSM_E_CUDA) set_error("ssm_scores_phase1: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}
+
+// lcr: (n_steps, 2) = per step [ sum of log credibility ratios | sum of their absolute values ]
+extern "C" int ssm_scores_phase2(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                 const double *mse, double *lcr, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    if (!x || !mean || !cov || !mse || !lcr) { set_error("ssm_scores_phase2: NULL buffer"); return SSM_E_INVALID; }
+    if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase2: bad sizes"); return SSM_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    switch (dx) {
+        case 1: rc = run_phase2<1>(x, mean, cov, status, mse, lcr, n_traj, n_steps, ld, s); break;
+        case 2: rc = run_phase2<2>(x, mean, cov, status, mse, lcr, n_traj, n_steps, ld, s); break;
+        case 5: rc = run_phase2<5>(x, mean, cov, status, mse, lcr, n_traj, n_steps, ld, s); break;
+        default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+    }
+    if (rc == SSM_E_CUDA) set_error("ssm_scores_phase2: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}

@@ -1,0 +1,322 @@
+// K1: batched simulation of state trajectories and measurements, one thread per trajectory.
+// Replaces TransitionModel.simulate_discrete / simulate_continuous (ssmod.py:168-244),
+// MeasurementModel.simulate_measurements (ssmod.py:1011-1039) and the samplers GaussRV.sample /
+// StudentRV.sample / multivariate_t (utils.py:349-382, 618-619, 670-671).
+//
+// Noise is either injected (device arrays, parity mode: results follow the reference bit for bit
+// up to libm) or drawn in-kernel with Philox4x32-10 keyed by (seed, GLOBAL trajectory index) and
+// counted by (time step, stream id, call), so the draws do not depend on the grid shape, on the
+// number of GPUs or on how trajectories are sharded.  numpy's MT19937 stream cannot be reproduced
+// (SURVEY.md Q10): Philox mode is validated statistically.
+#include "ssm_models.cuh"
+
+namespace ssm {
+
+void set_error(const char *fmt, ...);
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) -----------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    SSM_DEV static void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    SSM_DEV void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) const {
+        uint32_t c[4] = {c0, c1, c2, c3};
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, a, b);
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = c[i];
+    }
+};
+
+// uniform in (0, 1) from 64 random bits (53-bit mantissa, never 0)
+SSM_DEV double u01(uint32_t lo, uint32_t hi) {
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return ((double)(v >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct Rng {
+    Philox ph;
+    uint32_t t_lo, t_hi;
+    // two standard normals for (step, stream, call) by Box-Muller
+    SSM_DEV void normal2(uint32_t step, uint32_t stream, uint32_t call, double &z0, double &z1) const {
+        uint32_t r[4];
+        ph.gen(t_lo, t_hi, step, (stream << 16) | call, r);
+        const double u = u01(r[0], r[1]), v = u01(r[2], r[3]);
+        const double rad = sqrt(-2.0 * log(u));
+        double s, c;
+        sincospi(2.0 * v, &s, &c);
+        z0 = rad * c;
+        z1 = rad * s;
+    }
+    template <int DIM>
+    SSM_DEV void normals(uint32_t step, uint32_t stream, double (&z)[DIM]) const {
+#pragma unroll
+        for (int i = 0; i < DIM; i += 2) {
+            double a, b;
+            normal2(step, stream, i / 2, a, b);
+            z[i] = a;
+            if (i + 1 < DIM) z[i + 1] = b;
+        }
+    }
+    // Gamma(shape a >= 1, scale 1) by Marsaglia-Tsang; calls >= 64 are reserved for it
+    SSM_DEV double gamma(uint32_t step, uint32_t stream, double a) const {
+        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (uint32_t it = 0; it < 64; ++it) {
+            uint32_t r[4];
+            double x, unused;
+            normal2(step, stream, 64 + 2 * it, x, unused);
+            ph.gen(t_lo, t_hi, step, (stream << 16) | (65 + 2 * it), r);
+            const double u = u01(r[0], r[1]);
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+        }
+        return d;
+    }
+    // DIM-variate draw  F z  (Gaussian) or  F z / sqrt(g), g ~ Gamma(nu/2, 2/nu)  (Student, utils.py:380-382)
+    template <int DIM>
+    SSM_DEV void draw(uint32_t step, uint32_t stream, const double *F, double dof, double (&o)[DIM]) const {
+        double z[DIM];
+        normals<DIM>(step, stream, z);
+        double sc = 1.0;
+        if (dof > 0.0) sc = rsqrt(gamma(step, stream, 0.5 * dof) * (2.0 / dof));
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) s = fma(F[i * DIM + j], z[j], s);
+            o[i] = s * sc;
+        }
+    }
+};
+
+template <int DX, int DQ, int DY>
+struct SimPar {
+    double dyn_par[4], obs_par[4];
+    double x0_mean[DX], x0_F[DX * DX], q_F[DQ * DQ], r_F[DY * DY];
+    double x0_dof, q_dof, r_dof;
+    unsigned long long seed;
+    long long traj_offset;
+    const double *x0_inj, *q_inj, *r_inj;
+    double *x, *y;
+    long long n_traj, ld;
+    int n_steps, mode, sub, use_rng;
+    double dt;
+};
+
+enum { STREAM_X0 = 0, STREAM_Q = 1, STREAM_R = 2 };
+
+template <class Dyn, class Obs>
+__global__ void __launch_bounds__(128) sim_kernel(const __grid_constant__ SimPar<Dyn::DX, Dyn::DQ, Obs::DY> p) {
+    constexpr int DX = Dyn::DX, DQ = Dyn::DQ, DY = Obs::DY;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n_traj) return;
+    const int N = p.n_steps;
+    const long long ld = p.ld;
+    Rng rng;
+    rng.ph.k0 = (uint32_t)p.seed;
+    rng.ph.k1 = (uint32_t)(p.seed >> 32);
+    const unsigned long long gt = (unsigned long long)(p.traj_offset + t);
+    rng.t_lo = (uint32_t)gt;
+    rng.t_hi = (uint32_t)(gt >> 32);
+
+    double x[DX];
+    if (p.mode == SSM_SIM_MEASURE) {
+    } else if (p.x0_inj) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) x[a] = p.x0_inj[(long long)a * ld + t];
+    } else {
+        double z[DX];
+        rng.template draw<DX>(0, STREAM_X0, p.x0_F, p.x0_dof, z);
+#pragma unroll
+        for (int a = 0; a < DX; ++a) x[a] = p.x0_mean[a] + z[a];
+    }
+    const bool cont = p.mode == SSM_SIM_CONTINUOUS;
+    const int S = cont ? (N - 1) * p.sub + 1 : N;  // internal steps
+    const double qs = cont ? sqrt(p.dt) / p.dt : 1.0;  // ssmod.py:236
+
+    auto emit = [&](int k_out, int k_int) {  // store state k_out and its measurement
+        if (p.mode != SSM_SIM_MEASURE) {
+#pragma unroll
+            for (int a = 0; a < DX; ++a) st_stream(p.x + ((long long)a * N + k_out) * ld + t, x[a]);
+        }
+        if (!p.y) return;
+        double r[DY], o[DY];
+        if (p.r_inj) {
+#pragma unroll
+            for (int a = 0; a < DY; ++a) r[a] = p.r_inj[((long long)a * N + k_out) * ld + t];
+        } else {
+            rng.template draw<DY>((uint32_t)k_int, STREAM_R, p.r_F, p.r_dof, r);
+        }
+        Obs::template h<true>(p.obs_par, x, r, (double)(k_int + 1), o);  // time = k + 1, ssmod.py:1038
+#pragma unroll
+        for (int a = 0; a < DY; ++a) st_stream(p.y + ((long long)a * N + k_out) * ld + t, o[a]);
+    };
+
+    if (p.mode == SSM_SIM_MEASURE) {  // simulate_measurements(x) on a given state array
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int a = 0; a < DX; ++a) x[a] = ld_stream(p.x + ((long long)a * N + k) * ld + t);
+            emit(k, k);
+        }
+        return;
+    }
+    if (!cont) emit(0, 0);  // discrete: slot 0 is the initial state (ssmod.py:190)
+    for (int j = 1; j <= S; ++j) {
+        if (!cont && j == S) break;  // discrete: steps - 1 transitions
+        double q[DQ], o[DX];
+        if (p.q_inj) {
+            const int nq = cont ? S : N;
+#pragma unroll
+            for (int a = 0; a < DQ; ++a) q[a] = p.q_inj[((long long)a * nq + (j - 1)) * ld + t];
+        } else {
+            rng.template draw<DQ>((uint32_t)(j - 1), STREAM_Q, p.q_F, p.q_dof, q);
+        }
+        if (cont) {  // Euler-Maruyama, ssmod.py:238-243
+#pragma unroll
+            for (int a = 0; a < DQ; ++a) q[a] *= qs;
+            Dyn::fc(p.dyn_par, x, q, (double)(j - 1), o);
+#pragma unroll
+            for (int a = 0; a < DX; ++a) x[a] = x[a] + p.dt * o[a];
+            // returned array drops x0 (ssmod.py:244) and is sub-sampled [::sub] by the caller's convention
+            if ((j - 1) % p.sub == 0) emit((j - 1) / p.sub, j - 1);
+        } else {  // ssmod.py:198
+            Dyn::template f<true>(p.dyn_par, x, q, (double)(j - 1), o);
+#pragma unroll
+            for (int a = 0; a < DX; ++a) x[a] = o[a];
+            emit(j, j);
+        }
+    }
+}
+
+template <class Dyn, class Obs>
+static int launch_sim(const ssm_desc *d, const ssm_rng *rng, int mode, double dt, int sub, const double *x0_inj,
+                      const double *q_inj, const double *r_inj, double *x, double *y, long long n_traj, int n_steps,
+                      long long ld, cudaStream_t s) {
+    constexpr int DX = Dyn::DX, DQ = Dyn::DQ, DY = Obs::DY;
+    if (mode == SSM_SIM_CONTINUOUS && !Dyn::HAS_CONT) {
+        set_error("ssm_simulate: model %d has no continuous-time dynamics (dyn_fcn_cont)", d->dyn_model);
+        return SSM_E_UNSUPPORTED;
+    }
+    SimPar<DX, DQ, DY> p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d->dyn_par[i]; p.obs_par[i] = d->obs_par[i]; }
+    const bool meas_only = mode == SSM_SIM_MEASURE;
+    const bool need_rng = meas_only ? !r_inj : (!x0_inj || !q_inj || (y && !r_inj));
+    if (need_rng && meas_only) {
+        if (!rng || !rng->r_factor) { set_error("ssm_simulate: RNG description required when noise is not injected"); return SSM_E_INVALID; }
+        for (int i = 0; i < DY * DY; ++i) p.r_F[i] = rng->r_factor[i];
+        p.r_dof = rng->r_dof;
+        p.seed = rng->seed;
+        p.traj_offset = rng->traj_offset;
+    } else if (need_rng) {
+        if (!rng || !rng->x0_mean || !rng->x0_factor || !rng->q_factor || (y && !rng->r_factor)) {
+            set_error("ssm_simulate: RNG description required when noise is not injected");
+            return SSM_E_INVALID;
+        }
+        if (rng->dq != DQ) { set_error("ssm_simulate: noise dimension %d != %d", rng->dq, DQ); return SSM_E_INVALID; }
+        for (int i = 0; i < DX; ++i) p.x0_mean[i] = rng->x0_mean[i];
+        for (int i = 0; i < DX * DX; ++i) p.x0_F[i] = rng->x0_factor[i];
+        for (int i = 0; i < DQ * DQ; ++i) p.q_F[i] = rng->q_factor[i];
+        if (y) for (int i = 0; i < DY * DY; ++i) p.r_F[i] = rng->r_factor[i];
+        p.x0_dof = rng->x0_dof; p.q_dof = rng->q_dof; p.r_dof = rng->r_dof;
+        p.seed = rng->seed;
+        p.traj_offset = rng->traj_offset;
+    }
+    p.x0_inj = x0_inj; p.q_inj = q_inj; p.r_inj = r_inj;
+    p.x = x; p.y = y;
+    p.n_traj = n_traj; p.ld = ld; p.n_steps = n_steps; p.mode = mode; p.sub = sub < 1 ? 1 : sub; p.dt = dt;
+    const long long blocks = (n_traj + 127) / 128;
+    sim_kernel<Dyn, Obs><<<(unsigned)blocks, 128, 0, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+extern "C" int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mode, double dt_cont, int32_t sub,
+                            const double *x0_inj, const double *q_inj, const double *r_inj, double *x, double *y,
+                            int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    if (!desc || !x) { set_error("ssm_simulate: desc and x must not be NULL"); return SSM_E_INVALID; }
+    if (mode == SSM_SIM_MEASURE && !y) { set_error("ssm_simulate: y must not be NULL in measurement mode"); return SSM_E_INVALID; }
+    if (mode != SSM_SIM_DISCRETE && mode != SSM_SIM_CONTINUOUS && mode != SSM_SIM_MEASURE) { set_error("ssm_simulate: bad mode %d", mode); return SSM_E_INVALID; }
+    if (mode == SSM_SIM_CONTINUOUS && !(dt_cont > 0.0)) { set_error("ssm_simulate: dt must be > 0"); return SSM_E_INVALID; }
+    if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_simulate: bad sizes"); return SSM_E_INVALID; }
+    if (n_traj == 0 || n_steps == 0) return SSM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int dm = desc->dyn_model, om = desc->obs_model, nsi = desc->n_state_index;
+    const int32_t *si = desc->state_index;
+    int rc = SSM_E_UNSUPPORTED;
+#define SSM_SIM_ARGS desc, rng, mode, dt_cont, sub, x0_inj, q_inj, r_inj, x, y, n_traj, n_steps, ld, s
+    if (dm == SSM_DYN_UNGM && om == SSM_OBS_UNGM && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = launch_sim<DynUngm, ObsUngm<1, 0>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_PENDULUM && om == SSM_OBS_PENDULUM && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = launch_sim<DynPendulum, ObsPendulum<2, 0>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_REENTRY && om == SSM_OBS_RADAR && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = launch_sim<DynReentry, ObsRadar<5, 0, 1>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_COORDTURN && om == SSM_OBS_RADAR && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = launch_sim<DynCoordTurn, ObsRadar<5, 0, 2>>(SSM_SIM_ARGS);
+    else
+        set_error("ssm_simulate: no device implementation for dyn_model=%d obs_model=%d", dm, om);
+#undef SSM_SIM_ARGS
+    if (rc == SSM_E_CUDA) set_error("ssm_simulate: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}
+
+// ---- stand-alone sampler: GaussRV.sample / StudentRV.sample (utils.py:618-619, 670-671) ----------
+namespace ssm {
+constexpr int SAMPLE_MAXD = 8;
+struct SamplePar {
+    int dim;
+    double mean[SAMPLE_MAXD], F[SAMPLE_MAXD * SAMPLE_MAXD];
+    double dof;
+    unsigned long long seed;
+    long long offset, n, ld;
+    double *out;
+};
+__global__ void sample_kernel(const SamplePar p) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    Rng rng;
+    rng.ph.k0 = (uint32_t)p.seed;
+    rng.ph.k1 = (uint32_t)(p.seed >> 32);
+    const unsigned long long gt = (unsigned long long)(p.offset + t);
+    rng.t_lo = (uint32_t)gt;
+    rng.t_hi = (uint32_t)(gt >> 32);
+    double z[SAMPLE_MAXD];
+    rng.normals<SAMPLE_MAXD>(0, 3, z);
+    double sc = 1.0;
+    if (p.dof > 0.0) sc = rsqrt(rng.gamma(0, 3, 0.5 * p.dof) * (2.0 / p.dof));
+    for (int i = 0; i < p.dim; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < p.dim; ++j) s = fma(p.F[i * p.dim + j], z[j], s);
+        p.out[(long long)i * p.ld + t] = p.mean[i] + s * sc;
+    }
+}
+}  // namespace ssm
+
+extern "C" int ssm_sample(int32_t dim, const double *mean, const double *factor, double dof, uint64_t seed, int64_t offset,
+                          double *out, int64_t n, int64_t ld, void *stream) {
+    if (!mean || !factor || !out || dim < 1 || dim > SAMPLE_MAXD || n < 0 || ld < n) { set_error("ssm_sample: bad arguments"); return SSM_E_INVALID; }
+    if (n == 0) return SSM_OK;
+    SamplePar p;
+    memset(&p, 0, sizeof(p));
+    p.dim = dim;
+    for (int i = 0; i < dim; ++i) p.mean[i] = mean[i];
+    for (int i = 0; i < dim * dim; ++i) p.F[i] = factor[i];
+    p.dof = dof; p.seed = seed; p.offset = offset; p.n = n; p.ld = ld; p.out = out;
+    sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) { set_error("ssm_sample: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError())); return SSM_E_CUDA; }
+    return SSM_OK;
+}

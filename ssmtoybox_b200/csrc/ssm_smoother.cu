@@ -63,6 +63,15 @@ __global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict_
                     Pf[tri(r, c)] = ld_stream(fi_cov + at(r * DX + c, k));
                 }
             }
+        // scipy's cho_factor / cho_solve reject non-finite input (ValueError)        ssinf.py:342
+        bool fin = true;
+#pragma unroll
+        for (int a = 0; a < TX; ++a) fin = fin && finite_d(Pp[a]);
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) fin = fin && finite_d(Pxx[r][c]);
+        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; break; }
         // D = (Pp^-1 Pxx)^T                                                       ssinf.py:342
         double Dg[DX][DX], Ls[TX];
         if (!spd_gain<DX, DX>(Pp, Pxx, Dg, Ls)) { fail = SSM_FAIL_CHOL_SMOOTH; kfail = k; break; }

@@ -152,6 +152,9 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     if init_mean is not None:
         init_mean = init_mean.contiguous()
         init_cov = init_cov.contiguous()
+    if M == 0 or N == 0:
+        o['status'].zero_()
+        return o
     rc = lib.ssm_filter(C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
                         _p(o.get('pr_cov')), _p(o.get('pr_xx_cov')), _p(init_mean), _p(init_cov),
                         _p(o.get('last_mean')), _p(o.get('last_cov')), _p(t_offset), int(k0), _p(o['status']),
@@ -188,3 +191,110 @@ def fp64_peak(n_blocks=148 * 8, n_iters=4096, reps=5):
         e1.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3))
     return best
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: simulation
+# ------------------------------------------------------------------------------------------------
+def _cov_factor(cov):
+    """A with A A^T = cov for a (possibly singular) PSD matrix; same construction as
+    numpy.random.multivariate_normal's SVD path (the reference's sampler, utils.py:619)."""
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    u, s, vh = np.linalg.svd(cov)
+    return _c((vh.T * np.sqrt(s)))
+
+
+def make_rng(d, seed, traj_offset=0):
+    """dict description (m0, P0, q_cov, r_cov [, x0_dof, q_dof, r_dof]) -> (SsmRng, keepalive)."""
+    keep = [_c(d['m0']), _cov_factor(d['P0']), _cov_factor(d['q_cov']), _cov_factor(d['r_cov'])]
+    r = _lib.SsmRng()
+    r.seed, r.traj_offset = int(seed) & 0xFFFFFFFFFFFFFFFF, int(traj_offset)
+    r.x0_mean, r.x0_factor, r.q_factor, r.r_factor = (_ptr(a) for a in keep)
+    if d.get('sample_student', False):
+        r.x0_dof, r.q_dof, r.r_dof = float(d['x0_dof']), float(d['q_dof']), float(d['r_dof'])
+    r.dq = keep[2].shape[0]
+    return r, keep
+
+
+def simulate(low, n_traj, n_steps, rng=None, mode='discrete', dt=0.0, sub=1, x0=None, q=None, r=None,
+             want_y=True, device='cuda'):
+    """Simulate states (dx, N, M) and measurements (dy, N, M) with ssm_simulate.  rng = (SsmRng, keep)
+    from make_rng, or injected noise tensors x0 (dx, M), q (dq, Nq, M), r (dy, N, M)."""
+    kw = dict(dtype=torch.float64, device=device)
+    x = torch.empty((low.dx, n_steps, n_traj), **kw)
+    y = torch.empty((low.dy, n_steps, n_traj), **kw) if want_y else None
+    m = {'discrete': _lib.SIM_DISCRETE, 'continuous': _lib.SIM_CONTINUOUS}[mode]
+    for t in (x0, q, r):
+        if t is not None and (t.dtype != torch.float64 or not t.is_contiguous() or t.shape[-1] != n_traj):
+            raise ValueError('injected noise must be contiguous float64 with trajectory axis last')
+    rc = lib.ssm_simulate(C.byref(low.desc), C.byref(rng[0]) if rng is not None else None, m, float(dt), int(sub),
+                          _p(x0), _p(q), _p(r), _p(x), _p(y), n_traj, n_steps, n_traj, _stream())
+    _lib.check(rc, 'ssm_simulate')
+    return x, y
+
+
+def simulate_measurements(low, x, rng=None, r=None):
+    """Measurements of a given state array x (dx, N, M) (MeasurementModel.simulate_measurements)."""
+    dx, N, M = x.shape
+    y = torch.empty((low.dy, N, M), dtype=torch.float64, device=x.device)
+    rc = lib.ssm_simulate(C.byref(low.desc), C.byref(rng[0]) if rng is not None else None, _lib.SIM_MEASURE, 0.0, 1,
+                          None, None, _p(r), _p(x.contiguous()), _p(y), M, N, M, _stream())
+    _lib.check(rc, 'ssm_simulate')
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# K5: Bayesian-quadrature weights
+# ------------------------------------------------------------------------------------------------
+def bq_weights(par, points, mulind=None, device='cuda'):
+    """Batched BQ weights (ssm_bq_weights).  par (n_par, D+1), points (D, N), mulind (D, Q) or None.
+    Returns dict of numpy arrays: wm (n_par, N), Wc (n_par, N, N), Wcc (n_par, D, N), iK (n_par, N, N),
+    model_var (n_par,), integral_var (n_par,), info (n_par,)."""
+    par = _c(np.atleast_2d(par))
+    points = _c(points)
+    D, N = points.shape
+    n_par = par.shape[0]
+    if par.shape[1] != D + 1:
+        raise ValueError('kernel parameters must have D+1 = {} columns'.format(D + 1))
+    kw = dict(dtype=torch.float64, device=device)
+    wm, Wc, Wcc = torch.empty((n_par, N), **kw), torch.empty((n_par, N, N), **kw), torch.empty((n_par, D, N), **kw)
+    iK, scal = torch.empty((n_par, N, N), **kw), torch.empty((n_par, 2), **kw)
+    info = torch.empty((n_par,), dtype=torch.int32, device=device)
+    mi, nb = None, 0
+    if mulind is not None:
+        mi = np.ascontiguousarray(np.asarray(mulind, dtype=np.int32))
+        if mi.shape[0] != D:
+            raise ValueError('Dimension mismatch {:d} != {:d}. Dimension of monomials must be equal to the dimension'
+                             ' of the sigma-points.'.format(mi.shape[0], D))
+        nb = mi.shape[1]
+    rc = lib.ssm_bq_weights(D, N, n_par, _ptr(par), _ptr(points),
+                            mi.ctypes.data_as(_lib.c_int32_p) if mi is not None else None, nb,
+                            _p(wm), _p(Wc), _p(Wcc), _p(iK), _p(scal), _p(info), _stream())
+    _lib.check(rc, 'ssm_bq_weights')
+    sc = scal.cpu().numpy()
+    return dict(wm=wm.cpu().numpy(), Wc=Wc.cpu().numpy(), Wcc=Wcc.cpu().numpy(), iK=iK.cpu().numpy(),
+                model_var=sc[:, 0].copy(), integral_var=sc[:, 1].copy(), info=info.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# K6: scores
+# ------------------------------------------------------------------------------------------------
+def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True):
+    """Per-step packed statistics over trajectories: stats (N, W), W = dx + dx*dx + 3:
+    [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE."""
+    dx, N, M = x.shape
+    W = lib.ssm_scores_width(dx)
+    stats = torch.empty((N, W), dtype=torch.float64, device=x.device)
+    acc = torch.empty((dx, M), dtype=torch.float64, device=x.device) if want_rmse_acc else None
+    rc = lib.ssm_scores_phase1(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), M, N, M, _stream())
+    _lib.check(rc, 'ssm_scores_phase1')
+    return stats, acc
+
+
+def scores_phase2(x, mean, cov, mse, status=None):
+    """Per-step sums of the log credibility ratio and of its absolute value: (N, 2).  mse (dx, dx, N)."""
+    dx, N, M = x.shape
+    lcr = torch.empty((N, 2), dtype=torch.float64, device=x.device)
+    rc = lib.ssm_scores_phase2(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), M, N, M, _stream())
+    _lib.check(rc, 'ssm_scores_phase2')
+    return lcr

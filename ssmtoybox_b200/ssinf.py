@@ -1,0 +1,355 @@
+"""Local filters and smoothers (mirror of ssmtoybox/ssinf.py for the hot path).
+
+Class names, constructor signatures, public attributes and the forward_pass / backward_pass / reset
+protocol follow the reference (StateSpaceInference ssinf.py:19-212, GaussianInference :215-344,
+StudentianInference :555-740 and the concrete filters cited on each class).  The time loop, both moment
+transforms, the model functions and the measurement update run inside ONE CUDA kernel launch for all
+trajectories (ssm_filter); the RTS smoother is a second launch (ssm_smooth).
+
+Batched extension (new): forward_pass accepts data of shape (dy, N, M) -- the array the reference's
+research drivers loop over (research/gpq/icinco_demo.py:115-123) -- and returns (dx, N, M),
+(dx, dx, N, M).  numpy in -> numpy out; torch CUDA tensors in -> torch CUDA tensors out (no host
+round trip).  Every trajectory of a batch starts from the model's initial moments, like the reference
+after reset(); a single-trajectory call without reset() continues from the last posterior like the
+reference does (ssinf.py:93, 245).
+
+Failures: a single-trajectory call raises numpy.linalg.LinAlgError / ValueError where the reference
+does (mtran.py:139, bqmtran.py:98, ssinf.py:321); a batched call never raises for numerical failures:
+`self.status` (M,) holds 0 or (step << 8 | code) and the failed trajectory's outputs are NaN from the
+failing step on.
+"""
+import warnings
+from abc import ABCMeta
+
+import numpy as np
+import torch
+
+from . import _lib, device as dv
+from .bq.bqmtran import GaussianProcessTransform, StudentTProcessTransform, BayesSardTransform
+from .mtran import MomentTransform, SphericalRadialTransform, UnscentedTransform, GaussHermiteTransform, \
+    FullySymmetricStudentTransform
+from .ssmod import TransitionModel, MeasurementModel
+from .utils import StudentRV
+
+_DEFAULT_OBS = {1: ('UNGMMeasurement', []), 2: ('Pendulum2DMeasurement', []), 3: ('Radar2DMeasurement', []),
+                4: ('Radar2DMeasurement', [0, 2])}
+_DEFAULT_DYN = {('UNGMMeasurement', ()): ('UNGMTransition', 1, 1), ('Pendulum2DMeasurement', ()): ('Pendulum2DTransition', 2, 2),
+                ('Radar2DMeasurement', ()): ('ReentryVehicle2DTransition', 5, 3),
+                ('Radar2DMeasurement', (0, 1)): ('ReentryVehicle2DTransition', 5, 3),
+                ('Radar2DMeasurement', (0, 2)): ('CoordinatedTurnTransition', 5, 5)}
+
+
+def _sp_stub(dim, prefix):
+    pts = UnscentedTransform.unit_sigma_points(dim)
+    wm, wc = UnscentedTransform.weights(dim)
+    return {prefix + 'kind': 'sp', prefix + 'points': pts, prefix + 'wm': wm, prefix + 'Wc': np.diag(wc)}
+
+
+def lower_models(dyn, obs):
+    """Lower a (transition, measurement) model pair for the simulators; a missing side is filled with
+    the matching default model (it is not evaluated)."""
+    d = {}
+    if dyn is not None:
+        d.update(dyn._desc())
+    if obs is not None:
+        d.update(obs._desc())
+    if obs is None:
+        name, si = _DEFAULT_OBS[dyn._device_id]
+        dy = 2 if name == 'Radar2DMeasurement' else 1
+        d.update({'obs_name': name, 'state_index': si, 'radar_loc': [0.0, 0.0], 'r_cov': np.eye(dy)})
+    if dyn is None:
+        key = (type(obs).__name__, tuple(obs.state_index) if obs.state_index is not None else ())
+        if key not in _DEFAULT_DYN:
+            raise NotImplementedError('no device implementation for {} with state_index {}'.format(*key))
+        name, dx, dq = _DEFAULT_DYN[key]
+        d.update({'dyn_name': name, 'dyn_dt': 0.1, 'G': np.eye(dx, dq), 'm0': np.zeros(dx), 'P0': np.eye(dx),
+                  'q_cov': np.eye(dq)})
+    dx = np.asarray(d['m0']).shape[0]
+    d.update(_sp_stub(dx, 'dyn_'))
+    d.update(_sp_stub(dx, 'obs_'))
+    d.pop('x0_dof', None), d.pop('q_dof', None), d.pop('r_dof', None)
+    return dv.lower(d), d
+
+
+class StateSpaceInference(metaclass=ABCMeta):
+    """Base class of the local filters / smoothers (ssinf.py:19-212)."""
+
+    def __init__(self, mod_dyn, mod_obs, tf_dyn, tf_obs):
+        assert isinstance(mod_dyn, TransitionModel) and isinstance(mod_obs, MeasurementModel)
+        self.mod_dyn = mod_dyn
+        self.mod_obs = mod_obs
+        assert isinstance(tf_dyn, MomentTransform) and isinstance(tf_obs, MomentTransform)
+        self.tf_dyn = tf_dyn
+        self.tf_obs = tf_obs
+        self.flags = {'filtered': False, 'smoothed': False}
+        self.x_mean_pr, self.x_cov_pr, = None, None
+        self.x_mean_sm, self.x_cov_sm = None, None
+        self.xx_cov, self.xy_cov = None, None
+        self.pr_mean, self.pr_cov, self.pr_xx_cov = None, None, None
+        self.fi_mean, self.fi_cov = None, None
+        self.sm_mean, self.sm_cov = None, None
+        self.D, self.N = None, None
+        self.status = None
+        self._fwd = None          # device arrays of the last forward pass
+        self._carry = None        # per-trajectory (mean, cov) carried to the next call when reset() is skipped
+
+    def get_flag(self, key):
+        return self.flags[key]
+
+    def set_flag(self, key, value):
+        self.flags[key] = value
+
+    # -- lowering -----------------------------------------------------------------------------------
+    def _describe(self):
+        """Flat description of the CURRENT state of the filter object (read at forward_pass time, because
+        research code mutates transforms and model variances after construction)."""
+        d = {}
+        d.update(self.mod_dyn._desc())
+        d.update(self.mod_obs._desc())
+        d.update(self.tf_dyn._tf_dict('dyn_'))
+        d.update(self.tf_obs._tf_dict('obs_'))
+        d['m0'], d['P0'] = self.x0_mean, self.x0_cov
+        return d
+
+    def _forward_device(self, y, store_pred=True):
+        dy, N, M = y.shape
+        low = dv.lower(self._describe())
+        if low.dy != dy:
+            raise ValueError('data has {} rows, the measurement model has dim_out = {}'.format(dy, low.dy))
+        init_mean = init_cov = None
+        if self._carry is not None and self._carry[0].shape[-1] == M:
+            init_mean, init_cov = self._carry
+        fwd = dv.filter_forward(low, y, store_pred=store_pred, init_mean=init_mean, init_cov=init_cov, want_last=True)
+        fwd['init_mean'] = init_mean if init_mean is not None else \
+            torch.as_tensor(np.asarray(self.x0_mean, dtype=np.float64), device=y.device)[:, None].expand(-1, M)
+        fwd['init_cov'] = init_cov if init_cov is not None else \
+            torch.as_tensor(np.asarray(self.x0_cov, dtype=np.float64), device=y.device)[:, :, None].expand(-1, -1, M)
+        self._low = low
+        return fwd
+
+    @staticmethod
+    def _raise_for_status(st):
+        code = st & 0xFF
+        if code == _lib.FAIL_NONFINITE_GAIN:
+            raise ValueError('array must not contain infs or NaNs')  # scipy.linalg.cho_factor, ssinf.py:321
+        raise np.linalg.LinAlgError('Matrix is not positive definite (time step {})'.format(st >> 8))
+
+    def forward_pass(self, data):
+        """Filtering.  data (dy, N) -> (dx, N), (dx, dx, N); or batched (dy, N, M) -> (dx, N, M),
+        (dx, dx, N, M) (ssinf.py:66-118)."""
+        is_torch = isinstance(data, torch.Tensor)
+        y = data if is_torch else torch.as_tensor(np.ascontiguousarray(np.asarray(data, dtype=np.float64)), device='cuda')
+        single = y.ndim == 2
+        if single:
+            y = y[:, :, None]
+        y = y.to(dtype=torch.float64).contiguous()
+        if not y.is_cuda:
+            y = y.cuda()
+        self.D, self.N = y.shape[0], y.shape[1]
+        fwd = self._forward_device(y)
+        self._fwd = fwd
+        self.status = fwd['status']
+        # carry the last posterior to the next call (the reference keeps x_mean_fi / x_cov_fi, ssinf.py:93)
+        self._carry = (fwd['last_mean'], fwd['last_cov'])
+        self._single = single
+        if single:
+            st = int(fwd['status'][0].item())
+            if st != 0:
+                self._raise_for_status(st)
+        self._publish_forward(fwd, single, is_torch)
+        self.set_flag('filtered', True)
+        return self.fi_mean[:, 1:, ...], self.fi_cov[:, :, 1:, ...]
+
+    def _publish_forward(self, fwd, single, is_torch):
+        """Fill the reference's public attributes: arrays with N+1 time slots, slot 0 = initial moments
+        (ssinf.py:85-96)."""
+        cat = torch.cat
+        im, ic = fwd['init_mean'], fwd['init_cov']
+        fi_mean = cat([im[:, None, :], fwd['fi_mean']], dim=1)
+        fi_cov = cat([ic[:, :, None, :], fwd['fi_cov']], dim=2)
+        pr_mean = cat([im[:, None, :], fwd['pr_mean']], dim=1)
+        pr_cov = cat([ic[:, :, None, :], fwd['pr_cov']], dim=2)
+        pr_xx = cat([ic[:, :, None, :], fwd['pr_xx_cov']], dim=2)
+
+        def out(t):
+            if single:
+                t = t[..., 0]
+            return t if is_torch else t.cpu().numpy()
+        self.fi_mean, self.fi_cov = out(fi_mean), out(fi_cov)
+        self.pr_mean, self.pr_cov, self.pr_xx_cov = out(pr_mean), out(pr_cov), out(pr_xx)
+        self.x_mean_fi, self.x_cov_fi = self.fi_mean[:, -1, ...], self.fi_cov[:, :, -1, ...]
+        self.x_mean_pr, self.x_cov_pr = self.pr_mean[:, -1, ...], self.pr_cov[:, :, -1, ...]
+        self.xx_cov = self.pr_xx_cov[:, :, -1, ...]
+        self.x_mean_sm, self.x_cov_sm = self.x_mean_fi, self.x_cov_fi  # ssinf.py:117
+        if not is_torch:
+            self.status = fwd['status'].cpu().numpy()
+
+    def backward_pass(self):
+        """Smoothing over the stored forward pass (ssinf.py:120-147)."""
+        assert self.get_flag('filtered')  # require filtered state
+        fwd = self._fwd
+        sm = dv.smooth_backward(self._low.dx, fwd)
+        is_torch = isinstance(self.fi_mean, torch.Tensor)
+        if self._single:
+            st = int(sm['status'][0].item())
+            if st != 0:
+                self._raise_for_status(st)
+        sm_mean = torch.cat([fwd['init_mean'][:, None, :], sm['sm_mean']], dim=1)
+        sm_cov = torch.cat([fwd['init_cov'][:, :, None, :], sm['sm_cov']], dim=2)
+
+        def out(t):
+            if self._single:
+                t = t[..., 0]
+            return t if is_torch else t.cpu().numpy()
+        self.sm_mean, self.sm_cov = out(sm_mean), out(sm_cov)
+        self.status = sm['status'] if is_torch else sm['status'].cpu().numpy()
+        self.set_flag('smoothed', True)
+        return self.sm_mean[:, 1:, ...], self.sm_cov[:, :, 1:, ...]
+
+    def reset(self):
+        """Reset internal variables and flags (ssinf.py:149-158)."""
+        self.x_mean_pr, self.x_cov_pr = None, None
+        self.x_mean_sm, self.x_cov_sm = None, None
+        self.xx_cov, self.xy_cov = None, None
+        self.pr_mean, self.pr_cov, self.pr_xx_cov = None, None, None
+        self.fi_mean, self.fi_cov = None, None
+        self.sm_mean, self.sm_cov = None, None
+        self.D, self.N = None, None
+        self.flags = {'filtered': False, 'smoothed': False}
+        self._fwd, self._carry, self.status = None, None, None
+
+
+class GaussianInference(StateSpaceInference):
+    """Gaussian filters and smoothers (ssinf.py:215-344)."""
+
+    def __init__(self, mod_dyn, mod_obs, tf_dyn, tf_obs):
+        assert isinstance(mod_dyn, TransitionModel) and isinstance(mod_obs, MeasurementModel)
+        self.x0_mean, self.x0_cov = mod_dyn.init_rv.get_stats()
+        self.q_mean, self.q_cov = mod_dyn.noise_rv.get_stats()
+        self.r_mean, self.r_cov = mod_obs.noise_rv.get_stats()
+        self.G = mod_dyn.noise_gain
+        self.x_mean_fi, self.x_cov_fi = self.x0_mean, self.x0_cov
+        super(GaussianInference, self).__init__(mod_dyn, mod_obs, tf_dyn, tf_obs)
+
+    def reset(self):
+        self.x_mean_fi, self.x_cov_fi = self.x0_mean, self.x0_cov
+        super(GaussianInference, self).reset()
+
+
+class CubatureKalman(GaussianInference):
+    """Cubature Kalman filter and smoother (ssinf.py:360-366)."""
+
+    def __init__(self, dyn, obs):
+        tf = SphericalRadialTransform(dyn.dim_in)
+        th = SphericalRadialTransform(obs.dim_in)
+        super(CubatureKalman, self).__init__(dyn, obs, tf, th)
+
+
+class UnscentedKalman(GaussianInference):
+    """Unscented Kalman filter and smoother (ssinf.py:369-386)."""
+
+    def __init__(self, dyn, obs, kappa=None, alpha=1.0, beta=2.0):
+        tf = UnscentedTransform(dyn.dim_in, kappa=kappa, alpha=alpha, beta=beta)
+        th = UnscentedTransform(obs.dim_in, kappa=kappa, alpha=alpha, beta=beta)
+        super(UnscentedKalman, self).__init__(dyn, obs, tf, th)
+
+
+class GaussHermiteKalman(GaussianInference):
+    """Gauss-Hermite Kalman filter and smoother (ssinf.py:389-402)."""
+
+    def __init__(self, dyn, obs, deg=3):
+        tf = GaussHermiteTransform(dyn.dim_in, degree=deg)
+        th = GaussHermiteTransform(obs.dim_in, degree=deg)
+        super(GaussHermiteKalman, self).__init__(dyn, obs, tf, th)
+
+
+class GaussianProcessKalman(GaussianInference):
+    """Gaussian process quadrature Kalman filter and smoother (ssinf.py:405-451)."""
+
+    def __init__(self, dyn, obs, kern_par_dyn, kern_par_obs, kernel='rbf', points='ut', point_hyp=None):
+        t_dyn = GaussianProcessTransform(dyn.dim_in, dyn.dim_state, kern_par_dyn, kernel, points, point_hyp)
+        t_obs = GaussianProcessTransform(obs.dim_in, obs.dim_out, kern_par_obs, kernel, points, point_hyp)
+        super(GaussianProcessKalman, self).__init__(dyn, obs, t_dyn, t_obs)
+
+
+class BayesSardKalman(GaussianInference):
+    """Bayes-Sard quadrature Kalman filter and smoother (ssinf.py:454-500)."""
+
+    def __init__(self, dyn, obs, kern_par_dyn, kern_par_obs, mulind_dyn=2, mulind_obs=2, points='ut', point_hyp=None):
+        t_dyn = BayesSardTransform(dyn.dim_in, dyn.dim_state, kern_par_dyn, mulind_dyn, points, point_hyp)
+        t_obs = BayesSardTransform(obs.dim_in, obs.dim_out, kern_par_obs, mulind_obs, points, point_hyp)
+        super(BayesSardKalman, self).__init__(dyn, obs, t_dyn, t_obs)
+
+
+class StudentProcessKalman(GaussianInference):
+    """Student's t-process quadrature Kalman filter and smoother (ssinf.py:503-552).  The transforms are
+    built with dim_out = 1 like the reference, which makes the TPQ variance term a full matrix (Q6)."""
+
+    def __init__(self, dyn, obs, kern_par_dyn, kern_par_obs, kernel='rbf', points='ut', point_hyp=None, nu=3.0):
+        t_dyn = StudentTProcessTransform(dyn.dim_in, 1, kern_par_dyn, kernel, points, point_hyp, nu=nu)
+        t_obs = StudentTProcessTransform(obs.dim_in, 1, kern_par_obs, kernel, points, point_hyp, nu=nu)
+        super(StudentProcessKalman, self).__init__(dyn, obs, t_dyn, t_obs)
+
+
+class StudentianInference(StateSpaceInference):
+    """Filters assuming jointly Student-t state and measurement (ssinf.py:555-740)."""
+
+    def __init__(self, mod_dyn, mod_obs, tf_dyn, tf_obs, dof=4.0, fixed_dof=True):
+        if dof <= 2.0:
+            dof = 4.0
+            warnings.warn("You supplied invalid DoF (must be > 2). Setting to dof=4.")
+        self.x0_mean, self.x0_cov, self.x0_dof = mod_dyn.init_rv.get_stats()
+        self.x_mean_fi, self.x_cov_fi, self.dof_fi = self.x0_mean, self.x0_cov, self.x0_dof
+        self.q_mean, self.q_cov, self.q_dof = mod_dyn.noise_rv.get_stats()
+        self.q_gain = mod_dyn.noise_gain
+        self.r_mean, self.r_cov, self.r_dof = mod_obs.noise_rv.get_stats()
+        scale = (dof - 2) / dof
+        self.x_smat_fi = scale * self.x_cov_fi
+        self.q_smat = scale * self.q_cov
+        self.r_smat = scale * self.r_cov
+        self.x_smat_pr, self.y_smat_pr, self.xy_smat = None, None, None
+        self.dof = dof
+        self.fixed_dof = fixed_dof
+        super(StudentianInference, self).__init__(mod_dyn, mod_obs, tf_dyn, tf_obs)
+
+    def _describe(self):
+        d = super(StudentianInference, self)._describe()
+        d.update({'dof': float(self.dof), 'fixed_dof': int(self.fixed_dof), 'x0_dof': float(self.dof_fi),
+                  'q_dof': float(self.q_dof), 'r_dof': float(self.r_dof)})
+        return d
+
+    def forward_pass(self, data):
+        out = super(StudentianInference, self).forward_pass(data)
+        # the state carried between calls is the filtered SCALE matrix and the grown dof (ssinf.py:733-736)
+        self.dof_fi = self.dof_fi + self.N * self.mod_obs.dim_out
+        lc = self._fwd['last_cov']
+        self.x_smat_fi = lc if isinstance(self.fi_mean, torch.Tensor) else lc.cpu().numpy()
+        if self._single:
+            self.x_smat_fi = self.x_smat_fi[..., 0]
+        return out
+
+    def backward_pass(self):
+        """Student smoother has not been developed in the reference (ssinf.py:738-740): the smoothed
+        arrays are the filtered ones."""
+        assert self.get_flag('filtered')
+        self.sm_mean, self.sm_cov = self.fi_mean, self.fi_cov
+        self.set_flag('smoothed', True)
+        return self.sm_mean[:, 1:, ...], self.sm_cov[:, :, 1:, ...]
+
+    def reset(self):
+        self.x_mean_fi, self.x_cov_fi, self.dof_fi = self.x0_mean, self.x0_cov, self.x0_dof
+        scale = (self.dof - 2) / self.dof
+        self.x_smat_fi = scale * self.x_cov_fi
+        self.x_smat_pr, self.y_smat_pr, self.xy_smat = None, None, None
+        super(StudentianInference, self).reset()
+
+
+class FullySymmetricStudent(StudentianInference):
+    """Student filter with fully-symmetric rules ("Student-t UKF", ssinf.py:743-775)."""
+
+    def __init__(self, dyn, obs, degree=3, kappa=None, dof=4.0, fixed_dof=True):
+        dyn_dof = np.min((dyn.init_rv.dof, dyn.noise_rv.dof))
+        obs_dof = np.min((dyn_dof, obs.noise_rv.dof))
+        t_dyn = FullySymmetricStudentTransform(dyn.dim_in, degree, kappa, dyn_dof)
+        t_obs = FullySymmetricStudentTransform(obs.dim_in, degree, kappa, obs_dof)
+        super(FullySymmetricStudent, self).__init__(dyn, obs, t_dyn, t_obs, dof, fixed_dof)

@@ -1,0 +1,261 @@
+"""State-space models (mirror of ssmtoybox/ssmod.py for the models with a device implementation).
+
+Class names, constructor signatures, attributes and method signatures follow the reference
+(TransitionModel ssmod.py:9-244, MeasurementModel :858-1039 and the concrete models cited on each
+class).  Function evaluation and simulation run on the GPU (ssm_model_eval, ssm_simulate); random
+draws come from Philox streams keyed by (utils.seed, call counter, global trajectory index) instead
+of numpy's global MT19937, so simulated data are statistically, not bit-wise,
+equivalent to the reference's.
+"""
+import ctypes as C
+from abc import ABCMeta
+
+import numpy as np
+import torch
+
+from . import _lib, device as dv
+from ._lib import lib
+from .utils import StudentRV, next_stream_seed
+
+
+def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
+    """Evaluate a device model function at the columns of x (D, n) (or a single (D,) point)."""
+    x = np.asarray(x, dtype=np.float64)
+    single = x.ndim == 1
+    xs = np.ascontiguousarray(x.reshape(x.shape[0], -1))
+    n = xs.shape[1]
+    xt = torch.as_tensor(xs, device='cuda')
+    nt = None
+    if noise is not None:
+        nz = np.asarray(noise, dtype=np.float64)
+        nz = np.ascontiguousarray(np.broadcast_to(nz.reshape(nz.shape[0], -1), (nz.shape[0], n)))
+        nt = torch.as_tensor(nz, device='cuda')
+    out = torch.empty((dim_out, n), dtype=torch.float64, device='cuda')
+    p = (C.c_double * 4)(*par)
+    t = float(np.asarray(time).reshape(-1)[0]) if time is not None else 0.0
+    rc = lib.ssm_model_eval(which, model_id, dim_state, si[0], si[1], p, t, dv._p(xt), dv._p(nt), dv._p(out), n, n,
+                            dv._stream())
+    _lib.check(rc, 'ssm_model_eval')
+    o = out.cpu().numpy()
+    return o[:, 0] if single else o
+
+
+class TransitionModel(metaclass=ABCMeta):
+    """State transition model (ssmod.py:9-244)."""
+    dim_in = None
+    dim_state = None
+    dim_noise = None
+    noise_additive = None
+    _device_id = None  # SSM_DYN_*
+
+    def __init__(self, init_rv, noise_rv, noise_gain=None):
+        self.dim_in = self.dim_state if self.noise_additive else self.dim_state + self.dim_noise
+        self.init_rv = init_rv
+        self.noise_rv = noise_rv
+        self.zero_q = np.zeros(self.dim_noise)
+        if noise_gain is None:
+            noise_gain = np.eye(self.dim_state, self.dim_noise)
+        self.noise_gain = noise_gain
+
+    # -- description used by the lowering ---------------------------------------------------------
+    def _par(self):
+        return [float(getattr(self, 'dt', 0.0)), 0.0, 0.0, 0.0]
+
+    def _desc(self):
+        d = {'dyn_name': type(self).__name__, 'dyn_dt': float(getattr(self, 'dt', 0.0)), 'G': self.noise_gain}
+        st = self.init_rv.get_stats()
+        d['m0'], d['P0'] = st[0], st[1]
+        d['q_cov'] = self.noise_rv.get_stats()[1]
+        if len(st) == 3:
+            d['x0_dof'], d['q_dof'] = float(st[2]), float(self.noise_rv.dof)
+        return d
+
+    # -- function evaluation ------------------------------------------------------------------------
+    def dyn_fcn(self, x, q, time):
+        """Discrete-time dynamics f(x, q, time), evaluated on the device."""
+        return _eval(0, self._device_id, self.dim_state, (0, 0), self._par(), time, x, q, self.dim_state)
+
+    def dyn_eval(self, xq, time, dx=False):
+        """Dynamics according to noise additivity (ssmod.py:129-166).  Jacobians (dx=True) are used by
+        the out-of-scope linearisation transforms only."""
+        if dx:
+            raise NotImplementedError('Jacobians are not part of the device hot path')
+        xq = np.asarray(xq, dtype=np.float64)
+        assert xq.shape[0] == self.dim_state
+        return self.dyn_fcn(xq, self.zero_q, time)
+
+    # -- simulation ---------------------------------------------------------------------------------
+    def _sim_low(self, obs=None):
+        from .ssinf import lower_models  # local import: ssinf imports this module
+        return lower_models(self, obs)
+
+    def simulate_discrete(self, steps, mc_sims=1, device_out=False):
+        """x (dim_state, steps, mc_sims) with x[:, 0] ~ init_rv, x[:, k] = f(x[:, k-1], q[:, k-1], k-1)
+        (ssmod.py:168-199), one GPU thread per trajectory."""
+        low, d = self._sim_low()
+        rng = dv.make_rng(d, next_stream_seed())
+        x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='discrete', want_y=False)
+        return x if device_out else x.cpu().numpy()
+
+    def simulate_continuous(self, duration, dt=0.1, mc_sims=1, device_out=False):
+        """Euler-Maruyama SDE simulation, returns x[:, 1:] (ssmod.py:201-244)."""
+        low, d = self._sim_low()
+        steps = int(np.floor(duration / dt))
+        rng = dv.make_rng(d, next_stream_seed())
+        x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='continuous', dt=dt, sub=1, want_y=False)
+        return x if device_out else x.cpu().numpy()
+
+
+class UNGMTransition(TransitionModel):
+    """Univariate non-stationary growth model, additive noise (ssmod.py:247-275)."""
+    dim_state = 1
+    dim_noise = 1
+    noise_additive = True
+    _device_id = 1
+
+    def __init__(self, init_rv, noise_rv):
+        super(UNGMTransition, self).__init__(init_rv, noise_rv)
+
+
+class Pendulum2DTransition(TransitionModel):
+    """Pendulum with unit length and mass (ssmod.py:309-365)."""
+    dim_state = 2
+    dim_noise = 2
+    noise_additive = True
+    g = 9.81
+    _device_id = 2
+
+    def __init__(self, init_rv, noise_rv, dt=0.01):
+        super(Pendulum2DTransition, self).__init__(init_rv, noise_rv)
+        self.dt = dt
+
+
+class ReentryVehicle2DTransition(TransitionModel):
+    """Reentry vehicle, 5-D state, 3-D noise entering the last three components (ssmod.py:436-584)."""
+    dim_state = 5
+    dim_noise = 3
+    noise_additive = True
+    _device_id = 3
+
+    def __init__(self, init_rv, noise_rv, dt=0.1):
+        self.dt = dt
+        self.R0 = 6374
+        self.H0 = 13.406
+        self.Gm0 = 3.9860e5
+        self.b0 = -0.59783
+        noise_gain = np.vstack((np.zeros((2, self.dim_noise)), np.eye(self.dim_noise)))
+        super(ReentryVehicle2DTransition, self).__init__(init_rv, noise_rv, noise_gain)
+
+
+class CoordinatedTurnTransition(TransitionModel):
+    """Coordinated turn with time-varying turn rate (ssmod.py:587-696)."""
+    dim_state = 5
+    dim_noise = 5
+    noise_additive = True
+    _device_id = 4
+
+    def __init__(self, init_rv, noise_rv, dt=0.1):
+        super(CoordinatedTurnTransition, self).__init__(init_rv, noise_rv)
+        self.dt = dt
+
+
+class MeasurementModel(metaclass=ABCMeta):
+    """Measurement model (ssmod.py:858-1039)."""
+    dim_substate = None
+    dim_out = None
+    dim_noise = None
+    noise_additive = None
+    _device_id = None  # SSM_OBS_*
+
+    def __init__(self, noise_rv, dim_state, state_index):
+        self.noise_rv = noise_rv
+        self.zero_r = np.zeros(self.dim_noise)
+        self.state_index = state_index
+        self.dim_in = dim_state if self.noise_additive else dim_state + self.dim_noise
+        self.dim_state = dim_state
+
+    def _par(self):
+        rl = np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64)
+        return [float(rl[0]), float(rl[1]), 0.0, 0.0]
+
+    def _si(self):
+        si = list(self.state_index) if self.state_index is not None else list(range(self.dim_substate))
+        return (int(si[0]), int(si[1]) if len(si) > 1 else 0)
+
+    def _desc(self):
+        d = {'obs_name': type(self).__name__, 'r_cov': self.noise_rv.get_stats()[1],
+             'state_index': [] if self.state_index is None else list(self.state_index),
+             'radar_loc': np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64)}
+        if isinstance(self.noise_rv, StudentRV):
+            d['r_dof'] = float(self.noise_rv.dof)
+        return d
+
+    def meas_fcn(self, x, r, time):
+        """Measurement function h(x, r, time) of the (already index-selected) sub-state x."""
+        x = np.asarray(x, dtype=np.float64)
+        # the device function reads the sub-state from the full state through state_index
+        full = np.zeros((self.dim_state,) + x.shape[1:])
+        si = self._si()
+        for j in range(self.dim_substate):
+            full[si[j] if j < 2 else j] = x[j]
+        return _eval(1, self._device_id, self.dim_state, si, self._par(), time, full, r, self.dim_out)
+
+    def meas_eval(self, xr, time, dx=False):
+        """Measurement model according to noise additivity (ssmod.py:960-1009)."""
+        if dx:
+            raise NotImplementedError('Jacobians are not part of the device hot path')
+        xr = np.asarray(xr, dtype=np.float64)
+        return _eval(1, self._device_id, self.dim_state, self._si(), self._par(), time, xr, self.zero_r, self.dim_out)
+
+    def simulate_measurements(self, x, device_out=False):
+        """y[:, k, i] = h(x[state_index, k, i], r[:, k, i], k+1) (ssmod.py:1011-1039)."""
+        from .ssinf import lower_models
+        xt = x if isinstance(x, torch.Tensor) else torch.as_tensor(
+            np.ascontiguousarray(np.asarray(x, dtype=np.float64)), device='cuda')
+        if xt.ndim == 2:
+            xt = xt[:, :, None]
+        if xt.shape[0] != self.dim_state:
+            raise ValueError('state array must have dim_state = {} rows'.format(self.dim_state))
+        low, d = lower_models(None, self)
+        rng = dv.make_rng(d, next_stream_seed())
+        y = dv.simulate_measurements(low, xt.contiguous(), rng=rng)
+        return y if device_out else y.cpu().numpy()
+
+
+class UNGMMeasurement(MeasurementModel):
+    """z = 0.05 x^2 + r (ssmod.py:1042-1064)."""
+    dim_substate = 1
+    dim_out = 1
+    dim_noise = 1
+    noise_additive = True
+    _device_id = 1
+
+    def __init__(self, noise_rv, dim_state, state_index=None):
+        super(UNGMMeasurement, self).__init__(noise_rv, dim_state, state_index)
+
+
+class Pendulum2DMeasurement(MeasurementModel):
+    """z = sin(alpha) + r (ssmod.py:1090-1118)."""
+    dim_substate = 1
+    dim_out = 1
+    dim_noise = 1
+    noise_additive = True
+    _device_id = 2
+
+    def __init__(self, noise_rv, dim_state, state_index=None):
+        super(Pendulum2DMeasurement, self).__init__(noise_rv, dim_state, state_index)
+
+
+class Radar2DMeasurement(MeasurementModel):
+    """Range and bearing from a radar at radar_loc (ssmod.py:1199-1255)."""
+    dim_substate = 2
+    dim_out = 2
+    dim_noise = 2
+    noise_additive = True
+    _device_id = 3
+
+    def __init__(self, noise_rv, dim_state, state_index=None, radar_loc=None):
+        super(Radar2DMeasurement, self).__init__(noise_rv, dim_state, state_index)
+        if radar_loc is None:
+            radar_loc = np.array([0, 0])
+        self.radar_loc = radar_loc

@@ -1,0 +1,176 @@
+"""Random variables and performance scores (mirror of ssmtoybox/utils.py for the hot path).
+
+Arrays follow the reference's convention (D, N, M, ...): D dimension, N time steps, M Monte-Carlo
+trajectories.  All arithmetic runs on the GPU through the C-ABI library (K6 score kernels, Philox
+sampler); there is no CPU fallback.  Reference lines: RandomVariable / GaussRV / StudentRV
+utils.py:580-674, multivariate_t :349-382, squared_error :18-38, mse_matrix :41-64,
+log_cred_ratio :67-120, neg_log_likelihood :123-148.
+"""
+import ctypes as C
+from abc import ABCMeta, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _lib, device as dv
+from ._lib import lib
+
+_seed_state = {'seed': 0, 'calls': 0}
+
+
+def seed(s):
+    """Seed of the device Philox streams (the counterpart of np.random.seed for this package)."""
+    _seed_state['seed'], _seed_state['calls'] = int(s), 0
+
+
+def next_stream_seed():
+    """A fresh 64-bit Philox key derived from the package seed; every sampling call consumes one."""
+    _seed_state['calls'] += 1
+    return (_seed_state['seed'] * 0x9E3779B97F4A7C15 + _seed_state['calls'] * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+
+
+class RandomVariable(metaclass=ABCMeta):
+    @abstractmethod
+    def sample(self, size):
+        pass
+
+    @abstractmethod
+    def get_stats(self):
+        pass
+
+    def _sample(self, size, dof):
+        shape = (size,) if np.isscalar(size) else tuple(size)
+        n = int(np.prod(shape))
+        mean = dv._c(self.mean)
+        factor = dv._cov_factor(self.cov if dof == 0.0 else self.scale)
+        out = torch.empty((self.dim, n), dtype=torch.float64, device='cuda')
+        rc = lib.ssm_sample(self.dim, dv._ptr(mean), dv._ptr(factor), float(dof), C.c_uint64(next_stream_seed()), 0,
+                            dv._p(out), n, n, dv._stream())
+        _lib.check(rc, 'ssm_sample')
+        return out.cpu().numpy().reshape((self.dim,) + shape)
+
+
+class GaussRV(RandomVariable):
+    """Gaussian random variable (utils.py:580-623).  sample(size) -> (dim,) + size."""
+
+    def __init__(self, dim, mean=None, cov=None):
+        if mean is None:
+            mean = np.zeros((dim, ))
+        mean = np.atleast_1d(mean)
+        if cov is None:
+            cov = np.eye(dim)
+        cov = np.atleast_2d(cov)
+        self.dim = dim
+        self.mean = mean
+        self.cov = cov
+
+    def sample(self, size):
+        return self._sample(size, 0.0)
+
+    def get_stats(self):
+        return self.mean, self.cov
+
+
+class StudentRV(RandomVariable):
+    """Student's t random variable with scale matrix and dof (utils.py:626-674)."""
+
+    def __init__(self, dim, mean=None, scale=None, dof=3.0):
+        if mean is None:
+            mean = np.zeros((dim,))
+        mean = np.atleast_1d(mean)
+        if scale is None:
+            scale = np.eye(dim)
+        scale = np.atleast_2d(scale)
+        if dof <= 2.0:
+            dof = 3.0
+        self.dim = dim
+        self.mean = mean
+        self.scale = scale
+        self.dof = dof
+
+    def sample(self, size):
+        return self._sample(size, self.dof)
+
+    def get_stats(self):
+        return self.mean, self.scale, self.dof
+
+
+# ------------------------------------------------------------------------------------------------
+# scores
+# ------------------------------------------------------------------------------------------------
+def _dev(a):
+    if isinstance(a, torch.Tensor):
+        return a.to(device='cuda', dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device='cuda')
+
+
+def squared_error(x, m):
+    """(x - m)**2, broadcasting like the reference (utils.py:18-38)."""
+    xd, md = _dev(x), _dev(m)
+    out = (xd - md) ** 2
+    return out if isinstance(x, torch.Tensor) else out.cpu().numpy()
+
+
+def mse_matrix(x, m):
+    """Sample MSE matrix over MC simulations: x (d, 1) or (d, M), m (d, M) -> (d, d) (utils.py:41-64)."""
+    m = np.asarray(m, dtype=np.float64)
+    d, M = m.shape
+    x = np.broadcast_to(np.asarray(x, dtype=np.float64).reshape(d, -1), (d, M))
+    xd, md = _dev(x[:, None, :]), _dev(m[:, None, :])
+    cov = torch.eye(d, dtype=torch.float64, device='cuda')[:, :, None, None].expand(d, d, 1, M).contiguous()
+    stats, _ = dv.scores_phase1(xd, md, cov, want_rmse_acc=False)
+    st = stats.cpu().numpy()[0]
+    return st[d:d + d * d].reshape(d, d) / M
+
+
+def neg_log_likelihood(x, m, P):
+    """0.5 (log|P| + (x-m)' P^-1 (x-m) + d log 2 pi) for one estimate (utils.py:123-148)."""
+    x, m = np.atleast_1d(np.asarray(x, dtype=np.float64)), np.atleast_1d(np.asarray(m, dtype=np.float64))
+    d = x.shape[0]
+    P = np.asarray(P, dtype=np.float64).reshape(d, d)
+    stats, _ = dv.scores_phase1(_dev(x.reshape(d, 1, 1)), _dev(m.reshape(d, 1, 1)), _dev(P.reshape(d, d, 1, 1)),
+                                want_rmse_acc=False)
+    return float(stats.cpu().numpy()[0, d + d * d])
+
+
+def log_cred_ratio(x, m, P, MSE):
+    """10 (log10 dx'P^-1dx - log10 dx'MSE^-1dx) for one estimate (utils.py:67-120)."""
+    x, m = np.atleast_1d(np.asarray(x, dtype=np.float64)), np.atleast_1d(np.asarray(m, dtype=np.float64))
+    d = x.shape[0]
+    P = np.asarray(P, dtype=np.float64).reshape(d, d)
+    MSE = np.asarray(MSE, dtype=np.float64).reshape(d, d)
+    lcr = dv.scores_phase2(_dev(x.reshape(d, 1, 1)), _dev(m.reshape(d, 1, 1)), _dev(P.reshape(d, d, 1, 1)),
+                           _dev(MSE.reshape(d, d, 1)))
+    return float(lcr.cpu().numpy()[0, 0])
+
+
+def evaluate_performance(x, mean, cov, status=None, comm=None):
+    """Batched RMSE / NCI / NLL of one filter over all trajectories, aggregated exactly like
+    research/gpq/icinco_demo.py:17-52 (RMSE = trajectory-mean of sqrt(time-mean SE); NCI and NLL skip
+    k = 0 but divide by N), computed on the device in two reduction phases.
+    x, mean (dx, N, M); cov (dx, dx, N, M); status (M,) int32 or None (failed trajectories are excluded).
+    comm: optional ssmtoybox_b200.dist.Communicator -- trajectories are then sharded over ranks and the
+    packed statistics are all-reduced (one NCCL call per phase).
+    Returns dict(rmse (dx,), nci, nll, inc (inclination), mse (dx,dx,N), rmse_vs_time (N,), n_ok)."""
+    xd, md, Pd = _dev(x), _dev(mean), _dev(cov)
+    dx, N, M = xd.shape
+    stats, acc = dv.scores_phase1(xd, md, Pd, status)
+    ok = torch.ones(M, dtype=torch.bool, device=xd.device) if status is None else (status == 0)
+    # per-trajectory sqrt(time-mean SE), summed over the trajectories that completed
+    rm = torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)
+    pack = torch.cat([stats.reshape(-1), rm])
+    if comm is not None:
+        pack = comm.allreduce_sum(pack)
+    W = stats.shape[1]
+    st = pack[:N * W].reshape(N, W)
+    rm = pack[N * W:]
+    cnt = st[:, -1]
+    n_ok = cnt[0]
+    mse = (st[:, dx:dx + dx * dx] / cnt[:, None]).T.reshape(dx, dx, N).contiguous()
+    lcr = dv.scores_phase2(xd, md, Pd, mse, status)
+    if comm is not None:
+        lcr = comm.allreduce_sum(lcr)
+    out = dict(rmse=(rm / n_ok), nll=st[1:, dx + dx * dx].sum() / (N * n_ok), inc=lcr[1:, 0].sum() / (N * n_ok),
+               nci=lcr[1:, 0].sum() / (N * n_ok), abs_nci=lcr[1:, 1].sum() / (N * n_ok), mse=mse,
+               rmse_vs_time=st[:, dx + dx * dx + 1] / cnt, n_ok=n_ok)
+    return {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}

@@ -1,0 +1,89 @@
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+for p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason='no CUDA device in this container')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def golden_filter_cases():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, 'c*.npz')))
+
+
+def relstep(a, b):
+    """max over (step, trajectory) of the max-norm relative error; time axis -2, trajectory axis -1."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    ax = tuple(range(a.ndim - 2))
+    ok = np.isfinite(b).all(axis=ax)
+    if not ok.any():
+        return 0.0
+    num = np.abs(a - b).max(axis=ax)[ok]
+    den = np.abs(b).max(axis=ax)[ok]
+    return float(np.max(num / den))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def one_step_problems(g):
+    """All (trajectory, step) pairs of a golden filter run as independent one-step problems that restart
+    from the reference's own filtered moments: removes the chaotic amplification of rounding differences
+    over hundreds of steps, so the comparison isolates the per-step arithmetic."""
+    fm, fc = g['fi_mean'], g['fi_cov']
+    ok = np.isfinite(fm[0, 1:]) & np.isfinite(fm[0, :-1])
+    ks, ms = np.nonzero(ok)
+    return dict(init_mean=np.ascontiguousarray(fm[:, ks, ms]), init_cov=np.ascontiguousarray(fc[:, :, ks, ms]),
+                y=np.ascontiguousarray(g['y'][:, ks + 1, ms][:, None, :]), t0=(ks + 1).astype(np.int32),
+                fi_mean=fm[:, ks + 1, ms][:, None, :], fi_cov=fc[:, :, ks + 1, ms][:, :, None, :],
+                pr_mean=g['pr_mean'][:, ks + 2, ms][:, None, :], pr_cov=g['pr_cov'][:, :, ks + 2, ms][:, :, None, :],
+                pr_xx_cov=g['pr_xx_cov'][:, :, ks + 2, ms][:, :, None, :])
+
+
+# full-trajectory tolerance per golden case: the recursions amplify rounding-level differences; the
+# one-step tests carry the 1e-9 claim.  None = filter not contractive / weights noise-dominated, the
+# full-trajectory comparison is informative only ("Parity").
+FULL_TOL = {
+    'c1_ungm_ukf': 1e-8, 'c1_ungm_ckf': 1e-8, 'c1_ungm_ghkf5': 1e-8, 'c1_ungm_gpq_ut': 1e-7, 'c1_ungm_gpq_gh10': 1e-8,
+    'c1_ungm_tpq_ut': 1e-7, 'c1_ungm_bsq_ut': 1e-7,
+    'c3_reentry_ukf': 1e-9, 'c3_reentry_ukf_b0': 1e-9, 'c3_reentry_ckf': 1e-9, 'c3_reentry_gpq': 2e-6,
+    'c3_reentry_bsq': None, 'c3_reentry_gpq_fail': 1e-9, 'c3s_reentry_gpq': 2e-6,
+    'c4_ct_tpq': 1e-8, 'c4_ct_gpq': 1e-9, 'c4_ct_ukf': 1e-9, 'c4_ct_bsq': None,
+    'c4_ct_fsstudent': 1e-9, 'c4_ct_fsstudent_incdof': 1e-9, 'c4_ct_fsstudent_deg5': 1e-9,
+    'c5_pend_ukf': 1e-9, 'c5_pend_gpq': 1e-9, 'c5_pend_tpq': 1e-9, 'c5_pend_bsq': None, 'c5_pend_ghkf3': 1e-9,
+}
+for _i in range(11):
+    FULL_TOL['c2_ungm_gpq_el{:02d}'.format(_i)] = 1e-6
+# one-step tolerance: 1e-9 everywhere except the un-centred BQ covariances on the 5-D tracking models, whose
+# float64 noise floor in the REFERENCE itself is above 1e-9; those are checked against the
+# longdouble oracle instead (test_gpu_parity.py::test_bq_noise_floor)
+ONE_STEP_COV_TOL = {'c3_reentry_gpq': 1e-6, 'c3s_reentry_gpq': 1e-6, 'c3_reentry_bsq': 1e-2, 'c4_ct_bsq': 1e-6, 'c4_ct_tpq': 1e-8, 'c4_ct_gpq': 1e-9}

@@ -1,0 +1,286 @@
+"""The reference-facing Python API (same class names, constructors and methods as ssmtoybox) on the GPU,
+against the golden vectors of the reference.  These read like the reference's own tests
+(ssmtoybox/tests/test_ssinf.py, test_mtran.py, test_bqmtran.py, test_bqkern.py) with assertions added."""
+import numpy as np
+import pytest
+import torch
+
+import ssm_oracle as so
+from conftest import golden, relstep, rel
+
+pytestmark = pytest.mark.gpu
+
+MUL = lambda d: np.hstack((np.zeros((d, 1)), np.eye(d), 2 * np.eye(d))).astype(int)  # noqa: E731
+
+
+def ungm():
+    from ssmtoybox_b200.utils import GaussRV
+    from ssmtoybox_b200.ssmod import UNGMTransition, UNGMMeasurement
+    dyn = UNGMTransition(GaussRV(1, cov=np.atleast_2d(5.0)), GaussRV(1, cov=np.atleast_2d(10.0)))
+    return dyn, UNGMMeasurement(GaussRV(1), 1)
+
+
+def pendulum():
+    from ssmtoybox_b200.utils import GaussRV
+    from ssmtoybox_b200.ssmod import Pendulum2DTransition, Pendulum2DMeasurement
+    dt = 0.01
+    q = GaussRV(2, cov=0.01 * np.array([[(dt ** 3) / 3, (dt ** 2) / 2], [(dt ** 2) / 2, dt]]))
+    dyn = Pendulum2DTransition(GaussRV(2, mean=np.array([1.5, 0]), cov=0.01 * np.eye(2)), q, dt=dt)
+    return dyn, Pendulum2DMeasurement(GaussRV(1, cov=np.array([[0.1]])), dyn.dim_state)
+
+
+def reentry():
+    from ssmtoybox_b200.utils import GaussRV
+    from ssmtoybox_b200.ssmod import ReentryVehicle2DTransition, Radar2DMeasurement
+    m0 = np.array([6500, 350, -1.1, -6.1, 0.7])
+    dyn = ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 1])),
+                                     GaussRV(3, cov=np.diag([2.4e-5, 2.4e-5, 1e-6])), dt=0.1)
+    return dyn, Radar2DMeasurement(GaussRV(2, cov=np.diag([1e-6, 0.17e-6])), 5, radar_loc=np.array([6374, 0.0]))
+
+
+def coordinated_turn(student=False):
+    from ssmtoybox_b200.utils import GaussRV, StudentRV
+    from ssmtoybox_b200.ssmod import CoordinatedTurnTransition, Radar2DMeasurement
+    m0 = np.array([1000, 300, 1000, 0, np.deg2rad(-3.0)])
+    P0 = np.diag([100, 10, 100, 10, 0.1])
+    dt, rho_1, rho_2 = 0.1, 0.1, 1.75e-4
+    A = np.array([[dt ** 3 / 3, dt ** 2 / 2], [dt ** 2 / 2, dt]])
+    Q = np.zeros((5, 5))
+    Q[:2, :2], Q[2:4, 2:4], Q[4, 4] = rho_1 * A, rho_1 * A, rho_2 * dt
+    R = np.diag([100, 10e-6])
+    if not student:
+        return (CoordinatedTurnTransition(GaussRV(5, m0, P0), GaussRV(5, cov=Q), dt=dt),
+                Radar2DMeasurement(GaussRV(2, cov=R), 5, state_index=[0, 2]))
+    nu = 6.0
+    sc = (nu - 2) / nu
+    return (CoordinatedTurnTransition(StudentRV(5, m0, sc * P0, nu), StudentRV(5, scale=sc * Q, dof=nu), dt=dt),
+            Radar2DMeasurement(StudentRV(2, scale=sc * R, dof=nu), 5, state_index=[0, 2]))
+
+
+def check(alg, name, tol, smooth=True):
+    g = golden(name)
+    m, P = alg.forward_pass(g['y'])
+    assert m.shape == g['fi_mean'].shape and P.shape == g['fi_cov'].shape
+    assert relstep(m, g['fi_mean']) < tol and relstep(P, g['fi_cov']) < tol
+    assert alg.pr_mean.shape == g['pr_mean'].shape and relstep(alg.pr_mean[:, 1:], g['pr_mean'][:, 1:]) < tol
+    if smooth:
+        ms, Ps = alg.backward_pass()
+        assert relstep(ms, g['sm_mean']) < 10 * tol and relstep(Ps, g['sm_cov']) < 10 * tol
+    alg.reset()
+    return g
+
+
+def test_ungm_classical_filters():
+    from ssmtoybox_b200.ssinf import UnscentedKalman, CubatureKalman, GaussHermiteKalman
+    dyn, obs = ungm()
+    check(UnscentedKalman(dyn, obs), 'c1_ungm_ukf', 1e-8)
+    check(CubatureKalman(dyn, obs), 'c1_ungm_ckf', 1e-8)
+    check(GaussHermiteKalman(dyn, obs, deg=5), 'c1_ungm_ghkf5', 1e-8)       # generic (runtime-N) point path
+
+
+def test_ungm_bq_filters_with_device_weights():
+    """Weights computed by the K5 kernel at construction; well-conditioned kernels -> same filter output."""
+    from ssmtoybox_b200.ssinf import GaussianProcessKalman, StudentProcessKalman, BayesSardKalman
+    dyn, obs = ungm()
+    kp = np.array([[1.0, 3.0]])
+    alg = GaussianProcessKalman(dyn, obs, kp, kp, points='ut')
+    g = golden('c1_ungm_gpq_ut')
+    assert rel(alg.tf_dyn.wm, g['dyn_wm']) < 1e-11 and rel(alg.tf_dyn.Wc, g['dyn_Wc']) < 1e-10 and rel(alg.tf_dyn.Wcc, g['dyn_Wcc']) < 1e-11
+    assert abs(alg.tf_dyn.model.model_var - float(g['dyn_model_var'])) < 1e-12
+    check(alg, 'c1_ungm_gpq_ut', 1e-6)
+    check(StudentProcessKalman(dyn, obs, kp, kp), 'c1_ungm_tpq_ut', 1e-6)
+    check(BayesSardKalman(dyn, obs, kp, kp, MUL(1), MUL(1)), 'c1_ungm_bsq_ut', 1e-6)
+    kp = np.array([[1.0, 0.1]])
+    check(GaussianProcessKalman(dyn, obs, kp, kp, points='gh', point_hyp={'degree': 10}), 'c1_ungm_gpq_gh10', 1e-8)
+    with pytest.raises(AttributeError):   # integer multi-index is broken in the reference as well
+        BayesSardKalman(dyn, obs, kp, kp)
+
+
+def test_single_trajectory_protocol_and_carry_over():
+    """(dy, N) in -> (dx, N) out; without reset() the next call continues from the last posterior (Q4)."""
+    from ssmtoybox_b200.ssinf import UnscentedKalman
+    dyn, obs = ungm()
+    g = golden('c1_ungm_ukf')
+    alg = UnscentedKalman(dyn, obs)
+    with pytest.raises(AssertionError):
+        alg.backward_pass()                                  # asserts flags['filtered'], ssinf.py:134
+    y = g['y'][..., 0]
+    m, P = alg.forward_pass(y)
+    assert m.shape == (1, 500) and P.shape == (1, 1, 500) and alg.fi_mean.shape == (1, 501)
+    assert rel(m, g['fi_mean'][..., 0]) < 1e-8
+    assert np.array_equal(alg.x_mean_fi, m[:, -1]) and alg.get_flag('filtered')
+    ms, Ps = alg.backward_pass()
+    assert rel(ms, g['sm_mean'][..., 0]) < 1e-7 and alg.get_flag('smoothed')
+    m2, _ = alg.forward_pass(y[:, :5])                       # no reset: starts from the last posterior
+    assert alg.fi_mean[0, 0] == m[0, -1]
+    alg.reset()
+    m3, _ = alg.forward_pass(y[:, :5])
+    assert rel(m3, g['fi_mean'][:, :5, 0]) < 1e-10 and not np.allclose(m2, m3)
+
+
+def test_pendulum_filters():
+    from ssmtoybox_b200.ssinf import UnscentedKalman, GaussianProcessKalman, StudentProcessKalman, GaussHermiteKalman
+    dyn, obs = pendulum()
+    kp = np.array([[1.0, 1.0, 1.0]])
+    check(UnscentedKalman(dyn, obs), 'c5_pend_ukf', 1e-9)
+    check(GaussianProcessKalman(dyn, obs, kp, kp), 'c5_pend_gpq', 1e-9)
+    check(StudentProcessKalman(dyn, obs, kp, kp), 'c5_pend_tpq', 1e-9)
+    check(GaussHermiteKalman(dyn, obs, deg=3), 'c5_pend_ghkf3', 1e-9)
+
+
+def test_reentry_filters():
+    from ssmtoybox_b200.ssinf import UnscentedKalman, CubatureKalman, GaussianProcessKalman, BayesSardKalman
+    dyn, obs = reentry()
+    check(UnscentedKalman(dyn, obs), 'c3_reentry_ukf', 1e-9)
+    check(UnscentedKalman(dyn, obs, beta=0.0), 'c3_reentry_ukf_b0', 1e-9)
+    check(CubatureKalman(dyn, obs), 'c3_reentry_ckf', 1e-9)
+    # C3: the reference's obs-transform weights (cond(K) = 1e9) are rounding noise; with the reference's
+    # weights assigned from outside -- the pattern of research/tpq/tpq_ungm.py:114-124 -- the filter output
+    # agrees to the BQ noise floor
+    g = golden('c3_reentry_gpq')
+    alg = GaussianProcessKalman(dyn, obs, g['dyn_kern_par'], g['obs_kern_par'], 'rbf', 'ut')
+    assert rel(alg.tf_dyn.wm, g['dyn_wm']) < 1e-8 and rel(alg.tf_dyn.Wcc, g['dyn_Wcc']) < 1e-8
+    for tf, p in ((alg.tf_dyn, 'dyn_'), (alg.tf_obs, 'obs_')):
+        tf.wm, tf.Wc, tf.Wcc = g[p + 'wm'], g[p + 'Wc'], g[p + 'Wcc']
+        tf.model.model_var = float(g[p + 'model_var'])
+    check(alg, 'c3_reentry_gpq', 2e-6)
+    # model variance assigned from outside as a matrix (research/bsq/bsq_tracking.py:276-281)
+    g = golden('c3_reentry_bsq')
+    alg = BayesSardKalman(dyn, obs, g['dyn_kern_par'], g['obs_kern_par'], MUL(5), MUL(5), points='ut')
+    assert rel(alg.tf_dyn.wm, g['dyn_wm']) < 1e-9 and rel(alg.tf_dyn.Wc, g['dyn_Wc']) < 1e-9
+    alg.tf_dyn.model.model_var = 2e-6 * np.eye(5)
+    alg.tf_obs.model.model_var = 0 * np.eye(2)
+    m, P = alg.forward_pass(g['y'][:, :30])
+    assert relstep(m, g['fi_mean'][:, :30]) < 1e-6
+
+
+def test_failures_raise_like_the_reference():
+    from ssmtoybox_b200.ssinf import GaussianProcessKalman
+    dyn, obs = reentry()
+    g = golden('c3_reentry_gpq_fail')
+    one = np.array([[1.0, 1, 1, 1, 1, 1]])
+    alg = GaussianProcessKalman(dyn, obs, one, one)
+    with pytest.raises((np.linalg.LinAlgError, ValueError)):
+        alg.forward_pass(g['y'][..., 0])
+    alg.reset()
+    alg.forward_pass(g['y'])                                  # batched: no exception, status instead
+    assert (np.asarray(alg.status) >> 8 == 2).all() and np.isnan(alg.fi_mean[:, 2:]).all()
+
+
+def test_coordinated_turn_filters():
+    from ssmtoybox_b200.ssinf import UnscentedKalman, GaussianProcessKalman, StudentProcessKalman, FullySymmetricStudent
+    dyn, obs = coordinated_turn()
+    check(UnscentedKalman(dyn, obs), 'c4_ct_ukf', 1e-9)
+    par_dyn, par_obs = np.array([[1.0, 1, 1, 1, 1, 1]]), np.array([[1.0, 1, 1e2, 1, 1e2, 1e2]])
+    # l = 1e2 on three axes: cond(K) ~ 1e6, so the covariance weights (error ~ eps cond^2) of ANY float64
+    # evaluation -- the reference's included -- carry ~1e-4 noise; filter parity at 1e-9 is established with
+    # the reference's weights injected (test_gpu_parity.py), here the two independent evaluations must agree
+    # to that noise level
+    check(GaussianProcessKalman(dyn, obs, par_dyn, par_obs), 'c4_ct_gpq', 1e-3)
+    check(StudentProcessKalman(dyn, obs, par_dyn, par_obs), 'c4_ct_tpq', 1e-3)
+    dyn_s, obs_s = coordinated_turn(student=True)
+    check(FullySymmetricStudent(dyn_s, obs_s, kappa=None, dof=6.0), 'c4_ct_fsstudent', 1e-9, smooth=False)
+    check(FullySymmetricStudent(dyn_s, obs_s, dof=6.0, fixed_dof=False), 'c4_ct_fsstudent_incdof', 1e-9, smooth=False)
+    check(FullySymmetricStudent(dyn_s, obs_s, degree=5, dof=6.0), 'c4_ct_fsstudent_deg5', 1e-9, smooth=False)
+
+
+def test_torch_in_torch_out_batched():
+    from ssmtoybox_b200.ssinf import UnscentedKalman
+    dyn, obs = pendulum()
+    g = golden('c5_pend_ukf')
+    alg = UnscentedKalman(dyn, obs)
+    y = torch.as_tensor(g['y'], device='cuda')
+    m, P = alg.forward_pass(y)
+    assert isinstance(m, torch.Tensor) and m.is_cuda and relstep(m.cpu().numpy(), g['fi_mean']) < 1e-9
+    ms, Ps = alg.backward_pass()
+    assert isinstance(ms, torch.Tensor) and relstep(ms.cpu().numpy(), g['sm_mean']) < 1e-8
+
+
+def test_moment_transform_apply_and_model_functions():
+    from ssmtoybox_b200.mtran import UnscentedTransform, SphericalRadialTransform
+    from ssmtoybox_b200.bq.bqmtran import GaussianProcessTransform, StudentTProcessTransform
+    dyn, obs = reentry()
+    m0, P0 = dyn.init_rv.get_stats()
+    la = so._LA('lapack')
+    f = lambda xx: so.dyn_fcn('ReentryVehicle2DTransition', xx, 0.0, 0, 0.1)  # noqa: E731
+    h = lambda xx: so.meas_fcn('Radar2DMeasurement', xx, 0.0, 0, [6374, 0.0])  # noqa: E731
+    for tf in (UnscentedTransform(5), SphericalRadialTransform(5)):
+        mf, Cf, Cfx = tf.apply(dyn.dyn_eval, m0, P0, np.atleast_1d(0))
+        o = so.transform_apply(la, {'kind': 'sp', 'points': tf.unit_sp, 'wm': tf.wm, 'Wc': tf.Wc}, f, m0, P0, 1)
+        assert rel(mf, o[0]) < 1e-13 and rel(Cf, o[1]) < 1e-9 and rel(Cfx, o[2]) < 1e-9
+        assert np.array_equal(Cf, Cf.T) and np.all(np.linalg.eigvalsh(Cf) > 0)     # tests/test_bqmtran.py:66-85
+    kp = np.array([[1.0, 3, 3, 3, 3, 3]])
+    for cls, kind in ((GaussianProcessTransform, 'gp'), (StudentTProcessTransform, 'tp')):
+        tf = cls(5, 2 if kind == 'gp' else 1, kp)
+        my, Cy, Cyx = tf.apply(obs.meas_eval, m0, P0, np.atleast_1d(0))
+        d = {'kind': kind, 'points': tf.model.points, 'wm': tf.wm, 'Wc': tf.Wc, 'Wcc': tf.Wcc, 'model_var': tf.model.model_var,
+             'iK': tf.model.iK, 'nu': 4.0, 'dim_out': tf.I_out.shape[0]}
+        o = so.transform_apply(la, d, h, m0, P0, 1)
+        assert rel(my, o[0]) < 1e-12 and rel(Cy, o[1]) < 1e-6 and rel(Cyx, o[2]) < 1e-8
+    with pytest.raises(NotImplementedError):
+        UnscentedTransform(1).apply(lambda x, t: x, np.zeros(1), np.eye(1), None)   # no CPU fallback
+    with pytest.raises(np.linalg.LinAlgError):
+        UnscentedTransform(5).apply(dyn.dyn_eval, m0, -P0, np.atleast_1d(0))
+    # single-point model functions
+    assert rel(dyn.dyn_fcn(m0, np.array([0.1, -0.2, 0.3]), 0), so.dyn_fcn('ReentryVehicle2DTransition', m0, [0.1, -0.2, 0.3], 0, 0.1)) < 1e-14
+    assert rel(obs.meas_eval(m0, 0), so.meas_fcn('Radar2DMeasurement', m0, 0.0, 0, [6374, 0.0])) < 1e-14
+    udyn, uobs = ungm()
+    assert rel(udyn.dyn_fcn(np.array([0.7]), np.array([0.0]), 3), so.dyn_fcn('UNGMTransition', np.array([0.7]), 0.0, 3, 0.0)) < 1e-14
+    cdyn, cobs = coordinated_turn()
+    x = np.array([1000.0, 300, 1000, 0, -0.05])
+    assert rel(cobs.meas_eval(x, 0), so.meas_fcn('Radar2DMeasurement', x[[0, 2]], 0.0, 0, [0.0, 0.0])) < 1e-14
+    assert rel(cobs.meas_fcn(x[[0, 2]], np.array([1.0, 0.01]), 0), so.meas_fcn('Radar2DMeasurement', x[[0, 2]], [1.0, 0.01], 0, [0.0, 0.0])) < 1e-14
+
+
+def test_rbf_kernel_known_answers():
+    """reference tests/test_bqkern.py:23-173: kernel matrix and expectations against naive loops."""
+    from ssmtoybox_b200.bq.bqkern import RBFGauss
+    rng = np.random.RandomState(3)
+    x = rng.randn(2, 7)
+    par = np.array([[1.3, 0.8, 2.0]])
+    k = RBFGauss(2, par)
+    assert rel(k.eval(par, x), so.rbf_eval(par, x)) < 1e-14
+    assert rel(k.eval(par, x, scaling=False), so.rbf_eval(par, x, scaling=False)) < 1e-14
+    x2 = rng.randn(2, 3)
+    assert rel(k.eval(par, x, x2), so.rbf_eval(par, x, x2)) < 1e-14
+    assert rel(k.exp_x_kx(par, x), so.rbf_exp_x_kx(par, x)) < 1e-14
+    assert rel(k.exp_x_kx(par, x, scaling=True), so.rbf_exp_x_kx(par, x, scaling=True)) < 1e-14
+    assert rel(k.exp_x_xkx(par, x), so.rbf_exp_x_xkx(par, x)) < 1e-14
+    Q = k.exp_x_kxkx(par, par, x)
+    assert rel(Q, so.rbf_exp_x_kxkx(par, par, x)) < 1e-13 and np.all(np.linalg.eigvalsh(0.5 * (Q + Q.T)) > 0)
+    assert abs(k.exp_xy_kxy(par) - so.rbf_exp_xy_kxy(par)) < 1e-15 and k.exp_x_kxx(par) == 1.3 ** 2
+    assert rel(k.eval_inv_dot(par, x, scaling=False), so.rbf_inv(par, x)) < 1e-9
+
+
+def test_simulation_through_the_facade():
+    from ssmtoybox_b200 import utils as U
+    dyn, obs = ungm()
+    U.seed(42)
+    x = dyn.simulate_discrete(50, mc_sims=2000)
+    z = obs.simulate_measurements(x)
+    assert x.shape == (1, 50, 2000) and z.shape == (1, 50, 2000)
+    assert abs(x[0, 0].var() - 5.0) < 0.6 and abs((z - 0.05 * x ** 2).var() - 1.0) < 0.05
+    # the recursion itself is exact given the realised noise: q_k = x_{k+1} - f(x_k, 0, k)
+    q = x[:, 1:] - so.dyn_fcn('UNGMTransition', x[:, :-1], 0.0, np.arange(49)[None, :, None], 0.0)
+    assert abs(q.var() - 10.0) < 0.3 and abs(q.mean()) < 0.05
+    U.seed(42)
+    assert np.array_equal(dyn.simulate_discrete(50, mc_sims=2000), x)      # reproducible under the package seed
+    rdyn, robs = reentry()
+    xc = rdyn.simulate_continuous(duration=5, dt=0.05, mc_sims=8)
+    assert xc.shape == (5, 100, 8) and np.isfinite(xc).all()
+    assert robs.simulate_measurements(xc).shape == (2, 100, 8)
+
+
+def test_samplers_and_scalar_metrics():
+    from ssmtoybox_b200 import utils as U
+    C = np.array([[2.0, 0.5], [0.5, 1.0]])
+    s = U.GaussRV(2, mean=np.array([1.0, -2.0]), cov=C).sample(200000)
+    assert s.shape == (2, 200000) and np.abs(s.mean(axis=1) - [1, -2]).max() < 0.02 and np.abs(np.cov(s) - C).max() < 0.03
+    s = U.StudentRV(2, mean=np.array([1.0, -2.0]), scale=C, dof=6.0).sample((500, 400))
+    assert s.shape == (2, 500, 400) and np.abs(np.cov(s.reshape(2, -1)) - C * 6 / 4).max() < 0.08
+    g, gs = golden('c5_pend_gpq'), golden('scores')
+    x, m, P = g['x'], g['fi_mean'], g['fi_cov']
+    assert rel(U.mse_matrix(x[:, 5, :], m[:, 5, :]), gs['c5_pend_gpq_mse'][..., 5]) < 1e-13
+    assert abs(U.neg_log_likelihood(x[:, 5, 1], m[:, 5, 1], P[:, :, 5, 1]) - gs['c5_pend_gpq_nll'][5, 1]) < 1e-11
+    assert abs(U.log_cred_ratio(x[:, 5, 1], m[:, 5, 1], P[:, :, 5, 1], gs['c5_pend_gpq_mse'][..., 5]) - gs['c5_pend_gpq_lcr'][5, 1]) < 1e-9
+    assert np.array_equal(U.squared_error(x, m), (x - m) ** 2)

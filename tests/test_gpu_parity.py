@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI, ssmtoybox_b200.device) against the oracle and the golden
+vectors of the reference, plus size-independent properties at the benchmark size.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import ssm_oracle as so
+from conftest import golden, golden_filter_cases, relstep, rel, one_step_problems, FULL_TOL, ONE_STEP_COV_TOL
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_filter_cases()
+GAUSS = [c for c in CASES if 'fsstudent' not in c]
+
+
+def T(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device='cuda')
+
+
+def N_(t):
+    return t.cpu().numpy()
+
+
+def run_filter(g, y, **kw):
+    from ssmtoybox_b200 import device as dv
+    low = dv.lower(g)
+    o = dv.filter_forward(low, T(y), store_pred=True, **kw)
+    torch.cuda.synchronize()
+    return low, o
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors of the reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', CASES)
+def test_forward_and_smoother_vs_reference_golden(name):
+    from ssmtoybox_b200 import device as dv
+    g = golden(name)
+    low, o = run_filter(g, g['y'])
+    st = N_(o['status'])
+    assert np.array_equal(st >> 8, g['status']), 'failure steps differ from the reference'
+    tol = FULL_TOL[name]
+    if tol is None:
+        return  # recursion amplifies rounding differences (also between two CPU back-ends): see one-step test
+    assert relstep(N_(o['fi_mean']), g['fi_mean']) < tol
+    assert relstep(N_(o['fi_cov']), g['fi_cov']) < tol
+    assert relstep(N_(o['pr_mean']), g['pr_mean'][:, 1:]) < tol
+    assert relstep(N_(o['pr_cov']), g['pr_cov'][:, :, 1:]) < tol
+    assert relstep(N_(o['pr_xx_cov']), g['pr_xx_cov'][:, :, 1:]) < 10 * tol
+    if low.family == 1 and np.isfinite(g['sm_mean']).any():
+        sm = dv.smooth_backward(low.dx, o)
+        assert relstep(N_(sm['sm_mean']), g['sm_mean']) < 10 * tol
+        assert relstep(N_(sm['sm_cov']), g['sm_cov']) < 10 * tol
+        # slots N and N-1 are never smoothed
+        assert torch.equal(sm['sm_mean'][:, -2:], o['fi_mean'][:, -2:])
+
+
+@pytest.mark.parametrize('name', [c for c in GAUSS if c != 'c3_reentry_gpq_fail'])
+def test_one_step_parity_1e9(name):
+    """Per-step filtered means and covariances vs the reference on identical inputs, to 1e-9 relative:
+    every (trajectory, step) of the golden run restarted from the reference's own filtered moments."""
+    g = golden(name)
+    p = one_step_problems(g)
+    low, o = run_filter(g, p['y'], init_mean=T(p['init_mean']), init_cov=T(p['init_cov']), t_offset=T(p['t0'], torch.int32))
+    assert int((o['status'] != 0).sum()) == 0
+    assert relstep(N_(o['fi_mean']), p['fi_mean']) < (1e-9 if name != 'c3_reentry_bsq' else 1e-5)
+    assert relstep(N_(o['fi_cov']), p['fi_cov']) < ONE_STEP_COV_TOL.get(name, 1e-9)
+    assert relstep(N_(o['pr_mean']), p['pr_mean']) < (1e-9 if name != 'c3_reentry_bsq' else 1e-5)
+    assert relstep(N_(o['pr_cov']), p['pr_cov']) < ONE_STEP_COV_TOL.get(name, 1e-9)
+
+
+@pytest.mark.parametrize('name', ['c3_reentry_gpq', 'c3_reentry_bsq', 'c4_ct_bsq', 'c4_ct_tpq'])
+def test_bq_noise_floor(name):
+    """Un-centred BQ covariances (fx Wc fx' - m m') on the tracking models cancel ~1e7 against ~1e-6: the
+    REFERENCE's float64 result is itself only reproducible to ~1e-8..1e-4.  Arbiter: the
+    longdouble oracle.  The CUDA result must be as close to it as the reference's own arithmetic is."""
+    g = golden(name)
+    p = one_step_problems(g)
+    sel = slice(None, None, 7)
+    ld = so.forward_pass(g, p['y'][..., sel], backend='loops', dtype=np.longdouble, init_mean=p['init_mean'][..., sel],
+                         init_cov=p['init_cov'][..., sel], t0=p['t0'][sel])
+    low, o = run_filter(g, p['y'][..., sel], init_mean=T(p['init_mean'][..., sel]), init_cov=T(p['init_cov'][..., sel]),
+                        t_offset=T(p['t0'][sel], torch.int32))
+    truth = np.asarray(ld['fi_cov'], dtype=np.float64)
+    err_ref = relstep(p['fi_cov'][..., sel], truth)
+    err_gpu = relstep(N_(o['fi_cov']), truth)
+    assert err_gpu <= 4.0 * err_ref + 1e-12, (err_gpu, err_ref)
+    assert relstep(N_(o['fi_mean']), np.asarray(ld['fi_mean'], dtype=np.float64)) <= 4.0 * relstep(p['fi_mean'][..., sel], np.asarray(ld['fi_mean'], dtype=np.float64)) + 1e-12
+
+
+@pytest.mark.parametrize('name,M,N', [('c3_reentry_ukf', 2048, 60), ('c3_reentry_gpq', 1024, 60), ('c5_pend_tpq', 4096, 100),
+                                      ('c1_ungm_ukf', 4096, 40), ('c4_ct_ukf', 1024, 60), ('c4_ct_fsstudent', 1024, 60)])
+def test_batched_vs_oracle_seeded(name, M, N):
+    """Larger seeded batches vs the batched oracle (explicit-loop back-end)."""
+    from ssmtoybox_b200 import device as dv
+    g = golden(name)
+    rng = np.random.RandomState(123)
+    # measurements around the golden ones so that the filters stay in their operating regime
+    y0 = g['y'][:, :N, :1]
+    y = np.ascontiguousarray(y0 + rng.randn(g['y'].shape[0], N, M) * np.sqrt(np.diag(g['r_cov']))[:, None, None])
+    student = 'dof' in g
+    ref = (so.student_forward_pass if student else so.forward_pass)(g, y, backend='loops')
+    low, o = run_filter(g, y)
+    st = N_(o['status'])
+    assert np.array_equal(st, ref['status'])
+    ok = st == 0
+    assert ok.mean() > 0.9
+    # UNGM amplifies rounding differences along the trajectory (the two CPU back-ends of the oracle differ
+    # by up to 1e-8 over 500 steps as well); per-step parity is test_one_step_parity_1e9
+    tol = {'c1_ungm_ukf': 1e-5, 'c3_reentry_gpq': 2e-6}.get(name, 1e-9)
+    assert relstep(N_(o['fi_mean'])[..., ok], ref['fi_mean'][..., ok]) < tol
+    assert relstep(N_(o['fi_cov'])[..., ok], ref['fi_cov'][..., ok]) < tol
+    if not student:
+        sm = dv.smooth_backward(low.dx, o)
+        bw = so.backward_pass(g, ref, backend='loops')
+        assert relstep(N_(sm['sm_mean'])[..., ok], bw['sm_mean'][..., ok]) < 10 * tol
+        assert relstep(N_(sm['sm_cov'])[..., ok], bw['sm_cov'][..., ok]) < 10 * tol
+
+
+# ------------------------------------------------------------------------------------------------
+# failure semantics and edge cases
+# ------------------------------------------------------------------------------------------------
+def test_failure_status_and_nan_fill():
+    g = golden('c3_reentry_gpq_fail')
+    low, o = run_filter(g, g['y'])
+    st = N_(o['status'])
+    assert np.array_equal(st >> 8, [2, 2]) and np.array_equal(st & 0xFF, [so.FAIL_NONFINITE_GAIN] * 2)  # ValueError in the reference
+    fm = N_(o['fi_mean'])
+    assert np.isfinite(fm[:, 0]).all() and np.isnan(fm[:, 1:]).all()
+    g = golden('c2_ungm_gpq_el10')
+    low, o = run_filter(g, g['y'])
+    st = N_(o['status'])
+    assert st[0] == 0 and st[1] >> 8 == 406 and (st[1] & 0xFF) in (so.FAIL_CHOL_DYN, so.FAIL_CHOL_OBS)  # LinAlgError
+
+
+def test_coordinated_turn_zero_turn_rate_is_nan_like_the_reference():
+    """No omega == 0 guard: the UT centre point gives sin(0)/0 = NaN."""
+    g = golden('c4_ct_ukf')
+    g['m0'] = g['m0'].copy()
+    g['m0'][4] = 0.0
+    ref = so.forward_pass(g, g['y'][:, :5], backend='loops')
+    low, o = run_filter(g, g['y'][:, :5])
+    assert np.array_equal(N_(o['status']), ref['status']) and (ref['status'] != 0).all()
+
+
+@pytest.mark.parametrize('M,N', [(1, 1), (1, 7), (129, 3), (127, 2), (1000, 1)])
+def test_ragged_sizes(M, N):
+    g = golden('c5_pend_ukf')
+    rng = np.random.RandomState(M * 31 + N)
+    y = rng.randn(1, N, M) * 0.3 + 1.0
+    ref = so.forward_pass(g, y, backend='loops')
+    low, o = run_filter(g, y)
+    assert relstep(N_(o['fi_mean']), ref['fi_mean']) < 1e-9 and relstep(N_(o['fi_cov']), ref['fi_cov']) < 1e-9
+
+
+def test_empty_inputs_and_bad_arguments():
+    from ssmtoybox_b200 import device as dv, _lib
+    g = golden('c5_pend_ukf')
+    low = dv.lower(g)
+    o = dv.filter_forward(low, torch.empty((1, 5, 0), dtype=torch.float64, device='cuda'))
+    assert o['fi_mean'].shape == (2, 5, 0)
+    o = dv.filter_forward(low, torch.empty((1, 0, 4), dtype=torch.float64, device='cuda'))
+    assert o['fi_mean'].shape == (2, 0, 4)
+    with pytest.raises(ValueError):
+        dv.filter_forward(low, torch.zeros((1, 5, 4), dtype=torch.float32, device='cuda'))
+    bad = dict(g, dyn_points=so.gh_points(2, 9), dyn_wm=so.gh_weights(2, 9), dyn_Wc=np.diag(so.gh_weights(2, 9)))
+    with pytest.raises(NotImplementedError):  # 81 points > capacity of the generic path: loud, no fallback
+        dv.filter_forward(dv.lower(bad), torch.zeros((1, 5, 4), dtype=torch.float64, device='cuda'))
+
+
+# ------------------------------------------------------------------------------------------------
+# properties at the benchmark size (reentry GPQ, 125 000 x 500)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def big():
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_gpq')
+    low = dv.lower(g)
+    M, N = 125000, 500
+    rng = dv.make_rng({'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+                       'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}, seed=7)
+    x, y = dv.simulate(low, M, N, rng=rng, mode='continuous', dt=0.05, sub=2)
+    o = dv.filter_forward(low, y, store_pred=True)
+    torch.cuda.synchronize()
+    return g, low, x, y, o
+
+
+def test_full_size_determinism_and_validity(big):
+    from ssmtoybox_b200 import device as dv
+    g, low, x, y, o = big
+    assert int((o['status'] != 0).sum()) == 0
+    o2 = dv.filter_forward(low, y, store_pred=False)
+    assert torch.equal(o2['fi_mean'], o['fi_mean']) and torch.equal(o2['fi_cov'], o['fi_cov'])  # bitwise
+    P = o['fi_cov']
+    assert torch.equal(P, P.transpose(0, 1))                      # symmetric storage
+    d = torch.diagonal(P, dim1=0, dim2=1)
+    assert bool((d > 0).all())
+    # same tracking quality as the reference run of this configuration (golden: mean |position error| 0.48)
+    err = (o['fi_mean'][:2] - x[:2]).abs().mean().item()
+    gerr = np.abs(g['fi_mean'][:2] - g['x'][:2]).mean()
+    assert 0.8 * gerr < err < 1.2 * gerr
+
+
+def test_full_size_trajectory_permutation_and_time_chunking(big):
+    from ssmtoybox_b200 import device as dv
+    g, low, x, y, o = big
+    M = y.shape[-1]
+    idx = torch.randperm(M, device='cuda')[:20000]
+    ys = y[:, :, idx].contiguous()
+    o1 = dv.filter_forward(low, ys)
+    assert torch.equal(o1['fi_mean'], o['fi_mean'][:, :, idx]) and torch.equal(o1['fi_cov'], o['fi_cov'][:, :, :, idx])
+    # time chunking: 500 steps == 200 + 300 with the state carried (reset() skipped)
+    a = dv.filter_forward(low, ys[:, :200].contiguous(), want_last=True)
+    b = dv.filter_forward(low, ys[:, 200:].contiguous(), init_mean=a['last_mean'], init_cov=a['last_cov'], k0=200)
+    assert torch.equal(b['fi_mean'], o1['fi_mean'][:, 200:]) and torch.equal(b['fi_cov'], o1['fi_cov'][:, :, 200:])
+
+
+def test_full_size_sample_vs_oracle(big):
+    g, low, x, y, o = big
+    idx = np.arange(0, y.shape[-1], 977)[:96]
+    ys = N_(y[:, :120, idx])
+    ref = so.forward_pass(g, ys, backend='loops')
+    assert (ref['status'] == 0).all()
+    assert relstep(N_(o['fi_mean'][:, :120, idx]), ref['fi_mean']) < 1e-9
+    assert relstep(N_(o['fi_cov'][:, :, :120, idx]), ref['fi_cov']) < 2e-6   # BQ noise floor, see test_bq_noise_floor
+
+
+def test_full_size_smoother_and_scores(big):
+    from ssmtoybox_b200 import device as dv, utils as U
+    g, low, x, y, o = big
+    sm = dv.smooth_backward(low.dx, o)
+    assert int((sm['status'] != 0).sum()) == 0
+    # smoothing must not increase the error on average and must shrink the covariance trace
+    ef = ((o['fi_mean'] - x) ** 2).mean().item()
+    es = ((sm['sm_mean'] - x) ** 2).mean().item()
+    assert es <= ef * 1.0001
+    tf = torch.diagonal(o['fi_cov'], dim1=0, dim2=1).sum(-1).mean().item()
+    ts = torch.diagonal(sm['sm_cov'], dim1=0, dim2=1).sum(-1).mean().item()
+    assert ts < tf
+    # checksum of checksums: statistics of the two halves add up to the statistics of the whole
+    s_all, _ = dv.scores_phase1(x, o['fi_mean'], o['fi_cov'], o['status'])
+    h = y.shape[-1] // 2
+    s_a, _ = dv.scores_phase1(x[..., :h].contiguous(), o['fi_mean'][..., :h].contiguous(), o['fi_cov'][..., :h].contiguous())
+    s_b, _ = dv.scores_phase1(x[..., h:].contiguous(), o['fi_mean'][..., h:].contiguous(), o['fi_cov'][..., h:].contiguous())
+    assert torch.allclose(s_a + s_b, s_all, rtol=1e-11, atol=0)
+    sub = slice(0, 64)
+    e = U.evaluate_performance(x[:, :, sub].contiguous(), o['fi_mean'][:, :, sub].contiguous(), o['fi_cov'][:, :, :, sub].contiguous())
+    r = so.evaluate_performance(N_(x[:, :, sub]), N_(o['fi_mean'][:, :, sub]), N_(o['fi_cov'][:, :, :, sub]))
+    assert rel(e['rmse'], r['rmse']) < 1e-12 and abs(e['nll'] - r['nll']) < 1e-8 * abs(r['nll']) and abs(e['nci'] - r['nci']) < 1e-8 * abs(r['nci'])
+
+
+# ------------------------------------------------------------------------------------------------
+# simulators, weights, scores
+# ------------------------------------------------------------------------------------------------
+def _sim_desc(name):
+    g = golden('simulation')
+    d = {k[len(name) + 1:]: v for k, v in g.items() if k.startswith(name + '_')}
+    dx = d['m0'].shape[0]
+    pts, wm, Wc = so.classical_rule('ut', dx)
+    for pfx in ('dyn_', 'obs_'):
+        d.update({pfx + 'kind': 'sp', pfx + 'points': pts, pfx + 'wm': wm, pfx + 'Wc': Wc})
+    return d
+
+
+@pytest.mark.parametrize('name', ['ungm', 'pend', 'reentry', 'ct'])
+def test_simulation_injected_noise_vs_reference(name):
+    from ssmtoybox_b200 import device as dv
+    d = _sim_desc(name)
+    low = dv.lower(d)
+    M, N = d['x0'].shape[1], d['q'].shape[1]
+    x, y = dv.simulate(low, M, N, x0=T(d['x0']), q=T(d['q']), r=T(d['r']))
+    assert rel(N_(x), d['x']) < 1e-13 and rel(N_(y), d['y']) < 1e-13
+    assert rel(N_(dv.simulate_measurements(low, T(d['x']), r=T(d['r']))), d['y']) < 1e-13
+    if name == 'reentry':
+        S = d['qc'].shape[1] - 1
+        xc, _ = dv.simulate(low, M, S, mode='continuous', dt=float(d['dtc']), x0=T(d['x0']), q=T(d['qc'][:, :S]), want_y=False)
+        assert rel(N_(xc), d['xc']) < 1e-13
+        xc2, _ = dv.simulate(low, M, S // 2, mode='continuous', dt=float(d['dtc']), sub=2, x0=T(d['x0']), q=T(d['qc'][:, :S - 1]), want_y=False)
+        assert rel(N_(xc2), d['xc'][:, ::2]) < 1e-13
+
+
+@pytest.mark.parametrize('name', ['ungm', 'reentry', 'ct'])
+def test_simulation_philox_statistics_and_shard_invariance(name):
+    from ssmtoybox_b200 import device as dv
+    d = _sim_desc(name)
+    low = dv.lower(d)
+    M = 400000
+    x, y = dv.simulate(low, M, 3, rng=dv.make_rng(d, seed=11))
+    x0 = N_(x[:, 0])
+    se = np.sqrt(np.diag(d['P0']) / M)
+    assert (np.abs(x0.mean(axis=1) - d['m0']) < 5 * se + 1e-300).all()
+    C = np.atleast_2d(np.cov(x0))
+    assert np.abs(C - d['P0']).max() < 0.02 * np.abs(d['P0']).max()
+    # measurement noise: y - h(x) has covariance R
+    yn = N_(y) - so.simulate_measurements(d, N_(x), 0.0)
+    assert np.abs(np.atleast_2d(np.cov(yn[:, 1])) - d['r_cov']).max() < 0.02 * np.abs(d['r_cov']).max()
+    # draws are keyed by the global trajectory index: a shard reproduces its slice bit for bit
+    xs, ys = dv.simulate(low, 1000, 3, rng=dv.make_rng(d, seed=11, traj_offset=123456))
+    assert torch.equal(xs, x[:, :, 123456:124456]) and torch.equal(ys, y[:, :, 123456:124456])
+    x2, _ = dv.simulate(low, 1000, 3, rng=dv.make_rng(d, seed=12))
+    assert not torch.equal(x2, x[:, :, :1000])
+
+
+def test_bq_weights_vs_reference():
+    """K5 against the reference's weights.  iK / wm / Wcc carry a relative error ~ eps cond(K), Wc ~ eps
+    cond(K)^2: for cond > 1e7 the reference's own Wc is rounding noise and is not compared."""
+    from ssmtoybox_b200 import device as dv
+    g = golden('weights')
+    eps = np.finfo(float).eps
+    for i in range(int(g['n'])):
+        p = 'w{:02d}_'.format(i)
+        par, x = g[p + 'par'], g[p + 'points']
+        cond = np.linalg.cond(so.rbf_eval(par, x, scaling=False) + 1e-8 * np.eye(x.shape[1]))
+        w = dv.bq_weights(par, x)
+        assert w['info'][0] == 0
+        t1 = max(1e-12, 100 * eps * cond)
+        assert rel(w['iK'][0], g[p + 'iK']) < t1 and rel(w['wm'][0], g[p + 'gp_wm']) < t1 and rel(w['Wcc'][0], g[p + 'gp_Wcc']) < t1
+        assert abs(w['model_var'][0] - g[p + 'gp_emv']) < t1 and abs(w['integral_var'][0] - g[p + 'gp_ivar']) < t1
+        assert np.array_equal(w['Wc'][0], w['Wc'][0].T)
+        if cond < 1e7:
+            assert rel(w['Wc'][0], g[p + 'gp_Wc']) < max(1e-12, 100 * eps * cond * cond)
+        for b in ('bs', 'bsg'):
+            if p + b + '_wm' in g:
+                wb = dv.bq_weights(par, x, g[p + b + '_mulind'])
+                assert wb['info'][0] == 0
+                tb = max(1e-11, 1e4 * eps * cond)
+                assert rel(wb['wm'][0], g[p + b + '_wm']) < tb and rel(wb['Wcc'][0], g[p + b + '_Wcc']) < tb
+                if cond < 1e7:
+                    assert rel(wb['Wc'][0], g[p + b + '_Wc']) < max(1e-11, 1e4 * eps * cond * cond)
+                    assert abs(wb['model_var'][0] - g[p + b + '_emv']) < max(1e-11, 1e4 * eps * cond)
+
+
+def test_bq_weights_batched_sweep_and_scale_invariance():
+    from ssmtoybox_b200 import device as dv
+    x = so.ut_points(1, 0.0)
+    els = [1e-3, 3e-3, 1e-2, 3e-2, 1e-1, 3e-1, 1, 3, 1e1, 3e1]
+    par = np.array([[1.0, e] for e in els])
+    w = dv.bq_weights(par, x)                                   # research/gpq/icinco_demo.py:172, one CTA per vector
+    for i, e in enumerate(els):
+        r = so.gp_weights(par[i:i + 1], x)
+        cond = np.linalg.cond(so.rbf_eval(par[i:i + 1], x, scaling=False) + 1e-8 * np.eye(3))
+        assert rel(w['wm'][i], r['wm']) < max(1e-12, 100 * 2.2e-16 * cond)
+    par2 = par.copy()
+    par2[:, 0] = 7.3
+    w2 = dv.bq_weights(par2, x)
+    for k in ('wm', 'Wc', 'Wcc'):
+        assert np.array_equal(w[k], w2[k])                      # reference tests/test_bqmtran.py:40-46
+    assert (w['model_var'] >= -1e-12).all() and (w['integral_var'] >= -1e-12).all()
+
+
+@pytest.mark.parametrize('name', ['c1_ungm_ukf', 'c5_pend_gpq', 'c3s_reentry_gpq'])
+def test_scores_vs_reference(name):
+    from ssmtoybox_b200 import utils as U
+    gs, c = golden('scores'), golden(name)
+    e = U.evaluate_performance(c['x'], c['fi_mean'], c['fi_cov'])
+    assert rel(e['rmse'], gs[name + '_rmse_f'].ravel()) < 1e-12
+    assert rel(e['mse'], gs[name + '_mse']) < 1e-12
+    assert rel(e['rmse_vs_time'], gs[name + '_rmse_vs_time']) < 1e-12
+    assert abs(e['nll'] - gs[name + '_nll_f'].ravel()[0]) < 1e-8 * abs(e['nll'])
+    assert abs(e['nci'] - gs[name + '_nci_f'].ravel()[0]) < 1e-8 * abs(e['nci'])

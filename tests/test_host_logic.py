@@ -1,0 +1,119 @@
+"""Host-side logic of the facade that needs no GPU: point sets / classical weights (host constant tables),
+multi-index generation, trajectory sharding and the gloo-backed reduction of the packed statistics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import ssm_oracle as so
+from conftest import golden
+
+
+def test_facade_pointsets_match_reference():
+    from ssmtoybox_b200 import mtran
+    g = golden('pointsets')
+    for dim in (1, 2, 5):
+        assert np.array_equal(mtran.UnscentedTransform.unit_sigma_points(dim), g['ut%d_pts' % dim])
+        wm, wc = mtran.UnscentedTransform.weights(dim)
+        assert np.array_equal(wm, g['ut%d_wm' % dim]) and np.array_equal(wc, g['ut%d_wc' % dim])
+        wm, wc = mtran.UnscentedTransform.weights(dim, 2.0, 0.5, 1.0)
+        assert np.array_equal(wm, g['ut%dk2a_wm' % dim]) and np.array_equal(wc, g['ut%dk2a_wc' % dim])
+        assert np.array_equal(mtran.SphericalRadialTransform.unit_sigma_points(dim), g['sr%d_pts' % dim])
+        assert np.array_equal(mtran.SphericalRadialTransform.weights(dim), g['sr%d_wm' % dim])
+        for deg in (3, 5):
+            assert np.array_equal(mtran.FullySymmetricStudentTransform.unit_sigma_points(dim, deg, None, 6.0), g['fs%dd%d_pts' % (dim, deg)])
+            assert np.array_equal(mtran.FullySymmetricStudentTransform.weights(dim, deg, None, 6.0), g['fs%dd%d_wm' % (dim, deg)])
+    for dim, deg in ((1, 3), (1, 5), (1, 20), (2, 3), (2, 5), (5, 3)):
+        assert np.array_equal(mtran.GaussHermiteTransform.unit_sigma_points(dim, deg), g['gh%dd%d_pts' % (dim, deg)])
+        assert np.allclose(mtran.GaussHermiteTransform.weights(dim, deg), g['gh%dd%d_wm' % (dim, deg)], rtol=1e-14)
+
+
+def test_symmetric_set_shapes():
+    """reference tests/test_mtran.py:64-88"""
+    from ssmtoybox_b200.mtran import FullySymmetricStudentTransform as FS
+    assert FS.symmetric_set(3, []).shape == (3, 1)
+    assert FS.symmetric_set(3, [1.0]).shape == (3, 6)
+    assert FS.symmetric_set(3, [1.0, 1.0]).shape == (3, 12)
+    assert FS.symmetric_set(5, [2.0, 2.0]).shape == (5, 40)
+
+
+def test_n_sum_k():
+    from ssmtoybox_b200.bq.bqmod import n_sum_k
+    a = n_sum_k(3, 2)
+    assert a.shape == (3, 6) and (a.sum(axis=0) == 2).all()
+    assert len({tuple(c) for c in a.T}) == 6
+    assert np.array_equal(n_sum_k(2, 0), np.zeros((2, 1), dtype=int)) and np.array_equal(n_sum_k(2, 1), np.eye(2, dtype=int))
+
+
+def test_shard_ranges_cover_everything():
+    from ssmtoybox_b200.dist import shard_range
+    for n, ws in ((10 ** 6, 8), (1000, 3), (5, 8), (0, 2), (125000, 1)):
+        spans = [shard_range(n, r, ws) for r in range(ws)]
+        assert sum(c for _, c in spans) == n
+        off = 0
+        for o, c in spans:
+            assert o == off or c == 0
+            off += c
+    assert shard_range(10 ** 6, 3, 8) == (375000, 125000)
+
+
+def _packed_stats_numpy(x, m, P):
+    """numpy statement of the K6 phase-1 row layout [sum SE | sum dd' | sum NLL | sum |d| | count]."""
+    dx, N, M = x.shape
+    d = x - m
+    se = (d ** 2).sum(axis=2).T
+    outer = np.einsum('ikm,jkm->kij', d, d).reshape(N, dx * dx)
+    nll = so.neg_log_likelihood(x, m, P).sum(axis=1)[:, None]
+    nrm = np.sqrt((d ** 2).sum(axis=0)).sum(axis=1)[:, None]
+    return np.hstack([se, outer, nll, nrm, np.full((N, 1), float(M))]), np.sqrt((d ** 2).mean(axis=1)).sum(axis=1)
+
+
+def _worker(rank, world_size, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    from ssmtoybox_b200.dist import Communicator, finalize_scores
+    comm = Communicator.from_env(backend='gloo')
+    g = golden('c5_pend_gpq')
+    x, m, P = g['x'], g['fi_mean'], g['fi_cov']
+    dx, N, M = x.shape
+    off, cnt = comm.shard(M)
+    sl = slice(off, off + cnt)
+    stats, rm = _packed_stats_numpy(x[..., sl], m[..., sl], P[..., sl])
+    pack = torch.tensor(np.concatenate([stats.ravel(), rm]))
+    comm.allreduce_sum(pack)                                    # phase 1: one collective
+    st = pack[:stats.size].reshape(stats.shape).numpy()
+    sc = finalize_scores(st, pack[stats.size:].numpy(), None, dx, N)
+    lcr = so.log_cred_ratio(x[:, :, sl], m[:, :, sl], P[:, :, :, sl], sc['mse'])   # needs the GLOBAL mse
+    l2 = torch.tensor(np.stack([lcr.sum(axis=1), np.abs(lcr).sum(axis=1)], axis=1))
+    comm.allreduce_sum(l2)                                      # phase 2: one more, N x 2 doubles
+    sc = finalize_scores(st, pack[stats.size:].numpy(), l2.numpy(), dx, N)
+    tmax = comm.allreduce_max(float(rank + 1))
+    comm.barrier()
+    if rank == 0:
+        ret.put({k: np.asarray(v) for k, v in sc.items()} | {'tmax': tmax, 'ws': comm.world_size})
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_reduction_matches_single_process():
+    """world_size-2 gloo run of the sharded score reduction == the oracle on the whole set."""
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert out['ws'] == 2 and out['tmax'] == 2.0
+    g, gs = golden('c5_pend_gpq'), golden('scores')
+    e = so.evaluate_performance(g['x'], g['fi_mean'], g['fi_cov'])
+    assert np.allclose(out['rmse'], e['rmse'], rtol=1e-13)
+    assert np.allclose(out['mse'], e['mse'], rtol=1e-12, atol=1e-300)
+    assert abs(out['nll'] - e['nll']) < 1e-12 * abs(e['nll'])
+    assert abs(out['nci'] - e['nci']) < 1e-9 * abs(e['nci'])
+    assert abs(out['nci'] - gs['c5_pend_gpq_nci_f'].ravel()[0]) < 1e-9 * abs(e['nci'])
