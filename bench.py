@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on the configuration BASELINE.json's metric is quoted on.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config C3): 5-D reentry vehicle + radar, GaussianProcessKalman (RBF GPQ,
+UT points, the reference's hyper-parameters and weights) forward pass + RTS smoother + error scores,
+10^6 trajectories x 500 steps on 8 GPUs = 125 000 trajectories x 500 steps PER GPU (weak scaling:
+trajectories are independent, each rank owns a contiguous block, the only collective is the all-reduce
+of the packed error statistics).  One "step" = one pass of that hot path over the rank's batch.
+
+  value : filtered trajectory-steps/s, whole job, measurements and truth resident in HBM (CUDA events,
+          max over ranks)
+  e2e   : the same through the reference-facing Python API with HOST buffers: pinned y / x copied to the
+          device, forward_pass + backward_pass + evaluate_performance, scores read back -- all inside the
+          timed region
+  roofline : dominant kernel = the fused forward pass (FP64-pipe bound); achieved = algorithmic FLOPs per
+          launch / its CUDA-event duration; peak = FP64 FMA rate measured in this run by a DFMA
+          micro-kernel (MEASURED_PEAKS.json carries HBM and bf16 only)
+  cpu_baseline : the numpy port of the reference (oracle/, per-trajectory loop like the reference) on all
+          host cores, bounded sample of the same workload
+
+--impl reference times the reference's CPU implementation of the path.  The reference is pure Python and
+cannot travel to the GPU box (/root/reference does not exist there), so this arm runs the oracle port --
+the same calls in the same order, pinned to the reference by tests/golden -- on all host cores.
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_STEPS = 500
+TRAJ_PER_GPU = 125000           # 10^6 / 8
+FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filter, reentry N=11
+FLOP_SMOOTH = 902.0
+BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
+BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 25)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov); write sm_*
+METRIC = 'filtered trajectory-steps/sec (fp64)'
+UNIT = 'trajectory-steps/s'
+CONFIG = {'workload': 'C3: reentry 5-D + radar, GPQ (RBF, UT) filter + RTS smoother + scores, '
+                      '125000 trajectories x 500 steps per GPU (10^6 x 500 on 8 GPUs)',
+          'n_traj_per_gpu': TRAJ_PER_GPU, 'n_steps': N_STEPS,
+          'l2': 'inputs and outputs per step (>= 1 GB) are far larger than the 126 MB L2, no explicit flush'}
+
+
+def golden_c3():
+    return dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'c3_reentry_gpq.npz')))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ['OPENBLAS_NUM_THREADS'] = os.environ['OMP_NUM_THREADS'] = '1'
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ssm_oracle as so
+    g, y = args
+    t0 = time.perf_counter()
+    fw = so.forward_pass(g, y, backend='lapack')
+    so.backward_pass(g, fw, backend='lapack')
+    return time.perf_counter() - t0, int((fw['status'] == 0).sum())
+
+
+def cpu_port_rate(n_traj_per_core=2, cores=None, seed=0):
+    """trajectory-steps/s of the per-trajectory numpy port (forward + backward) using `cores` processes."""
+    g = golden_c3()
+    cores = cores or len(os.sched_getaffinity(0))
+    rng = np.random.RandomState(seed)
+    ys = []
+    for c in range(cores):
+        base = g['y'][:, :, [c % g['y'].shape[2]] * n_traj_per_core]
+        ys.append(np.ascontiguousarray(base + rng.randn(*base.shape) * np.sqrt(np.diag(g['r_cov']))[:, None, None] * 0.1))
+    gl = {k: v for k, v in g.items() if not k.startswith(('fi_', 'pr_', 'sm_')) and k not in ('x', 'y')}
+    t0 = time.perf_counter()
+    with multiprocessing.get_context('spawn').Pool(cores) as pool:
+        pool.map(_cpu_worker, [(gl, ys[0][..., :1])] * cores)           # warm-up: imports, one trajectory each
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(gl, y) for y in ys])
+        wall = time.perf_counter() - t0
+    n = cores * n_traj_per_core * N_STEPS
+    return n / wall, cores, 'oracle numpy port (per-trajectory loop like the reference), forward + backward pass, ' \
+        '{} trajectories x {} steps on {} processes, {:.1f} s wall'.format(cores * n_traj_per_core, N_STEPS, cores, wall)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    sample = ''
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_port_rate(n_traj_per_core=8, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * cores * 8 * N_STEPS / value, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': CONFIG,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.strip().lower() == 'active':
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(rows[0][1]) if rows else None,
+                'power_w_max': max([float(r[2]) for r in rows if r[2].replace('.', '').isdigit()] or [0.0]),
+                'samples': len(rows), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_filter():
+    """The C3 filter through the reference-facing API (research/gpq/gpq_tracking.py:41-44 on the model of
+    research/bsq/bsq_tracking.py:230-261).  The reference's own weights are assigned from outside (the pattern
+    of research/tpq/tpq_ungm.py:114-124): its obs-transform kernel matrix has cond 1e9, so its covariance
+    weights are LAPACK rounding noise that no independent evaluation reproduces."""
+    from ssmtoybox_b200.ssinf import GaussianProcessKalman
+    from ssmtoybox_b200.ssmod import ReentryVehicle2DTransition, Radar2DMeasurement
+    from ssmtoybox_b200.utils import GaussRV
+    g = golden_c3()
+    m0 = np.array([6500, 350, -1.1, -6.1, 0.7])
+    dyn = ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 1])),
+                                     GaussRV(3, cov=np.diag([2.4e-5, 2.4e-5, 1e-6])), dt=0.1)
+    obs = Radar2DMeasurement(GaussRV(2, cov=np.diag([1e-6, 0.17e-6])), 5, radar_loc=np.array([6374, 0.0]))
+    alg = GaussianProcessKalman(dyn, obs, g['dyn_kern_par'], g['obs_kern_par'], kernel='rbf', points='ut')
+    for tf, p in ((alg.tf_dyn, 'dyn_'), (alg.tf_obs, 'obs_')):
+        tf.wm, tf.Wc, tf.Wcc = g[p + 'wm'], g[p + 'Wc'], g[p + 'Wcc']
+        tf.model.model_var = float(g[p + 'model_var'])
+    return alg, g
+
+
+def run_gpu_arm(args):
+    import torch
+    from ssmtoybox_b200 import device as dv, utils as U
+    from ssmtoybox_b200.dist import Communicator
+    comm = Communicator.from_env()
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    M, N = args.traj, N_STEPS
+    alg, g = build_filter()
+    low = dv.lower(alg._describe())
+
+    # ---- synthetic truth and measurements: Euler-Maruyama at dt = 0.05, every 2nd state (bsq_tracking.py:248-254)
+    truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+             'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}
+    off = comm.rank * M                                     # weak scaling: every rank owns M trajectories
+    x, y = dv.simulate(low, M, N, rng=dv.make_rng(truth, seed=2026, traj_offset=off), mode='continuous', dt=0.05, sub=2,
+                       device=dev)
+    fwd, sm = {}, {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def hot_path(timers=None):
+        """forward pass (stores predictive moments) -> RTS smoother -> two-phase scores (+ all-reduce)."""
+        e = [ev() for _ in range(4)] if timers is not None else None
+        if e: e[0].record()
+        dv.filter_forward(low, y, store_pred=True, out=fwd)
+        if e: e[1].record()
+        dv.smooth_backward(low.dx, fwd, out=sm)
+        if e: e[2].record()
+        sc = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], comm=comm, to_host=False)
+        if e:
+            e[3].record()
+            timers.append(e)
+        return sc
+
+    for _ in range(max(args.warmup, 3)):
+        sc = hot_path()
+    torch.cuda.synchronize()
+    n_failed = int((sm['status'] != 0).sum().item())
+
+    # ---- value: device-resident inputs ---------------------------------------------------------
+    clocks = ClockSampler(local_rank) if comm.rank == 0 else None
+    timers = []
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        sc = hot_path(timers)
+    t1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    ms_total = comm.allreduce_max(t0.elapsed_time(t1))
+    clk = clocks.stop() if clocks else None
+    ms_step = ms_total / args.steps
+    value = comm.world_size * M * N / (ms_step * 1e-3)
+    k_filter = float(np.mean([e[0].elapsed_time(e[1]) for e in timers]))
+    k_smooth = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
+    k_scores = float(np.mean([e[2].elapsed_time(e[3]) for e in timers]))
+    scores = {k: (v.tolist() if hasattr(v, 'tolist') else v) for k, v in sc.items() if k in ('rmse', 'nci', 'nll', 'n_ok')}
+
+    # ---- e2e: host buffers through the reference-facing API --------------------------------------
+    yh = torch.empty(y.shape, dtype=torch.float64, pin_memory=True).copy_(y)
+    xh = torch.empty(x.shape, dtype=torch.float64, pin_memory=True).copy_(x)
+    del fwd, sm
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        yd = yh.to(dev, non_blocking=True)
+        xd = xh.to(dev, non_blocking=True)
+        alg.reset()
+        alg.forward_pass(yd)
+        ms_, Ps_ = alg.backward_pass()
+        out = U.evaluate_performance(xd, ms_, Ps_, status=alg.status, comm=comm)     # scores land on the host
+        return out
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        out = e2e_step()
+    comm.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        out = e2e_step()
+    t1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    e2e_ms = comm.allreduce_max(t0.elapsed_time(t1)) / args.steps
+    e2e_wall_ms = comm.allreduce_max((time.perf_counter() - w0) * 1e3) / args.steps
+    e2e_value = comm.world_size * M * N / (max(e2e_ms, e2e_wall_ms) * 1e-3)
+    d2h = 8 * (5 + 4 + 25 * N + N + 1)
+
+    if comm.rank != 0:
+        return
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    fp64_peak = dv.fp64_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    ach_tf = M * N * FLOP_FILTER / (k_filter * 1e-3) / 1e12
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except (OSError, ValueError):
+        pass
+    roofline = {'kernel': 'filter_kernel<DynReentry, ObsRadar<5,0,1>, AXIS_C, 11, BQ, GAUSS> (fused forward pass)',
+                'bound': 'fp64', 'achieved': ach_tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s', 'frac': ach_tf / (fp64_peak / 1e12),
+                'peak_source': 'measured in this run: DFMA micro-kernel ssm_fp64_peak_kernel (MEASURED_PEAKS.json has no fp64 figure)',
+                'flop_per_unit': FLOP_FILTER, 'units_per_launch': M * N, 'launch_ms': k_filter,
+                'traffic': prof.get('filter_kernel_dram_bytes_per_launch'),
+                'hbm': {'achieved': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_FILTER,
+                        'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s'}}
+    roofline_smoother = {'kernel': 'smoother_kernel<5>', 'bound': 'hbm',
+                         'achieved': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_SMOOTH,
+                         'launch_ms': k_smooth, 'traffic': prof.get('smoother_kernel_dram_bytes_per_launch')}
+    cpu = None
+    if comm.world_size == 1 and not args.no_cpu:
+        v, cores, sample = cpu_port_rate(n_traj_per_core=32)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': comm.world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic (Philox Euler-Maruyama truth + radar measurements, seed 2026, keyed by global trajectory index)',
+            'config': dict(CONFIG, n_traj_per_gpu=M),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(yh.numel() + xh.numel()) * 8,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': max(e2e_ms, e2e_wall_ms),
+                    'api': 'GaussianProcessKalman.forward_pass + backward_pass + utils.evaluate_performance on pinned host y, x'},
+            'gpu_launches': 6 * args.steps,
+            'kernel_ms': {'filter_forward': k_filter, 'rts_smoother': k_smooth, 'scores_2phase_incl_allreduce': k_scores},
+            'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
+            'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,
+            'clocks': clk, 'n_failed_trajectories': n_failed, 'scores': scores}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--traj', type=int, default=TRAJ_PER_GPU, help='trajectories per GPU (default: the C3 share)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

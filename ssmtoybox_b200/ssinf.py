@@ -90,7 +90,7 @@ class StateSpaceInference(metaclass=ABCMeta):
         self.sm_mean, self.sm_cov = None, None
         self.D, self.N = None, None
         self.status = None
-        self._fwd = None          # device arrays of the last forward pass
+        self._fwd, self._sm, self._lazy = None, None, {}   # device arrays of the last passes
         self._carry = None        # per-trajectory (mean, cov) carried to the next call when reset() is skipped
 
     def get_flag(self, key):
@@ -156,55 +156,68 @@ class StateSpaceInference(metaclass=ABCMeta):
             st = int(fwd['status'][0].item())
             if st != 0:
                 self._raise_for_status(st)
+        self._sm = None
         self._publish_forward(fwd, single, is_torch)
         self.set_flag('filtered', True)
-        return self.fi_mean[:, 1:, ...], self.fi_cov[:, :, 1:, ...]
+        return self._out(fwd['fi_mean']), self._out(fwd['fi_cov'])
 
     def _publish_forward(self, fwd, single, is_torch):
-        """Fill the reference's public attributes: arrays with N+1 time slots, slot 0 = initial moments
-        (ssinf.py:85-96)."""
-        cat = torch.cat
-        im, ic = fwd['init_mean'], fwd['init_cov']
-        fi_mean = cat([im[:, None, :], fwd['fi_mean']], dim=1)
-        fi_cov = cat([ic[:, :, None, :], fwd['fi_cov']], dim=2)
-        pr_mean = cat([im[:, None, :], fwd['pr_mean']], dim=1)
-        pr_cov = cat([ic[:, :, None, :], fwd['pr_cov']], dim=2)
-        pr_xx = cat([ic[:, :, None, :], fwd['pr_xx_cov']], dim=2)
+        """Expose the reference's public attributes.  The arrays with N+1 time slots (slot 0 = initial
+        moments, ssinf.py:85-96) are assembled lazily on first access: the hot path returns views of the
+        kernel's own N-slot output arrays and never pays for the copy."""
+        self._lazy = {}
+        self._is_torch = is_torch
 
         def out(t):
             if single:
                 t = t[..., 0]
             return t if is_torch else t.cpu().numpy()
-        self.fi_mean, self.fi_cov = out(fi_mean), out(fi_cov)
-        self.pr_mean, self.pr_cov, self.pr_xx_cov = out(pr_mean), out(pr_cov), out(pr_xx)
-        self.x_mean_fi, self.x_cov_fi = self.fi_mean[:, -1, ...], self.fi_cov[:, :, -1, ...]
-        self.x_mean_pr, self.x_cov_pr = self.pr_mean[:, -1, ...], self.pr_cov[:, :, -1, ...]
-        self.xx_cov = self.pr_xx_cov[:, :, -1, ...]
+        self._out = out
+        self.x_mean_fi, self.x_cov_fi = out(fwd['fi_mean'][:, -1]), out(fwd['fi_cov'][:, :, -1])
+        self.x_mean_pr, self.x_cov_pr = out(fwd['pr_mean'][:, -1]), out(fwd['pr_cov'][:, :, -1])
+        self.xx_cov = out(fwd['pr_xx_cov'][:, :, -1])
         self.x_mean_sm, self.x_cov_sm = self.x_mean_fi, self.x_cov_fi  # ssinf.py:117
         if not is_torch:
             self.status = fwd['status'].cpu().numpy()
+
+    def _with_slot0(self, name, key, is_cov, init_key=None, src=None):
+        """(N+1)-slot array of the reference: initial moments followed by the kernel output."""
+        if name not in self._lazy:
+            src = self._fwd if src is None else src
+            init = self._fwd['init_cov' if is_cov else 'init_mean']
+            t = torch.cat([init[:, :, None, :] if is_cov else init[:, None, :], src[key]], dim=2 if is_cov else 1)
+            self._lazy[name] = self._out(t)
+        return self._lazy[name]
+
+    fi_mean = property(lambda self: None if self._fwd is None else self._with_slot0('fi_mean', 'fi_mean', False),
+                       lambda self, v: None)
+    fi_cov = property(lambda self: None if self._fwd is None else self._with_slot0('fi_cov', 'fi_cov', True),
+                      lambda self, v: None)
+    pr_mean = property(lambda self: None if self._fwd is None else self._with_slot0('pr_mean', 'pr_mean', False),
+                       lambda self, v: None)
+    pr_cov = property(lambda self: None if self._fwd is None else self._with_slot0('pr_cov', 'pr_cov', True),
+                      lambda self, v: None)
+    pr_xx_cov = property(lambda self: None if self._fwd is None else self._with_slot0('pr_xx_cov', 'pr_xx_cov', True),
+                         lambda self, v: None)
+    sm_mean = property(lambda self: None if getattr(self, '_sm', None) is None else
+                       self._with_slot0('sm_mean', 'sm_mean', False, src=self._sm), lambda self, v: None)
+    sm_cov = property(lambda self: None if getattr(self, '_sm', None) is None else
+                      self._with_slot0('sm_cov', 'sm_cov', True, src=self._sm), lambda self, v: None)
 
     def backward_pass(self):
         """Smoothing over the stored forward pass (ssinf.py:120-147)."""
         assert self.get_flag('filtered')  # require filtered state
         fwd = self._fwd
         sm = dv.smooth_backward(self._low.dx, fwd)
-        is_torch = isinstance(self.fi_mean, torch.Tensor)
         if self._single:
             st = int(sm['status'][0].item())
             if st != 0:
                 self._raise_for_status(st)
-        sm_mean = torch.cat([fwd['init_mean'][:, None, :], sm['sm_mean']], dim=1)
-        sm_cov = torch.cat([fwd['init_cov'][:, :, None, :], sm['sm_cov']], dim=2)
-
-        def out(t):
-            if self._single:
-                t = t[..., 0]
-            return t if is_torch else t.cpu().numpy()
-        self.sm_mean, self.sm_cov = out(sm_mean), out(sm_cov)
-        self.status = sm['status'] if is_torch else sm['status'].cpu().numpy()
+        self._sm = sm
+        self._lazy.pop('sm_mean', None), self._lazy.pop('sm_cov', None)
+        self.status = sm['status'] if self._is_torch else sm['status'].cpu().numpy()
         self.set_flag('smoothed', True)
-        return self.sm_mean[:, 1:, ...], self.sm_cov[:, :, 1:, ...]
+        return self._out(sm['sm_mean']), self._out(sm['sm_cov'])
 
     def reset(self):
         """Reset internal variables and flags (ssinf.py:149-158)."""
@@ -216,7 +229,7 @@ class StateSpaceInference(metaclass=ABCMeta):
         self.sm_mean, self.sm_cov = None, None
         self.D, self.N = None, None
         self.flags = {'filtered': False, 'smoothed': False}
-        self._fwd, self._carry, self.status = None, None, None
+        self._fwd, self._sm, self._lazy, self._carry, self.status = None, None, {}, None, None
 
 
 class GaussianInference(StateSpaceInference):
@@ -323,7 +336,7 @@ class StudentianInference(StateSpaceInference):
         # the state carried between calls is the filtered SCALE matrix and the grown dof (ssinf.py:733-736)
         self.dof_fi = self.dof_fi + self.N * self.mod_obs.dim_out
         lc = self._fwd['last_cov']
-        self.x_smat_fi = lc if isinstance(self.fi_mean, torch.Tensor) else lc.cpu().numpy()
+        self.x_smat_fi = lc if self._is_torch else lc.cpu().numpy()
         if self._single:
             self.x_smat_fi = self.x_smat_fi[..., 0]
         return out
@@ -332,9 +345,9 @@ class StudentianInference(StateSpaceInference):
         """Student smoother has not been developed in the reference (ssinf.py:738-740): the smoothed
         arrays are the filtered ones."""
         assert self.get_flag('filtered')
-        self.sm_mean, self.sm_cov = self.fi_mean, self.fi_cov
+        self._sm = {'sm_mean': self._fwd['fi_mean'], 'sm_cov': self._fwd['fi_cov']}
         self.set_flag('smoothed', True)
-        return self.sm_mean[:, 1:, ...], self.sm_cov[:, :, 1:, ...]
+        return self._out(self._fwd['fi_mean']), self._out(self._fwd['fi_cov'])
 
     def reset(self):
         self.x_mean_fi, self.x_cov_fi, self.dof_fi = self.x0_mean, self.x0_cov, self.x0_dof

@@ -144,14 +144,15 @@ def log_cred_ratio(x, m, P, MSE):
     return float(lcr.cpu().numpy()[0, 0])
 
 
-def evaluate_performance(x, mean, cov, status=None, comm=None):
+def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True):
     """Batched RMSE / NCI / NLL of one filter over all trajectories, aggregated exactly like
     research/gpq/icinco_demo.py:17-52 (RMSE = trajectory-mean of sqrt(time-mean SE); NCI and NLL skip
     k = 0 but divide by N), computed on the device in two reduction phases.
     x, mean (dx, N, M); cov (dx, dx, N, M); status (M,) int32 or None (failed trajectories are excluded).
     comm: optional ssmtoybox_b200.dist.Communicator -- trajectories are then sharded over ranks and the
     packed statistics are all-reduced (one NCCL call per phase).
-    Returns dict(rmse (dx,), nci, nll, inc (inclination), mse (dx,dx,N), rmse_vs_time (N,), n_ok)."""
+    Returns dict(rmse (dx,), nci, nll, inc (inclination), mse (dx,dx,N), rmse_vs_time (N,), n_ok); device
+    tensors instead of numpy / floats when to_host=False (no synchronisation)."""
     xd, md, Pd = _dev(x), _dev(mean), _dev(cov)
     dx, N, M = xd.shape
     stats, acc = dv.scores_phase1(xd, md, Pd, status)
@@ -173,4 +174,6 @@ def evaluate_performance(x, mean, cov, status=None, comm=None):
     out = dict(rmse=(rm / n_ok), nll=st[1:, dx + dx * dx].sum() / (N * n_ok), inc=lcr[1:, 0].sum() / (N * n_ok),
                nci=lcr[1:, 0].sum() / (N * n_ok), abs_nci=lcr[1:, 1].sum() / (N * n_ok), mse=mse,
                rmse_vs_time=st[:, dx + dx * dx + 1] / cnt, n_ok=n_ok)
+    if not to_host:
+        return out
     return {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}
