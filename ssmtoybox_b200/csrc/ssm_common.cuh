@@ -25,6 +25,23 @@ SSM_DEV void st_stream(double *p, double v) { __stcs(p, v); }
 
 SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// Out-of-line fp64 math.  The fused forward pass for the 5-D models is one straight-line body; with
+// libm inlined at every use (16 exp, ~20 sqrt, ~25 divisions, 5 atan2 per step) it is ~144 KB of SASS and
+// the SMs run instruction-fetch bound at ~1.9 IPC (profiles/: sm__icc_request_hit_rate 58-75 %,
+// stall_no_instruction dominant at saturation).  Calling one shared copy of each routine keeps the
+// body inside the instruction cache; scalar arguments and results stay in registers, and the results
+// are bit-identical to the inlined calls.
+#ifndef SSM_INLINE_MATH
+#define SSM_MATH_FN static __device__ __noinline__
+#else
+#define SSM_MATH_FN static __device__ __forceinline__
+#endif
+SSM_MATH_FN double m_exp(double x) { return exp(x); }
+SSM_MATH_FN double m_sqrt(double x) { return sqrt(x); }
+SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
+SSM_MATH_FN double m_div(double a, double b) { return a / b; }
+SSM_MATH_FN double m_atan2(double y, double x) { return atan2(y, x); }
+
 // Lower Cholesky factor of a symmetric matrix given by its packed lower triangle.
 // Mirrors dpotrf('L') as called by numpy.linalg.cholesky (mtran.py:139, bqmtran.py:98): only the
 // lower triangle is read and a pivot <= 0 is a failure (LinAlgError).  A NaN pivot is NOT a failure:
@@ -40,8 +57,8 @@ SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSiz
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[tri(j, k)], L[tri(j, k)], s);
         ok = ok && !(s <= 0.0);
-        const double d = sqrt(s);
-        const double inv = 1.0 / d;
+        const double d = m_sqrt(s);
+        const double inv = m_rcp(d);
         L[tri(j, j)] = d;
 #pragma unroll
         for (int i = j + 1; i < D; ++i) {
@@ -62,7 +79,7 @@ SSM_DEV bool spd_gain(const double (&S)[TriSize<E>::value], const double (&C)[E]
     const bool ok = chol_lower<E>(S, Ls);
     double inv[E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) inv[i] = 1.0 / Ls[tri(i, i)];
+    for (int i = 0; i < E; ++i) inv[i] = m_rcp(Ls[tri(i, i)]);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         double z[E];

@@ -101,6 +101,11 @@ SSM_DEV void sigma_point(const Tf &tf, int i, const double (&m)[D], const double
 // Outputs: mf (E), Cf packed lower (E), Cfx (E x D) when want_cross.  Returns false when the input
 // covariance is not positive definite.
 // ------------------------------------------------------------------------------------------------
+#ifdef SSM_EXPERIMENT_NOINLINE_F
+template <class F, int D, int E>
+__device__ __noinline__ void call_model(F f, const double (&x)[D], double (&o)[E]) { f(x, o); }
+#endif
+
 template <int D, int E, int PTS, int NPTS, int KIND, class Tf, class F>
 SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (&P)[TriSize<D>::value], F f,
                               double (&mf)[E], double (&Cf)[TriSize<E>::value], double (&Cfx)[E][D],
@@ -115,7 +120,11 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
     for (int i = 0; i < n; ++i) {
         double x[D], o[E];
         sigma_point<D, PTS>(tf, i, m, L, x);
+#ifdef SSM_EXPERIMENT_NOINLINE_F
+        call_model<F, D, E>(f, x, o);
+#else
         f(x, o);
+#endif
 #pragma unroll
         for (int a = 0; a < E; ++a) fx[a][i] = o[a];
     }
@@ -300,13 +309,18 @@ SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef SSM_SYNC_STEPS
+#define SSM_SYNC_STEPS 1
+#endif
 template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, class Par, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_constant__ Par p) {
+    constexpr bool SYNC_STEPS = SSM_SYNC_STEPS != 0;
     constexpr int DX = Dyn::DX, DY = Obs::DY;
     constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
     const FilterBuffers &b = p.b;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= b.n_traj) return;
+    const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t_raw < b.n_traj;
+    const long long t = active ? t_raw : b.n_traj - 1;  // idle lanes shadow the last trajectory, never store
     const int N = b.n_steps;
     const long long ld = b.ld;
 
@@ -330,8 +344,13 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 #pragma unroll
     for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N) * ld + t);
 
-    int fail = 0, kfail = 0;
+    int fail = active ? 0 : -1, kfail = 0;
     for (int k = 0; k < N; ++k) {
+        // The fully unrolled step body is ~140 KB of SASS, far beyond the instruction caches.  Re-aligning
+        // the warps of the CTA once per step makes them stream the body together, so one instruction fetch
+        // from L2 serves all of them instead of one per warp (profiles/: stall_no_inst, fetch-bound).
+        if (SYNC_STEPS) __syncthreads();
+        if (fail) continue;
         double yk[DY];
 #pragma unroll
         for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
@@ -358,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 Dyn::template f<false>(p.dyn_par, x, q0, time, o);
             },
             mp, Pp, Cxx, want_xx);
-        if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; break; }
+        if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
             if (b.pr_cov) {
                 double Cp[TX];
@@ -385,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 Obs::template h<false>(p.obs_par, x, r0, time, o);
             },
             my, Sy, Syx, true);
-        if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; break; }
+        if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
 #pragma unroll
             for (int a = 0; a < TY; ++a) Sy[a] = fma(scale, Sy[a], p.s0 * p.R[a]);
@@ -406,10 +425,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         for (int a = 0; a < DY; ++a)
 #pragma unroll
             for (int d = 0; d < DX; ++d) fin = fin && finite_d(Syx[a][d]);
-        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; break; }
+        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; continue; }
         double K[DX][DY], Ls[TY];
         ok = spd_gain<DY, DX>(Sy, Syx, K, Ls);
-        if (!ok) { fail = SSM_FAIL_CHOL_GAIN; kfail = k; break; }
+        if (!ok) { fail = SSM_FAIL_CHOL_GAIN; kfail = k; continue; }
         double e[DY];
 #pragma unroll
         for (int a = 0; a < DY; ++a) e[a] = yk[a] - my[a];
@@ -451,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 double s = e[i];
 #pragma unroll
                 for (int c = 0; c < i; ++c) s = fma(-Ls[tri(i, c)], z[c], s);
-                z[i] = s / Ls[tri(i, i)];
+                z[i] = m_div(s, Ls[tri(i, i)]);
                 dd = fma(z[i], z[i], dd);
             }
             const double sc = (p.dof + dd) / (p.dof + (double)DY);
@@ -460,6 +479,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         }
     }
 
+    if (!active) return;
     if (fail) {
         fill_nan(b.fi_mean, DX, N, ld, kfail, t);
         fill_nan(b.fi_cov, DX * DX, N, ld, kfail, t);

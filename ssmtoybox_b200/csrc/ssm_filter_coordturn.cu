@@ -1,5 +1,5 @@
 // forward-pass instantiations: coordinated turn (5-D state) + radar on state_index = [0, 2]
 #include "ssm_filter_dispatch.cuh"
 namespace ssm {
-int filter_coordturn(const FilterLaunch &L) { return dispatch_filter_model<DynCoordTurn, ObsRadar<5, 0, 2>, 128, 2>(L); }
+int filter_coordturn(const FilterLaunch &L) { return dispatch_filter_model<DynCoordTurn, ObsRadar<5, 0, 2>, 128, 3>(L); }
 }  // namespace ssm

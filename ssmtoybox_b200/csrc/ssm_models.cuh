@@ -41,11 +41,11 @@ struct DynReentry {
     static constexpr bool HAS_CONT = true;
     SSM_DEV static void forces(const double (&x)[5], double &D, double &G) {
         const double R0 = 6374.0, H0 = 13.406, Gm0 = 3.9860e5, b0 = -0.59783;
-        const double b = b0 * exp(x[4]);
-        const double R = sqrt(x[0] * x[0] + x[1] * x[1]);
-        const double V = sqrt(x[2] * x[2] + x[3] * x[3]);
-        D = b * exp((R0 - R) / H0) * V;
-        G = -Gm0 / (R * R * R);
+        const double b = b0 * m_exp(x[4]);
+        const double R = m_sqrt(x[0] * x[0] + x[1] * x[1]);
+        const double V = m_sqrt(x[2] * x[2] + x[3] * x[3]);
+        D = b * m_exp(m_div(R0 - R, H0)) * V;
+        G = m_div(-Gm0, R * R * R);
     }
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[3], double, double (&o)[5]) {
@@ -87,8 +87,8 @@ struct DynCoordTurn {
         const double om = x[4];
         double a, b;
         sincos(om * dt, &a, &b);
-        const double c = a / om;
-        const double d = (1.0 - b) / om;
+        const double c = m_div(a, om);
+        const double d = m_div(1.0 - b, om);
         o[0] = x[0] + c * x[1] - d * x[3];
         if (NOISE) o[0] += q[0];
         o[1] = b * x[1] - a * x[3];
@@ -137,9 +137,9 @@ struct ObsRadar {
     template <bool NOISE>
     SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[2], double, double (&o)[2]) {
         const double ex = x[I0] - par[0], ey = x[I1] - par[1];
-        o[0] = sqrt(ex * ex + ey * ey);
+        o[0] = m_sqrt(ex * ex + ey * ey);
         if (NOISE) o[0] += r[0];
-        o[1] = atan2(ey, ex);
+        o[1] = m_atan2(ey, ex);
         if (NOISE) o[1] += r[1];
     }
 };

@@ -159,15 +159,29 @@ extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_co
     return rc;
 }
 
-// ---- FP64 FMA micro-benchmark: 8 independent DFMA chains per thread -----------------------------
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int n_iters) {
+// ---- FP64 FMA micro-benchmarks: 8 independent DFMA chains per thread --------------------------------
+// mode 0: acc = fma(acc, const, const)  one register operand   (the headline "peak" form)
+// mode 1: acc = fma(x, const, acc)      two register operands  (quadrature sums with weights in the constant bank)
+// mode 2: acc = fma(x, y, acc)          three register operands (general small-matrix products)
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int n_iters, double xin, double yin) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double b = 1.0000001, c = 1e-9;
+    // x*, y* are runtime values in registers (not foldable)
+    double x0 = xin + threadIdx.x, x1 = x0 * 1.5, x2 = x0 * 2.5, x3 = x0 * 3.5, y0 = yin - threadIdx.x, y1 = y0 * 0.5, y2 = y0 * 0.25, y3 = y0 * 0.125;
     for (int i = 0; i < n_iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+            if (MODE == 0) {
+                a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+                a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+            } else if (MODE == 1) {
+                a0 = fma(x0, b, a0); a1 = fma(x1, b, a1); a2 = fma(x2, b, a2); a3 = fma(x3, b, a3);
+                a4 = fma(y0, b, a4); a5 = fma(y1, b, a5); a6 = fma(y2, b, a6); a7 = fma(y3, b, a7);
+            } else {
+                a0 = fma(x0, y0, a0); a1 = fma(x1, y1, a1); a2 = fma(x2, y2, a2); a3 = fma(x3, y3, a3);
+                a4 = fma(x0, y1, a4); a5 = fma(x1, y2, a5); a6 = fma(x2, y3, a6); a7 = fma(x3, y0, a7);
+            }
         }
     }
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
@@ -175,8 +189,14 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int n_iter
 }
 
 extern "C" int ssm_fp64_peak_kernel(int32_t n_blocks, int32_t n_iters, double *sink, double *flops, void *stream) {
-    if (n_blocks <= 0 || n_iters <= 0 || !sink) { set_error("ssm_fp64_peak_kernel: bad arguments"); return SSM_E_INVALID; }
-    fp64_peak_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(sink, n_iters);
-    if (flops) *flops = 2.0 * 64.0 * (double)n_iters * 256.0 * (double)n_blocks;
+    if (n_blocks <= 0 || n_iters == 0 || !sink) { set_error("ssm_fp64_peak_kernel: bad arguments"); return SSM_E_INVALID; }
+    // n_iters < 0 selects the operand form: -(mode * 2^24 + iters)
+    int mode = 0, iters = n_iters;
+    if (n_iters < 0) { mode = (-n_iters) >> 24; iters = (-n_iters) & 0xFFFFFF; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == 0) fp64_peak_kernel<0><<<n_blocks, 256, 0, s>>>(sink, iters, 1.25, 2.5);
+    else if (mode == 1) fp64_peak_kernel<1><<<n_blocks, 256, 0, s>>>(sink, iters, 1.25e-9, 2.5e-9);
+    else fp64_peak_kernel<2><<<n_blocks, 256, 0, s>>>(sink, iters, 1.25e-9, 2.5e-9);
+    if (flops) *flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)n_blocks;
     return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }

@@ -177,9 +177,12 @@ def smooth_backward(dx, fwd, out=None):
     return o
 
 
-def fp64_peak(n_blocks=148 * 8, n_iters=4096, reps=5):
+def fp64_peak(n_blocks=148 * 8, n_iters=4096, reps=5, mode=0):
     """Measured FP64 FMA throughput (FLOP/s) of the device: the roofline denominator for the
-    FP64-bound kernels (MEASURED_PEAKS.json carries HBM and bf16 only)."""
+    FP64-bound kernels (MEASURED_PEAKS.json carries HBM and bf16 only).  mode = number of register
+    operands beyond the first: 0 acc=fma(acc,c,c) (headline peak), 1 acc=fma(x,c,acc), 2 acc=fma(x,y,acc)."""
+    if mode:
+        n_iters = -((mode << 24) + n_iters)
     sink = torch.zeros(1, dtype=torch.float64, device='cuda')
     flops = C.c_double(0.0)
     best = 0.0
