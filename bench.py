@@ -238,14 +238,12 @@ def run_gpu_arm(args):
     del fwd, sm
     torch.cuda.empty_cache()
 
+    from ssmtoybox_b200 import mc
+
     def e2e_step():
-        yd = yh.to(dev, non_blocking=True)
-        xd = xh.to(dev, non_blocking=True)
-        alg.reset()
-        alg.forward_pass(yd)
-        ms_, Ps_ = alg.backward_pass()
-        out = U.evaluate_performance(xd, ms_, Ps_, status=alg.status, comm=comm)     # scores land on the host
-        return out
+        """The user-level call: filter + smoother + scores of one Monte-Carlo batch held in HOST memory.  Inside:
+        chunked H2D of y and x overlapped with the kernels, scores copied back to the host."""
+        return mc.filter_scores(alg, yh, xh, smooth=True, n_chunks=args.chunks, comm=comm)
 
     for _ in range(max(1, min(args.warmup, 2))):
         out = e2e_step()
@@ -262,7 +260,7 @@ def run_gpu_arm(args):
     e2e_ms = comm.allreduce_max(t0.elapsed_time(t1)) / args.steps
     e2e_wall_ms = comm.allreduce_max((time.perf_counter() - w0) * 1e3) / args.steps
     e2e_value = comm.world_size * M * N / (max(e2e_ms, e2e_wall_ms) * 1e-3)
-    d2h = 8 * (5 + 4 + 25 * N + N + 1)
+    d2h = 8 * (5 + 4 + 25 * N + N + 1) + 4 * M
 
     if comm.rank != 0:
         return
@@ -302,7 +300,9 @@ def run_gpu_arm(args):
             'config': dict(CONFIG, n_traj_per_gpu=M),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(yh.numel() + xh.numel()) * 8,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': max(e2e_ms, e2e_wall_ms),
-                    'api': 'GaussianProcessKalman.forward_pass + backward_pass + utils.evaluate_performance on pinned host y, x'},
+                    'api': 'ssmtoybox_b200.mc.filter_scores(GaussianProcessKalman, y, x, smooth=True) on pinned host y, x: '
+                           'chunked H2D overlapped with forward pass + RTS smoother + scores; scores and status read back',
+                    'chunks': args.chunks},
             'gpu_launches': 6 * args.steps,
             'kernel_ms': {'filter_forward': k_filter, 'rts_smoother': k_smooth, 'scores_2phase_incl_allreduce': k_scores},
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
@@ -319,11 +319,15 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--traj', type=int, default=TRAJ_PER_GPU, help='trajectories per GPU (default: the C3 share)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--chunks', type=int, default=10, help='trajectory chunks of the host-streaming (e2e) pipeline')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

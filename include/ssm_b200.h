@@ -251,6 +251,13 @@ int ssm_rbf_expectations(int32_t dim, int32_t n_pts, const double *par, const do
 int ssm_sample(int32_t dim, const double *mean, const double *factor, double dof, uint64_t seed, int64_t offset,
                double *out, int64_t n, int64_t ld, void *stream);
 
+/* ---- strided copy of a trajectory range ---------------------------------------------------------
+ * height rows of width bytes with row pitches dpitch / spitch (bytes): moves columns [a, b) of a host array laid
+ * out [component][step][trajectory] into a compact device chunk (or back).  Asynchronous on the stream when the
+ * host side is pinned.  Used by the host-streaming Monte-Carlo driver (research loops over y[..., i]). */
+int ssm_memcpy2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height,
+                 int32_t host_to_device, void *stream);
+
 /* ---- FP64 FMA micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no fp64 figure) --
  * Launches a dependent-chain-free DFMA loop; returns the number of FLOPs it executes in *flops.
  * The caller times it with CUDA events. */

@@ -68,3 +68,15 @@ extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
 }
+
+// Strided host <-> device copy of a trajectory range of a [component][step][trajectory] array:
+// `height` rows of `width` bytes, row pitches in bytes.  Pinned host memory -> asynchronous DMA on the stream.
+extern "C" int ssm_memcpy2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height,
+                            int32_t host_to_device, void *stream) {
+    if (!dst || !src) { set_error("ssm_memcpy2d: NULL pointer"); return SSM_E_INVALID; }
+    if (width == 0 || height == 0) return SSM_OK;
+    const cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height,
+                                            host_to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ssm_memcpy2d: CUDA error: %s", cudaGetErrorString(e)); return SSM_E_CUDA; }
+    return SSM_OK;
+}

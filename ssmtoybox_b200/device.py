@@ -127,13 +127,30 @@ def _check_bulk(t, lead, n_steps, ld, name):
         raise ValueError('{} has shape {}, expected {}'.format(name, tuple(t.shape), tuple(lead) + (n_steps, ld)))
 
 
+def bulk_ld(t):
+    """Leading dimension of a [component..., step, trajectory] tensor that may be a trajectory-range view
+    t_full[..., a:b] of a contiguous array: trajectory stride 1, step stride ld, component strides N*ld multiples."""
+    if t.dtype != torch.float64 or not t.is_cuda:
+        raise ValueError('bulk arrays must be float64 CUDA tensors')
+    st, sh = t.stride(), t.shape
+    ld = st[-2] if sh[-2] > 1 else max(sh[-1], 1)
+    ok = (st[-1] == 1 or sh[-1] <= 1) and ld >= sh[-1]
+    exp = ld * sh[-2]
+    for d in range(t.ndim - 3, -1, -1):
+        ok = ok and (st[d] == exp or sh[d] <= 1)
+        exp *= sh[d]
+    if not ok:
+        raise ValueError('bulk array must be C-contiguous or a trajectory-range view of a C-contiguous array')
+    return int(ld)
+
+
 def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, init_cov=None, t_offset=None, k0=0,
                    want_last=False, out=None):
     """Run the fused forward pass (ssm_filter) on y (dy, N, M) -> dict of device tensors."""
     dy, N, M = y.shape
     dx = low.dx
     dev = y.device
-    _check_bulk(y, (dy,), N, M, 'y')
+    ld = bulk_ld(y)
     kw = dict(dtype=torch.float64, device=dev)
     o = out if out is not None else {}
     if 'fi_mean' not in o:
@@ -155,10 +172,15 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     if M == 0 or N == 0:
         o['status'].zero_()
         return o
+    for k in ('fi_mean', 'fi_cov', 'pr_mean', 'pr_cov', 'pr_xx_cov'):
+        if o.get(k) is not None and bulk_ld(o[k]) != ld and M > 1:
+            raise ValueError('all bulk arrays of one call must share the leading dimension (y: {}, {}: {})'.format(ld, k, bulk_ld(o[k])))
+    if (init_mean is not None or want_last) and ld != M:
+        raise ValueError('init / last moments are not supported on trajectory-range views')
     rc = lib.ssm_filter(C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
                         _p(o.get('pr_cov')), _p(o.get('pr_xx_cov')), _p(init_mean), _p(init_cov),
                         _p(o.get('last_mean')), _p(o.get('last_cov')), _p(t_offset), int(k0), _p(o['status']),
-                        M, N, M, _stream())
+                        M, N, ld, _stream())
     _lib.check(rc, 'ssm_filter')
     return o
 
@@ -170,9 +192,15 @@ def smooth_backward(dx, fwd, out=None):
     if 'sm_mean' not in o:
         o['sm_mean'] = torch.empty_like(fwd['fi_mean'])
         o['sm_cov'] = torch.empty_like(fwd['fi_cov'])
-    o['status'] = fwd['status'].clone()
+    if 'status' in o and o['status'].shape == fwd['status'].shape:
+        o['status'].copy_(fwd['status'])
+    else:
+        o['status'] = fwd['status'].clone()
+    ld = bulk_ld(fwd['fi_mean'])
+    if any(bulk_ld(t) != ld for t in (fwd['fi_cov'], fwd['pr_mean'], fwd['pr_cov'], fwd['pr_xx_cov'], o['sm_mean'], o['sm_cov'])) and M > 1:
+        raise ValueError('all bulk arrays of one ssm_smooth call must share the leading dimension')
     rc = lib.ssm_smooth(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
-                        _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']), M, N, M, _stream())
+                        _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']), M, N, ld, _stream())
     _lib.check(rc, 'ssm_smooth')
     return o
 

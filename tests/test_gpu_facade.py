@@ -284,3 +284,32 @@ def test_samplers_and_scalar_metrics():
     assert abs(U.neg_log_likelihood(x[:, 5, 1], m[:, 5, 1], P[:, :, 5, 1]) - gs['c5_pend_gpq_nll'][5, 1]) < 1e-11
     assert abs(U.log_cred_ratio(x[:, 5, 1], m[:, 5, 1], P[:, :, 5, 1], gs['c5_pend_gpq_mse'][..., 5]) - gs['c5_pend_gpq_lcr'][5, 1]) < 1e-9
     assert np.array_equal(U.squared_error(x, m), (x - m) ** 2)
+
+
+def test_mc_filter_scores_streaming_matches_reference_scores():
+    """One-call Monte-Carlo driver with host inputs (chunked H2D pipeline) == the reference's scores."""
+    from ssmtoybox_b200 import mc
+    from ssmtoybox_b200.ssinf import UnscentedKalman, GaussianProcessKalman
+    gs = golden('scores')
+    dyn, obs = pendulum()
+    g = golden('c5_pend_gpq')
+    alg = GaussianProcessKalman(dyn, obs, np.array([[1.0, 1.0, 1.0]]), np.array([[1.0, 1.0, 1.0]]))
+    r = mc.filter_scores(alg, g['y'], g['x'], smooth=False, n_chunks=2)
+    assert rel(r['rmse'], gs['c5_pend_gpq_rmse_f'].ravel()) < 1e-9
+    assert abs(r['nll'] - gs['c5_pend_gpq_nll_f'].ravel()[0]) < 1e-8 * abs(r['nll'])
+    assert abs(r['nci'] - gs['c5_pend_gpq_nci_f'].ravel()[0]) < 1e-8 * abs(r['nci'])
+    assert (r['status'] == 0).all()
+    # larger batch, many chunks, pinned host tensors: identical to the single-shot device evaluation
+    from ssmtoybox_b200 import utils as U, device as dv
+    udyn, uobs = ungm()
+    U.seed(5)
+    x = udyn.simulate_discrete(60, mc_sims=3000)
+    y = uobs.simulate_measurements(x)
+    alg = UnscentedKalman(udyn, uobs)
+    xh, yh = torch.as_tensor(x).pin_memory(), torch.as_tensor(y).pin_memory()
+    r1 = mc.filter_scores(alg, yh, xh, smooth=True, n_chunks=7)
+    m, P = alg.forward_pass(torch.as_tensor(y, device='cuda'))
+    ms, Ps = alg.backward_pass()
+    r2 = U.evaluate_performance(torch.as_tensor(x, device='cuda'), ms, Ps, status=alg.status)
+    assert rel(r1['rmse'], r2['rmse']) < 1e-12 and abs(r1['nll'] - r2['nll']) < 1e-11 * abs(r2['nll'])
+    assert abs(r1['nci'] - r2['nci']) < 1e-10 * abs(r2['nci']) + 1e-12
