@@ -192,11 +192,14 @@ int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mode, double 
  * Outputs are DEVICE arrays: wm (n_par, N), Wc (n_par, N, N), Wcc (n_par, D, N),
  * iK (n_par, N, N), scal (n_par, 2) = [model_var, integral_var]; info (n_par) int32 != 0 when a
  * Cholesky factorisation failed.
+ * precision: 0 = float64 arithmetic (the reference's own: error ~ eps cond(K) on wm / Wcc, eps cond(K)^2 on Wc,
+ * i.e. rounding noise for the cond ~ 1e9 kernels of the reference's tracking scripts); 1 = double-double
+ * arithmetic rounded once at the end (the correctly rounded value of the same formulas).
  */
 int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const double *par, const double *points,
                    const int32_t *mulind, int32_t n_basis,
                    double *wm, double *Wc, double *Wcc, double *iK, double *scal, int32_t *info,
-                   void *stream);
+                   int32_t precision, void *stream);
 
 /* ---- K6: error statistics -------------------------------------------------------------------
  * Replaces utils.squared_error / mse_matrix / neg_log_likelihood / log_cred_ratio

@@ -73,7 +73,7 @@ def _load():
         lib.ssm_simulate.argtypes = [C.POINTER(SsmDesc), C.POINTER(SsmRng), i32, dbl, i32, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     if True:
         lib.ssm_bq_weights.restype = C.c_int
-        lib.ssm_bq_weights.argtypes = [i32, i32, i32, c_double_p, c_double_p, c_int32_p, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.ssm_bq_weights.argtypes = [i32, i32, i32, c_double_p, c_double_p, c_int32_p, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     if True:
         lib.ssm_scores_width.restype = i32
         lib.ssm_scores_width.argtypes = [i32]

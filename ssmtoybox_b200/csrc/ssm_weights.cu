@@ -13,7 +13,7 @@
 // integer combinatorics of the multi-index and are evaluated by the host part of this file.
 #include <vector>
 
-#include "ssm_common.cuh"
+#include "ssm_dd.cuh"
 
 namespace ssm {
 
@@ -34,16 +34,17 @@ struct WeightsPar {
     long long work_stride;
 };
 
-// ---- CTA-cooperative dense helpers (row-major, global/L2 memory) --------------------------------
+// ---- CTA-cooperative dense helpers (row-major, global/L2 memory), scalar type T = double or dd ------
 // C (m x n) = op(A) (m x k) . op(B) (k x n); lda/ldb are the leading dimensions of the stored arrays
-__device__ void mm(double *C, const double *A, bool tA, int lda, const double *B, bool tB, int ldb, int m, int k, int n) {
+template <class T, class TA, class TB>
+__device__ void mm(T *C, const TA *A, bool tA, int lda, const TB *B, bool tB, int ldb, int m, int k, int n) {
     for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
         const int i = e / n, j = e % n;
-        double s = 0.0;
+        T s(0.0);
         for (int l = 0; l < k; ++l) {
-            const double a = tA ? A[l * lda + i] : A[i * lda + l];
-            const double b = tB ? B[j * ldb + l] : B[l * ldb + j];
-            s = fma(a, b, s);
+            const T a(tA ? A[l * lda + i] : A[i * lda + l]);
+            const T b(tB ? B[j * ldb + l] : B[l * ldb + j]);
+            s = s + a * b;
         }
         C[e] = s;
     }
@@ -51,21 +52,22 @@ __device__ void mm(double *C, const double *A, bool tA, int lda, const double *B
 }
 
 // in-place lower Cholesky of the n x n matrix A; returns false when not positive definite
-__device__ bool chol_cta(double *A, int n, int *flag) {
+template <class T>
+__device__ bool chol_cta(T *A, int n, int *flag) {
     if (threadIdx.x == 0) *flag = 0;
     __syncthreads();
     for (int j = 0; j < n; ++j) {
         if (threadIdx.x == 0) {
-            double s = A[j * n + j];
-            for (int k = 0; k < j; ++k) s = fma(-A[j * n + k], A[j * n + k], s);
+            T s = A[j * n + j];
+            for (int k = 0; k < j; ++k) s = s - A[j * n + k] * A[j * n + k];
             if (!(s > 0.0)) *flag = 1;
-            A[j * n + j] = sqrt(s);
+            A[j * n + j] = tsqrt(s);
         }
         __syncthreads();
-        const double d = A[j * n + j];
+        const T d = A[j * n + j];
         for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) {
-            double t = A[i * n + j];
-            for (int k = 0; k < j; ++k) t = fma(-A[i * n + k], A[j * n + k], t);
+            T t = A[i * n + j];
+            for (int k = 0; k < j; ++k) t = t - A[i * n + k] * A[j * n + k];
             A[i * n + j] = t / d;
         }
         __syncthreads();
@@ -73,41 +75,43 @@ __device__ bool chol_cta(double *A, int n, int *flag) {
     return *flag == 0;
 }
 
-// X = (L L^T)^-1 via column-wise forward/back substitution with the identity (cho_solve(., I)),
-// then symmetrised 0.5 (X + X^T) as Kernel._cho_inv does (bqkern.py:59-63).  T is scratch (n x n).
-__device__ void chol_inverse_sym(double *X, const double *L, double *T, int n) {
+// X = (L L^T)^-1 by column-wise forward/back substitution with the identity (cho_solve(., I)); symmetrised
+// 0.5 (X + X^T) when sym (Kernel._cho_inv, bqkern.py:59-63).  T_ is scratch (n x n).
+template <class T>
+__device__ void chol_inverse(T *X, const T *L, T *T_, int n, bool sym) {
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
         for (int i = 0; i < n; ++i) {  // L y = e_c
-            double t = (i == c) ? 1.0 : 0.0;
-            for (int k = 0; k < i; ++k) t = fma(-L[i * n + k], T[k * n + c], t);
-            T[i * n + c] = t / L[i * n + i];
+            T t((i == c) ? 1.0 : 0.0);
+            for (int k = 0; k < i; ++k) t = t - L[i * n + k] * T_[k * n + c];
+            T_[i * n + c] = t / L[i * n + i];
         }
         for (int i = n - 1; i >= 0; --i) {  // L^T x = y
-            double t = T[i * n + c];
-            for (int k = i + 1; k < n; ++k) t = fma(-L[k * n + i], T[k * n + c], t);
-            T[i * n + c] = t / L[i * n + i];
+            T t = T_[i * n + c];
+            for (int k = i + 1; k < n; ++k) t = t - L[k * n + i] * T_[k * n + c];
+            T_[i * n + c] = t / L[i * n + i];
         }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         const int i = e / n, j = e % n;
-        X[e] = 0.5 * (T[i * n + j] + T[j * n + i]);
+        X[e] = sym ? T(0.5) * (T_[i * n + j] + T_[j * n + i]) : T_[e];
     }
     __syncthreads();
 }
 
 // general inverse by Gaussian elimination with partial pivoting (scipy.linalg.solve(V, I), bqmod.py:949)
 // A is destroyed, X receives A^-1.  Serial pivot search, parallel row updates.
-__device__ bool lu_inverse(double *X, double *A, int n, int *flag) {
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) X[e] = (e / n == e % n) ? 1.0 : 0.0;
+template <class T>
+__device__ bool lu_inverse(T *X, T *A, int n, int *flag) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) X[e] = T((e / n == e % n) ? 1.0 : 0.0);
     if (threadIdx.x == 0) *flag = 0;
     __syncthreads();
     for (int j = 0; j < n; ++j) {
         if (threadIdx.x == 0) {
             int piv = j;
-            double best = fabs(A[j * n + j]);
+            double best = fabs(to_double(A[j * n + j]));
             for (int i = j + 1; i < n; ++i)
-                if (fabs(A[i * n + j]) > best) { best = fabs(A[i * n + j]); piv = i; }
+                if (fabs(to_double(A[i * n + j])) > best) { best = fabs(to_double(A[i * n + j])); piv = i; }
             if (!(best > 0.0)) *flag = 1;
             flag[1] = piv;
         }
@@ -115,294 +119,282 @@ __device__ bool lu_inverse(double *X, double *A, int n, int *flag) {
         const int piv = flag[1];
         if (piv != j) {
             for (int c = threadIdx.x; c < n; c += blockDim.x) {
-                double t = A[j * n + c]; A[j * n + c] = A[piv * n + c]; A[piv * n + c] = t;
+                T t = A[j * n + c]; A[j * n + c] = A[piv * n + c]; A[piv * n + c] = t;
                 t = X[j * n + c]; X[j * n + c] = X[piv * n + c]; X[piv * n + c] = t;
             }
         }
         __syncthreads();
-        const double d = A[j * n + j];
+        const T d = A[j * n + j];
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             if (i == j) continue;
-            const double f = A[i * n + j] / d;
+            const T f = A[i * n + j] / d;
             for (int c = 0; c < n; ++c) {
-                if (c > j) A[i * n + c] = fma(-f, A[j * n + c], A[i * n + c]);
-                X[i * n + c] = fma(-f, X[j * n + c], X[i * n + c]);
+                if (c > j) A[i * n + c] = A[i * n + c] - f * A[j * n + c];
+                X[i * n + c] = X[i * n + c] - f * X[j * n + c];
             }
-            A[i * n + j] = 0.0;
+            A[i * n + j] = T(0.0);
         }
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) X[e] /= A[(e / n) * n + (e / n)];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) X[e] = X[e] / A[(e / n) * n + (e / n)];
     __syncthreads();
     return *flag == 0;
 }
 
-__device__ double trace_prod(const double *A, const double *B, int n, int m, double *red) {
-    // tr(A B) with A (n x m), B (m x n)
-    double s = 0.0;
-    for (int e = threadIdx.x; e < n * m; e += blockDim.x) s = fma(A[e], B[(e % m) * n + e / m], s);
-    red[threadIdx.x] = s;
-    __syncthreads();
+// tr(A B) with A (n x m), B (m x n); serial in thread 0 (tiny, deterministic)
+template <class T, class TA, class TB>
+__device__ T trace_prod(const TA *A, const TB *B, int n, int m, T *red) {
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < (int)blockDim.x; ++i) t += red[i];  // fixed order: deterministic
-        red[0] = t;
+        T s(0.0);
+        for (int e = 0; e < n * m; ++e) s = s + T(A[e]) * T(B[(e % m) * n + e / m]);
+        red[0] = s;
     }
     __syncthreads();
-    const double r = red[0];
+    const T r = red[0];
     __syncthreads();
     return r;
 }
 
-__device__ double dot_cta(const double *a, const double *b, int n, double *red) {
+template <class T, class TA, class TB>
+__device__ T dot_cta(const TA *a, const TB *b, int n, T *red) {
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < n; ++i) t = fma(a[i], b[i], t);
+        T t(0.0);
+        for (int i = 0; i < n; ++i) t = t + T(a[i]) * T(b[i]);
         red[0] = t;
     }
     __syncthreads();
-    const double r = red[0];
+    const T r = red[0];
     __syncthreads();
     return r;
 }
 
+template <class T>
 __global__ void __launch_bounds__(128) bq_weights_kernel(const WeightsPar p) {
-    __shared__ double red[128];
+    __shared__ T red[2];
     __shared__ int flag[2];
-    __shared__ double ell[W_MAXD], il2[W_MAXD];  // length-scales, 1 / l^2
+    __shared__ double ell[W_MAXD];
     const int D = p.D, N = p.N, Q = p.Q, ip = blockIdx.x;
     const double *par = p.par + (long long)ip * (D + 1);
     const double *x = p.x;
-    double *w = p.work + (long long)ip * p.work_stride;
+    T *w = reinterpret_cast<T *>(p.work + (long long)ip * p.work_stride);
     const int NN = N * N;
     // workspace carving
-    double *K = w;            w += NN;   // kernel matrix, then its Cholesky factor
-    double *iK = w;           w += NN;
-    double *Qm = w;           w += NN;
-    double *T1 = w;           w += NN;
-    double *T2 = w;           w += NN;
-    double *q = w;            w += N;
-    double *R = w;            w += D * N;
-    double *xs = w;           w += D * N;   // scaled points
-    double *x2 = w;           w += N;
+    T *K = w;            w += NN;   // kernel matrix, then its Cholesky factor
+    T *iK = w;           w += NN;
+    T *Qm = w;           w += NN;
+    T *T1 = w;           w += NN;
+    T *T2 = w;           w += NN;
+    T *q = w;            w += N;
+    T *R = w;            w += D * N;
+    T *xs = w;           w += D * N;   // scaled points
+    T *x2 = w;           w += N;
+    T *wmT = w;          w += N;
+    T *WccT = w;         w += D * N;
     int info = 0;
-    const double alpha = par[0];
-    if (threadIdx.x < D) {
-        ell[threadIdx.x] = par[1 + threadIdx.x];
-        il2[threadIdx.x] = 1.0 / (par[1 + threadIdx.x] * par[1 + threadIdx.x]);
-    }
+    const T alpha(par[0]);
+    if (threadIdx.x < D) ell[threadIdx.x] = par[1 + threadIdx.x];
     __syncthreads();
+    auto il2 = [&](int d) { return T(1.0) / (T(ell[d]) * T(ell[d])); };   // 1 / l^2
 
     // ---- K = exp(-0.5 maha(x / l)), scaling=False                      bqkern.py:329-343
-    for (int e = threadIdx.x; e < D * N; e += blockDim.x) xs[e] = (1.0 / ell[e / N]) * x[e];
+    for (int e = threadIdx.x; e < D * N; e += blockDim.x) xs[e] = (T(1.0) / T(ell[e / N])) * T(x[e]);
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        double s = 0.0;
-        for (int d = 0; d < D; ++d) s = fma(xs[d * N + i], xs[d * N + i], s);
+        T s(0.0);
+        for (int d = 0; d < D; ++d) s = s + xs[d * N + i] * xs[d * N + i];
         x2[i] = s;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < NN; e += blockDim.x) {
         const int i = e / N, j = e % N;
-        double cr = 0.0;
-        for (int d = 0; d < D; ++d) cr = fma(xs[d * N + i], xs[d * N + j], cr);
-        const double mh = (x2[i] + x2[j]) - 2.0 * cr;
-        K[e] = exp(-0.5 * mh) + ((i == j) ? 1e-8 : 0.0);  // + jitter I, bqkern.py:120
+        T cr(0.0);
+        for (int d = 0; d < D; ++d) cr = cr + xs[d * N + i] * xs[d * N + j];
+        const T mh = (x2[i] + x2[j]) - T(2.0) * cr;
+        K[e] = texp(T(-0.5) * mh) + T((i == j) ? 1e-8 : 0.0);  // + jitter I, bqkern.py:120
     }
     __syncthreads();
     // ---- iK = sym(cho_solve(cho_factor(K + jitter I), I))               bqkern.py:38-64
-    if (!chol_cta(K, N, flag)) info |= 1;
-    chol_inverse_sym(iK, K, T1, N);
+    if (!chol_cta<T>(K, N, flag)) info |= 1;
+    chol_inverse<T>(iK, K, T1, N, true);
 
     // ---- q = E[k(x, x_i)], R = E[x k(x, x_i)]                           bqkern.py:345-364
-    double cdet = 1.0, rdet = 1.0, kdet = 1.0;
+    T cdet(1.0), rdet(1.0);
     for (int d = 0; d < D; ++d) {
-        cdet *= il2[d] + 1.0;
-        rdet *= 2.0 * il2[d] + 1.0;   // |2 Lambda^-1 + I| is also det(r) of exp_x_kxkx
-        kdet *= 2.0 * il2[d] + 1.0;
+        cdet = cdet * (il2(d) + T(1.0));
+        rdet = rdet * (T(2.0) * il2(d) + T(1.0));   // |2 Lambda^-1 + I|, also det(r) of exp_x_kxkx
     }
-    const double cq = 1.0 / sqrt(cdet);
+    const T cq = T(1.0) / tsqrt(cdet);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        double s = 0.0;
+        T s(0.0);
         for (int d = 0; d < D; ++d) {
-            const double lam1 = 1.0 / (ell[d] * ell[d] + 1.0);  // (Lambda + I)^-1
-            s = fma(x[d * N + i], lam1 * x[d * N + i], s);
+            const T lam1 = T(1.0) / (T(ell[d]) * T(ell[d]) + T(1.0));  // (Lambda + I)^-1
+            s = s + T(x[d * N + i]) * (lam1 * T(x[d * N + i]));
         }
-        q[i] = cq * exp(-0.5 * s);
+        q[i] = cq * texp(T(-0.5) * s);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < D * N; e += blockDim.x) {
         const int d = e / N;
-        R[e] = q[e % N] * ((1.0 / (ell[d] * ell[d] + 1.0)) * x[e]);
+        R[e] = q[e % N] * ((T(1.0) / (T(ell[d]) * T(ell[d]) + T(1.0))) * T(x[e]));
     }
     // ---- Q_ij = E[k(x, x_i) k(x, x_j)]                                  bqkern.py:366-415
-    const double cQ = 1.0 / sqrt(rdet);
+    const T cQ = T(1.0) / tsqrt(rdet);
     for (int e = threadIdx.x; e < NN; e += blockDim.x) {
         const int i = e / N, j = e % N;
-        double n = -0.5 * x2[i] + -0.5 * x2[j];
-        double mh = 0.0;
+        const T n = T(-0.5) * x2[i] + T(-0.5) * x2[j];
+        T mh(0.0);
         for (int d = 0; d < D; ++d) {
-            const double a = il2[d] * x[d * N + i] + il2[d] * x[d * N + j];
-            mh = fma(a * a, 1.0 / (2.0 * il2[d] + 1.0), mh);
+            const T a = il2(d) * T(x[d * N + i]) + il2(d) * T(x[d * N + j]);
+            mh = mh + (a * a) * (T(1.0) / (T(2.0) * il2(d) + T(1.0)));
         }
-        Qm[e] = cQ * exp(n + 0.5 * mh);
+        Qm[e] = cQ * texp(n + T(0.5) * mh);
     }
     __syncthreads();
-    const double kbar = alpha * alpha / sqrt(kdet);   // bqkern.py:421-424
+    const T kbar = alpha * alpha / tsqrt(rdet);   // bqkern.py:421-424
 
     double *wm = p.wm + (long long)ip * N;
     double *Wc = p.Wc + (long long)ip * NN;
     double *Wcc = p.Wcc + (long long)ip * D * N;
-    double model_var, integral_var;
+    T model_var, integral_var;
 
     if (Q == 0) {
         // ---- GP weights                                                   bqmod.py:508-517
-        mm(wm, q, false, N, iK, false, N, 1, N, N);
-        mm(T1, iK, false, N, Qm, false, N, N, N, N);
-        mm(T2, T1, false, N, iK, false, N, N, N, N);
-        mm(Wcc, R, false, N, iK, false, N, D, N, N);
-        model_var = alpha * alpha * (1.0 - trace_prod(Qm, iK, N, N, red));
-        integral_var = kbar - dot_cta(wm, q, N, red);
+        mm<T>(wmT, q, false, N, iK, false, N, 1, N, N);
+        mm<T>(T1, iK, false, N, Qm, false, N, N, N, N);
+        mm<T>(T2, T1, false, N, iK, false, N, N, N, N);
+        mm<T>(WccT, R, false, N, iK, false, N, D, N, N);
+        model_var = alpha * alpha * (T(1.0) - trace_prod<T>(Qm, iK, N, N, red));
+        integral_var = kbar - dot_cta<T>(wmT, q, N, red);
     } else {
-        double *V = w;        w += N * Q;     // Vandermonde (N x Q)
-        double *kxpx = w;     w += N * Q;
-        double *iViKV = w;    w += Q * Q;
-        double *S1 = w;       w += (N > Q ? N : Q) * (N > Q ? N : Q);
-        double *S2 = w;       w += (N > Q ? N : Q) * (N > Q ? N : Q);
-        double *S3 = w;       w += (N > Q ? N : Q) * (N > Q ? N : Q);
-        double *v1 = w;       w += (N > Q ? N : Q);
-        double *v2 = w;       w += (N > Q ? N : Q);
+        const int M = N > Q ? N : Q;
+        T *V = w;        w += N * Q;     // Vandermonde (N x Q)
+        T *kxpx = w;     w += N * Q;
+        T *iViKV = w;    w += Q * Q;
+        T *S1 = w;       w += M * M;
+        T *S2 = w;       w += M * M;
+        T *S3 = w;       w += M * M;
+        T *v1 = w;       w += M;
+        T *v2 = w;       w += M;
         // V[n, b] = prod_d x[d, n] ** mulind[d, b]                          utils.py:478-502
         for (int e = threadIdx.x; e < N * Q; e += blockDim.x) {
             const int n = e / Q, b = e % Q;
-            double pr = 1.0;
-            for (int d = 0; d < D; ++d) {
-                double t = 1.0;
-                for (int m = 0; m < p.mulind[d * Q + b]; ++m) t *= x[d * N + n];
-                pr *= t;
-            }
+            T pr(1.0);
+            for (int d = 0; d < D; ++d) pr = pr * tpowi<T>(T(x[d * N + n]), p.mulind[d * Q + b]);
             V[e] = pr;
         }
         // kxpx[n, q] = prod_d a_d b_d                                       bqmod.py:733-797
         // (quirk reproduced: the reference's "ell" is the SQUARED length-scale and is squared again)
         for (int e = threadIdx.x; e < N * Q; e += blockDim.x) {
             const int n = e / Q, b = e % Q;
-            double pr = 1.0;
+            T pr(1.0);
             for (int d = 0; d < D; ++d) {
                 const int a = p.mulind[d * Q + b];
-                const double el = 1.0 / il2[d];            // l^2
-                const double el2 = el * el;                // "ell ** 2"
-                const double xv = x[d * N + n];
-                const double ea = el * pow(1.0 + el2, -0.5 * (1.0 + a)) * exp(-(xv * xv) / (2.0 * (1.0 + el2)));
-                double bs = 0.0;
+                const T el = T(ell[d]) * T(ell[d]);  // l^2
+                const T el2 = el * el;                // "ell ** 2"
+                const T xv(x[d * N + n]);
+                const T one_el2 = T(1.0) + el2;
+                // (1 + el2) ** (-(1 + a) / 2)
+                T pw = T(1.0) / tpowi<T>(tsqrt(one_el2), 1 + a);
+                const T ea = el * pw * texp(-(xv * xv) / (T(2.0) * one_el2));
+                T bs(0.0);
+                const T xn = xv / tsqrt(one_el2);
                 for (int m = 0; m <= a / 2; ++m) {
                     double fa = 1.0, fm = 1.0, fam = 1.0;
                     for (int u = 2; u <= a; ++u) fa *= u;
                     for (int u = 2; u <= m; ++u) fm *= u;
                     for (int u = 2; u <= a - 2 * m; ++u) fam *= u;
-                    const double p1 = fa / (ldexp(1.0, m) * fm * fam);
-                    const double p2 = pow(el, 2.0 * m) * pow(xv / sqrt(1.0 + el2), (double)(a - 2 * m));
-                    bs += p1 * p2;
+                    const T p1(fa / (ldexp(1.0, m) * fm * fam));
+                    const T p2 = tpowi<T>(el, 2 * m) * tpowi<T>(xn, a - 2 * m);
+                    bs = bs + p1 * p2;
                 }
-                pr *= ea * bs;
+                pr = pr * (ea * bs);
             }
             kxpx[e] = pr;
         }
         __syncthreads();
-        // iViKV = inv(V^T iK V + 1e-8 I) by Cholesky                         bqmod.py:936
-        mm(S1, V, true, Q, iK, false, N, Q, N, N);          // Z = V^T iK  (Q x N)
-        mm(S2, S1, false, N, V, false, Q, Q, N, Q);          // V^T iK V
-        for (int i = threadIdx.x; i < Q; i += blockDim.x) S2[i * Q + i] += 1e-8;
+        // iViKV = inv(V^T iK V + 1e-8 I) by Cholesky (NOT symmetrised in the reference)   bqmod.py:936
+        mm<T>(S1, V, true, Q, iK, false, N, Q, N, N);          // Z = V^T iK  (Q x N)
+        mm<T>(S2, S1, false, N, V, false, Q, Q, N, Q);          // V^T iK V
+        for (int i = threadIdx.x; i < Q; i += blockDim.x) S2[i * Q + i] = S2[i * Q + i] + T(1e-8);
         __syncthreads();
-        if (!chol_cta(S2, Q, flag)) info |= 2;
-        // plain cho_solve(., I): NOT symmetrised in the reference
-        for (int c = threadIdx.x; c < Q; c += blockDim.x) {
-            for (int i = 0; i < Q; ++i) {
-                double t = (i == c) ? 1.0 : 0.0;
-                for (int k = 0; k < i; ++k) t = fma(-S2[i * Q + k], iViKV[k * Q + c], t);
-                iViKV[i * Q + c] = t / S2[i * Q + i];
-            }
-            for (int i = Q - 1; i >= 0; --i) {
-                double t = iViKV[i * Q + c];
-                for (int k = i + 1; k < Q; ++k) t = fma(-S2[k * Q + i], iViKV[k * Q + c], t);
-                iViKV[i * Q + c] = t / S2[i * Q + i];
-            }
-        }
-        __syncthreads();
+        if (!chol_cta<T>(S2, Q, flag)) info |= 2;
+        chol_inverse<T>(iViKV, S2, S3, Q, false);
         if (Q == N) {
             // ---- pi-unisolvent special case: classical rule via iV = V^-1   bqmod.py:948-961
-            double *iV = S3;
+            T *iV = S3;
             for (int e = threadIdx.x; e < NN; e += blockDim.x) S2[e] = V[e];
             __syncthreads();
-            if (!lu_inverse(iV, S2, N, flag)) info |= 4;
-            mm(wm, p.px, false, Q, iV, false, N, 1, Q, N);                  // iV^T px
-            mm(T1, iV, true, N, p.pxpx, false, Q, N, Q, Q);                 // iV^T pxpx
-            mm(T2, T1, false, Q, iV, false, N, N, Q, N);                    // . iV
-            mm(Wcc, p.xpx, false, Q, iV, false, N, D, Q, N);                // xpx iV
+            if (!lu_inverse<T>(iV, S2, N, flag)) info |= 4;
+            mm<T>(wmT, p.px, false, Q, iV, false, N, 1, Q, N);                  // iV^T px
+            mm<T>(T1, iV, true, N, p.pxpx, false, Q, N, Q, Q);                  // iV^T pxpx
+            mm<T>(T2, T1, false, Q, iV, false, N, N, Q, N);                     // . iV
+            mm<T>(WccT, p.xpx, false, Q, iV, false, N, D, Q, N);                // xpx iV
             // model_var = a^2 (1 - tr(kxpx^T iV^T + kxpx iV - pxpx iViKV))
-            const double t1 = trace_prod(kxpx, iV, N, Q, red);              // tr(kxpx iV) = tr(kxpx^T iV^T)
-            const double t3 = trace_prod(p.pxpx, iViKV, Q, Q, red);
-            model_var = alpha * alpha * (1.0 - (t1 + t1 - t3));
+            const T t1 = trace_prod<T>(kxpx, iV, N, Q, red);                    // tr(kxpx iV) = tr(kxpx^T iV^T)
+            const T t3 = trace_prod<T>(p.pxpx, iViKV, Q, Q, red);
+            model_var = alpha * alpha * (T(1.0) - (t1 + t1 - t3));
             // integral_var = kbar - q^T iV^T px - px^T iV q + px^T iViKV px
-            const double a1 = dot_cta(wm, q, N, red);
-            mm(v1, p.px, false, Q, iViKV, false, Q, 1, Q, Q);
-            const double a3 = dot_cta(v1, p.px, Q, red);
+            const T a1 = dot_cta<T>(wmT, q, N, red);
+            mm<T>(v1, p.px, false, Q, iViKV, false, Q, 1, Q, Q);
+            const T a3 = dot_cta<T>(v1, p.px, Q, red);
             integral_var = kbar - a1 - a1 + a3;
         } else {
             // ---- general case                                              bqmod.py:963-982
-            double *Z = S1;                                   // (Q x N), still holds V^T iK
-            double *A = w;      w += N * Q;                   // V iViKV (N x Q)
-            double *B = w;      w += Q * Q;
-            double *Dm = w;     w += D * Q;
-            double *b = w;      w += Q;
-            mm(A, V, false, Q, iViKV, false, Q, N, Q, Q);
-            mm(b, Z, false, N, q, false, 1, Q, N, 1);
-            for (int i = threadIdx.x; i < Q; i += blockDim.x) b[i] -= p.px[i];
+            T *Z = S1;                                   // (Q x N), still holds V^T iK
+            T *A = w;      w += N * Q;                   // V iViKV (N x Q)
+            T *B = w;      w += Q * Q;
+            T *Dm = w;     w += D * Q;
+            T *b = w;      w += Q;
+            mm<T>(A, V, false, Q, iViKV, false, Q, N, Q, Q);
+            mm<T>(b, Z, false, N, q, false, 1, Q, N, 1);
+            for (int i = threadIdx.x; i < Q; i += blockDim.x) b[i] = b[i] - T(p.px[i]);
             // B = Z Q Z^T + pxpx - Z kxpx - kxpx^T Z^T
-            mm(S2, Z, false, N, Qm, false, N, Q, N, N);
-            mm(B, S2, false, N, Z, true, N, Q, N, Q);
-            mm(S3, Z, false, N, kxpx, false, Q, Q, N, Q);      // Z kxpx (Q x Q)
+            mm<T>(S2, Z, false, N, Qm, false, N, Q, N, N);
+            mm<T>(B, S2, false, N, Z, true, N, Q, N, Q);
+            mm<T>(S3, Z, false, N, kxpx, false, Q, Q, N, Q);      // Z kxpx (Q x Q)
             for (int e = threadIdx.x; e < Q * Q; e += blockDim.x)
-                B[e] = B[e] + p.pxpx[e] - S3[e] - S3[(e % Q) * Q + e / Q];
+                B[e] = B[e] + T(p.pxpx[e]) - S3[e] - S3[(e % Q) * Q + e / Q];
             __syncthreads();
             // D = R Z^T - xpx
-            mm(Dm, R, false, N, Z, true, N, D, N, Q);
-            for (int e = threadIdx.x; e < D * Q; e += blockDim.x) Dm[e] -= p.xpx[e];
+            mm<T>(Dm, R, false, N, Z, true, N, D, N, Q);
+            for (int e = threadIdx.x; e < D * Q; e += blockDim.x) Dm[e] = Dm[e] - T(p.xpx[e]);
             __syncthreads();
             // w_m = iK (q - A b)
-            mm(v1, A, false, Q, b, false, 1, N, Q, 1);
+            mm<T>(v1, A, false, Q, b, false, 1, N, Q, 1);
             for (int i = threadIdx.x; i < N; i += blockDim.x) v1[i] = q[i] - v1[i];
             __syncthreads();
-            mm(wm, iK, false, N, v1, false, 1, N, N, 1);
+            mm<T>(wmT, iK, false, N, v1, false, 1, N, N, 1);
             // w_c = iK (Q - A B A^T) iK
-            mm(S2, A, false, Q, B, false, Q, N, Q, Q);
-            mm(S3, S2, false, Q, A, true, Q, N, Q, N);
+            mm<T>(S2, A, false, Q, B, false, Q, N, Q, Q);
+            mm<T>(S3, S2, false, Q, A, true, Q, N, Q, N);
             for (int e = threadIdx.x; e < NN; e += blockDim.x) S3[e] = Qm[e] - S3[e];
             __syncthreads();
-            mm(T1, iK, false, N, S3, false, N, N, N, N);
-            mm(T2, T1, false, N, iK, false, N, N, N, N);
+            mm<T>(T1, iK, false, N, S3, false, N, N, N, N);
+            mm<T>(T2, T1, false, N, iK, false, N, N, N, N);
             // w_cc = (R - D A^T) iK
-            mm(S2, Dm, false, Q, A, true, Q, D, Q, N);
+            mm<T>(S2, Dm, false, Q, A, true, Q, D, Q, N);
             for (int e = threadIdx.x; e < D * N; e += blockDim.x) S2[e] = R[e] - S2[e];
             __syncthreads();
-            mm(Wcc, S2, false, N, iK, false, N, D, N, N);
-            model_var = alpha * alpha * (1.0 - trace_prod(Qm, iK, N, N, red) + trace_prod(B, iViKV, Q, Q, red));
-            mm(v2, q, false, N, iK, false, N, 1, N, N);
-            const double a1 = dot_cta(v2, q, N, red);
-            mm(v2, b, false, Q, iViKV, false, Q, 1, Q, Q);
-            integral_var = kbar - a1 + dot_cta(v2, b, Q, red);
+            mm<T>(WccT, S2, false, N, iK, false, N, D, N, N);
+            model_var = alpha * alpha * (T(1.0) - trace_prod<T>(Qm, iK, N, N, red) + trace_prod<T>(B, iViKV, Q, Q, red));
+            mm<T>(v2, q, false, N, iK, false, N, 1, N, N);
+            const T a1 = dot_cta<T>(v2, q, N, red);
+            mm<T>(v2, b, false, Q, iViKV, false, Q, 1, Q, Q);
+            integral_var = kbar - a1 + dot_cta<T>(v2, b, Q, red);
         }
     }
-    // covariance weights symmetrised (bqmod.py:520-521, 985-986); T2 holds the raw product
+    // results rounded to float64 once; covariance weights symmetrised (bqmod.py:520-521, 985-986)
+    for (int e = threadIdx.x; e < N; e += blockDim.x) wm[e] = to_double(wmT[e]);
+    for (int e = threadIdx.x; e < D * N; e += blockDim.x) Wcc[e] = to_double(WccT[e]);
     for (int e = threadIdx.x; e < NN; e += blockDim.x) {
         const int i = e / N, j = e % N;
-        Wc[e] = 0.5 * (T2[i * N + j] + T2[j * N + i]);
+        Wc[e] = to_double(T(0.5) * (T2[i * N + j] + T2[j * N + i]));
     }
     if (p.iK)
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) p.iK[(long long)ip * NN + e] = iK[e];
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) p.iK[(long long)ip * NN + e] = to_double(iK[e]);
     if (threadIdx.x == 0) {
-        p.scal[2 * ip] = model_var;
-        p.scal[2 * ip + 1] = integral_var;
+        p.scal[2 * ip] = to_double(model_var);
+        p.scal[2 * ip + 1] = to_double(integral_var);
         p.info[ip] = info;
     }
 }
@@ -459,7 +451,7 @@ using namespace ssm;
 
 extern "C" int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const double *par, const double *points,
                               const int32_t *mulind, int32_t n_basis, double *wm, double *Wc, double *Wcc, double *iK,
-                              double *scal, int32_t *info, void *stream) {
+                              double *scal, int32_t *info, int32_t precision, void *stream) {
     if (!par || !points || !wm || !Wc || !Wcc || !scal || !info) { set_error("ssm_bq_weights: NULL argument"); return SSM_E_INVALID; }
     if (dim < 1 || dim > W_MAXD || n_pts < 1 || n_pts > W_MAXN) {
         set_error("ssm_bq_weights: dim %d (<= %d) / n_pts %d (<= %d) out of range", dim, W_MAXD, n_pts, W_MAXN);
@@ -477,7 +469,8 @@ extern "C" int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const d
     std::vector<double> px, xpx, pxpx;
     if (Q) poly_expectations(D, Q, mulind, px, xpx, pxpx);
     const size_t n_in = (size_t)n_par * (D + 1) + (size_t)D * N + (size_t)Q + (size_t)D * Q + (size_t)Q * Q;
-    const long long work_stride = 5LL * N * N + 2LL * N + 2LL * D * N + 3LL * N * Q + 2LL * Q * Q + 3LL * M * M + 2LL * M + (long long)D * Q + Q + 64;
+    const long long work_elems = 5LL * N * N + 3LL * N + 3LL * D * N + 3LL * N * Q + 2LL * Q * Q + 3LL * M * M + 2LL * M + (long long)D * Q + Q + 64;
+    const long long work_stride = work_elems * (precision ? 2 : 1);   // in doubles; dd = 2 doubles per element
     const size_t bytes = (n_in + (size_t)work_stride * n_par) * sizeof(double) + (size_t)(D * Q + 2) * sizeof(int);
     double *dev = nullptr;
     if (cudaMallocAsync(&dev, bytes, s) != cudaSuccess) { set_error("ssm_bq_weights: cudaMallocAsync failed"); return SSM_E_CUDA; }
@@ -503,7 +496,8 @@ extern "C" int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const d
     p.mulind = dmi;
     p.D = D; p.N = N; p.Q = Q; p.n_par = n_par;
     p.wm = wm; p.Wc = Wc; p.Wcc = Wcc; p.iK = iK; p.scal = scal; p.info = info;
-    bq_weights_kernel<<<n_par, 128, 0, s>>>(p);
+    if (precision) bq_weights_kernel<dd><<<n_par, 128, 0, s>>>(p);
+    else bq_weights_kernel<double><<<n_par, 128, 0, s>>>(p);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(dev, s);
     if (e != cudaSuccess) { set_error("ssm_bq_weights: CUDA error: %s", cudaGetErrorString(e)); return SSM_E_CUDA; }

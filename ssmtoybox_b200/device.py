@@ -277,10 +277,12 @@ def simulate_measurements(low, x, rng=None, r=None):
 # ------------------------------------------------------------------------------------------------
 # K5: Bayesian-quadrature weights
 # ------------------------------------------------------------------------------------------------
-def bq_weights(par, points, mulind=None, device='cuda'):
+def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
     """Batched BQ weights (ssm_bq_weights).  par (n_par, D+1), points (D, N), mulind (D, Q) or None.
     Returns dict of numpy arrays: wm (n_par, N), Wc (n_par, N, N), Wcc (n_par, D, N), iK (n_par, N, N),
-    model_var (n_par,), integral_var (n_par,), info (n_par,)."""
+    model_var (n_par,), integral_var (n_par,), info (n_par,).
+    precision 'dd' (default): double-double arithmetic, rounded once -> correctly rounded weights even for the
+    cond(K) ~ 1e9 kernels of the reference's tracking scripts; 'float64': plain float64 like the reference."""
     par = _c(np.atleast_2d(par))
     points = _c(points)
     D, N = points.shape
@@ -300,7 +302,8 @@ def bq_weights(par, points, mulind=None, device='cuda'):
         nb = mi.shape[1]
     rc = lib.ssm_bq_weights(D, N, n_par, _ptr(par), _ptr(points),
                             mi.ctypes.data_as(_lib.c_int32_p) if mi is not None else None, nb,
-                            _p(wm), _p(Wc), _p(Wcc), _p(iK), _p(scal), _p(info), _stream())
+                            _p(wm), _p(Wc), _p(Wcc), _p(iK), _p(scal), _p(info), 0 if precision == 'float64' else 1,
+                            _stream())
     _lib.check(rc, 'ssm_bq_weights')
     sc = scal.cpu().numpy()
     return dict(wm=wm.cpu().numpy(), Wc=Wc.cpu().numpy(), Wcc=Wcc.cpu().numpy(), iK=iK.cpu().numpy(),

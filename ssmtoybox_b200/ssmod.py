@@ -28,7 +28,7 @@ def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
     nt = None
     if noise is not None:
         nz = np.asarray(noise, dtype=np.float64)
-        nz = np.ascontiguousarray(np.broadcast_to(nz.reshape(nz.shape[0], -1), (nz.shape[0], n)))
+        nz = np.array(np.broadcast_to(nz.reshape(nz.shape[0], -1), (nz.shape[0], n)), dtype=np.float64, order='C')
         nt = torch.as_tensor(nz, device='cuda')
     out = torch.empty((dim_out, n), dtype=torch.float64, device='cuda')
     p = (C.c_double * 4)(*par)

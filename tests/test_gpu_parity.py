@@ -302,8 +302,10 @@ def test_simulation_philox_statistics_and_shard_invariance(name):
 
 
 def test_bq_weights_vs_reference():
-    """K5 against the reference's weights.  iK / wm / Wcc carry a relative error ~ eps cond(K), Wc ~ eps
-    cond(K)^2: for cond > 1e7 the reference's own Wc is rounding noise and is not compared."""
+    """K5 in float64 mode (the reference's own arithmetic) against the reference's weights.  iK / wm / Wcc carry a
+    relative error ~ eps cond(K), Wc ~ eps cond(K)^2: for cond > 1e7 the reference's own Wc is rounding noise
+     and is not compared.  The default double-double mode is checked against exact arithmetic in
+    test_bq_weights_double_double_matches_exact_arithmetic."""
     from ssmtoybox_b200 import device as dv
     g = golden('weights')
     eps = np.finfo(float).eps
@@ -311,7 +313,7 @@ def test_bq_weights_vs_reference():
         p = 'w{:02d}_'.format(i)
         par, x = g[p + 'par'], g[p + 'points']
         cond = np.linalg.cond(so.rbf_eval(par, x, scaling=False) + 1e-8 * np.eye(x.shape[1]))
-        w = dv.bq_weights(par, x)
+        w = dv.bq_weights(par, x, precision='float64')
         assert w['info'][0] == 0
         t1 = max(1e-12, 100 * eps * cond)
         assert rel(w['iK'][0], g[p + 'iK']) < t1 and rel(w['wm'][0], g[p + 'gp_wm']) < t1 and rel(w['Wcc'][0], g[p + 'gp_Wcc']) < t1
@@ -321,7 +323,7 @@ def test_bq_weights_vs_reference():
             assert rel(w['Wc'][0], g[p + 'gp_Wc']) < max(1e-12, 100 * eps * cond * cond)
         for b in ('bs', 'bsg'):
             if p + b + '_wm' in g:
-                wb = dv.bq_weights(par, x, g[p + b + '_mulind'])
+                wb = dv.bq_weights(par, x, g[p + b + '_mulind'], precision='float64')
                 assert wb['info'][0] == 0
                 tb = max(1e-11, 1e4 * eps * cond)
                 assert rel(wb['wm'][0], g[p + b + '_wm']) < tb and rel(wb['Wcc'][0], g[p + b + '_Wcc']) < tb
@@ -335,14 +337,14 @@ def test_bq_weights_batched_sweep_and_scale_invariance():
     x = so.ut_points(1, 0.0)
     els = [1e-3, 3e-3, 1e-2, 3e-2, 1e-1, 3e-1, 1, 3, 1e1, 3e1]
     par = np.array([[1.0, e] for e in els])
-    w = dv.bq_weights(par, x)                                   # research/gpq/icinco_demo.py:172, one CTA per vector
+    w = dv.bq_weights(par, x, precision='float64')              # research/gpq/icinco_demo.py:172, one CTA per vector
     for i, e in enumerate(els):
         r = so.gp_weights(par[i:i + 1], x)
         cond = np.linalg.cond(so.rbf_eval(par[i:i + 1], x, scaling=False) + 1e-8 * np.eye(3))
         assert rel(w['wm'][i], r['wm']) < max(1e-12, 100 * 2.2e-16 * cond)
     par2 = par.copy()
     par2[:, 0] = 7.3
-    w2 = dv.bq_weights(par2, x)
+    w2 = dv.bq_weights(par2, x, precision='float64')
     for k in ('wm', 'Wc', 'Wcc'):
         assert np.array_equal(w[k], w2[k])                      # reference tests/test_bqmtran.py:40-46
     assert (w['model_var'] >= -1e-12).all() and (w['integral_var'] >= -1e-12).all()
@@ -358,3 +360,77 @@ def test_scores_vs_reference(name):
     assert rel(e['rmse_vs_time'], gs[name + '_rmse_vs_time']) < 1e-12
     assert abs(e['nll'] - gs[name + '_nll_f'].ravel()[0]) < 1e-8 * abs(e['nll'])
     assert abs(e['nci'] - gs[name + '_nci_f'].ravel()[0]) < 1e-8 * abs(e['nci'])
+
+
+def _exact_gp_weights(par, x, digits=60):
+    """GaussianProcessModel.bq_weights (bqmod.py:495-523) evaluated with mpmath at `digits` digits."""
+    mp = pytest.importorskip('mpmath')
+    mp.mp.dps = digits
+    D, N = x.shape
+    ell = [mp.mpf(float(v)) for v in np.asarray(par).ravel()[1:]]
+    alpha = mp.mpf(float(np.asarray(par).ravel()[0]))
+    X = [[mp.mpf(float(x[d, i])) for i in range(N)] for d in range(D)]
+    K, Qm, qv, Rm = mp.matrix(N, N), mp.matrix(N, N), mp.matrix(1, N), mp.matrix(D, N)
+    cdet = rdet = mp.mpf(1)
+    for d in range(D):
+        cdet *= 1 / ell[d] ** 2 + 1
+        rdet *= 2 / ell[d] ** 2 + 1
+    for i in range(N):
+        s = sum(X[d][i] ** 2 / (ell[d] ** 2 + 1) for d in range(D))
+        qv[i] = mp.exp(-s / 2) / mp.sqrt(cdet)
+        for d in range(D):
+            Rm[d, i] = qv[i] * X[d][i] / (ell[d] ** 2 + 1)
+        for j in range(N):
+            K[i, j] = mp.exp(-sum(((X[d][i] - X[d][j]) / ell[d]) ** 2 for d in range(D)) / 2) + (mp.mpf('1e-8') if i == j else 0)
+            n = -sum((X[d][i] / ell[d]) ** 2 + (X[d][j] / ell[d]) ** 2 for d in range(D)) / 2 + \
+                sum((X[d][i] / ell[d] ** 2 + X[d][j] / ell[d] ** 2) ** 2 / (2 / ell[d] ** 2 + 1) for d in range(D)) / 2
+            Qm[i, j] = mp.exp(n) / mp.sqrt(rdet)
+    iK = K ** -1
+    tof = lambda M: np.array([[float(M[i, j]) for j in range(M.cols)] for i in range(M.rows)])  # noqa: E731
+    QiK = Qm * iK
+    return dict(wm=tof(qv * iK).ravel(), Wc=tof(iK * Qm * iK), Wcc=tof(Rm * iK),
+                model_var=float(alpha ** 2 * (1 - sum(QiK[i, i] for i in range(N)))),
+                integral_var=float(alpha ** 2 / mp.sqrt(rdet) - (qv * iK * qv.T)[0, 0]))
+
+
+def test_bq_weights_double_double_matches_exact_arithmetic():
+    """K5 in double-double == the 60-digit evaluation of the reference's formulas, including the kernels with
+    cond(K) = 1e8..1e9 where any float64 evaluation (the reference's too) returns rounding noise in Wc."""
+    from ssmtoybox_b200 import device as dv
+    g = golden('weights')
+    worst_ref = 0.0
+    for i in (0, 1, 2, 6, 9, 10, 13):
+        p = 'w{:02d}_'.format(i)
+        par, x = g[p + 'par'], g[p + 'points']
+        ex = _exact_gp_weights(par, x)
+        w = dv.bq_weights(par, x, precision='dd')
+        assert w['info'][0] == 0
+        for k in ('wm', 'Wc', 'Wcc'):
+            assert rel(w[k][0], ex[k]) < 1e-12, (i, k, rel(w[k][0], ex[k]))
+        assert abs(w['model_var'][0] - ex['model_var']) < 1e-12 and abs(w['integral_var'][0] - ex['integral_var']) < 1e-12
+        worst_ref = max(worst_ref, rel(g[p + 'gp_Wc'], ex['Wc']))
+        w64 = dv.bq_weights(par, x, precision='float64')
+        cond = np.linalg.cond(so.rbf_eval(par, x, scaling=False) + 1e-8 * np.eye(x.shape[1]))
+        assert rel(w64['wm'][0], ex['wm']) < max(1e-9, 100 * 2.2e-16 * cond)
+    assert worst_ref > 0.1      # the reference's own Wc is O(1) wrong on its C3 measurement kernel (DESIGN.md)
+
+
+def test_c3_filter_with_device_weights_runs_and_matches_oracle():
+    """The reference's C3 filter built with K5's (double-double) weights: no trajectory fails -- with float64
+    weights, a 1-ulp perturbation of K makes 45 % of evaluations fail at step 1 -- and the kernel agrees with the
+    oracle run on the SAME weights to the un-centred BQ noise floor."""
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_gpq')
+    g2 = dict(g)
+    for pfx in ('dyn_', 'obs_'):
+        w = dv.bq_weights(g[pfx + 'kern_par'], g[pfx + 'points'])
+        g2[pfx + 'wm'], g2[pfx + 'Wc'], g2[pfx + 'Wcc'] = w['wm'][0], w['Wc'][0], w['Wcc'][0]
+        g2[pfx + 'model_var'] = w['model_var'][0]
+    ref = so.forward_pass(g2, g['y'], backend='loops')
+    assert (ref['status'] == 0).all()
+    low, o = run_filter(g2, g['y'])
+    assert int((o['status'] != 0).sum()) == 0
+    assert relstep(N_(o['fi_mean']), ref['fi_mean']) < 1e-8
+    assert relstep(N_(o['fi_cov']), ref['fi_cov']) < 2e-5
+    # and the filter tracks much better than with the reference's noise weights (golden: 0.48)
+    assert np.abs(N_(o['fi_mean'])[:2] - g['x'][:2]).mean() < 0.2
