@@ -42,13 +42,13 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) P[tri(r, c)] = p.cov[(long long)(r * D + c) * p.ld + t];
-    const bool ok = moment_transform<D, E, PTS_GENERIC, 0, KIND>(
+    const bool ok = moment_transform<D, E, PTS_GENERIC, 0, KIND, 0>(
         p.tf, m, P,
         [&](const double (&x)[D], double (&o)[E]) {
             const double z[Fn::NQ] = {};
             Fn::template ev<false>(p.par, x, z, p.time, o);
         },
-        mf, Cf, Cfx, true);
+        mf, Cf, Cfx, true, nullptr);
 #pragma unroll
     for (int a = 0; a < E; ++a) p.mean_f[(long long)a * p.ld + t] = ok ? mf[a] : qnan();
 #pragma unroll

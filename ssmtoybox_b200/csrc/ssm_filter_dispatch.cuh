@@ -111,7 +111,7 @@ int launch_filter_global(const FilterLaunch &L) {
     p.fixed_dof = d.fixed_dof;
     p.b = L.buf;
     const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
-    filter_kernel<Dyn, Obs, PTS_GENERIC, 0, KIND, FAMILY, Par, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
+    filter_kernel<Dyn, Obs, PTS_GENERIC, 0, KIND, FAMILY, Par, THREADS, MINB, false><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(dev, L.stream);
     free(host);
