@@ -14,8 +14,12 @@ print('stalls (warps per issue):', ', '.join('%s %.2f' % kv for kv in sorted(st.
 src = list(csv.reader(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.splitlines()))
 h2 = src[1]; si, ei = h2.index('Source'), h2.index('Instructions Executed')
 ops = collections.Counter(); tot = 0; static = 0
+first_kernel_done = False
 for row in src[2:]:
-    if len(row) < len(h2): continue
+    if row and row[0] == 'Kernel Name':
+        break
+    if len(row) < len(h2) or not row[ei].isdigit(): continue
+    if row[0].startswith('Kernel Name'): break
     m = re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)', row[si]); op = m.group(2) if m else '?'
     n = int(row[ei]); ops[op] += n; tot += n; static += 1
 print('static SASS lines', static, ' dynamic warp-inst', tot, (' per unit %.0f' % (tot / units)) if units else '')
