@@ -110,7 +110,7 @@ def run_reference_arm(args):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,7 +124,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -308,10 +308,23 @@ def run_gpu_arm(args):
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
             'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,
             'clocks': clk, 'n_failed_trajectories': n_failed, 'scores': scores}
-    print(json.dumps(line))
+    _emit(line)
+
+
+def _emit(line):
+    """Print THE one JSON line on the real stdout (fd 1 is pointed at stderr while the job runs so that
+    library banners such as 'NCCL version ...' cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
