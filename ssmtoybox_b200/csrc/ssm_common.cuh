@@ -39,6 +39,7 @@ SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 SSM_MATH_FN double m_exp(double x) { return exp(x); }
 SSM_MATH_FN double m_sqrt(double x) { return sqrt(x); }
 SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
+SSM_MATH_FN double m_rsqrt(double x) { return rsqrt(x); }
 SSM_MATH_FN double m_div(double a, double b) { return a / b; }
 SSM_MATH_FN double m_atan2(double y, double x) { return atan2(y, x); }
 
@@ -49,7 +50,7 @@ SSM_MATH_FN double m_atan2(double y, double x) { return atan2(y, x); }
 // scipy's check_finite in cho_factor raises ValueError (measured on the golden case
 // c3_reentry_gpq_fail); the kernels reproduce that sequence.  Returns false on failure.
 template <int D>
-SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSize<D>::value]) {
+SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSize<D>::value], double *inv_diag = nullptr) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -57,9 +58,12 @@ SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSiz
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[tri(j, k)], L[tri(j, k)], s);
         ok = ok && !(s <= 0.0);
-        const double d = m_sqrt(s);
-        const double inv = m_rcp(d);
+        // one out-of-line call per pivot: r = 1/sqrt(s) (<= 1 ulp), L_jj = s r, 1/L_jj = r.  LAPACK computes
+        // sqrt and divides; the difference is ~1 ulp of L, far below the 1e-9 parity tolerance.
+        const double inv = m_rsqrt(s);
+        const double d = s * inv;
         L[tri(j, j)] = d;
+        if (inv_diag) inv_diag[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < D; ++i) {
             double t = A[tri(i, j)];
@@ -76,10 +80,8 @@ SSM_DEV bool chol_lower(const double (&A)[TriSize<D>::value], double (&L)[TriSiz
 template <int E, int D>
 SSM_DEV bool spd_gain(const double (&S)[TriSize<E>::value], const double (&C)[E][D], double (&K)[D][E],
                       double (&Ls)[TriSize<E>::value]) {
-    const bool ok = chol_lower<E>(S, Ls);
     double inv[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) inv[i] = m_rcp(Ls[tri(i, i)]);
+    const bool ok = chol_lower<E>(S, Ls, inv);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         double z[E];

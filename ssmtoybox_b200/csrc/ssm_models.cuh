@@ -44,7 +44,7 @@ struct DynReentry {
         const double b = b0 * m_exp(x[4]);
         const double R = m_sqrt(x[0] * x[0] + x[1] * x[1]);
         const double V = m_sqrt(x[2] * x[2] + x[3] * x[3]);
-        D = b * m_exp(m_div(R0 - R, H0)) * V;
+        D = b * m_exp((R0 - R) * (1.0 / H0)) * V;  // (R0 - R) / H0 up to 1 ulp: one division call less per point
         G = m_div(-Gm0, R * R * R);
     }
     template <bool NOISE>
