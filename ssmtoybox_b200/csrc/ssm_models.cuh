@@ -42,10 +42,14 @@ struct DynReentry {
     SSM_DEV static void forces(const double (&x)[5], double &D, double &G) {
         const double R0 = 6374.0, H0 = 13.406, Gm0 = 3.9860e5, b0 = -0.59783;
         const double b = b0 * m_exp(x[4]);
-        const double R = m_sqrt(x[0] * x[0] + x[1] * x[1]);
+        // R = sqrt(r2) and 1/R^3 from ONE out-of-line call: ir = 1/sqrt(r2), R = r2 ir, R^-3 = ir^3 (a few ulp
+        // from the reference's sqrt + pow + divide, far below the parity tolerance; r2 = 0 gives NaN/inf in both)
+        const double r2 = x[0] * x[0] + x[1] * x[1];
+        const double ir = m_rsqrt(r2);
+        const double R = r2 * ir;
         const double V = m_sqrt(x[2] * x[2] + x[3] * x[3]);
-        D = b * m_exp((R0 - R) * (1.0 / H0)) * V;  // (R0 - R) / H0 up to 1 ulp: one division call less per point
-        G = m_div(-Gm0, R * R * R);
+        D = b * m_exp((R0 - R) * (1.0 / H0)) * V;  // (R0 - R) / H0 up to 1 ulp: no division call
+        G = -Gm0 * (ir * ir * ir);
     }
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[3], double, double (&o)[5]) {
