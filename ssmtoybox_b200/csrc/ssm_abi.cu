@@ -50,7 +50,7 @@ extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean
     L.desc = desc;
     L.stream = (cudaStream_t)stream;
     L.buf = FilterBuffers{y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
-                          t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0};
+                          t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0, nullptr, nullptr, 0, 0};
     const int dm = desc->dyn_model, om = desc->obs_model;
     const int nsi = desc->n_state_index;
     const int32_t *si = desc->state_index;

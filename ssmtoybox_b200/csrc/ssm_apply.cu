@@ -48,7 +48,12 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
             const double z[Fn::NQ] = {};
             Fn::template ev<false>(p.par, x, z, p.time, o);
         },
-        mf, Cf, Cfx, true, nullptr);
+        mf, Cf, true,
+        [&](int a, const double (&row)[D]) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) Cfx[a][c] = row[c];
+        },
+        nullptr);
 #pragma unroll
     for (int a = 0; a < E; ++a) p.mean_f[(long long)a * p.ld + t] = ok ? mf[a] : qnan();
 #pragma unroll

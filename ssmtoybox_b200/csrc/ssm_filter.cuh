@@ -12,6 +12,9 @@
 //   BQTransform.apply (+ _mean/_covariance/_cross_covariance)  bq/bqmtran.py:60-223
 //   StudentTProcessTransform._covariance        bq/bqmtran.py:394-415 (bq/bqmod.py:1132-1160)
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "ssm_models.cuh"
 
 namespace ssm {
@@ -120,10 +123,13 @@ struct FxStore<E, NCAP, 0> {  // registers
 // (a, i) of this thread at sfx[(a * N + i) * SMT] (sfx already offset by threadIdx.x, conflict-free 8-byte
 // accesses).  The arithmetic and its order are identical in both variants; the shared-memory variant frees
 // ~2 E N registers per thread, which buys a higher occupancy for the 5-D models.
-template <int D, int E, int PTS, int NPTS, int KIND, int SMT, class Tf, class F>
+// The cross-covariance is handed out row by row through `sink(a, row)` (row = Cov(f_a, x), D values) so that the
+// caller decides where it lives: the measurement transform keeps it in registers for the gain, the dynamics
+// transform streams it straight to HBM (no 25-double live array between the transform and the stores).
+template <int D, int E, int PTS, int NPTS, int KIND, int SMT, class Tf, class F, class Sink>
 SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (&P)[TriSize<D>::value], F f,
-                              double (&mf)[E], double (&Cf)[TriSize<E>::value], double (&Cfx)[E][D],
-                              const bool want_cross, double *sfx) {
+                              double (&mf)[E], double (&Cf)[TriSize<E>::value], const bool want_cross, Sink sink,
+                              double *sfx) {
     constexpr int NCAP = (NPTS > 0) ? NPTS : GEN_CAP;
     const int n = (NPTS > 0) ? NPTS : tf.n;
     double L[TriSize<D>::value];
@@ -167,6 +173,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
             }
         }
         if (want_cross) {
+            double Cfx[E][D];
 #pragma unroll
             for (int a = 0; a < E; ++a)
 #pragma unroll
@@ -186,6 +193,8 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                     for (int a = 0; a < E; ++a) Cfx[a][r] = fma(fx(a, i) * w, dxr, Cfx[a][r]);
                 }
             }
+#pragma unroll
+            for (int a = 0; a < E; ++a) sink(a, Cfx[a]);
         }
     } else {
         // un-centred form with dense weights                    bqmtran.py:198-199, 223
@@ -201,13 +210,15 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
 #pragma unroll
                     for (int d = 0; d < D; ++d) T[d] = fma(v, tf.Wcc(d, i), T[d]);
                 }
+                double crow[D];
 #pragma unroll
                 for (int r = 0; r < D; ++r) {  // (T L^T)[a][r] = sum_{d<=r} T[d] L[r][d]
                     double s = 0.0;
 #pragma unroll
                     for (int d = 0; d <= r; ++d) s = fma(T[d], L[tri(r, d)], s);
-                    Cfx[a][r] = s;
+                    crow[r] = s;
                 }
+                sink(a, crow);
             }
         }
 #pragma unroll
@@ -275,6 +286,11 @@ struct FilterBuffers {
     int32_t *status;
     long long n_traj, ld;
     int n_steps, k0;
+    // ticket scheduler (multi-wave launches): work item = (block of THREADS trajectories, chunk of time steps)
+    int *sched;        // [0] ticket counter, [1 + blk] chunks completed for trajectory block blk; NULL = plain mode
+    double *state;     // carried filter state between chunks: [blk][component][thread]
+    int chunk;         // time steps per work item
+    int n_blocks;      // trajectory blocks
 };
 
 template <int DX, int DY, class TfD, class TfO>
@@ -325,6 +341,12 @@ SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, 
 #ifndef SSM_SYNC_STEPS
 #define SSM_SYNC_STEPS 1
 #endif
+#ifndef SSM_TICKET_SCHED
+#define SSM_TICKET_SCHED 1
+#endif
+#ifndef SSM_TICKET_CHUNK
+#define SSM_TICKET_CHUNK 25
+#endif
 #ifndef SSM_SMEM_FX_MIN_DX
 #define SSM_SMEM_FX_MIN_DX 99  // state dimension from which the function evaluations move to shared memory
                                // (measured on B200: registers win for dx = 5, 21.2 vs 27.1 ms; kept as an option)
@@ -338,14 +360,55 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     constexpr int DX = Dyn::DX, DY = Obs::DY;
     constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
     const FilterBuffers &b = p.b;
-    const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t_raw < b.n_traj;
-    const long long t = active ? t_raw : b.n_traj - 1;  // idle lanes shadow the last trajectory, never store
     const int N = b.n_steps;
     const long long ld = b.ld;
+    constexpr int NSTATE = DX + TX + 2;
+    __shared__ int s_ticket;
+    // Ticket scheduling.  A trajectory is a 500-step serial recursion, so a plain launch is quantised in waves of
+    // (resident CTAs x THREADS) whole trajectories: 125 000 trajectories = 2.2 waves cost 3 (measured -14 %).  With
+    // a scheduler workspace the grid is persistent and CTAs draw (trajectory block, time chunk) items from an
+    // atomic ticket counter in chunk-major order; the filter state crosses chunks through global memory.  Item
+    // (blk, kc) waits for done[blk] >= kc, which a CTA that drew an EARLIER ticket -- hence already running --
+    // publishes, so the wait cannot deadlock.  Arithmetic is unchanged: results are bitwise identical.
+    const bool ticketed = b.sched != nullptr;
+    const int n_chunks = ticketed ? (N + b.chunk - 1) / b.chunk : 1;
+    const long long n_items = ticketed ? (long long)b.n_blocks * n_chunks : 0;
+  for (;;) {
+    long long blk = blockIdx.x;
+    int kc = 0;
+    if (ticketed) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(b.sched, 1);
+        __syncthreads();
+        const long long tk = s_ticket;
+        if (tk >= n_items) break;
+        kc = (int)(tk / b.n_blocks);
+        blk = tk % b.n_blocks;
+    }
+    const int k_begin = ticketed ? kc * b.chunk : 0;
+    const int k_end = ticketed ? min(N, k_begin + b.chunk) : N;
+    const long long t_raw = blk * blockDim.x + threadIdx.x;
+    const bool active = t_raw < b.n_traj;
+    const long long t = active ? t_raw : b.n_traj - 1;  // idle lanes shadow the last trajectory, never store
 
     double m[DX], P[TX];  // filtered mean and covariance (Student family: scale matrix x_smat_fi)
-    if (b.init_mean) {
+    int fail = active ? 0 : -1, kfail = 0;
+    if (k_begin > 0) {
+        if (threadIdx.x == 0) {
+            int spins = 0;
+            while (atomicAdd(b.sched + 1 + blk, 0) < kc) { __nanosleep(200); ++spins; }
+            if (spins) atomicAdd(b.sched + 1 + b.n_blocks, spins);  // diagnostic: total polls that had to wait
+            __threadfence();
+        }
+        __syncthreads();
+        const double *st = b.state + (blk * NSTATE) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int a = 0; a < DX; ++a) m[a] = __ldcg(st + (long long)a * blockDim.x);
+#pragma unroll
+        for (int a = 0; a < TX; ++a) P[a] = __ldcg(st + (long long)(DX + a) * blockDim.x);
+        fail = (int)__ldcg(st + (long long)(DX + TX) * blockDim.x);
+        kfail = (int)__ldcg(st + (long long)(DX + TX + 1) * blockDim.x);
+    } else if (b.init_mean) {
 #pragma unroll
         for (int a = 0; a < DX; ++a) m[a] = b.init_mean[(long long)a * ld + t];
 #pragma unroll
@@ -362,10 +425,9 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 
     double ynext[DY];
 #pragma unroll
-    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N) * ld + t);
+    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N + k_begin) * ld + t);
 
-    int fail = active ? 0 : -1, kfail = 0;
-    for (int k = 0; k < N; ++k) {
+    for (int k = k_begin; k < k_end; ++k) {
         // The fully unrolled step body is ~140 KB of SASS, far beyond the instruction caches.  Re-aligning
         // the warps of the CTA once per step makes them stream the body together, so one instruction fetch
         // from L2 serves all of them instead of one per warp (profiles/: stall_no_inst, fetch-bound).
@@ -388,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         }
 
         // ---- time update: predictive state moments (ssinf.py:276-279 / 669-676) ----------------
-        double mp[DX], Pp[TX], Cxx[DX][DX];
+        double mp[DX], Pp[TX];
         const bool want_xx = b.pr_xx != nullptr;
         bool ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT>(
             p.tf_dyn, m, P,
@@ -396,7 +458,12 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 const double q0[Dyn::DQ] = {};
                 Dyn::template f<false>(p.dyn_par, x, q0, time, o);
             },
-            mp, Pp, Cxx, want_xx, sfx);
+            mp, Pp, want_xx,
+            [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
+#pragma unroll
+                for (int c = 0; c < DX; ++c) st_stream(b.pr_xx + ((long long)(a * DX + c) * N + k) * ld + t, row[c]);
+            },
+            sfx);
         if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
             if (b.pr_cov) {
@@ -413,7 +480,6 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             store_sym<DX>(b.pr_cov, N, ld, k, t, Pp);
         }
         store_vec<DX>(b.pr_mean, N, ld, k, t, mp);
-        if (want_xx) store_mat<DX, DX>(b.pr_xx, N, ld, k, t, Cxx);
 
         // ---- predictive measurement moments (ssinf.py:287-291 / 684-693) ------------------------
         double my[DY], Sy[TY], Syx[DY][DX];
@@ -423,7 +489,12 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 const double r0[DY] = {};
                 Obs::template h<false>(p.obs_par, x, r0, time, o);
             },
-            my, Sy, Syx, true, sfx);
+            my, Sy, true,
+            [&](int a, const double (&row)[DX]) {
+#pragma unroll
+                for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
+            },
+            sfx);
         if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
 #pragma unroll
@@ -499,29 +570,44 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         }
     }
 
-    if (!active) return;
-    if (fail) {
-        fill_nan(b.fi_mean, DX, N, ld, kfail, t);
-        fill_nan(b.fi_cov, DX * DX, N, ld, kfail, t);
-        fill_nan(b.pr_mean, DX, N, ld, kfail, t);
-        fill_nan(b.pr_cov, DX * DX, N, ld, kfail, t);
-        fill_nan(b.pr_xx, DX * DX, N, ld, kfail, t);
+    if (k_end < N) {
+        // hand the state to whichever CTA draws the next chunk of this trajectory block
+        double *st = b.state + (blk * NSTATE) * blockDim.x + threadIdx.x;
 #pragma unroll
-        for (int a = 0; a < DX; ++a) m[a] = qnan();
+        for (int a = 0; a < DX; ++a) __stcg(st + (long long)a * blockDim.x, m[a]);
 #pragma unroll
-        for (int a = 0; a < TX; ++a) P[a] = qnan();
+        for (int a = 0; a < TX; ++a) __stcg(st + (long long)(DX + a) * blockDim.x, P[a]);
+        __stcg(st + (long long)(DX + TX) * blockDim.x, (double)fail);
+        __stcg(st + (long long)(DX + TX + 1) * blockDim.x, (double)kfail);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(b.sched + 1 + blk, kc + 1);
+    } else if (active) {
+        if (fail) {
+            fill_nan(b.fi_mean, DX, N, ld, kfail, t);
+            fill_nan(b.fi_cov, DX * DX, N, ld, kfail, t);
+            fill_nan(b.pr_mean, DX, N, ld, kfail, t);
+            fill_nan(b.pr_cov, DX * DX, N, ld, kfail, t);
+            fill_nan(b.pr_xx, DX * DX, N, ld, kfail, t);
+    #pragma unroll
+            for (int a = 0; a < DX; ++a) m[a] = qnan();
+    #pragma unroll
+            for (int a = 0; a < TX; ++a) P[a] = qnan();
+        }
+        if (b.last_mean) {
+    #pragma unroll
+            for (int a = 0; a < DX; ++a) b.last_mean[(long long)a * ld + t] = m[a];
+        }
+        if (b.last_cov) {
+    #pragma unroll
+            for (int r = 0; r < DX; ++r)
+    #pragma unroll
+                for (int c = 0; c < DX; ++c) b.last_cov[(long long)(r * DX + c) * ld + t] = P[sym(r, c)];
+        }
+        b.status[t] = fail ? (((kfail + 1) << 8) | fail) : 0;
     }
-    if (b.last_mean) {
-#pragma unroll
-        for (int a = 0; a < DX; ++a) b.last_mean[(long long)a * ld + t] = m[a];
-    }
-    if (b.last_cov) {
-#pragma unroll
-        for (int r = 0; r < DX; ++r)
-#pragma unroll
-            for (int c = 0; c < DX; ++c) b.last_cov[(long long)(r * DX + c) * ld + t] = P[sym(r, c)];
-    }
-    b.status[t] = fail ? (((kfail + 1) << 8) | fail) : 0;
+    if (!ticketed) break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -598,6 +684,8 @@ inline void fill_tf(TfConst<D, E, NCAP, KIND, PTS> &o, const ssm_transform &tf, 
             for (int i = 0; i < N; ++i) o.U_[d % o.DU][i] = tf.points[d * N + i];
 }
 
+void set_error(const char *fmt, ...);
+
 struct FilterLaunch {
     const ssm_desc *desc;
     FilterBuffers buf;
@@ -632,9 +720,40 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     auto kern = filter_kernel<Dyn, Obs, PTS, NPTS, KIND, FAMILY, Par, THREADS, MINB, SMEM_FX>;
     const size_t smem = SMEM_FX ? sizeof(double) * DX * NPTS * THREADS : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)blocks, THREADS, smem, L.stream>>>(p);
+    // multi-wave launches: persistent grid + ticket scheduler over (trajectory block, time chunk) items
+    long long grid = blocks;
+    void *work = nullptr;
+    int occ = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+    const long long cap = (long long)occ * sms;
+    // developer overrides: SSM_TICKET=0 disables the scheduler, SSM_TICKET_CHUNK=<steps> sets the item length
+    const char *env_on = getenv("SSM_TICKET"), *env_chunk = getenv("SSM_TICKET_CHUNK");
+    const int CHUNK = env_chunk ? atoi(env_chunk) : SSM_TICKET_CHUNK;
+    const bool want_ticket = SSM_TICKET_SCHED && !(env_on && atoi(env_on) == 0);
+    if (want_ticket && CHUNK > 0 && cap > 0 && blocks > cap && L.buf.n_steps >= 2 * CHUNK) {
+        const size_t n_int = ((size_t)blocks + 2 + 1) / 2 * 2;  // ticket, done[blocks], wait counter; doubles stay 8-byte aligned
+        const size_t bytes = n_int * sizeof(int) + (size_t)blocks * THREADS * (DX + TriSize<DX>::value + 2) * sizeof(double);
+        if (cudaMallocAsync(&work, bytes, L.stream) != cudaSuccess) { delete pp; set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
+        cudaMemsetAsync(work, 0, n_int * sizeof(int), L.stream);
+        p.b.sched = (int *)work;
+        p.b.state = (double *)((int *)work + n_int);
+        p.b.chunk = CHUNK;
+        p.b.n_blocks = (int)blocks;
+        grid = cap;
+    }
+    kern<<<(unsigned)grid, THREADS, smem, L.stream>>>(p);
+    const cudaError_t err = cudaGetLastError();
+    if (work && getenv("SSM_TICKET_DEBUG")) {
+        int waits = 0;
+        cudaMemcpyAsync(&waits, (int *)work + 1 + blocks, sizeof(int), cudaMemcpyDeviceToHost, L.stream);
+        cudaStreamSynchronize(L.stream);
+        fprintf(stderr, "[ssm ticket] blocks=%lld grid=%lld chunk=%d dependency polls that waited: %d\n", blocks, grid, CHUNK, waits);
+    }
+    if (work) cudaFreeAsync(work, L.stream);
     delete pp;
-    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+    return err == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
 }  // namespace ssm
