@@ -45,7 +45,7 @@ TRAJ_PER_GPU = 125000           # 10^6 / 8
 FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filter, reentry N=11
 FLOP_SMOOTH = 902.0
 BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
-BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 25)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov); write sm_*
+BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 25)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write sm_*
 METRIC = 'filtered trajectory-steps/sec (fp64)'
 UNIT = 'trajectory-steps/s'
 CONFIG = {'workload': 'C3: reentry 5-D + radar, GPQ (RBF, UT) filter + RTS smoother + scores, '
@@ -193,14 +193,16 @@ def run_gpu_arm(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def hot_path(timers=None):
-        """forward pass (stores predictive moments) -> RTS smoother -> two-phase scores (+ all-reduce)."""
+        """forward pass (stores predictive moments) -> RTS smoother with in-kernel score accumulation ->
+        all-reduce of the packed statistics -> second score phase (log credibility ratio) -> all-reduce."""
         e = [ev() for _ in range(4)] if timers is not None else None
         if e: e[0].record()
         dv.filter_forward(low, y, store_pred=True, out=fwd)
         if e: e[1].record()
-        dv.smooth_backward(low.dx, fwd, out=sm)
+        dv.smooth_backward(low.dx, fwd, out=sm, x_truth=x)      # RTS smoother + in-kernel phase-1 statistics
         if e: e[2].record()
-        sc = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], comm=comm, to_host=False)
+        sc = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], comm=comm, to_host=False,
+                                    phase1=(sm['stats'], sm['rmse_acc']))
         if e:
             e[3].record()
             timers.append(e)
@@ -286,7 +288,7 @@ def run_gpu_arm(args):
                 'hbm': {'achieved': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_FILTER,
                         'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s'}}
-    roofline_smoother = {'kernel': 'smoother_kernel<5>', 'bound': 'hbm',
+    roofline_smoother = {'kernel': 'smoother_kernel<5, SCORE> (RTS smoother + in-kernel phase-1 score accumulation)', 'bound': 'hbm',
                          'achieved': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_SMOOTH,
                          'launch_ms': k_smooth, 'traffic': prof.get('smoother_kernel_dram_bytes_per_launch')}
@@ -303,8 +305,8 @@ def run_gpu_arm(args):
                     'api': 'ssmtoybox_b200.mc.filter_scores(GaussianProcessKalman, y, x, smooth=True) on pinned host y, x: '
                            'chunked H2D overlapped with forward pass + RTS smoother + scores; scores and status read back',
                     'chunks': args.chunks},
-            'gpu_launches': 6 * args.steps,
-            'kernel_ms': {'filter_forward': k_filter, 'rts_smoother': k_smooth, 'scores_2phase_incl_allreduce': k_scores},
+            'gpu_launches': 5 * args.steps,   # filter, smoother, finalize, scores phase 2, finalize
+            'kernel_ms': {'filter_forward': k_filter, 'rts_smoother_with_phase1_scores': k_smooth, 'scores_phase2_incl_allreduce': k_scores},
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
             'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,
             'clocks': clk, 'n_failed_trajectories': n_failed, 'scores': scores}

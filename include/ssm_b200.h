@@ -144,10 +144,15 @@ int ssm_filter(const ssm_desc *desc, const double *y,
  * Replaces StateSpaceInference.backward_pass + GaussianInference._smoothing_update
  * (ssinf.py:120-147, 325-344), including the reference's index range (slots N and N-1 are never
  * smoothed).  Arrays as produced by ssm_filter (n_steps slots = steps 1..N).
+ * In-kernel score accumulation (optional): with x_truth (dx, n_steps, ld) the kernel also accumulates the
+ * phase-1 error statistics of the SMOOTHED moments while they are in registers -- stats (n_steps, W) and
+ * rmse_acc (dx, ld, nullable) exactly as ssm_scores_phase1 would return them for (x_truth, sm_mean, sm_cov) --
+ * which saves a full read pass.  x_truth = NULL: plain smoother.
  */
 int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov,
                const double *pr_mean, const double *pr_cov, const double *pr_xx_cov,
                double *sm_mean, double *sm_cov, int32_t *status,
+               const double *x_truth, double *stats, double *rmse_acc,
                int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
 
 /* ---- K1: batched simulation -----------------------------------------------------------------

@@ -65,7 +65,7 @@ def _load():
     lib.ssm_filter.restype = C.c_int
     lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
     lib.ssm_smooth.restype = C.c_int
-    lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
+    lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     lib.ssm_fp64_peak_kernel.restype = C.c_int
     lib.ssm_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]
     if True:

@@ -8,35 +8,11 @@
 // second kernel sums the partial rows in CTA order: the result is bitwise reproducible for a given
 // trajectory count, and the packed rows are what the multi-GPU driver all-reduces (NCCL).
 // The log credibility ratio needs the GLOBAL per-step MSE matrix first (two-phase reduction).
-#include "ssm_common.cuh"
+#include "ssm_scores.cuh"
 
 namespace ssm {
 
 void set_error(const char *fmt, ...);
-
-constexpr int SC_THREADS = 128;
-
-template <int W>
-SSM_DEV void block_reduce_store(double (&v)[W], double *smem /* [SC_THREADS/32][W] */, double *dst) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < W; ++i) smem[wid * W + i] = v[i];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < W; i += blockDim.x) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < SC_THREADS / 32; ++w) s += smem[w * W + i];
-        dst[i] = s;
-    }
-    __syncthreads();
-}
 
 template <int DX>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double *__restrict__ x, const double *__restrict__ mean,
@@ -56,40 +32,16 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = 0.0;
         if (live) {
-            double d[DX], P[TX], L[TX];
+            double d[DX], P[TX], se[DX];
 #pragma unroll
             for (int a = 0; a < DX; ++a) d[a] = ld_stream(x + at(a, k)) - ld_stream(mean + at(a, k));
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
                 for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(cov + at(r * DX + c, k));
-            double sse = 0.0;
+            score_step<DX>(d, P, v, se);
 #pragma unroll
-            for (int a = 0; a < DX; ++a) {
-                const double s = d[a] * d[a];  // squared_error, utils.py:38
-                v[a] = s;
-                se_acc[a] += s;
-                sse += s;
-            }
-#pragma unroll
-            for (int r = 0; r < DX; ++r)
-#pragma unroll
-                for (int c = 0; c < DX; ++c) v[DX + r * DX + c] = d[r] * d[c];  // mse_matrix summand, utils.py:62-64
-            // neg_log_likelihood = 0.5 (log|P| + d' P^-1 d + dx log 2 pi), utils.py:143-148, through chol(P)
-            const bool ok = chol_lower<DX>(P, L);
-            double logdet = 0.0, quad = 0.0, z[DX];
-#pragma unroll
-            for (int i = 0; i < DX; ++i) {
-                double s = d[i];
-#pragma unroll
-                for (int c = 0; c < i; ++c) s = fma(-L[tri(i, c)], z[c], s);
-                z[i] = s / L[tri(i, i)];
-                quad = fma(z[i], z[i], quad);
-                logdet += log(L[tri(i, i)]);
-            }
-            v[DX + DX * DX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
-            v[DX + DX * DX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
-            v[DX + DX * DX + 2] = 1.0;
+            for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
         block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * N + k) * W);
     }
@@ -99,7 +51,6 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
     }
 }
 
-// stats[k][w] = sum over CTAs (fixed order) of partial[cta][k][w]
 __global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row) return;

@@ -2,51 +2,87 @@
 // stored by the forward pass.  Pure small-matrix algebra on five streamed arrays: HBM-bound.
 // Replaces StateSpaceInference.backward_pass (ssinf.py:120-147) and
 // GaussianInference._smoothing_update (ssinf.py:325-344).
-#include "ssm_common.cuh"
+#include "ssm_scores.cuh"
 
 namespace ssm {
 
 void set_error(const char *fmt, ...);
 
-template <int DX>
-__global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
-                                                       const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
-                                                       const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
-                                                       double *__restrict__ sm_cov, int32_t *__restrict__ status,
-                                                       long long n_traj, int N, long long ld) {
-    constexpr int TX = TriSize<DX>::value;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_traj) return;
+// SCORE: also accumulate the phase-1 error statistics of the SMOOTHED moments against the truth x while they are
+// in registers (same per-CTA reduction and row layout as scores_phase1_kernel, so the finalised statistics are
+// identical), which saves one full read pass over sm_mean / sm_cov.
+template <int DX, bool SCORE>
+__global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
+                                                              const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
+                                                              const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
+                                                              double *__restrict__ sm_cov, int32_t *__restrict__ status,
+                                                              const double *__restrict__ x_truth, double *__restrict__ partial,
+                                                              double *__restrict__ rmse_acc, long long n_traj, int N, long long ld) {
+    constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::W;
+    __shared__ double smem[SCORE ? (SC_THREADS / 32) * W : 1];
+    const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = t_raw < n_traj;
+    if (!SCORE && !in_range) return;
+    const long long t = in_range ? t_raw : n_traj - 1;   // idle lanes of the last CTA only take part in the reductions
     auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
-    if (status[t] != 0) {  // the forward pass failed: nothing to smooth
+    double se_acc[DX];
+#pragma unroll
+    for (int a = 0; a < DX; ++a) se_acc[a] = 0.0;
+    // score the smoothed moments (ms, Ps) of step k; every thread of the CTA calls this once per step
+    auto score = [&](int k, bool live, const double (&ms_)[DX], const double (&Ps_)[TX]) {
+        double v[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = 0.0;
+        if (live) {
+            double d[DX], se[DX];
+#pragma unroll
+            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x_truth + at(a, k)) - ms_[a];
+            score_step<DX>(d, Ps_, v, se);
+#pragma unroll
+            for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
+        }
+        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * N + k) * W);
+    };
+    bool alive = in_range && status[t] == 0;
+    if (in_range && !alive) {  // the forward pass failed: nothing to smooth
         for (int k = 0; k < N; ++k) {
             for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
             for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
         }
-        return;
+        if (!SCORE) return;
     }
     // The reference iterates k = N-2 .. 1 over arrays with N+1 slots (slot 0 = initial moments):
     // slots N and N-1 (indices N-1, N-2 here) keep their filtered values, and the recursion starts
     // from the filtered moments of slot N (ssinf.py:117, 137).
     double ms[DX], Ps[TX];
     for (int k = N - 1; k >= 0 && k >= N - 2; --k) {
+        double mk[DX], Pk[TX];
+        if (alive) {
 #pragma unroll
-        for (int a = 0; a < DX; ++a) {
-            const double v = ld_stream(fi_mean + at(a, k));
-            if (k == N - 1) ms[a] = v;
-            st_stream(sm_mean + at(a, k), v);
-        }
-#pragma unroll
-        for (int r = 0; r < DX; ++r)
-#pragma unroll
-            for (int c = 0; c < DX; ++c) {
-                const double v = ld_stream(fi_cov + at(r * DX + c, k));
-                if (k == N - 1 && c <= r) Ps[tri(r, c)] = v;
-                st_stream(sm_cov + at(r * DX + c, k), v);
+            for (int a = 0; a < DX; ++a) {
+                const double v = ld_stream(fi_mean + at(a, k));
+                mk[a] = v;
+                if (k == N - 1) ms[a] = v;
+                st_stream(sm_mean + at(a, k), v);
             }
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c < DX; ++c) {
+                    const double v = ld_stream(fi_cov + at(r * DX + c, k));
+                    if (c <= r) Pk[tri(r, c)] = v;
+                    if (k == N - 1 && c <= r) Ps[tri(r, c)] = v;
+                    st_stream(sm_cov + at(r * DX + c, k), v);
+                }
+        }
+        if (SCORE) score(k, alive, mk, Pk);
     }
     int fail = 0, kfail = 0;
     for (int k = N - 3; k >= 0; --k) {
+      // ONE score() call site per iteration: its warp shuffles and CTA barriers must be reached by every thread
+      // through the same instruction, so failures leave the step body with `break`, never `continue`.
+      do {
+        if (!alive) break;
         double mp[DX], Pp[TX], Pxx[DX][DX], mf[DX], Pf[TX];
 #pragma unroll
         for (int a = 0; a < DX; ++a) {
@@ -71,10 +107,10 @@ __global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict_
         for (int r = 0; r < DX; ++r)
 #pragma unroll
             for (int c = 0; c < DX; ++c) fin = fin && finite_d(Pxx[r][c]);
-        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; break; }
+        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; alive = false; break; }
         // D = (Pp^-1 Pxx)^T                                                       ssinf.py:342
         double Dg[DX][DX], Ls[TX];
-        if (!spd_gain<DX, DX>(Pp, Pxx, Dg, Ls)) { fail = SSM_FAIL_CHOL_SMOOTH; kfail = k; break; }
+        if (!spd_gain<DX, DX>(Pp, Pxx, Dg, Ls)) { fail = SSM_FAIL_CHOL_SMOOTH; kfail = k; alive = false; break; }
         // m_s = m_f + D (m_s+ - m_p)                                              ssinf.py:343
         double dm[DX];
 #pragma unroll
@@ -114,8 +150,14 @@ __global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict_
         for (int r = 0; r < DX; ++r)
 #pragma unroll
             for (int c = 0; c < DX; ++c) st_stream(sm_cov + at(r * DX + c, k), Ps[sym(r, c)]);
+      } while (0);
+        if (SCORE) score(k, alive, ms, Ps);
     }
-    if (fail) {
+    if (SCORE && rmse_acc && in_range) {
+#pragma unroll
+        for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = (alive && !fail) ? se_acc[a] : qnan();
+    }
+    if (fail && in_range) {
         for (int k = kfail; k >= 0; --k) {
             for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
             for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
@@ -126,12 +168,24 @@ __global__ void __launch_bounds__(128) smoother_kernel(const double *__restrict_
 
 template <int DX>
 static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
-                           const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, long long n_traj, int N,
-                           long long ld, cudaStream_t s) {
-    const long long blocks = (n_traj + 127) / 128;
-    smoother_kernel<DX><<<(unsigned)blocks, 128, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status,
-                                                         n_traj, N, ld);
-    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+                           const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, const double *x_truth,
+                           double *stats, double *rmse_acc, long long n_traj, int N, long long ld, cudaStream_t s) {
+    const long long blocks = (n_traj + SC_THREADS - 1) / SC_THREADS;
+    if (!x_truth) {
+        smoother_kernel<DX, false><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean,
+                                                                          sm_cov, status, nullptr, nullptr, nullptr, n_traj, N, ld);
+        return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+    }
+    constexpr int W = ScoreRow<DX>::W;
+    double *partial = nullptr;
+    if (cudaMallocAsync(&partial, (size_t)blocks * N * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    smoother_kernel<DX, true><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov,
+                                                                     status, x_truth, partial, rmse_acc, n_traj, N, ld);
+    const long long row = (long long)N * W;
+    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, (int)blocks, row);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, s);
+    return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
 }  // namespace ssm
@@ -140,19 +194,21 @@ using namespace ssm;
 
 extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
                           const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
-                          int32_t *status, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+                          int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
+                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
     if (!fi_mean || !fi_cov || !pr_mean || !pr_cov || !pr_xx_cov || !sm_mean || !sm_cov || !status) {
         set_error("ssm_smooth: NULL buffer");
         return SSM_E_INVALID;
     }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_smooth: bad sizes"); return SSM_E_INVALID; }
+    if (x_truth && !stats) { set_error("ssm_smooth: stats must not be NULL when x_truth is given"); return SSM_E_INVALID; }
     if (n_traj == 0 || n_steps == 0) return SSM_OK;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
-        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
-        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, n_traj, n_steps, ld, s); break;
+        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
         default: set_error("ssm_smooth: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));

@@ -185,8 +185,10 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     return o
 
 
-def smooth_backward(dx, fwd, out=None):
-    """Run the RTS smoother (ssm_smooth) over the arrays stored by filter_forward(store_pred=True)."""
+def smooth_backward(dx, fwd, out=None, x_truth=None):
+    """Run the RTS smoother (ssm_smooth) over the arrays stored by filter_forward(store_pred=True).
+    With x_truth (dx, N, M) the kernel also accumulates the phase-1 score statistics of the smoothed moments:
+    out['stats'] (N, W) and out['rmse_acc'] (dx, M), identical to scores_phase1(x_truth, sm_mean, sm_cov, status)."""
     _, N, M = fwd['fi_mean'].shape
     o = out if out is not None else {}
     if 'sm_mean' not in o:
@@ -199,8 +201,17 @@ def smooth_backward(dx, fwd, out=None):
     ld = bulk_ld(fwd['fi_mean'])
     if any(bulk_ld(t) != ld for t in (fwd['fi_cov'], fwd['pr_mean'], fwd['pr_cov'], fwd['pr_xx_cov'], o['sm_mean'], o['sm_cov'])) and M > 1:
         raise ValueError('all bulk arrays of one ssm_smooth call must share the leading dimension')
+    if x_truth is not None:
+        if bulk_ld(x_truth) != ld and M > 1:
+            raise ValueError('x_truth must share the leading dimension of the other bulk arrays')
+        W = lib.ssm_scores_width(dx)
+        if 'stats' not in o:
+            o['stats'] = torch.empty((N, W), dtype=torch.float64, device=fwd['fi_mean'].device)
+            o['rmse_acc'] = torch.empty((dx, M), dtype=torch.float64, device=fwd['fi_mean'].device)
     rc = lib.ssm_smooth(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
-                        _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']), M, N, ld, _stream())
+                        _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']),
+                        _p(x_truth), _p(o.get('stats') if x_truth is not None else None),
+                        _p(o.get('rmse_acc') if x_truth is not None else None), M, N, ld, _stream())
     _lib.check(rc, 'ssm_smooth')
     return o
 

@@ -82,11 +82,13 @@ def filter_scores(alg, y, x, smooth=True, n_chunks=8, comm=None, keep=False):
             scratch = {'m': m, 'fwd': {}}
         fwd = dv.filter_forward(low, ys, store_pred=do_smooth, out=scratch['fwd'])
         if do_smooth:
-            sm = dv.smooth_backward(low.dx, fwd)          # fresh outputs: they stay resident for phase 2
+            # fresh outputs (they stay resident for phase 2); phase-1 statistics accumulated inside the smoother
+            sm = dv.smooth_backward(low.dx, fwd, x_truth=xs)
             mean, cov, st = sm['sm_mean'], sm['sm_cov'], sm['status']
+            s1, acc = sm['stats'], sm['rmse_acc']
         else:
             mean, cov, st = fwd['fi_mean'].clone(), fwd['fi_cov'].clone(), fwd['status'].clone()
-        s1, acc = dv.scores_phase1(xs, mean, cov, st)
+            s1, acc = dv.scores_phase1(xs, mean, cov, st)
         stats += s1
         ok = (st == 0)
         rm += torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)

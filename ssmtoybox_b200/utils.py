@@ -144,18 +144,20 @@ def log_cred_ratio(x, m, P, MSE):
     return float(lcr.cpu().numpy()[0, 0])
 
 
-def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True):
+def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, phase1=None):
     """Batched RMSE / NCI / NLL of one filter over all trajectories, aggregated exactly like
     research/gpq/icinco_demo.py:17-52 (RMSE = trajectory-mean of sqrt(time-mean SE); NCI and NLL skip
     k = 0 but divide by N), computed on the device in two reduction phases.
     x, mean (dx, N, M); cov (dx, dx, N, M); status (M,) int32 or None (failed trajectories are excluded).
     comm: optional ssmtoybox_b200.dist.Communicator -- trajectories are then sharded over ranks and the
     packed statistics are all-reduced (one NCCL call per phase).
+    phase1: optional (stats, rmse_acc) already accumulated in-kernel by the smoother (device.smooth_backward(...,
+    x_truth=x)); the first reduction pass over the arrays is then skipped.
     Returns dict(rmse (dx,), nci, nll, inc (inclination), mse (dx,dx,N), rmse_vs_time (N,), n_ok); device
     tensors instead of numpy / floats when to_host=False (no synchronisation)."""
     xd, md, Pd = _dev(x), _dev(mean), _dev(cov)
     dx, N, M = xd.shape
-    stats, acc = dv.scores_phase1(xd, md, Pd, status)
+    stats, acc = phase1 if phase1 is not None else dv.scores_phase1(xd, md, Pd, status)
     ok = torch.ones(M, dtype=torch.bool, device=xd.device) if status is None else (status == 0)
     # per-trajectory sqrt(time-mean SE), summed over the trajectories that completed
     rm = torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)

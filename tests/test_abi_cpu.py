@@ -57,7 +57,7 @@ def test_argument_validation_needs_no_gpu():
     lib = _lib.lib
     assert lib.ssm_filter(None, None, None, None, None, None, None, None, None, None, None, None, 0, None, 1, 1, 1, None) == _lib.SSM_E_INVALID
     assert b'NULL' in lib.ssm_last_error()
-    assert lib.ssm_smooth(5, None, None, None, None, None, None, None, None, 1, 1, 1, None) == _lib.SSM_E_INVALID
+    assert lib.ssm_smooth(5, None, None, None, None, None, None, None, None, None, None, None, 1, 1, 1, None) == _lib.SSM_E_INVALID
     assert lib.ssm_scores_width(5) == 5 + 25 + 3
     with pytest.raises(ValueError):
         _lib.check(_lib.SSM_E_INVALID, 'x')

@@ -237,6 +237,12 @@ def test_full_size_smoother_and_scores(big):
     tf = torch.diagonal(o['fi_cov'], dim1=0, dim2=1).sum(-1).mean().item()
     ts = torch.diagonal(sm['sm_cov'], dim1=0, dim2=1).sum(-1).mean().item()
     assert ts < tf
+    # in-kernel accumulation inside the smoother == the separate phase-1 pass over its outputs
+    sm2 = dv.smooth_backward(low.dx, o, x_truth=x)
+    s_sep, acc_sep = dv.scores_phase1(x, sm['sm_mean'], sm['sm_cov'], sm['status'])
+    assert torch.equal(sm2['sm_mean'], sm['sm_mean']) and torch.equal(sm2['sm_cov'], sm['sm_cov'])
+    assert torch.equal(sm2['stats'], s_sep)                       # same CTA partition, same reduction order
+    assert torch.allclose(sm2['rmse_acc'], acc_sep, rtol=1e-13, atol=0)   # time sum runs backwards: order differs
     # checksum of checksums: statistics of the two halves add up to the statistics of the whole
     s_all, _ = dv.scores_phase1(x, o['fi_mean'], o['fi_cov'], o['status'])
     h = y.shape[-1] // 2
