@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    double *__restrict__ partial, double *__restrict__ rmse_acc,
                                                                    long long n_traj, int N, long long ld) {
-    constexpr int TX = TriSize<DX>::value, W = DX + DX * DX + 3;
+    constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     __shared__ double smem[(SC_THREADS / 32) * W];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_traj && (status == nullptr || status[t] == 0);
@@ -57,6 +57,24 @@ __global__ void scores_finalize_kernel(const double *__restrict__ partial, doubl
     double s = 0.0;
     for (int c = 0; c < n_cta; ++c) s += partial[(long long)c * row + i];
     stats[i] = s;
+}
+
+__global__ void scores_finalize_packed_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, int n_steps, int dx) {
+    const int tx = dx * (dx + 1) / 2, wp = dx + tx + 3, w = dx + dx * dx + 3;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_steps * wp) return;
+    const int k = (int)(i / wp), j = (int)(i % wp);
+    double s = 0.0;
+    for (int c = 0; c < n_cta; ++c) s += partial[((long long)c * n_steps + k) * wp + j];
+    double *row = stats + (long long)k * w;
+    if (j < dx) row[j] = s;
+    else if (j < dx + tx) {
+        int r = 0, q = j - dx;
+        while ((r + 1) * (r + 2) / 2 <= q) ++r;
+        const int cc = q - r * (r + 1) / 2;
+        row[dx + r * dx + cc] = s;
+        row[dx + cc * dx + r] = s;
+    } else row[dx + dx * dx + (j - dx - tx)] = s;
 }
 
 template <int DX>
@@ -109,13 +127,13 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
 template <int DX>
 static int run_phase1(const double *x, const double *mean, const double *cov, const int32_t *status, double *stats,
                       double *rmse_acc, long long n_traj, int N, long long ld, cudaStream_t s) {
-    constexpr int W = DX + DX * DX + 3;
+    constexpr int W = ScoreRow<DX>::WP;
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     double *partial = nullptr;
     if (cudaMallocAsync(&partial, (size_t)n_cta * N * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, n_traj, N, ld);
     const long long row = (long long)N * W;
-    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, n_cta, row);
+    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, n_cta, N, DX);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;

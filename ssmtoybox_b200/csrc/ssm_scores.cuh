@@ -11,12 +11,15 @@ constexpr int SC_THREADS = 128;
 
 template <int DX>
 struct ScoreRow {
-    static constexpr int W = DX + DX * DX + 3;
+    static constexpr int W = DX + DX * DX + 3;                    // public row width (full d d^T)
+    static constexpr int WP = DX + TriSize<DX>::value + 3;        // packed row reduced in-kernel: lower triangle of d d^T
 };
 
 // d = x - m, P = packed lower covariance; fills v[W]; returns the squared errors through se[]
+// packed row: [ squared error (DX) | lower triangle of d d^T (DX(DX+1)/2) | NLL | |d| | 1 ]; the finalise kernel
+// mirrors the triangle into the public full-matrix layout (a third fewer shuffles in the per-step reduction)
 template <int DX>
-SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::value], double (&v)[ScoreRow<DX>::W], double (&se)[DX]) {
+SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::value], double (&v)[ScoreRow<DX>::WP], double (&se)[DX]) {
     constexpr int TX = TriSize<DX>::value;
     double sse = 0.0;
 #pragma unroll
@@ -29,7 +32,7 @@ SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::va
 #pragma unroll
     for (int r = 0; r < DX; ++r)
 #pragma unroll
-        for (int c = 0; c < DX; ++c) v[DX + r * DX + c] = d[r] * d[c];
+        for (int c = 0; c <= r; ++c) v[DX + tri(r, c)] = d[r] * d[c];
     // 0.5 (log|P| + d' P^-1 d + dx log 2 pi) through chol(P)
     double L[TX];
     const bool ok = chol_lower<DX>(P, L);
@@ -43,9 +46,9 @@ SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::va
         quad = fma(z[i], z[i], quad);
         logdet += log(L[tri(i, i)]);
     }
-    v[DX + DX * DX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
-    v[DX + DX * DX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
-    v[DX + DX * DX + 2] = 1.0;
+    v[DX + TX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
+    v[DX + TX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
+    v[DX + TX + 2] = 1.0;
 }
 
 // sum v[] over the CTA (warp shuffles, then one shared-memory pass in fixed order) and store the row
@@ -72,5 +75,7 @@ SSM_DEV void block_reduce_store(double (&v)[W], double *smem /* [blockDim/32][W]
 
 // stats[i] = sum over CTAs (fixed order) of partial[cta][i]
 __global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row);
+// same, expanding packed rows (width WP) into public rows (width W) with the symmetric matrix mirrored
+__global__ void scores_finalize_packed_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, int n_steps, int dx);
 
 }  // namespace ssm

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                                                               double *__restrict__ sm_cov, int32_t *__restrict__ status,
                                                               const double *__restrict__ x_truth, double *__restrict__ partial,
                                                               double *__restrict__ rmse_acc, long long n_traj, int N, long long ld) {
-    constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::W;
+    constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     __shared__ double smem[SCORE ? (SC_THREADS / 32) * W : 1];
     const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = t_raw < n_traj;
@@ -176,13 +176,13 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
                                                                           sm_cov, status, nullptr, nullptr, nullptr, n_traj, N, ld);
         return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
     }
-    constexpr int W = ScoreRow<DX>::W;
+    constexpr int W = ScoreRow<DX>::WP;
     double *partial = nullptr;
     if (cudaMallocAsync(&partial, (size_t)blocks * N * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     smoother_kernel<DX, true><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov,
                                                                      status, x_truth, partial, rmse_acc, n_traj, N, ld);
     const long long row = (long long)N * W;
-    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, (int)blocks, row);
+    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, (int)blocks, N, DX);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
