@@ -244,8 +244,9 @@ def run_gpu_arm(args):
 
     def e2e_step():
         """The user-level call: filter + smoother + scores of one Monte-Carlo batch held in HOST memory.  Inside:
-        chunked H2D of y and x overlapped with the kernels, scores copied back to the host."""
-        return mc.filter_scores(alg, yh, xh, smooth=True, n_chunks=args.chunks, comm=comm)
+        time-windowed H2D of y (forward) and x (backward) overlapped with the kernels (ssm_filter_window,
+        ssm_smooth_window, ssm_scores_phase2_window), scores copied back to the host."""
+        return mc.filter_scores(alg, yh, xh, smooth=True, n_windows=args.windows, comm=comm)
 
     for _ in range(max(1, min(args.warmup, 2))):
         out = e2e_step()
@@ -303,8 +304,9 @@ def run_gpu_arm(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(yh.numel() + xh.numel()) * 8,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': max(e2e_ms, e2e_wall_ms),
                     'api': 'ssmtoybox_b200.mc.filter_scores(GaussianProcessKalman, y, x, smooth=True) on pinned host y, x: '
-                           'chunked H2D overlapped with forward pass + RTS smoother + scores; scores and status read back',
-                    'chunks': args.chunks},
+                           'time-windowed H2D (y forward in time, x backward) overlapped with forward pass + RTS smoother + '
+                           'scores of the windows that have landed; scores and status read back',
+                    'windows': args.windows},
             'gpu_launches': 5 * args.steps,   # filter, smoother, finalize, scores phase 2, finalize
             'kernel_ms': {'filter_forward': k_filter, 'rts_smoother_with_phase1_scores': k_smooth, 'scores_phase2_incl_allreduce': k_scores},
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
@@ -334,7 +336,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--traj', type=int, default=TRAJ_PER_GPU, help='trajectories per GPU (default: the C3 share)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
-    ap.add_argument('--chunks', type=int, default=10, help='trajectory chunks of the host-streaming (e2e) pipeline')
+    ap.add_argument('--windows', type=int, default=20, help='time windows of the host-streaming (e2e) pipeline')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

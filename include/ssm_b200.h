@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 1
+#define SSM_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define SSM_OK             0
@@ -140,6 +140,22 @@ int ssm_filter(const ssm_desc *desc, const double *y,
                const int32_t *t_offset, int32_t k0,
                int32_t *status, int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
 
+/* Time-window form: the arrays have n_steps slots, only the steps [k_lo, k_hi) are processed (time index k0 + k).
+ * Successive windows of the same arrays carry the filter state through last_mean / last_cov -> init_mean /
+ * init_cov; for k_lo > 0 status[] must hold the status left by the preceding window (failed trajectories stay
+ * failed, keep their status and are NaN-filled).  Results are bitwise identical to one ssm_filter call.  This is
+ * what lets the host-streaming driver (ssmtoybox_b200/mc.py) start filtering as soon as the first time slice of
+ * the measurements has reached the device, with every launch spanning all trajectories (the loops it replaces:
+ * research/gpq/icinco_demo.py:115-125, research/gpq/gpq_tracking.py:52-57). */
+int ssm_filter_window(const ssm_desc *desc, const double *y,
+                      double *fi_mean, double *fi_cov,
+                      double *pr_mean, double *pr_cov, double *pr_xx_cov,
+                      const double *init_mean, const double *init_cov,
+                      double *last_mean, double *last_cov,
+                      const int32_t *t_offset, int32_t k0,
+                      int32_t *status, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld,
+                      void *stream);
+
 /* ---- K3: RTS smoother -----------------------------------------------------------------------
  * Replaces StateSpaceInference.backward_pass + GaussianInference._smoothing_update
  * (ssinf.py:120-147, 325-344), including the reference's index range (slots N and N-1 are never
@@ -154,6 +170,16 @@ int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov,
                double *sm_mean, double *sm_cov, int32_t *status,
                const double *x_truth, double *stats, double *rmse_acc,
                int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+
+/* Time-window form (windows must be walked from the last to the first on one stream): the window [k_lo, k_hi) with
+ * k_hi < n_steps continues the recursion from the smoothed moments the later window left in sm_mean / sm_cov and,
+ * with x_truth, continues the per-trajectory sums in rmse_acc; it fills stats rows [k_lo, k_hi).  Bitwise identical
+ * to one ssm_smooth call. */
+int ssm_smooth_window(int32_t dx, const double *fi_mean, const double *fi_cov,
+                      const double *pr_mean, const double *pr_cov, const double *pr_xx_cov,
+                      double *sm_mean, double *sm_cov, int32_t *status,
+                      const double *x_truth, double *stats, double *rmse_acc,
+                      int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
 /* ---- K1: batched simulation -----------------------------------------------------------------
  * Replaces TransitionModel.simulate_discrete / simulate_continuous (ssmod.py:168-244),
@@ -225,6 +251,15 @@ int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const dou
 int ssm_scores_phase2(int32_t dx, const double *x, const double *mean, const double *cov,
                       const int32_t *status, const double *mse, double *lcr,
                       int64_t n_traj, int32_t n_steps, int64_t ld, void *stream);
+/* Time-window forms: rows [k_lo, k_hi) of stats / lcr (and of mse) only; phase 1 walks the windows first to last
+ * (rmse_acc continues the per-trajectory sums when k_lo > 0).  The per-step MSE matrix of step k depends on step k
+ * alone, so phase 2 of a window can follow its phase 1 (and the all-reduce of those rows) immediately. */
+int ssm_scores_phase1_window(int32_t dx, const double *x, const double *mean, const double *cov,
+                             const int32_t *status, double *stats, double *rmse_acc,
+                             int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, const double *cov,
+                             const int32_t *status, const double *mse, double *lcr,
+                             int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
 /* ---- stand-alone moment transform / model evaluation -----------------------------------------
  * ssm_transform_apply replaces MomentTransform.apply(f, mean, cov, fcn_pars) as a public call

@@ -64,6 +64,14 @@ def _load():
     lib.ssm_last_error.restype = C.c_char_p
     lib.ssm_filter.restype = C.c_int
     lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
+    lib.ssm_filter_window.restype = C.c_int
+    lib.ssm_filter_window.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_smooth_window.restype = C.c_int
+    lib.ssm_smooth_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase1_window.restype = C.c_int
+    lib.ssm_scores_phase1_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase2_window.restype = C.c_int
+    lib.ssm_scores_phase2_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_smooth.restype = C.c_int
     lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     lib.ssm_fp64_peak_kernel.restype = C.c_int

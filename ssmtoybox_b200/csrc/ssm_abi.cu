@@ -35,22 +35,24 @@ using namespace ssm;
 extern "C" int ssm_abi_version(void) { return SSM_ABI_VERSION; }
 extern "C" const char *ssm_last_error(void) { return g_err; }
 
-extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
-                          double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
-                          double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
-                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                                 double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                                 double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!desc || !y || !status) { set_error("ssm_filter: desc, y and status must not be NULL"); return SSM_E_INVALID; }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_filter: bad sizes (n_traj=%lld n_steps=%d ld=%lld)", (long long)n_traj, n_steps, (long long)ld); return SSM_E_INVALID; }
+    if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_filter: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
     if (!desc->m0 || !desc->P0 || !desc->GQG || !desc->R) { set_error("ssm_filter: m0, P0, GQG, R must not be NULL"); return SSM_E_INVALID; }
     if ((init_mean == nullptr) != (init_cov == nullptr)) { set_error("ssm_filter: init_mean and init_cov go together"); return SSM_E_INVALID; }
     if (!tf_valid(desc->tf_dyn) || !tf_valid(desc->tf_obs)) { set_error("ssm_filter: incomplete transform description"); return SSM_E_INVALID; }
     if (desc->family != SSM_FAMILY_GAUSS && desc->family != SSM_FAMILY_STUDENT) { set_error("ssm_filter: unknown family %d", desc->family); return SSM_E_INVALID; }
-    if (n_traj == 0 || n_steps == 0) return SSM_OK;
+    if (n_traj == 0 || k_hi == k_lo) return SSM_OK;
     FilterLaunch L;
     L.desc = desc;
     L.stream = (cudaStream_t)stream;
     L.buf = FilterBuffers{y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
-                          t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0, nullptr, nullptr, 0, 0};
+                          t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0, nullptr, nullptr, 0, 0,
+                          k_lo, k_hi, k_lo > 0 ? 1 : 0};
     const int dm = desc->dyn_model, om = desc->obs_model;
     const int nsi = desc->n_state_index;
     const int32_t *si = desc->state_index;
@@ -67,6 +69,14 @@ extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean
         set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                          double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                          double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    return ssm_filter_window(desc, y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
+                             t_offset, k0, status, n_traj, n_steps, 0, n_steps, ld, stream);
 }
 
 // Strided host <-> device copy of a trajectory range of a [component][step][trajectory] array:

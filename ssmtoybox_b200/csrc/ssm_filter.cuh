@@ -291,6 +291,9 @@ struct FilterBuffers {
     double *state;     // carried filter state between chunks: [blk][component][thread]
     int chunk;         // time steps per work item
     int n_blocks;      // trajectory blocks
+    // time window [k_lo, k_hi) of the n_steps slots to process (ssm_filter_window); resume: trajectories whose
+    // status is already non-zero (failed in an earlier window) stay failed and keep their status
+    int k_lo, k_hi, resume;
 };
 
 template <int DX, int DY, class TfD, class TfO>
@@ -329,10 +332,10 @@ SSM_DEV void store_mat(double *base, long long n_steps, long long ld, int k, lon
 #pragma unroll
         for (int c = 0; c < D; ++c) st_stream(base + ((long long)(r * D + c) * n_steps + k) * ld + t, M[r][c]);
 }
-SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, int k_from, long long t) {
+SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, int k_from, int k_to, long long t) {
     if (!base) return;
     for (int c = 0; c < comps; ++c)
-        for (int k = k_from; k < n_steps; ++k) base[((long long)c * n_steps + k) * ld + t] = qnan();
+        for (int k = k_from; k < k_to; ++k) base[((long long)c * n_steps + k) * ld + t] = qnan();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     // (blk, kc) waits for done[blk] >= kc, which a CTA that drew an EARLIER ticket -- hence already running --
     // publishes, so the wait cannot deadlock.  Arithmetic is unchanged: results are bitwise identical.
     const bool ticketed = b.sched != nullptr;
-    const int n_chunks = ticketed ? (N + b.chunk - 1) / b.chunk : 1;
+    const int n_chunks = ticketed ? (b.k_hi - b.k_lo + b.chunk - 1) / b.chunk : 1;
     const long long n_items = ticketed ? (long long)b.n_blocks * n_chunks : 0;
   for (;;) {
     long long blk = blockIdx.x;
@@ -385,15 +388,15 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         kc = (int)(tk / b.n_blocks);
         blk = tk % b.n_blocks;
     }
-    const int k_begin = ticketed ? kc * b.chunk : 0;
-    const int k_end = ticketed ? min(N, k_begin + b.chunk) : N;
+    const int k_begin = b.k_lo + (ticketed ? kc * b.chunk : 0);
+    const int k_end = ticketed ? min(b.k_hi, k_begin + b.chunk) : b.k_hi;
     const long long t_raw = blk * blockDim.x + threadIdx.x;
     const bool active = t_raw < b.n_traj;
     const long long t = active ? t_raw : b.n_traj - 1;  // idle lanes shadow the last trajectory, never store
 
     double m[DX], P[TX];  // filtered mean and covariance (Student family: scale matrix x_smat_fi)
     int fail = active ? 0 : -1, kfail = 0;
-    if (k_begin > 0) {
+    if (kc > 0) {
         if (threadIdx.x == 0) {
             int spins = 0;
             while (atomicAdd(b.sched + 1 + blk, 0) < kc) { __nanosleep(200); ++spins; }
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 #pragma unroll
         for (int a = 0; a < TX; ++a) P[a] = (FAMILY == SSM_FAMILY_STUDENT) ? p.s0 * p.P0[a] : p.P0[a];
     }
+    if (kc == 0 && b.resume && active && b.status[t] != 0) { fail = b.status[t] & 0xff; kfail = b.k_lo; }
     const double tbase = (double)(b.k0 + (b.t_offset ? b.t_offset[t] : 0));
 
     double ynext[DY];
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         double yk[DY];
 #pragma unroll
         for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
-        if (k + 1 < N) {
+        if (k + 1 < k_end) {
 #pragma unroll
             for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N + k + 1) * ld + t);
         }
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         }
     }
 
-    if (k_end < N) {
+    if (k_end < b.k_hi) {
         // hand the state to whichever CTA draws the next chunk of this trajectory block
         double *st = b.state + (blk * NSTATE) * blockDim.x + threadIdx.x;
 #pragma unroll
@@ -584,11 +588,11 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         if (threadIdx.x == 0) atomicExch(b.sched + 1 + blk, kc + 1);
     } else if (active) {
         if (fail) {
-            fill_nan(b.fi_mean, DX, N, ld, kfail, t);
-            fill_nan(b.fi_cov, DX * DX, N, ld, kfail, t);
-            fill_nan(b.pr_mean, DX, N, ld, kfail, t);
-            fill_nan(b.pr_cov, DX * DX, N, ld, kfail, t);
-            fill_nan(b.pr_xx, DX * DX, N, ld, kfail, t);
+            fill_nan(b.fi_mean, DX, N, ld, kfail, b.k_hi, t);
+            fill_nan(b.fi_cov, DX * DX, N, ld, kfail, b.k_hi, t);
+            fill_nan(b.pr_mean, DX, N, ld, kfail, b.k_hi, t);
+            fill_nan(b.pr_cov, DX * DX, N, ld, kfail, b.k_hi, t);
+            fill_nan(b.pr_xx, DX * DX, N, ld, kfail, b.k_hi, t);
     #pragma unroll
             for (int a = 0; a < DX; ++a) m[a] = qnan();
     #pragma unroll
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     #pragma unroll
                 for (int c = 0; c < DX; ++c) b.last_cov[(long long)(r * DX + c) * ld + t] = P[sym(r, c)];
         }
-        b.status[t] = fail ? (((kfail + 1) << 8) | fail) : 0;
+        if (!(b.resume && b.status[t] != 0)) b.status[t] = fail ? (((kfail + 1) << 8) | fail) : 0;
     }
     if (!ticketed) break;
   }
@@ -730,9 +734,19 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     const long long cap = (long long)occ * sms;
     // developer overrides: SSM_TICKET=0 disables the scheduler, SSM_TICKET_CHUNK=<steps> sets the item length
     const char *env_on = getenv("SSM_TICKET"), *env_chunk = getenv("SSM_TICKET_CHUNK");
-    const int CHUNK = env_chunk ? atoi(env_chunk) : SSM_TICKET_CHUNK;
+    const int win = L.buf.k_hi - L.buf.k_lo;
+    int CHUNK = env_chunk ? atoi(env_chunk) : SSM_TICKET_CHUNK;
+    if (!env_chunk && cap > 0 && win < 8 * CHUNK) {
+        // short windows (host-streaming driver): pick the item length that minimises the rounds x length product
+        long long best = -1;
+        for (int c : {25, 20, 16, 12, 10, 8}) {
+            const long long items = blocks * ((win + c - 1) / c);
+            const long long cost = ((items + cap - 1) / cap) * c;
+            if (best < 0 || cost < best) { best = cost; CHUNK = c; }
+        }
+    }
     const bool want_ticket = SSM_TICKET_SCHED && !(env_on && atoi(env_on) == 0);
-    if (want_ticket && CHUNK > 0 && cap > 0 && blocks > cap && L.buf.n_steps >= 2 * CHUNK) {
+    if (want_ticket && CHUNK > 0 && cap > 0 && blocks > cap && win >= 2 * CHUNK) {
         const size_t n_int = ((size_t)blocks + 2 + 1) / 2 * 2;  // ticket, done[blocks], wait counter; doubles stay 8-byte aligned
         const size_t bytes = n_int * sizeof(int) + (size_t)blocks * THREADS * (DX + TriSize<DX>::value + 2) * sizeof(double);
         if (cudaMallocAsync(&work, bytes, L.stream) != cudaSuccess) { delete pp; set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }

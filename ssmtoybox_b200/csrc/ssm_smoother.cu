@@ -17,8 +17,13 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                                                               const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
                                                               double *__restrict__ sm_cov, int32_t *__restrict__ status,
                                                               const double *__restrict__ x_truth, double *__restrict__ partial,
-                                                              double *__restrict__ rmse_acc, long long n_traj, int N, long long ld) {
+                                                              double *__restrict__ rmse_acc, long long n_traj, int N, int k_lo, int k_hi,
+                                                              long long ld) {
+    // Time window [k_lo, k_hi) of the N slots (ssm_smooth_window): a window with k_hi < N continues the recursion
+    // from the smoothed moments the later window left in sm_mean / sm_cov (same stream => ordered), so walking the
+    // windows from the last to the first reproduces the one-pass result bit for bit.
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
+    const int WLEN = k_hi - k_lo;
     __shared__ double smem[SCORE ? (SC_THREADS / 32) * W : 1];
     const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = t_raw < n_traj;
@@ -27,7 +32,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
     double se_acc[DX];
 #pragma unroll
-    for (int a = 0; a < DX; ++a) se_acc[a] = 0.0;
+    for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? rmse_acc[(long long)a * ld + t] : 0.0;
     // score the smoothed moments (ms, Ps) of step k; every thread of the CTA calls this once per step
     auto score = [&](int k, bool live, const double (&ms_)[DX], const double (&Ps_)[TX]) {
         double v[W];
@@ -41,11 +46,11 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
-        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * N + k) * W);
+        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
     };
     bool alive = in_range && status[t] == 0;
     if (in_range && !alive) {  // the forward pass failed: nothing to smooth
-        for (int k = 0; k < N; ++k) {
+        for (int k = k_lo; k < k_hi; ++k) {
             for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
             for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
         }
@@ -55,7 +60,16 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     // slots N and N-1 (indices N-1, N-2 here) keep their filtered values, and the recursion starts
     // from the filtered moments of slot N (ssinf.py:117, 137).
     double ms[DX], Ps[TX];
-    for (int k = N - 1; k >= 0 && k >= N - 2; --k) {
+    if (k_hi < N && alive) {
+        const int ki = (k_hi >= N - 2) ? N - 1 : k_hi;   // slots N-1, N-2 hold filtered values; the recursion starts from slot N-1
+#pragma unroll
+        for (int a = 0; a < DX; ++a) ms[a] = ld_stream(sm_mean + at(a, ki));
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) Ps[tri(r, c)] = ld_stream(sm_cov + at(r * DX + c, ki));
+    }
+    for (int k = k_hi - 1; k >= k_lo && k >= N - 2; --k) {
         double mk[DX], Pk[TX];
         if (alive) {
 #pragma unroll
@@ -78,7 +92,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
         if (SCORE) score(k, alive, mk, Pk);
     }
     int fail = 0, kfail = 0;
-    for (int k = N - 3; k >= 0; --k) {
+    for (int k = min(k_hi - 1, N - 3); k >= k_lo; --k) {
       // ONE score() call site per iteration: its warp shuffles and CTA barriers must be reached by every thread
       // through the same instruction, so failures leave the step body with `break`, never `continue`.
       do {
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
         for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = (alive && !fail) ? se_acc[a] : qnan();
     }
     if (fail && in_range) {
-        for (int k = kfail; k >= 0; --k) {
+        for (int k = kfail; k >= k_lo; --k) {
             for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
             for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
         }
@@ -169,20 +183,21 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
 template <int DX>
 static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
                            const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, const double *x_truth,
-                           double *stats, double *rmse_acc, long long n_traj, int N, long long ld, cudaStream_t s) {
+                           double *stats, double *rmse_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     const long long blocks = (n_traj + SC_THREADS - 1) / SC_THREADS;
+    const int WLEN = k_hi - k_lo;
     if (!x_truth) {
         smoother_kernel<DX, false><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean,
-                                                                          sm_cov, status, nullptr, nullptr, nullptr, n_traj, N, ld);
+                                                                          sm_cov, status, nullptr, nullptr, nullptr, n_traj, N, k_lo, k_hi, ld);
         return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
     }
     constexpr int W = ScoreRow<DX>::WP;
     double *partial = nullptr;
-    if (cudaMallocAsync(&partial, (size_t)blocks * N * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    if (cudaMallocAsync(&partial, (size_t)blocks * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     smoother_kernel<DX, true><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov,
-                                                                     status, x_truth, partial, rmse_acc, n_traj, N, ld);
-    const long long row = (long long)N * W;
-    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats, (int)blocks, N, DX);
+                                                                     status, x_truth, partial, rmse_acc, n_traj, N, k_lo, k_hi, ld);
+    const long long row = (long long)WLEN * W;
+    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, (int)blocks, WLEN, DX);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
@@ -192,27 +207,36 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
 
 using namespace ssm;
 
-extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
-                          const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
-                          int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
-                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+extern "C" int ssm_smooth_window(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                                 const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
+                                 int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!fi_mean || !fi_cov || !pr_mean || !pr_cov || !pr_xx_cov || !sm_mean || !sm_cov || !status) {
         set_error("ssm_smooth: NULL buffer");
         return SSM_E_INVALID;
     }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_smooth: bad sizes"); return SSM_E_INVALID; }
+    if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_smooth: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
     if (x_truth && !stats) { set_error("ssm_smooth: stats must not be NULL when x_truth is given"); return SSM_E_INVALID; }
-    if (n_traj == 0 || n_steps == 0) return SSM_OK;
+    if (n_traj == 0 || k_hi == k_lo) return SSM_OK;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
-        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
-        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, ld, s); break;
+        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_smooth: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                          const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
+                          int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
+                          int64_t n_traj, int32_t n_steps, int64_t ld, void *stream) {
+    return ssm_smooth_window(dx, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc,
+                             n_traj, n_steps, 0, n_steps, ld, stream);
 }
 
 // ---- FP64 FMA micro-benchmarks: 8 independent DFMA chains per thread --------------------------------

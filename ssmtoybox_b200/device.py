@@ -145,8 +145,10 @@ def bulk_ld(t):
 
 
 def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, init_cov=None, t_offset=None, k0=0,
-                   want_last=False, out=None):
-    """Run the fused forward pass (ssm_filter) on y (dy, N, M) -> dict of device tensors."""
+                   want_last=False, out=None, window=None):
+    """Run the fused forward pass (ssm_filter) on y (dy, N, M) -> dict of device tensors.
+    window = (k_lo, k_hi): process only those time steps of the N slots (ssm_filter_window); successive windows
+    carry the state through out['last_mean'/'last_cov'] -> init_mean / init_cov and the status through out['status']."""
     dy, N, M = y.shape
     dx = low.dx
     dev = y.device
@@ -161,7 +163,7 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
         for k, shp in (('pr_mean', (dx, N, M)), ('pr_cov', (dx, dx, N, M)), ('pr_xx_cov', (dx, dx, N, M))):
             if k not in o:
                 o[k] = torch.empty(shp, **kw)
-    if want_last:
+    if want_last and 'last_mean' not in o:
         o['last_mean'] = torch.empty((dx, M), **kw)
         o['last_cov'] = torch.empty((dx, dx, M), **kw)
     if 'status' not in o:
@@ -177,16 +179,19 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
             raise ValueError('all bulk arrays of one call must share the leading dimension (y: {}, {}: {})'.format(ld, k, bulk_ld(o[k])))
     if (init_mean is not None or want_last) and ld != M:
         raise ValueError('init / last moments are not supported on trajectory-range views')
-    rc = lib.ssm_filter(C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
-                        _p(o.get('pr_cov')), _p(o.get('pr_xx_cov')), _p(init_mean), _p(init_cov),
-                        _p(o.get('last_mean')), _p(o.get('last_cov')), _p(t_offset), int(k0), _p(o['status']),
-                        M, N, ld, _stream())
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    rc = lib.ssm_filter_window(C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
+                               _p(o.get('pr_cov')), _p(o.get('pr_xx_cov')), _p(init_mean), _p(init_cov),
+                               _p(o.get('last_mean') if want_last else None), _p(o.get('last_cov') if want_last else None),
+                               _p(t_offset), int(k0), _p(o['status']), M, N, k_lo, k_hi, ld, _stream())
     _lib.check(rc, 'ssm_filter')
     return o
 
 
-def smooth_backward(dx, fwd, out=None, x_truth=None):
+def smooth_backward(dx, fwd, out=None, x_truth=None, window=None):
     """Run the RTS smoother (ssm_smooth) over the arrays stored by filter_forward(store_pred=True).
+    window = (k_lo, k_hi): smooth only those steps (ssm_smooth_window); windows must be walked from the last to the
+    first with the same `out` (the first call, k_hi == N, copies the forward-pass status).
     With x_truth (dx, N, M) the kernel also accumulates the phase-1 score statistics of the smoothed moments:
     out['stats'] (N, W) and out['rmse_acc'] (dx, M), identical to scores_phase1(x_truth, sm_mean, sm_cov, status)."""
     _, N, M = fwd['fi_mean'].shape
@@ -194,10 +199,12 @@ def smooth_backward(dx, fwd, out=None, x_truth=None):
     if 'sm_mean' not in o:
         o['sm_mean'] = torch.empty_like(fwd['fi_mean'])
         o['sm_cov'] = torch.empty_like(fwd['fi_cov'])
-    if 'status' in o and o['status'].shape == fwd['status'].shape:
-        o['status'].copy_(fwd['status'])
-    else:
-        o['status'] = fwd['status'].clone()
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    if k_hi == N or 'status' not in o:
+        if 'status' in o and o['status'].shape == fwd['status'].shape:
+            o['status'].copy_(fwd['status'])
+        else:
+            o['status'] = fwd['status'].clone()
     ld = bulk_ld(fwd['fi_mean'])
     if any(bulk_ld(t) != ld for t in (fwd['fi_cov'], fwd['pr_mean'], fwd['pr_cov'], fwd['pr_xx_cov'], o['sm_mean'], o['sm_cov'])) and M > 1:
         raise ValueError('all bulk arrays of one ssm_smooth call must share the leading dimension')
@@ -208,10 +215,10 @@ def smooth_backward(dx, fwd, out=None, x_truth=None):
         if 'stats' not in o:
             o['stats'] = torch.empty((N, W), dtype=torch.float64, device=fwd['fi_mean'].device)
             o['rmse_acc'] = torch.empty((dx, M), dtype=torch.float64, device=fwd['fi_mean'].device)
-    rc = lib.ssm_smooth(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
-                        _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']),
-                        _p(x_truth), _p(o.get('stats') if x_truth is not None else None),
-                        _p(o.get('rmse_acc') if x_truth is not None else None), M, N, ld, _stream())
+    rc = lib.ssm_smooth_window(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
+                               _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']),
+                               _p(x_truth), _p(o.get('stats') if x_truth is not None else None),
+                               _p(o.get('rmse_acc') if x_truth is not None else None), M, N, k_lo, k_hi, ld, _stream())
     _lib.check(rc, 'ssm_smooth')
     return o
 
@@ -324,22 +331,29 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
 # ------------------------------------------------------------------------------------------------
 # K6: scores
 # ------------------------------------------------------------------------------------------------
-def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True):
+def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None):
     """Per-step packed statistics over trajectories: stats (N, W), W = dx + dx*dx + 3:
-    [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE."""
+    [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE.
+    window = (k_lo, k_hi) fills only those rows of out = (stats, rmse_acc) (walk the windows first to last)."""
     dx, N, M = x.shape
     W = lib.ssm_scores_width(dx)
-    stats = torch.empty((N, W), dtype=torch.float64, device=x.device)
-    acc = torch.empty((dx, M), dtype=torch.float64, device=x.device) if want_rmse_acc else None
-    rc = lib.ssm_scores_phase1(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), M, N, M, _stream())
+    if out is not None:
+        stats, acc = out
+    else:
+        stats = torch.empty((N, W), dtype=torch.float64, device=x.device)
+        acc = torch.empty((dx, M), dtype=torch.float64, device=x.device) if want_rmse_acc else None
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    rc = lib.ssm_scores_phase1_window(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase1')
     return stats, acc
 
 
-def scores_phase2(x, mean, cov, mse, status=None):
-    """Per-step sums of the log credibility ratio and of its absolute value: (N, 2).  mse (dx, dx, N)."""
+def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None):
+    """Per-step sums of the log credibility ratio and of its absolute value: (N, 2).  mse (dx, dx, N).
+    window = (k_lo, k_hi) fills only those rows of out (N, 2) and reads only those columns of mse."""
     dx, N, M = x.shape
-    lcr = torch.empty((N, 2), dtype=torch.float64, device=x.device)
-    rc = lib.ssm_scores_phase2(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), M, N, M, _stream())
+    lcr = out if out is not None else torch.empty((N, 2), dtype=torch.float64, device=x.device)
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    rc = lib.ssm_scores_phase2_window(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase2')
     return lcr

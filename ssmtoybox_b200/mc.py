@@ -2,11 +2,22 @@
 research/gpq/gpq_tracking.py:52-57, research/bsq/bsq_tracking.py:300-337 on the GPU).
 
 `filter_scores` runs filter (+ RTS smoother) and the error scores over all trajectories of host or device arrays.
-Host inputs are streamed: the trajectory axis is cut into chunks, chunk c+1 is copied host -> device on a second
-CUDA stream while chunk c is filtered, smoothed and reduced; only the per-chunk smoothed (or filtered) moments
-and the truth stay resident for the second score phase (the log credibility ratio needs the GLOBAL per-step MSE
-matrix first, utils.py:113-120).  With a Communicator, every rank handles its own trajectories and the packed
-statistics are all-reduced (one NCCL call per phase).
+
+Host inputs are streamed along the TIME axis (default path, everything resident): a trajectory is a serial
+recursion, so a launch is only efficient when it spans (at least) a full wave of trajectories -- cutting the
+trajectory axis into chunks leaves the GPU mostly idle (measured on B200, 125 000 x 500: 10 trajectory chunks
+123 ms, PCIe alone 64 ms).  Instead the measurements are copied window by window in time order and every forward
+pass launch (ssm_filter_window) covers ALL trajectories for one window as soon as that window has landed; the
+truth follows in REVERSE time order while the forward pass is still running, and the RTS smoother
+(ssm_smooth_window, in-kernel phase-1 statistics) chases it backwards.  The per-step MSE matrix of step k needs
+step k only, so the second score phase of a window (log credibility ratio, utils.py:113-120) follows its smoother
+window immediately: after the last byte of x has arrived only one window of smoother + scores remains.
+With a Communicator, every rank handles its own trajectories; the packed statistics rows of each window are
+all-reduced (tiny, latency-bound) before its second phase.
+
+When the arrays of the batch do not fit in device memory the trajectory axis is cut into chunks instead
+(`_filter_scores_chunked`): chunk c+1 is copied while chunk c is processed, and only the moments needed by the
+second score phase stay resident.
 """
 import ctypes as C
 
@@ -24,7 +35,129 @@ def _as_host_or_device(a):
     return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
 
 
-def filter_scores(alg, y, x, smooth=True, n_chunks=8, comm=None, keep=False):
+def _windows(N, n):
+    n = max(1, min(int(n), N))
+    w = -(-N // n)
+    return [(a, min(a + w, N)) for a in range(0, N, w)]
+
+
+def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n_chunks=None):
+    """RMSE / NCI / NLL of filter `alg` on measurements y (dy, N, M) against the truth x (dx, N, M).
+    y, x: numpy arrays, CPU torch tensors (pinned for full copy speed) or CUDA tensors.
+    Returns the dict of ssmtoybox_b200.utils.evaluate_performance (+ 'status' (M,) int32 on the host, and the
+    device arrays under 'arrays' when keep=True).  n_windows: time windows of the streaming pipeline;
+    n_chunks forces the trajectory-chunked fallback."""
+    y, x = _as_host_or_device(y), _as_host_or_device(x)
+    dy, N, M = y.shape
+    dx = x.shape[0]
+    dev = torch.device('cuda', torch.cuda.current_device())
+    low = dv.lower(alg._describe())
+    do_smooth = smooth and not isinstance(alg, StudentianInference)
+    if low.dy != dy or low.dx != dx:
+        raise ValueError('data dimensions do not match the model')
+    per_traj = 8 * N * ((0 if y.is_cuda else dy) + (0 if x.is_cuda else dx) + (dx + dx * dx)
+                        + ((2 * dx + 3 * dx * dx) if do_smooth else 0))
+    free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+    if n_chunks is not None or per_traj * M > 0.85 * free or N < 4:
+        return _filter_scores_chunked(alg, y, x, smooth=smooth, n_chunks=n_chunks or 8, comm=comm, keep=keep)
+    for src in (y, x):
+        if not src.is_cuda and (src.dtype != torch.float64 or not src.is_contiguous()):
+            raise ValueError('host arrays must be C-contiguous float64')
+    wins = _windows(N, n_windows)
+    comp = torch.cuda.current_stream()
+    copy = torch.cuda.Stream()
+    kw = dict(dtype=torch.float64, device=dev)
+
+    def h2d_window(src, dst, k0, k1):
+        """time steps [k0, k1) of a host (c, N, M) array -> the same slots of the device array: one strided DMA
+        (c rows of (k1 - k0) * M contiguous doubles)"""
+        rc = dv.lib.ssm_memcpy2d(C.c_void_p(dst.data_ptr() + k0 * M * 8), N * M * 8, C.c_void_p(src.data_ptr() + k0 * M * 8),
+                                 N * M * 8, (k1 - k0) * M * 8, src.shape[0], 1, C.c_void_p(copy.cuda_stream))
+        dv._lib.check(rc, 'ssm_memcpy2d')
+        e = torch.cuda.Event()
+        e.record(copy)
+        return e
+
+    # ---- copies: y in time order, then x in the order its consumer walks the windows ---------------
+    ev_y, ev_x = [None] * len(wins), [None] * len(wins)
+    copy.wait_stream(comp)
+    yd = y if y.is_cuda else torch.empty((dy, N, M), **kw)
+    xd = x if x.is_cuda else torch.empty((dx, N, M), **kw)
+    with torch.cuda.stream(copy):
+        if not y.is_cuda:
+            yd.record_stream(copy)
+            for c, (k0, k1) in enumerate(wins):
+                ev_y[c] = h2d_window(y, yd, k0, k1)
+        if not x.is_cuda:
+            xd.record_stream(copy)
+            order = range(len(wins) - 1, -1, -1) if do_smooth else range(len(wins))
+            for c in order:
+                ev_x[c] = h2d_window(x, xd, *wins[c])
+    W = dv.lib.ssm_scores_width(dx)
+    stats = torch.empty((N, W), **kw)
+    acc = torch.empty((dx, M), **kw)
+    mse = torch.empty((dx * dx, N), **kw)
+    lcr = torch.empty((N, 2), **kw)
+
+    def second_phase(k0, k1, mean, cov, status):
+        """stats rows [k0, k1) are complete on this rank: all-reduce them, form the MSE matrices, second phase"""
+        rows = stats[k0:k1]
+        if comm is not None:
+            comm.allreduce_sum(rows)
+        mse[:, k0:k1] = (rows[:, dx:dx + dx * dx] / rows[:, -1:]).T
+        dv.scores_phase2(xd, mean, cov, mse, status, window=(k0, k1), out=lcr)
+
+    # ---- forward pass, window by window --------------------------------------------------------------
+    fwd = {}
+    for c, (k0, k1) in enumerate(wins):
+        if ev_y[c] is not None:
+            comp.wait_event(ev_y[c])
+        dv.filter_forward(low, yd, store_pred=do_smooth, out=fwd, window=(k0, k1), want_last=True,
+                          init_mean=fwd['last_mean'] if c else None, init_cov=fwd['last_cov'] if c else None)
+        if not do_smooth:
+            if ev_x[c] is not None:
+                comp.wait_event(ev_x[c])
+            dv.scores_phase1(xd, fwd['fi_mean'], fwd['fi_cov'], fwd['status'], window=(k0, k1), out=(stats, acc))
+            if c == 0:
+                cnt0 = stats[0, -1].clone()      # trajectories of this rank alive after the first window
+            second_phase(k0, k1, fwd['fi_mean'], fwd['fi_cov'], fwd['status'])
+    mean, cov, st = fwd['fi_mean'], fwd['fi_cov'], fwd['status']
+    n_bad = torch.zeros((), **kw)
+    # ---- RTS smoother + scores, walking the windows backwards ------------------------------------------
+    if do_smooth:
+        sm = {'stats': stats, 'rmse_acc': acc}
+        for c in range(len(wins) - 1, -1, -1):
+            k0, k1 = wins[c]
+            if ev_x[c] is not None:
+                comp.wait_event(ev_x[c])
+            dv.smooth_backward(dx, fwd, out=sm, x_truth=xd, window=(k0, k1))
+            second_phase(k0, k1, sm['sm_mean'], sm['sm_cov'], sm['status'])
+        mean, cov, st = sm['sm_mean'], sm['sm_cov'], sm['status']
+        # trajectories that failed INSIDE the smoother were still alive in the rows of later steps
+        n_bad = ((st != 0).sum() - (fwd['status'] != 0).sum()).to(torch.float64)
+    else:
+        # a trajectory that fails in a later window was still alive in the rows of earlier ones
+        n_bad = (st != 0).sum().to(torch.float64) - (M - cnt0)
+    ok = (st == 0)
+    rm = torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)
+    pack = torch.cat([rm, lcr.reshape(-1), n_bad.reshape(1)])
+    if comm is not None:
+        pack = comm.allreduce_sum(pack)
+    rm_g, lcr_g, bad = pack[:dx], pack[dx:dx + 2 * N].reshape(N, 2), pack[-1]
+    out = finalize_scores(stats, rm_g, lcr_g, dx, N)
+    out['n_bad'] = bad
+    res = {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}
+    if res.pop('n_bad') != 0.0:
+        # rare: some trajectories failed after they had contributed to some rows -> exact two-pass recomputation
+        from . import utils as U
+        res = U.evaluate_performance(xd, mean, cov, status=st, comm=comm)
+    res['status'] = st.cpu().numpy()
+    if keep:
+        res['arrays'] = dict(x=xd, y=yd, mean=mean, cov=cov, status=st, fwd=fwd)
+    return res
+
+
+def _filter_scores_chunked(alg, y, x, smooth=True, n_chunks=8, comm=None, keep=False):
     """RMSE / NCI / NLL of filter `alg` on measurements y (dy, N, M) against the truth x (dx, N, M).
     y, x: numpy arrays, CPU torch tensors (pinned for full copy speed) or CUDA tensors.
     Returns the dict of ssmtoybox_b200.utils.evaluate_performance (+ 'status' (M,) int32 on the host, and the

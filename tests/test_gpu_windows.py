@@ -1,0 +1,147 @@
+"""Time-window entry points (ssm_filter_window / ssm_smooth_window / ssm_scores_phase{1,2}_window) and the
+time-streaming Monte-Carlo driver built on them: walking the windows must reproduce the one-pass results bit for
+bit, failures included.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device='cuda')
+
+
+def eq(a, b):
+    """bitwise equality, NaNs at the same places"""
+    return torch.equal(torch.nan_to_num(a, nan=-1.2345e300), torch.nan_to_num(b, nan=-1.2345e300)) and \
+        torch.equal(torch.isnan(a), torch.isnan(b))
+
+
+def _sim(g, M, N, seed=3):
+    from ssmtoybox_b200 import device as dv
+    low = dv.lower(g)
+    rng = dv.make_rng({'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+                       'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}, seed=seed)
+    x, y = dv.simulate(low, M, N, rng=rng, mode='continuous', dt=0.05, sub=2)
+    return low, x, y
+
+
+def _windowed_forward(dv, low, y, wins, store_pred=True):
+    o = {}
+    for c, (a, b) in enumerate(wins):
+        dv.filter_forward(low, y, store_pred=store_pred, out=o, window=(a, b), want_last=True,
+                          init_mean=o['last_mean'] if c else None, init_cov=o['last_cov'] if c else None)
+    return o
+
+
+@pytest.mark.parametrize('M,N,wins', [
+    (300, 40, [(0, 13), (13, 30), (30, 40)]),                    # plain launches
+    (300, 7, [(0, 1), (1, 2), (2, 6), (6, 7)]),                  # one-step windows, windows touching slots N-1, N-2
+    (60000, 64, [(0, 32), (32, 64)]),                            # more CTAs than fit: ticket scheduler inside each window
+])
+def test_windows_equal_one_pass_bitwise(M, N, wins):
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_gpq')
+    low, x, y = _sim(g, M, N)
+    # make a few trajectories fail at different steps: a wild measurement drives the covariance indefinite
+    bad = [1, 77, M - 1]
+    for i, t in enumerate(bad):
+        y[:, min(N - 2, 3 + 9 * i), t] = float('nan')
+    ref = dv.filter_forward(low, y, store_pred=True, want_last=True)
+    st = ref['status'].cpu().numpy()
+    assert (st[bad] != 0).all() and (np.delete(st, bad) == 0).all()
+    o = _windowed_forward(dv, low, y, wins)
+    for k in ('fi_mean', 'fi_cov', 'pr_mean', 'pr_cov', 'pr_xx_cov', 'last_mean', 'last_cov'):
+        assert eq(o[k], ref[k]), k
+    assert torch.equal(o['status'], ref['status'])
+    # smoother (+ in-kernel statistics), windows walked backwards
+    sref = dv.smooth_backward(low.dx, ref, x_truth=x)
+    sm = {}
+    for a, b in reversed(wins):
+        dv.smooth_backward(low.dx, o, out=sm, x_truth=x, window=(a, b))
+    for k in ('sm_mean', 'sm_cov', 'stats', 'rmse_acc'):
+        assert eq(sm[k], sref[k]), k
+    assert torch.equal(sm['status'], sref['status'])
+    # plain smoother windows (no statistics)
+    sm2 = {}
+    for a, b in reversed(wins):
+        dv.smooth_backward(low.dx, o, out=sm2, window=(a, b))
+    assert eq(sm2['sm_mean'], sref['sm_mean']) and eq(sm2['sm_cov'], sref['sm_cov'])
+    # score phases
+    s1, acc1 = dv.scores_phase1(x, ref['fi_mean'], ref['fi_cov'], ref['status'])
+    W = s1.shape[1]
+    s2, acc2 = torch.empty((N, W), dtype=torch.float64, device='cuda'), torch.empty((low.dx, M), dtype=torch.float64, device='cuda')
+    for a, b in wins:
+        dv.scores_phase1(x, ref['fi_mean'], ref['fi_cov'], ref['status'], window=(a, b), out=(s2, acc2))
+    assert eq(s2, s1) and eq(acc2, acc1)
+    mse = (s1[:, low.dx:low.dx + low.dx ** 2] / s1[:, -1:]).T.reshape(low.dx, low.dx, N).contiguous()
+    l1 = dv.scores_phase2(x, ref['fi_mean'], ref['fi_cov'], mse, ref['status'])
+    l2 = torch.empty((N, 2), dtype=torch.float64, device='cuda')
+    for a, b in wins:
+        dv.scores_phase2(x, ref['fi_mean'], ref['fi_cov'], mse, ref['status'], window=(a, b), out=l2)
+    assert eq(l2, l1)
+
+
+def test_window_argument_validation():
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_gpq')
+    low, x, y = _sim(g, 64, 10)
+    for w in ((-1, 5), (5, 4), (0, 11)):
+        with pytest.raises(ValueError):
+            dv.filter_forward(low, y, window=w)
+    o = dv.filter_forward(low, y, window=(3, 3))      # empty window: nothing to do
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('smooth', [True, False])
+def test_time_streaming_driver_matches_device_evaluation(smooth):
+    """mc.filter_scores on HOST arrays (time-window pipeline: y forward, x backward, smoother chasing the copies) ==
+    forward_pass / backward_pass / evaluate_performance on device arrays == the trajectory-chunked fallback."""
+    from ssmtoybox_b200 import mc, utils as U, device as dv
+    import bench
+    alg, g = bench.build_filter()
+    M, N = 5000, 60
+    low, x, y = _sim(g, M, N, seed=11)
+    xh = torch.empty(x.shape, dtype=torch.float64).pin_memory().copy_(x)
+    yh = torch.empty(y.shape, dtype=torch.float64).pin_memory().copy_(y)
+    r1 = mc.filter_scores(alg, yh, xh, smooth=smooth, n_windows=7)
+    fwd = dv.filter_forward(low, y, store_pred=True)
+    if smooth:
+        sm = dv.smooth_backward(low.dx, fwd)
+        mean, cov, st = sm['sm_mean'], sm['sm_cov'], sm['status']
+    else:
+        mean, cov, st = fwd['fi_mean'], fwd['fi_cov'], fwd['status']
+    r2 = U.evaluate_performance(x, mean, cov, status=st)
+    r3 = mc.filter_scores(alg, yh, xh, smooth=smooth, n_chunks=3)
+    for r in (r2, r3):
+        assert rel(r1['rmse'], r['rmse']) < 1e-12
+        assert abs(r1['nll'] - r['nll']) < 1e-11 * abs(r['nll'])
+        assert abs(r1['nci'] - r['nci']) < 1e-10 * abs(r['nci']) + 1e-12
+        assert rel(r1['mse'], r['mse']) < 1e-12
+    assert (r1['status'] == 0).all()
+    # numpy in, device in: same numbers
+    r4 = mc.filter_scores(alg, yh.numpy(), xh.numpy(), smooth=smooth, n_windows=3)
+    r5 = mc.filter_scores(alg, y, x, smooth=smooth, n_windows=4)
+    for r in (r4, r5):
+        assert rel(r1['rmse'], r['rmse']) < 1e-12 and abs(r1['nci'] - r['nci']) < 1e-10 * abs(r['nci']) + 1e-12
+
+
+def test_time_streaming_driver_with_failures_falls_back_to_exact_scores():
+    """Trajectories that fail after they have contributed to the rows of an earlier window are excluded from every
+    row, like a one-pass evaluation (and like the reference, whose failing runs never reach the score loops)."""
+    from ssmtoybox_b200 import mc, utils as U, device as dv
+    import bench
+    alg, g = bench.build_filter()
+    M, N = 2000, 40
+    low, x, y = _sim(g, M, N, seed=5)
+    y[:, 25, 17] = float('nan')
+    y[:, 3, 900] = float('nan')
+    r1 = mc.filter_scores(alg, y.cpu().numpy(), x.cpu().numpy(), smooth=False, n_windows=4)
+    fwd = dv.filter_forward(low, y)
+    r2 = U.evaluate_performance(x, fwd['fi_mean'], fwd['fi_cov'], status=fwd['status'])
+    assert (r1['status'] != 0).sum() == 2 and r1['n_ok'] == M - 2
+    assert rel(r1['rmse'], r2['rmse']) < 1e-12 and abs(r1['nci'] - r2['nci']) < 1e-10 * abs(r2['nci']) + 1e-12
+    assert abs(r1['nll'] - r2['nll']) < 1e-11 * abs(r2['nll'])
