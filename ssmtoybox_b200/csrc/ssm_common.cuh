@@ -23,6 +23,16 @@ struct TriSize {
 SSM_DEV double ld_stream(const double *p) { return __ldcs(p); }
 SSM_DEV void st_stream(double *p, double v) { __stcs(p, v); }
 
+// Row pointer of a bulk array: base + (k * ld + t), computed once per array and step and made opaque to the
+// optimiser, which otherwise re-associates base + (rk + c * cs) into a 64-bit add plus a 64-bit scaled add (LEA
+// pair) per access.  With the row pointer pinned every access is `q + c * cs` = one add with a uniform operand.
+template <class T>
+SSM_DEV T *row_ptr(T *base, long long rk) {
+    T *q = base + rk;
+    asm volatile("" : "+l"(q));
+    return q;
+}
+
 SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // Out-of-line fp64 math.  The fused forward pass for the 5-D models is one straight-line body; with

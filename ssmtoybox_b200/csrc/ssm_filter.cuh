@@ -310,27 +310,23 @@ struct FilterPar {
     FilterBuffers b;
 };
 
+// Element (c, k, t) of a bulk array = base + rk + c * cs with rk = k * ld + t (per thread, once per step) and the
+// kernel-uniform component stride cs = n_steps * ld: one 64-bit add per access instead of a 64-bit multiply chain.
 template <int C>
-SSM_DEV void store_vec(double *base, long long n_steps, long long ld, int k, long long t, const double (&v)[C]) {
+SSM_DEV void store_vec(double *base, long long cs, long long rk, const double (&v)[C]) {
     if (!base) return;
+    double *q = row_ptr(base, rk);
 #pragma unroll
-    for (int c = 0; c < C; ++c) st_stream(base + ((long long)c * n_steps + k) * ld + t, v[c]);
+    for (int c = 0; c < C; ++c) st_stream(q + c * cs, v[c]);
 }
 template <int D>
-SSM_DEV void store_sym(double *base, long long n_steps, long long ld, int k, long long t, const double (&P)[TriSize<D>::value]) {
+SSM_DEV void store_sym(double *base, long long cs, long long rk, const double (&P)[TriSize<D>::value]) {
     if (!base) return;
+    double *q = row_ptr(base, rk);
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-        for (int c = 0; c < D; ++c) st_stream(base + ((long long)(r * D + c) * n_steps + k) * ld + t, P[sym(r, c)]);
-}
-template <int E, int D>
-SSM_DEV void store_mat(double *base, long long n_steps, long long ld, int k, long long t, const double (&M)[E][D]) {
-    if (!base) return;
-#pragma unroll
-    for (int r = 0; r < E; ++r)
-#pragma unroll
-        for (int c = 0; c < D; ++c) st_stream(base + ((long long)(r * D + c) * n_steps + k) * ld + t, M[r][c]);
+        for (int c = 0; c < D; ++c) st_stream(q + (r * D + c) * cs, P[sym(r, c)]);
 }
 SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, int k_from, int k_to, long long t) {
     if (!base) return;
@@ -365,6 +361,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     const FilterBuffers &b = p.b;
     const int N = b.n_steps;
     const long long ld = b.ld;
+    const long long cs = (long long)N * ld;  // component stride of the [component][step][trajectory] arrays
     constexpr int NSTATE = DX + TX + 2;
     __shared__ int s_ticket;
     // Ticket scheduling.  A trajectory is a 500-step serial recursion, so a plain launch is quantised in waves of
@@ -429,7 +426,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 
     double ynext[DY];
 #pragma unroll
-    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N + k_begin) * ld + t);
+    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + ((long long)k_begin * ld + t));
 
     for (int k = k_begin; k < k_end; ++k) {
         // The fully unrolled step body is ~140 KB of SASS, far beyond the instruction caches.  Re-aligning
@@ -437,12 +434,13 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         // from L2 serves all of them instead of one per warp (profiles/: stall_no_inst, fetch-bound).
         if (SYNC_STEPS) __syncthreads();
         if (fail) continue;
+        const long long rk = (long long)k * ld + t;  // row offset of step k (see store_vec)
         double yk[DY];
 #pragma unroll
         for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
         if (k + 1 < k_end) {
 #pragma unroll
-            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + ((long long)a * N + k + 1) * ld + t);
+            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + (rk + ld));
         }
         const double time = tbase + (double)k;  // the reference passes time = k - 1, k 1-based (ssinf.py:104)
 
@@ -456,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         // ---- time update: predictive state moments (ssinf.py:276-279 / 669-676) ----------------
         double mp[DX], Pp[TX];
         const bool want_xx = b.pr_xx != nullptr;
+        double *q_xx = b.pr_xx ? row_ptr(b.pr_xx, rk) : nullptr;
         bool ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT>(
             p.tf_dyn, m, P,
             [&](const double (&x)[DX], double (&o)[DX]) {
@@ -465,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             mp, Pp, want_xx,
             [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
 #pragma unroll
-                for (int c = 0; c < DX; ++c) st_stream(b.pr_xx + ((long long)(a * DX + c) * N + k) * ld + t, row[c]);
+                for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
             },
             sfx);
         if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; continue; }
@@ -474,16 +473,16 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 double Cp[TX];
 #pragma unroll
                 for (int a = 0; a < TX; ++a) Cp[a] = Pp[a] + p.GQG[a];  // x_cov_pr, ssinf.py:675
-                store_sym<DX>(b.pr_cov, N, ld, k, t, Cp);
+                store_sym<DX>(b.pr_cov, cs, rk, Cp);
             }
 #pragma unroll
             for (int a = 0; a < TX; ++a) Pp[a] = fma(scale, Pp[a], p.s0 * p.GQG[a]);  // x_smat_pr, ssinf.py:672, 676
         } else {
 #pragma unroll
             for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:279
-            store_sym<DX>(b.pr_cov, N, ld, k, t, Pp);
+            store_sym<DX>(b.pr_cov, cs, rk, Pp);
         }
-        store_vec<DX>(b.pr_mean, N, ld, k, t, mp);
+        store_vec<DX>(b.pr_mean, cs, rk, mp);
 
         // ---- predictive measurement moments (ssinf.py:287-291 / 684-693) ------------------------
         double my[DY], Sy[TY], Syx[DY][DX];
@@ -555,8 +554,8 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                     P[tri(r, c)] = Pp[tri(r, c)] - s;
                 }
         }
-        store_vec<DX>(b.fi_mean, N, ld, k, t, m);
-        store_sym<DX>(b.fi_cov, N, ld, k, t, P);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
+        store_vec<DX>(b.fi_mean, cs, rk, m);
+        store_sym<DX>(b.fi_cov, cs, rk, P);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
         if (FAMILY == SSM_FAMILY_STUDENT) {
             // delta = chol(Sy)^-1 e ; x_smat_fi = (dof + delta'delta) / (dof + dy) x_cov_fi   ssinf.py:731-733
             double dd = 0.0, z[DY];

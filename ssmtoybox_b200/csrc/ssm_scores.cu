@@ -21,10 +21,10 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     const int WLEN = k_hi - k_lo;
-    __shared__ double smem[(SC_THREADS / 32) * W];
+    __shared__ double smem[BlockReduce<W>::SIZE];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_traj && (status == nullptr || status[t] == 0);
-    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    const long long cs = (long long)N * ld;  // component stride (row_ptr, ssm_common.cuh)
     double se_acc[DX];
 #pragma unroll
     for (int a = 0; a < DX; ++a) se_acc[a] = (rmse_acc && k_lo > 0 && t < n_traj) ? rmse_acc[(long long)a * ld + t] : 0.0;
@@ -34,17 +34,19 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
         for (int i = 0; i < W; ++i) v[i] = 0.0;
         if (live) {
             double d[DX], P[TX], se[DX];
+            const long long rk = (long long)k * ld + t;
+            const double *qx = row_ptr(x, rk), *qm = row_ptr(mean, rk), *qc = row_ptr(cov, rk);
 #pragma unroll
-            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x + at(a, k)) - ld_stream(mean + at(a, k));
+            for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - ld_stream(qm + a * cs);
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(cov + at(r * DX + c, k));
+                for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
             score_step<DX>(d, P, v, se);
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
-        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
+        block_reduce_store<W>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
     }
     if (rmse_acc && t < n_traj) {
 #pragma unroll
@@ -85,21 +87,23 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value;
     const int WLEN = k_hi - k_lo;
-    __shared__ double smem[(SC_THREADS / 32) * 2];
+    __shared__ double smem[BlockReduce<2>::SIZE];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_traj && (status == nullptr || status[t] == 0);
-    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    const long long cs = (long long)N * ld;
     for (int k = k_lo; k < k_hi; ++k) {
         double v[2] = {0.0, 0.0};
         if (live) {
             double d[DX], P[TX], S[TX], L[TX], Ls[TX];
+            const long long rk = (long long)k * ld + t;
+            const double *qx = row_ptr(x, rk), *qm = row_ptr(mean, rk), *qc = row_ptr(cov, rk);
 #pragma unroll
-            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x + at(a, k)) - ld_stream(mean + at(a, k));
+            for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - ld_stream(qm + a * cs);
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
                 for (int c = 0; c <= r; ++c) {
-                    P[tri(r, c)] = ld_stream(cov + at(r * DX + c, k));
+                    P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
                     S[tri(r, c)] = __ldg(mse + (long long)(r * DX + c) * N + k);
                 }
             // log_cred_ratio, utils.py:113-120: both quadratic forms through Cholesky factors
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
             v[0] = g;
             v[1] = fabs(g);
         }
-        block_reduce_store<2>(v, smem, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * 2);
+        block_reduce_store<2>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * 2);
     }
 }
 

@@ -34,43 +34,62 @@ SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::va
 #pragma unroll
         for (int c = 0; c <= r; ++c) v[DX + tri(r, c)] = d[r] * d[c];
     // 0.5 (log|P| + d' P^-1 d + dx log 2 pi) through chol(P)
-    double L[TX];
-    const bool ok = chol_lower<DX>(P, L);
-    double logdet = 0.0, quad = 0.0, z[DX];
+    // One log per step: log|P| = 2 log(prod L_ii) (the product of DX <= 5 pivots cannot leave the double range for
+    // any covariance a filter produces), and the forward substitution multiplies by the reciprocal pivots that the
+    // factorisation already has.  A few ulp from the reference's slogdet / solve, far below the 1e-8 score tolerance.
+    double L[TX], inv[DX];
+    const bool ok = chol_lower<DX>(P, L, inv);
+    double pdiag = 1.0, quad = 0.0, z[DX];
 #pragma unroll
     for (int i = 0; i < DX; ++i) {
         double s = d[i];
 #pragma unroll
         for (int c = 0; c < i; ++c) s = fma(-L[tri(i, c)], z[c], s);
-        z[i] = s / L[tri(i, i)];
+        z[i] = s * inv[i];
         quad = fma(z[i], z[i], quad);
-        logdet += log(L[tri(i, i)]);
+        pdiag *= L[tri(i, i)];
     }
+    const double logdet = log(pdiag);
     v[DX + TX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
     v[DX + TX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
     v[DX + TX + 2] = 1.0;
 }
 
-// sum v[] over the CTA (warp shuffles, then one shared-memory pass in fixed order) and store the row
+// Sum v[] over the CTA and store the row.  The values are transposed through shared memory ([W][SC_THREADS + 1],
+// conflict-free stores), then four threads per row add 32 values each in a fixed rotated order and combine with two
+// shuffles: W stores + 32 loads/adds per thread instead of 5 W shuffle pairs (the shuffle tree was a fifth of the
+// smoother's instructions).  Two buffers alternate by step parity, so one barrier per step is enough: a buffer is
+// rewritten two steps later, after the barrier of the step in between.  Fixed order => bitwise reproducible.
 template <int W>
-SSM_DEV void block_reduce_store(double (&v)[W], double *smem /* [blockDim/32][W] */, double *dst) {
+struct BlockReduce {
+    static constexpr int LD = SC_THREADS + 1;
+    static constexpr int SIZE = 2 * W * LD;  // doubles of shared memory
+    static_assert(4 * W <= SC_THREADS, "four threads per row");
+};
+template <int W>
+SSM_DEV void block_reduce_store(const double (&v)[W], double *smem /* [BlockReduce<W>::SIZE] */, int parity, double *dst) {
+    constexpr int LD = BlockReduce<W>::LD;
+    double *buf = smem + (parity & 1) * (W * LD);
+    const int tid = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < W; ++i) smem[wid * W + i] = v[i];
-    }
+    for (int i = 0; i < W; ++i) buf[i * LD + tid] = v[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < W; i += blockDim.x) {
-        double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += smem[w * W + i];
-        dst[i] = s;
+    if ((tid & ~31) < 4 * W) {  // warp-uniform
+        const int row = tid >> 2, seg = tid & 3;
+        const double *src = buf + (row < W ? row : W - 1) * LD + seg * 32;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {  // element order rotated by 4 seg: the 16 lanes of a half-warp hit 16 banks
+            s0 += src[(i + 4 * seg) & 31];
+            s1 += src[(i + 1 + 4 * seg) & 31];
+            s2 += src[(i + 2 + 4 * seg) & 31];
+            s3 += src[(i + 3 + 4 * seg) & 31];
+        }
+        double s = (s0 + s1) + (s2 + s3);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (seg == 0 && row < W) dst[row] = s;
     }
-    __syncthreads();
 }
 
 // stats[i] = sum over CTAs (fixed order) of partial[cta][i]

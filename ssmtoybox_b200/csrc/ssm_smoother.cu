@@ -2,7 +2,9 @@
 // stored by the forward pass.  Pure small-matrix algebra on five streamed arrays: HBM-bound.
 // Replaces StateSpaceInference.backward_pass (ssinf.py:120-147) and
 // GaussianInference._smoothing_update (ssinf.py:325-344).
-#include "ssm_scores.cuh"
+#include <stdlib.h>
+
+#include "ssm_smoother_tma.cuh"
 
 namespace ssm {
 
@@ -24,12 +26,16 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     // windows from the last to the first reproduces the one-pass result bit for bit.
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     const int WLEN = k_hi - k_lo;
-    __shared__ double smem[SCORE ? (SC_THREADS / 32) * W : 1];
+    __shared__ double smem[SCORE ? BlockReduce<W>::SIZE : 1];
     const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = t_raw < n_traj;
     if (!SCORE && !in_range) return;
     const long long t = in_range ? t_raw : n_traj - 1;   // idle lanes of the last CTA only take part in the reductions
-    auto at = [&](int c, int k) { return ((long long)c * N + k) * ld + t; };
+    // element (c, k, t) = row(k) + c * cs: per-thread row offset + kernel-uniform component stride, so an access
+    // costs one 64-bit add instead of the 64-bit multiply chain of ((c * N + k) * ld + t)
+    const long long cs = (long long)N * ld;
+    auto row = [&](int k) { return (long long)k * ld + t; };
+    auto at = [&](int c, int k) { return c * cs + row(k); };
     double se_acc[DX];
 #pragma unroll
     for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? rmse_acc[(long long)a * ld + t] : 0.0;
@@ -46,7 +52,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
-        block_reduce_store<W>(v, smem, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
+        block_reduce_store<W>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
     };
     bool alive = in_range && status[t] == 0;
     if (in_range && !alive) {  // the forward pass failed: nothing to smooth
@@ -98,19 +104,22 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
       do {
         if (!alive) break;
         double mp[DX], Pp[TX], Pxx[DX][DX], mf[DX], Pf[TX];
+        const long long rk = row(k);
+        const double *q_pm = row_ptr(pr_mean, rk + ld), *q_pc = row_ptr(pr_cov, rk + ld), *q_px = row_ptr(pr_xx, rk + ld);
+        const double *q_fm = row_ptr(fi_mean, rk), *q_fc = row_ptr(fi_cov, rk);
 #pragma unroll
         for (int a = 0; a < DX; ++a) {
-            mp[a] = ld_stream(pr_mean + at(a, k + 1));
-            mf[a] = ld_stream(fi_mean + at(a, k));
+            mp[a] = ld_stream(q_pm + a * cs);
+            mf[a] = ld_stream(q_fm + a * cs);
         }
 #pragma unroll
         for (int r = 0; r < DX; ++r)
 #pragma unroll
             for (int c = 0; c < DX; ++c) {
-                Pxx[r][c] = ld_stream(pr_xx + at(r * DX + c, k + 1));
+                Pxx[r][c] = ld_stream(q_px + (r * DX + c) * cs);
                 if (c <= r) {
-                    Pp[tri(r, c)] = ld_stream(pr_cov + at(r * DX + c, k + 1));
-                    Pf[tri(r, c)] = ld_stream(fi_cov + at(r * DX + c, k));
+                    Pp[tri(r, c)] = ld_stream(q_pc + (r * DX + c) * cs);
+                    Pf[tri(r, c)] = ld_stream(q_fc + (r * DX + c) * cs);
                 }
             }
         // scipy's cho_factor / cho_solve reject non-finite input (ValueError)        ssinf.py:342
@@ -158,12 +167,13 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                 for (int e = 0; e < DX; ++e) s = fma(T[r][e], Dg[c][e], s);
                 Ps[tri(r, c)] = Pf[tri(r, c)] + s;
             }
+        double *q_sm = row_ptr(sm_mean, rk), *q_sc = row_ptr(sm_cov, rk);
 #pragma unroll
-        for (int a = 0; a < DX; ++a) st_stream(sm_mean + at(a, k), ms[a]);
+        for (int a = 0; a < DX; ++a) st_stream(q_sm + a * cs, ms[a]);
 #pragma unroll
         for (int r = 0; r < DX; ++r)
 #pragma unroll
-            for (int c = 0; c < DX; ++c) st_stream(sm_cov + at(r * DX + c, k), Ps[sym(r, c)]);
+            for (int c = 0; c < DX; ++c) st_stream(q_sc + (r * DX + c) * cs, Ps[sym(r, c)]);
       } while (0);
         if (SCORE) score(k, alive, ms, Ps);
     }
@@ -180,26 +190,57 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     }
 }
 
+template <int DX, bool SCORE>
+static cudaError_t launch_tma(const SmootherArgs &a, long long n_full, cudaStream_t s) {
+    using Lay = SmootherTmaLayout<DX, SCORE>;
+    auto kern = smoother_tma_kernel<DX, SCORE>;
+    static bool configured = false;
+    if (!configured) {  // all of the SM's L1/shared array as shared memory: 7 resident warp-CTAs for DX = 5
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (Lay::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::SMEM);
+        configured = true;
+    }
+    kern<<<(unsigned)n_full, 32, Lay::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int DX>
 static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
                            const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, const double *x_truth,
                            double *stats, double *rmse_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
-    const long long blocks = (n_traj + SC_THREADS - 1) / SC_THREADS;
     const int WLEN = k_hi - k_lo;
-    if (!x_truth) {
-        smoother_kernel<DX, false><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean,
-                                                                          sm_cov, status, nullptr, nullptr, nullptr, n_traj, N, k_lo, k_hi, ld);
-        return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
-    }
+    SmootherArgs a{fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, nullptr, rmse_acc, ld, N, k_lo, k_hi};
+    // TMA path: warp-CTAs over the full blocks of 32 trajectories; the ragged tail (and unaligned problems) take the
+    // per-thread ld/st kernel.  Both write partial statistics rows that one finalise kernel sums in block order.
+    const long long n_full = smoother_tma_eligible(a, n_traj) ? n_traj / 32 : 0;
+    const long long t_tail = n_full * 32, rem = n_traj - t_tail;
+    const long long tail_blocks = (rem + SC_THREADS - 1) / SC_THREADS;
     constexpr int W = ScoreRow<DX>::WP;
     double *partial = nullptr;
-    if (cudaMallocAsync(&partial, (size_t)blocks * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
-    smoother_kernel<DX, true><<<(unsigned)blocks, SC_THREADS, 0, s>>>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov,
-                                                                     status, x_truth, partial, rmse_acc, n_traj, N, k_lo, k_hi, ld);
-    const long long row = (long long)WLEN * W;
-    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, (int)blocks, WLEN, DX);
-    const cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(partial, s);
+    if (x_truth && cudaMallocAsync(&partial, (size_t)(n_full + tail_blocks) * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    a.partial = partial;
+    cudaError_t e = cudaSuccess;
+    if (n_full) e = x_truth ? launch_tma<DX, true>(a, n_full, s) : launch_tma<DX, false>(a, n_full, s);
+    if (rem && e == cudaSuccess) {
+        auto off = [&](const double *p) { return p ? p + t_tail : nullptr; };
+        auto offw = [&](double *p) { return p ? p + t_tail : nullptr; };
+        if (x_truth)
+            smoother_kernel<DX, true><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
+                off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
+                off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), rem, N, k_lo, k_hi, ld);
+        else
+            smoother_kernel<DX, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
+                off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
+                nullptr, nullptr, nullptr, rem, N, k_lo, k_hi, ld);
+        e = cudaGetLastError();
+    }
+    if (x_truth) {
+        const long long row = (long long)WLEN * W;
+        scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W,
+                                                                                    (int)(n_full + tail_blocks), WLEN, DX);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        cudaFreeAsync(partial, s);
+    }
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
