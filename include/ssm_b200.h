@@ -261,6 +261,25 @@ int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, co
                              const int32_t *status, const double *mse, double *lcr,
                              int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
+/* Same two passes with per-trajectory time-sums next to the per-step sums: nll_acc (ld, nullable) = sum over the
+ * window of the negative log-likelihood of each trajectory, lcr_acc (ld, nullable) = sum of its log credibility
+ * ratios (continued when k_lo > 0; the caller zeroes them before a window that does not start at 0 -- e.g. [1, N)
+ * for the research tables, which skip k = 0).  These are the per-simulation nllData / nciData of
+ * evaluate_performance (research/gpq/icinco_demo.py:28-48, research/bsq/bsq_ungm.py:38-58) that feed bootstrap_var. */
+int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, const double *cov,
+                           const int32_t *status, double *stats, double *rmse_acc, double *nll_acc,
+                           int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov,
+                           const int32_t *status, const double *mse, double *lcr, double *lcr_acc,
+                           int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+
+/* ---- bootstrap variance of a sample mean -------------------------------------------------------
+ * Replaces utils.bootstrap_var (utils.py:223-244): var[0] = population variance of the means of n_boot resamples
+ * (with replacement, size n) of data (n, device).  means (n_boot, device) is caller-provided scratch that returns
+ * the resample means.  Philox-keyed by (seed, resample index): deterministic for a given seed. */
+int ssm_bootstrap_var(const double *data, int64_t n, int32_t n_boot, uint64_t seed, double *means, double *var,
+                      void *stream);
+
 /* ---- stand-alone moment transform / model evaluation -----------------------------------------
  * ssm_transform_apply replaces MomentTransform.apply(f, mean, cov, fcn_pars) as a public call
  * (mtran.py:105-149, bq/bqmtran.py:60-109) for n (mean, cov) pairs: mean (D, ld), cov (D*D, ld) ->

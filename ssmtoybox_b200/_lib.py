@@ -72,6 +72,12 @@ def _load():
     lib.ssm_scores_phase1_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase2_window.restype = C.c_int
     lib.ssm_scores_phase2_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase1_traj.restype = C.c_int
+    lib.ssm_scores_phase1_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase2_traj.restype = C.c_int
+    lib.ssm_scores_phase2_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_bootstrap_var.restype = C.c_int
+    lib.ssm_bootstrap_var.argtypes = [vp, i64, i32, C.c_uint64, vp, vp, vp]
     lib.ssm_smooth.restype = C.c_int
     lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     lib.ssm_fp64_peak_kernel.restype = C.c_int

@@ -18,6 +18,7 @@ template <int DX>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    double *__restrict__ partial, double *__restrict__ rmse_acc,
+                                                                   double *__restrict__ nll_acc,
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     const int WLEN = k_hi - k_lo;
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
     double se_acc[DX];
 #pragma unroll
     for (int a = 0; a < DX; ++a) se_acc[a] = (rmse_acc && k_lo > 0 && t < n_traj) ? rmse_acc[(long long)a * ld + t] : 0.0;
+    // per-trajectory time-sum of the NLL (the nllData of research/gpq/icinco_demo.py:28-48 before its time mean)
+    double nll_sum = (nll_acc && k_lo > 0 && t < n_traj) ? nll_acc[t] : 0.0;
     for (int k = k_lo; k < k_hi; ++k) {
         double v[W];
 #pragma unroll
@@ -45,6 +48,7 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
             score_step<DX>(d, P, v, se);
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
+            nll_sum += v[DX + TX];
         }
         block_reduce_store<W>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
     }
@@ -52,6 +56,7 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
 #pragma unroll
         for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = live ? se_acc[a] : qnan();
     }
+    if (nll_acc && t < n_traj) nll_acc[t] = live ? nll_sum : qnan();
 }
 
 __global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row) {
@@ -84,6 +89,7 @@ template <int DX>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    const double *__restrict__ mse, double *__restrict__ partial,
+                                                                   double *__restrict__ lcr_acc,
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value;
     const int WLEN = k_hi - k_lo;
@@ -91,6 +97,8 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_traj && (status == nullptr || status[t] == 0);
     const long long cs = (long long)N * ld;
+    // per-trajectory time-sum of the log credibility ratio (nciData of research/gpq/icinco_demo.py:36-47)
+    double lcr_sum = (lcr_acc && k_lo > 0 && t < n_traj) ? lcr_acc[t] : 0.0;
     for (int k = k_lo; k < k_hi; ++k) {
         double v[2] = {0.0, 0.0};
         if (live) {
@@ -125,20 +133,22 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
             const double g = ok ? 10.0 * (log10(qa) - log10(qb)) : qnan();
             v[0] = g;
             v[1] = fabs(g);
+            lcr_sum += g;
         }
         block_reduce_store<2>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * 2);
     }
+    if (lcr_acc && t < n_traj) lcr_acc[t] = live ? lcr_sum : qnan();
 }
 
 template <int DX>
 static int run_phase1(const double *x, const double *mean, const double *cov, const int32_t *status, double *stats,
-                      double *rmse_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+                      double *rmse_acc, double *nll_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     constexpr int W = ScoreRow<DX>::WP;
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
     double *partial = nullptr;
     if (cudaMallocAsync(&partial, (size_t)n_cta * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
-    scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, n_traj, N, k_lo, k_hi, ld);
+    scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, nll_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * W;
     scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, n_cta, WLEN, DX);
     const cudaError_t e = cudaGetLastError();
@@ -148,12 +158,12 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
 
 template <int DX>
 static int run_phase2(const double *x, const double *mean, const double *cov, const int32_t *status, const double *mse,
-                      double *lcr, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+                      double *lcr, double *lcr_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
     double *partial = nullptr;
     if (cudaMallocAsync(&partial, (size_t)n_cta * WLEN * 2 * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
-    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, mse, partial, n_traj, N, k_lo, k_hi, ld);
+    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, mse, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * 2;
     scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);
     const cudaError_t e = cudaGetLastError();
@@ -167,22 +177,28 @@ using namespace ssm;
 
 extern "C" int32_t ssm_scores_width(int32_t dx) { return dx + dx * dx + 3; }
 
-extern "C" int ssm_scores_phase1_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
-                                        double *stats, double *rmse_acc, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi,
-                                        int64_t ld, void *stream) {
+extern "C" int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                      double *stats, double *rmse_acc, double *nll_acc, int64_t n_traj, int32_t n_steps,
+                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!x || !mean || !cov || !stats) { set_error("ssm_scores_phase1: NULL buffer"); return SSM_E_INVALID; }
     if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase1: bad sizes"); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi <= k_lo || k_hi > n_steps) { set_error("ssm_scores_phase1: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase1: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_scores_phase1_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                        double *stats, double *rmse_acc, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi,
+                                        int64_t ld, void *stream) {
+    return ssm_scores_phase1_traj(dx, x, mean, cov, status, stats, rmse_acc, nullptr, n_traj, n_steps, k_lo, k_hi, ld, stream);
 }
 
 extern "C" int ssm_scores_phase1(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
@@ -191,22 +207,28 @@ extern "C" int ssm_scores_phase1(int32_t dx, const double *x, const double *mean
 }
 
 // lcr: (n_steps, 2) = per step [ sum of log credibility ratios | sum of their absolute values ]
-extern "C" int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
-                                        const double *mse, double *lcr, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi,
-                                        int64_t ld, void *stream) {
+extern "C" int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                      const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!x || !mean || !cov || !mse || !lcr) { set_error("ssm_scores_phase2: NULL buffer"); return SSM_E_INVALID; }
     if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase2: bad sizes"); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi <= k_lo || k_hi > n_steps) { set_error("ssm_scores_phase2: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = run_phase2<1>(x, mean, cov, status, mse, lcr, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 2: rc = run_phase2<2>(x, mean, cov, status, mse, lcr, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 5: rc = run_phase2<5>(x, mean, cov, status, mse, lcr, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 1: rc = run_phase2<1>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = run_phase2<2>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = run_phase2<5>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase2: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                        const double *mse, double *lcr, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi,
+                                        int64_t ld, void *stream) {
+    return ssm_scores_phase2_traj(dx, x, mean, cov, status, mse, lcr, nullptr, n_traj, n_steps, k_lo, k_hi, ld, stream);
 }
 
 extern "C" int ssm_scores_phase2(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,

@@ -331,10 +331,11 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
 # ------------------------------------------------------------------------------------------------
 # K6: scores
 # ------------------------------------------------------------------------------------------------
-def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None):
+def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None, nll_acc=None):
     """Per-step packed statistics over trajectories: stats (N, W), W = dx + dx*dx + 3:
     [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE.
-    window = (k_lo, k_hi) fills only those rows of out = (stats, rmse_acc) (walk the windows first to last)."""
+    window = (k_lo, k_hi) fills only those rows of out = (stats, rmse_acc) (walk the windows first to last).
+    nll_acc (M,): optional per-trajectory time-sum of the NLL (continued, not reset, when k_lo > 0)."""
     dx, N, M = x.shape
     W = lib.ssm_scores_width(dx)
     if out is not None:
@@ -343,17 +344,29 @@ def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, ou
         stats = torch.empty((N, W), dtype=torch.float64, device=x.device)
         acc = torch.empty((dx, M), dtype=torch.float64, device=x.device) if want_rmse_acc else None
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
-    rc = lib.ssm_scores_phase1_window(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), M, N, k_lo, k_hi, M, _stream())
+    rc = lib.ssm_scores_phase1_traj(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), _p(nll_acc), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase1')
     return stats, acc
 
 
-def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None):
+def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None, lcr_acc=None):
     """Per-step sums of the log credibility ratio and of its absolute value: (N, 2).  mse (dx, dx, N).
-    window = (k_lo, k_hi) fills only those rows of out (N, 2) and reads only those columns of mse."""
+    window = (k_lo, k_hi) fills only those rows of out (N, 2) and reads only those columns of mse.
+    lcr_acc (M,): optional per-trajectory time-sum of the ratio (continued, not reset, when k_lo > 0)."""
     dx, N, M = x.shape
     lcr = out if out is not None else torch.empty((N, 2), dtype=torch.float64, device=x.device)
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
-    rc = lib.ssm_scores_phase2_window(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), M, N, k_lo, k_hi, M, _stream())
+    rc = lib.ssm_scores_phase2_traj(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), _p(lcr_acc), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase2')
     return lcr
+
+
+def bootstrap_var(data, samples=1000, seed=0):
+    """Bootstrap variance of the mean of `data` (any shape, squeezed to 1-D like utils.py:236), on the device:
+    returns a 0-d device tensor.  Deterministic for a given seed (Philox keyed by (seed, resample index))."""
+    d = data.reshape(-1).contiguous()
+    means = torch.empty(int(samples), dtype=torch.float64, device=d.device)
+    var = torch.empty(1, dtype=torch.float64, device=d.device)
+    rc = lib.ssm_bootstrap_var(_p(d), d.numel(), int(samples), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(means), _p(var), _stream())
+    _lib.check(rc, 'ssm_bootstrap_var')
+    return var[0]

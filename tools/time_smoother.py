@@ -24,8 +24,8 @@ s1 = t(lambda: dv.scores_phase1(x, sm['sm_mean'], sm['sm_cov'], sm['status']))
 st, acc = dv.scores_phase1(x, sm['sm_mean'], sm['sm_cov'], sm['status'])
 mse = (st[:, 5:30] / st[:, -1:]).T.reshape(5, 5, N).contiguous()
 s2 = t(lambda: dv.scores_phase2(x, sm['sm_mean'], sm['sm_cov'], mse, sm['status']))
-print('TMA=%s M=%d N=%d  smoother %.2f/%.2f ms  smoother+scores %.2f/%.2f ms  phase1 %.2f/%.2f  phase2 %.2f/%.2f  (min/median)' % (
-    os.environ.get('SSM_SMOOTH_TMA', '1'), M, N, *a, *b, *s1, *s2))
+print('TMA=%s PF=%s MINB=%s M=%d N=%d  smoother %.2f/%.2f ms  smoother+scores %.2f/%.2f ms  phase1 %.2f/%.2f  phase2 %.2f/%.2f  (min/median)' % (
+    os.environ.get('SSM_SMOOTH_TMA', '0'), os.environ.get('SSM_SMOOTH_PF', '1'), os.environ.get('SSM_SMOOTH_MINB', '2'), M, N, *a, *b, *s1, *s2))
 print('fails', int((sm['status'] != 0).sum()), 'checksum %.17g %.17g' % (sm['sm_mean'].double().sum().item(), sm['sm_cov'].double().sum().item()),
       'stats %.17g' % sm2['stats'].sum().item(), 'eq', torch.equal(sm['sm_mean'], sm2['sm_mean']), torch.equal(sm['sm_cov'], sm2['sm_cov']),
       'stats vs phase1 rel %.2e' % ((sm2['stats'] - st).abs().max() / st.abs().max()).item())
