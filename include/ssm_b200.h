@@ -56,9 +56,11 @@ extern "C" {
 #define SSM_DYN_PENDULUM  2  /* Pendulum2DTransition.dyn_fcn        ssmod.py:357-358  par[0] = dt                 */
 #define SSM_DYN_REENTRY   3  /* ReentryVehicle2DTransition.dyn_fcn  ssmod.py:530-564  par[0] = dt                 */
 #define SSM_DYN_COORDTURN 4  /* CoordinatedTurnTransition.dyn_fcn   ssmod.py:675-690  par[0] = dt                 */
+#define SSM_DYN_REENTRY1D 5  /* ReentryVehicle1DTransition.dyn_fcn  ssmod.py:418-421  par[0] = dt                 */
 #define SSM_OBS_UNGM      1  /* UNGMMeasurement.meas_fcn            ssmod.py:1060-1061                            */
 #define SSM_OBS_PENDULUM  2  /* Pendulum2DMeasurement.meas_fcn      ssmod.py:1114-1115                            */
 #define SSM_OBS_RADAR     3  /* Radar2DMeasurement.meas_fcn         ssmod.py:1227-1252 par[0..1] = radar_loc      */
+#define SSM_OBS_RANGE     4  /* RangeMeasurement.meas_fcn           ssmod.py:1146-1148 par[0..1] = (sx, sy)       */
 
 /* ---- moment-transform kinds ---------------------------------------------------------------- */
 #define SSM_TF_SP 1  /* sigma-point rule, centred form, diagonal Wc   SigmaPointTransform.apply mtran.py:105-149   */

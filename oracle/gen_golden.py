@@ -98,6 +98,8 @@ def model_dict(dyn, obs):
     d['G'] = dyn.noise_gain
     d['state_index'] = np.asarray(obs.state_index if obs.state_index is not None else [], dtype=np.int64)
     d['radar_loc'] = np.asarray(getattr(obs, 'radar_loc', [0.0, 0.0]), dtype=float)
+    if hasattr(obs, 'sx'):  # RangeMeasurement: the sensor position (ssmod.py:1143-1144) travels in the same slot
+        d['radar_loc'] = np.array([float(obs.sx), float(obs.sy)])
     st = dyn.init_rv.get_stats()
     d['m0'], d['P0'] = st[0], st[1]
     d['q_mean'], d['q_cov'] = dyn.noise_rv.get_stats()[:2]
@@ -238,6 +240,19 @@ def coordinated_turn(steps, mc, student=False, dt=0.1):
     return dyn_s, obs_s, x, y
 
 
+def reentry1d(steps, mc):
+    """research/gpq/gpq_tracking.py:135-166: vertically falling body + range sensor, truth by Euler-Maruyama at the
+    filter's own step, mis-specified ballistic coefficient in the filter model, zero process noise."""
+    tau = 0.1
+    P0 = np.diag([0.0929, 1.4865, 1e-4])
+    sysm = ssmod.ReentryVehicle1DTransition(GaussRV(3, np.array([90, 6, 1.5]), P0), GaussRV(3, cov=np.zeros((3, 3))), dt=tau)
+    x = sysm.simulate_continuous(steps * tau, mc_sims=mc)
+    obs = ssmod.RangeMeasurement(GaussRV(1, cov=np.array([[0.03048 ** 2]])), 3)
+    y = obs.simulate_measurements(x)
+    dyn = ssmod.ReentryVehicle1DTransition(GaussRV(3, np.array([90, 6, 1.7]), P0), GaussRV(3, cov=np.zeros((3, 3))), dt=tau)
+    return dyn, obs, x[:, :steps], y[:, :steps]
+
+
 MUL_UT = lambda d: np.hstack((np.zeros((d, 1)), np.eye(d), 2 * np.eye(d))).astype(int)  # noqa: E731
 
 
@@ -318,6 +333,34 @@ def gen_filters():
                 x[..., :2], y[..., :2], smooth=False)
     filter_case('c4_ct_fsstudent_deg5', ssinf.FullySymmetricStudent(dyn_s, obs_s, degree=5, dof=6.0),
                 x[..., :1], y[..., :1], smooth=False)
+
+
+def gen_reentry1d():
+    """C6: ReentryVehicle1DTransition + RangeMeasurement, the second tracking experiment of the GPQ paper
+    (research/gpq/gpq_tracking.py:114-176): GPQKF with its kernel parameters and the UKF, + RTS smoother."""
+    np.random.seed(2)
+    dyn, obs, x, y = reentry1d(300, 4)
+    kd, ko = np.array([[0.5, 10, 10, 10]]), np.array([[0.5, 15, 20, 20]])
+    filter_case('c6_reentry1d_gpq', ssinf.GaussianProcessKalman(dyn, obs, kd, ko, kernel='rbf', points='ut'), x, y)
+    filter_case('c6_reentry1d_ukf', ssinf.UnscentedKalman(dyn, obs), x[..., :2], y[..., :2])
+    # simulators with injected noise (ssmod.py:168-244, 1011-1039), process noise switched on to exercise its path
+    rng = np.random.RandomState(12)
+    steps, mc, dt = 40, 3, 0.1
+    dyn = ssmod.ReentryVehicle1DTransition(GaussRV(3, np.array([90, 6, 1.5]), np.diag([0.0929, 1.4865, 1e-4])),
+                                           GaussRV(3, cov=np.diag([1e-4, 1e-4, 1e-6])), dt=dt)
+    x0 = dyn.init_rv.mean[:, None] + rng.randn(3, mc) * 0.1
+    q = rng.randn(3, steps, mc) * np.sqrt(np.diag(dyn.noise_rv.cov))[:, None, None]
+    qc = rng.randn(3, steps + 1, mc) * np.sqrt(np.diag(dyn.noise_rv.cov))[:, None, None]
+    r = rng.randn(1, steps, mc) * 0.03048
+    dyn.init_rv = InjectedRV(dyn.init_rv, [x0, x0])
+    dyn.noise_rv = InjectedRV(dyn.noise_rv, [q, qc])
+    obs.noise_rv = InjectedRV(obs.noise_rv, [r])
+    xd = dyn.simulate_discrete(steps, mc_sims=mc)
+    xc = dyn.simulate_continuous(duration=steps * dt, dt=dt, mc_sims=mc)
+    yd = obs.simulate_measurements(xd)
+    d = {'x0': x0, 'q': q, 'qc': qc, 'r': r, 'x': xd, 'xc': xc, 'y': yd, 'dtc': np.asarray(dt)}
+    d.update(model_dict(dyn, obs))
+    save('simulation_reentry1d', **d)
 
 
 def gen_weights():
@@ -441,7 +484,7 @@ def gen_scores():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    gen_filters()
-    gen_weights()
-    gen_simulation()
-    gen_scores()
+    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'weights': gen_weights, 'simulation': gen_simulation,
+            'scores': gen_scores}
+    for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
+        sets[name]()

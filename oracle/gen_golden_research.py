@@ -217,8 +217,63 @@ def gen_tpq_base(steps=30, mc=6):
          kern_par_dyn=kd, kern_par_obs=ko)
 
 
+def gen_gpq_tracking(mc=6):
+    """Scores behind the plots of gpq_tracking.py:72-111 and :178-313.  The two demo functions only plot and print,
+    so their filter loops and score loops run here on the reference's classes / utils, at a reduced size."""
+    from gen_golden import reentry1d
+    # --- reentry_simple_gpq_demo
+    np.random.seed(4)
+    dyn, obs, x, y = reentry1d(100, mc)
+    kd, ko = np.array([[0.5, 10, 10, 10]]), np.array([[0.5, 15, 20, 20]])
+    alg = (ssinf.GaussianProcessKalman(dyn, obs, kd, ko, kernel='rbf', points='ut'), ssinf.UnscentedKalman(dyn, obs))
+    mean, cov, _, _ = run_all(alg, y, smooth=False)
+    d, steps, _ = x.shape
+    err2 = np.zeros((d, steps, mc, 2))
+    lcr = np.zeros((d, steps, mc, 2))
+    for a in range(2):
+        for k in range(steps):
+            for i in range(d):
+                M = mse_matrix(x[i, None, k, :], mean[i, None, k, :, a])
+                for s in range(mc):
+                    lcr[i, k, s, a] = log_cred_ratio(x[i, k, s], mean[i, k, s, a], cov[i, i, k, s, a], M)
+            for s in range(mc):
+                err2[:, k, s, a] = squared_error(x[:, k, s], mean[:, k, s, a])
+    out = {'simple_x': x, 'simple_y': y, 'simple_mean': mean, 'simple_cov': cov,
+           'simple_avg_rmse': np.sqrt(err2.sum(axis=0)).mean(axis=(0, 1))}
+    for i, nm in enumerate(('pos', 'vel', 'theta')):
+        out['simple_' + nm + '_rmse_vs_time'] = np.sqrt(err2[i]).mean(axis=1)
+        out['simple_' + nm + '_inc_vs_time'] = lcr[i].mean(axis=1)
+    # --- reentry_gpq_demo (5-D): its own models (gpq_tracking.py:14-44), 60 steps
+    np.random.seed(5)
+    disc_tau = 0.1
+    m0 = np.array([6500.4, 349.14, -1.8093, -6.7967, 0.6932])
+    Q = np.diag([2.4064e-5, 2.4064e-5, 0])
+    sysm = ssmod.ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0])), GaussRV(3, cov=Q), dt=disc_tau)
+    obs = ssmod.Radar2DMeasurement(GaussRV(2, cov=np.diag([1e-6, 0.17e-6])), 5, radar_loc=np.array([sysm.R0, 0]))
+    x = sysm.simulate_continuous(duration=6, dt=disc_tau, mc_sims=mc)
+    y = obs.simulate_measurements(x)
+    m0 = np.array([6500.4, 349.14, -1.8093, -6.7967, 0])
+    dyn = ssmod.ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 1])), GaussRV(3, cov=disc_tau * Q), dt=disc_tau)
+    hdyn, hobs = np.array([[1.0, 25, 25, 25, 25, 25]]), np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
+    alg = (ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut'), ssinf.UnscentedKalman(dyn, obs))
+    mean, cov, _, _ = run_all(alg, y, smooth=False)
+    d, steps, _ = x.shape
+    err2, lcr = np.zeros((d, steps, mc, 2)), np.zeros((steps, mc, 2))
+    for a in range(2):
+        for k in range(steps):
+            M = mse_matrix(x[:4, k, :], mean[:4, k, :, a])
+            for s in range(mc):
+                err2[:, k, s, a] = squared_error(x[:, k, s], mean[:, k, s, a])
+                lcr[k, s, a] = log_cred_ratio(x[:4, k, s], mean[:4, k, s, a], cov[:4, :4, k, s, a], M)
+    out.update({'x': x, 'y': y, 'mean': mean, 'cov': cov, 'pos_rmse_vs_time': np.sqrt(err2[:2].sum(axis=0)).mean(axis=1),
+                'inc_ind_vs_time': lcr.mean(axis=1), 'dyn_wm': alg[0].tf_dyn.wm, 'dyn_Wc': alg[0].tf_dyn.Wc, 'dyn_Wcc': alg[0].tf_dyn.Wcc,
+                'obs_wm': alg[0].tf_obs.wm, 'obs_Wc': alg[0].tf_obs.Wc, 'obs_Wcc': alg[0].tf_obs.Wcc,
+                'dyn_model_var': np.asarray(alg[0].tf_dyn.model.model_var), 'obs_model_var': np.asarray(alg[0].tf_obs.model.model_var)})
+    save('research_gpq_tracking', **out)
+
+
 if __name__ == '__main__':
     cases = {'icinco_tables': gen_icinco_tables, 'icinco_hypers': gen_icinco_hypers, 'bsq_ungm_tables': gen_bsq_ungm_tables,
-             'bsq_reentry_demo': gen_bsq_reentry_demo, 'tpq_base': gen_tpq_base}
+             'bsq_reentry_demo': gen_bsq_reentry_demo, 'tpq_base': gen_tpq_base, 'gpq_tracking': gen_gpq_tracking}
     for name in (sys.argv[1:] or list(cases)):   # optional: only the named cases
         cases[name]()

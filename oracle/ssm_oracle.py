@@ -373,6 +373,10 @@ def dyn_fcn(name, x, q, time, dt):
                          xp[2] + dt * (D * xp[2] + G * xp[0]) + q[0],
                          xp[3] + dt * (D * xp[3] + G * xp[1]) + q[1],
                          xp[4] + q[2]])
+    if name == 'ReentryVehicle1DTransition':  # ssmod.py:418-421, Gamma = 1 / 6.096 (ssmod.py:416)
+        return np.stack([xp[0] - dt * xp[1] + q[0],
+                         xp[1] - dt * np.exp(-(1 / 6.096) * xp[0]) * xp[1] ** 2 * xp[2] + q[1],
+                         xp[2] + q[2]])
     if name == 'CoordinatedTurnTransition':  # ssmod.py:675-690 (no omega == 0 guard: NaN, Q11)
         om = xp[4]
         with np.errstate(all='ignore'):
@@ -400,6 +404,8 @@ def dyn_fcn_cont(name, x, q, time):
         D = b * np.exp((c['R0'] - R) / c['H0']) * V
         G = -c['Gm0'] / R ** 3
         return np.stack([x[2], x[3], D * x[2] + G * x[0] + q[0], D * x[3] + G * x[1] + q[1], q[2] + 0 * x[4]])
+    if name == 'ReentryVehicle1DTransition':  # ssmod.py:423-426
+        return np.stack([-x[1] + q[0], -np.exp(-(1 / 6.096) * x[0]) * x[1] ** 2 * x[2] + q[1], q[2] + 0 * x[2]])
     raise NotImplementedError(name)
 
 
@@ -411,6 +417,8 @@ def meas_fcn(name, x, r, time, radar_loc=(0.0, 0.0)):
         return (0.05 * x[0] ** 2 + r[0])[None]
     if name == 'Pendulum2DMeasurement':  # ssmod.py:1114-1115
         return (np.sin(x[0]) + r[0])[None]
+    if name == 'RangeMeasurement':  # ssmod.py:1146-1148; (sx, sy) travels in radar_loc
+        return (np.sqrt(radar_loc[0] ** 2 + (x[0] - radar_loc[1]) ** 2) + r[0])[None]
     if name == 'Radar2DMeasurement':  # ssmod.py:1227-1252
         rng = np.sqrt((x[0] - radar_loc[0]) ** 2 + (x[1] - radar_loc[1]) ** 2)
         theta = np.arctan2((x[1] - radar_loc[1]), (x[0] - radar_loc[0]))

@@ -17,8 +17,8 @@ c_int32_p = C.POINTER(C.c_int32)
 SSM_OK, SSM_E_INVALID, SSM_E_UNSUPPORTED, SSM_E_CUDA = 0, -1, -2, -3
 FAIL_CHOL_DYN, FAIL_CHOL_OBS, FAIL_CHOL_GAIN, FAIL_NONFINITE_GAIN, FAIL_CHOL_SMOOTH = 1, 2, 3, 4, 5
 DYN_IDS = {'UNGMTransition': 1, 'Pendulum2DTransition': 2, 'ReentryVehicle2DTransition': 3,
-           'CoordinatedTurnTransition': 4}
-OBS_IDS = {'UNGMMeasurement': 1, 'Pendulum2DMeasurement': 2, 'Radar2DMeasurement': 3}
+           'CoordinatedTurnTransition': 4, 'ReentryVehicle1DTransition': 5}
+OBS_IDS = {'UNGMMeasurement': 1, 'Pendulum2DMeasurement': 2, 'Radar2DMeasurement': 3, 'RangeMeasurement': 4}
 TF_SP, TF_BQ, TF_TP = 1, 2, 3
 FAMILY_GAUSS, FAMILY_STUDENT = 1, 2
 SIM_DISCRETE, SIM_CONTINUOUS, SIM_MEASURE = 1, 2, 3

@@ -19,6 +19,7 @@ int filter_ungm(const FilterLaunch &L);
 int filter_pendulum(const FilterLaunch &L);
 int filter_reentry(const FilterLaunch &L);
 int filter_coordturn(const FilterLaunch &L);
+int filter_reentry1d(const FilterLaunch &L);
 
 static bool tf_valid(const ssm_transform &t) {
     if (t.n_pts < 1 || !t.points || !t.wm || !t.Wc) return false;
@@ -65,6 +66,8 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
         rc = filter_reentry(L);
     else if (dm == SSM_DYN_COORDTURN && om == SSM_OBS_RADAR && desc->dx == 5 && desc->dy == 2 && nsi == 2 && si[0] == 0 && si[1] == 2)
         rc = filter_coordturn(L);
+    else if (dm == SSM_DYN_REENTRY1D && om == SSM_OBS_RANGE && desc->dx == 3 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = filter_reentry1d(L);
     else
         set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));

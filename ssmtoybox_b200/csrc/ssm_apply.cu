@@ -14,6 +14,8 @@ struct FnDynUngm { static constexpr int D = 1, E = 1, NQ = 1; template <bool NZ>
 struct FnDynPend { static constexpr int D = 2, E = 2, NQ = 2; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[2], double t, double (&o)[2]) { DynPendulum::f<NZ>(p, x, n, t, o); } };
 struct FnDynReentry { static constexpr int D = 5, E = 5, NQ = 3; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[3], double t, double (&o)[5]) { DynReentry::f<NZ>(p, x, n, t, o); } };
 struct FnDynCt { static constexpr int D = 5, E = 5, NQ = 5; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[5], double t, double (&o)[5]) { DynCoordTurn::f<NZ>(p, x, n, t, o); } };
+struct FnDynReentry1D { static constexpr int D = 3, E = 3, NQ = 3; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[3], double t, double (&o)[3]) { DynReentry1D::f<NZ>(p, x, n, t, o); } };
+struct FnObsRange { static constexpr int D = 3, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[1], double t, double (&o)[1]) { ObsRange<3, 0>::h<NZ>(p, x, n, t, o); } };
 struct FnObsUngm { static constexpr int D = 1, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { ObsUngm<1, 0>::h<NZ>(p, x, n, t, o); } };
 struct FnObsPend { static constexpr int D = 2, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[1], double t, double (&o)[1]) { ObsPendulum<2, 0>::h<NZ>(p, x, n, t, o); } };
 struct FnObsRadar01 { static constexpr int D = 5, E = 2, NQ = 2; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<5, 0, 1>::h<NZ>(p, x, n, t, o); } };
@@ -145,6 +147,8 @@ using namespace ssm;
     else if (which == 0 && model == SSM_DYN_PENDULUM) { CALL(FnDynPend) }                              \
     else if (which == 0 && model == SSM_DYN_REENTRY) { CALL(FnDynReentry) }                            \
     else if (which == 0 && model == SSM_DYN_COORDTURN) { CALL(FnDynCt) }                               \
+    else if (which == 0 && model == SSM_DYN_REENTRY1D) { CALL(FnDynReentry1D) }                        \
+    else if (which == 1 && model == SSM_OBS_RANGE && dim_state == 3 && si0 == 0) { CALL(FnObsRange) }  \
     else if (which == 1 && model == SSM_OBS_UNGM && dim_state == 1) { CALL(FnObsUngm) }                \
     else if (which == 1 && model == SSM_OBS_PENDULUM && dim_state == 2) { CALL(FnObsPend) }            \
     else if (which == 1 && model == SSM_OBS_RADAR && dim_state == 5 && si0 == 0 && si1 == 1) { CALL(FnObsRadar01) } \

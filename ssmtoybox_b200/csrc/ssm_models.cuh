@@ -110,6 +110,30 @@ struct DynCoordTurn {
     }
 };
 
+// ---- ReentryVehicle1DTransition, ssmod.py:418-426; par[0] = dt, Gamma = 1 / 6.096 (ssmod.py:416) ----
+// state [altitude, velocity, ballistic coefficient], additive 3-D noise
+struct DynReentry1D {
+    static constexpr int DX = 3, DQ = 3, ID = SSM_DYN_REENTRY1D;
+    static constexpr bool HAS_CONT = true;
+    SSM_DEV static double drag(const double (&x)[3]) { return m_exp(-(1.0 / 6.096) * x[0]) * (x[1] * x[1]) * x[2]; }
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[3], const double (&q)[3], double, double (&o)[3]) {
+        const double dt = par[0];
+        o[0] = x[0] - dt * x[1];
+        if (NOISE) o[0] += q[0];
+        o[1] = x[1] - dt * m_exp(-(1.0 / 6.096) * x[0]) * (x[1] * x[1]) * x[2];
+        if (NOISE) o[1] += q[1];
+        o[2] = x[2];
+        if (NOISE) o[2] += q[2];
+    }
+    // dyn_fcn_cont, ssmod.py:423-426
+    SSM_DEV static void fc(const double *, const double (&x)[3], const double (&q)[3], double, double (&o)[3]) {
+        o[0] = -x[1] + q[0];
+        o[1] = -drag(x) + q[1];
+        o[2] = q[2];
+    }
+};
+
 // ---- UNGMMeasurement.meas_fcn, ssmod.py:1060-1061 ----------------------------------------------
 template <int DXS, int I0>
 struct ObsUngm {
@@ -128,6 +152,18 @@ struct ObsPendulum {
     template <bool NOISE>
     SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
         o[0] = sin(x[I0]);
+        if (NOISE) o[0] += r[0];
+    }
+};
+
+// ---- RangeMeasurement.meas_fcn, ssmod.py:1146-1148; par[0..1] = sensor position (sx, sy) ---------
+template <int DXS, int I0>
+struct ObsRange {
+    static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_RANGE;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
+        const double ey = x[I0] - par[1];
+        o[0] = m_sqrt(par[0] * par[0] + ey * ey);
         if (NOISE) o[0] += r[0];
     }
 };

@@ -188,8 +188,10 @@ extern "C" int ssm_scores_phase1_traj(int32_t dx, const double *x, const double 
     switch (dx) {
         case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = run_phase1<3>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = run_phase1<4>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+        default: set_error("ssm_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase1: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
@@ -218,8 +220,10 @@ extern "C" int ssm_scores_phase2_traj(int32_t dx, const double *x, const double 
     switch (dx) {
         case 1: rc = run_phase2<1>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 2: rc = run_phase2<2>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = run_phase2<3>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = run_phase2<4>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 5: rc = run_phase2<5>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        default: set_error("ssm_scores: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+        default: set_error("ssm_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase2: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;

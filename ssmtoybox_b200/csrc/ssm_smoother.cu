@@ -265,8 +265,10 @@ extern "C" int ssm_smooth_window(int32_t dx, const double *fi_mean, const double
     switch (dx) {
         case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = launch_smoother<3>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = launch_smoother<4>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        default: set_error("ssm_smooth: state dimension %d has no device implementation (1, 2, 5)", dx); return SSM_E_UNSUPPORTED;
+        default: set_error("ssm_smooth: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;

@@ -130,6 +130,19 @@ class Pendulum2DTransition(TransitionModel):
         self.dt = dt
 
 
+class ReentryVehicle1DTransition(TransitionModel):
+    """Vertically falling reentry body: altitude, velocity, ballistic coefficient (ssmod.py:368-429)."""
+    dim_state = 3
+    dim_noise = 3
+    noise_additive = True
+    _device_id = 5
+
+    def __init__(self, init_rv, noise_rv, dt=0.1):
+        super(ReentryVehicle1DTransition, self).__init__(init_rv, noise_rv)
+        self.dt = dt
+        self.Gamma = 1 / 6.096
+
+
 class ReentryVehicle2DTransition(TransitionModel):
     """Reentry vehicle, 5-D state, 3-D noise entering the last three components (ssmod.py:436-584)."""
     dim_state = 5
@@ -244,6 +257,23 @@ class Pendulum2DMeasurement(MeasurementModel):
 
     def __init__(self, noise_rv, dim_state, state_index=None):
         super(Pendulum2DMeasurement, self).__init__(noise_rv, dim_state, state_index)
+
+
+class RangeMeasurement(MeasurementModel):
+    """Range of a vertically moving object from a sensor at (sx, sy) = (30, 30) (ssmod.py:1121-1151)."""
+    dim_substate = 1
+    dim_out = 1
+    dim_noise = 1
+    noise_additive = True
+    _device_id = 4
+
+    def __init__(self, noise_rv, dim_state, state_index=None):
+        super(RangeMeasurement, self).__init__(noise_rv, dim_state, state_index)
+        self.sx = 30
+        self.sy = 30
+
+    # the sensor position travels in the radar_loc slot of the descriptor (obs_par[0..1])
+    radar_loc = property(lambda self: np.array([float(self.sx), float(self.sy)]))
 
 
 class Radar2DMeasurement(MeasurementModel):

@@ -154,6 +154,39 @@ def test_reentry_filters():
     assert relstep(m, g['fi_mean'][:, :30]) < 1e-6
 
 
+def test_reentry1d_range_filters():
+    """ReentryVehicle1DTransition + RangeMeasurement (research/gpq/gpq_tracking.py:135-166): GPQKF with weights from
+    the K5 kernel, UKF, RTS smoother, model functions and simulators, all through the reference's class names"""
+    from ssmtoybox_b200.utils import GaussRV
+    from ssmtoybox_b200.ssmod import ReentryVehicle1DTransition, RangeMeasurement
+    from ssmtoybox_b200.ssinf import UnscentedKalman, GaussianProcessKalman
+    P0 = np.diag([0.0929, 1.4865, 1e-4])
+    dyn = ReentryVehicle1DTransition(GaussRV(3, np.array([90, 6, 1.7]), P0), GaussRV(3, cov=np.zeros((3, 3))), dt=0.1)
+    obs = RangeMeasurement(GaussRV(1, cov=np.array([[0.03048 ** 2]])), 3)
+    check(UnscentedKalman(dyn, obs), 'c6_reentry1d_ukf', 1e-10)
+    kd, ko = np.array([[0.5, 10, 10, 10]]), np.array([[0.5, 15, 20, 20]])
+    alg = GaussianProcessKalman(dyn, obs, kd, ko, kernel='rbf', points='ut')
+    g = golden('c6_reentry1d_gpq')
+    # kernel [0.5, 15, 20, 20] on UT points: cond(K) ~ 1e5; the reference's float64 Wc = iK Q iK carries ~1e-6 of noise
+    # (its entries that are equal by symmetry differ in the 6th digit), the double-double weights here do not
+    assert rel(alg.tf_dyn.wm, g['dyn_wm']) < 1e-8 and rel(alg.tf_obs.Wc, g['obs_Wc']) < 1e-4
+    # ... and the un-centred covariance fx Wc fx' - m m' cancels 8100 against 1e-3: 1e-9 of weight noise is 1 % of it
+    m, P = alg.forward_pass(g['y'])
+    assert relstep(m, g['fi_mean']) < 1e-4 and relstep(P, g['fi_cov']) < 5e-2
+    alg.reset()
+    for tf, pfx in ((alg.tf_dyn, 'dyn_'), (alg.tf_obs, 'obs_')):      # with the reference's weights assigned: 1e-9
+        tf.wm, tf.Wc, tf.Wcc = g[pfx + 'wm'], g[pfx + 'Wc'], g[pfx + 'Wcc']
+        tf.model.model_var = float(g[pfx + 'model_var'])
+    check(alg, 'c6_reentry1d_gpq', 1e-8)
+    x = np.array([80.0, 5.0, 1.6])
+    f = so.dyn_fcn('ReentryVehicle1DTransition', x, 0.0, 0, 0.1)
+    assert rel(dyn.dyn_fcn(x, np.zeros(3), 0), f) < 1e-15 and rel(dyn.dyn_eval(x, 0), f) < 1e-15
+    assert rel(obs.meas_eval(x, 0), np.sqrt(30.0 ** 2 + 50.0 ** 2)) < 1e-15
+    xs = dyn.simulate_continuous(10, mc_sims=64)
+    assert xs.shape == (3, 100, 64) and np.isfinite(xs).all() and (np.diff(xs[0], axis=0) < 0).all()   # it falls
+    assert obs.simulate_measurements(xs).shape == (1, 100, 64)
+
+
 def test_failures_raise_like_the_reference():
     from ssmtoybox_b200.ssinf import GaussianProcessKalman
     dyn, obs = reentry()

@@ -285,6 +285,21 @@ def test_simulation_injected_noise_vs_reference(name):
         assert rel(N_(xc2), d['xc'][:, ::2]) < 1e-13
 
 
+def test_simulation_reentry1d_vs_reference():
+    from ssmtoybox_b200 import device as dv
+    d = dict(golden('simulation_reentry1d'))
+    pts, wm, Wc = so.classical_rule('ut', 3)
+    for pfx in ('dyn_', 'obs_'):
+        d.update({pfx + 'kind': 'sp', pfx + 'points': pts, pfx + 'wm': wm, pfx + 'Wc': Wc})
+    low = dv.lower(d)
+    M, N = d['x0'].shape[1], d['q'].shape[1]
+    x, y = dv.simulate(low, M, N, x0=T(d['x0']), q=T(d['q']), r=T(d['r']))
+    assert rel(N_(x), d['x']) < 1e-13 and rel(N_(y), d['y']) < 1e-13
+    S = d['qc'].shape[1] - 1
+    xc, _ = dv.simulate(low, M, S, mode='continuous', dt=float(d['dtc']), x0=T(d['x0']), q=T(d['qc'][:, :S]), want_y=False)
+    assert rel(N_(xc), d['xc']) < 1e-13
+
+
 @pytest.mark.parametrize('name', ['ungm', 'reentry', 'ct'])
 def test_simulation_philox_statistics_and_shard_invariance(name):
     from ssmtoybox_b200 import device as dv

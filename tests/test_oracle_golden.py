@@ -162,6 +162,14 @@ def test_simulation_injected_noise():
             assert rel(so.simulate_continuous(d, d['x0'], d['qc'], float(d['dtc'])), d['xc']) < 1e-14
 
 
+def test_simulation_reentry1d_injected_noise():
+    """ReentryVehicle1DTransition / RangeMeasurement (ssmod.py:418-426, 1146-1148): discrete, Euler-Maruyama, range"""
+    d = golden('simulation_reentry1d')
+    x = so.simulate_discrete(d, d['x0'], d['q'])
+    assert rel(x, d['x']) < 1e-14 and rel(so.simulate_measurements(d, x, d['r']), d['y']) < 1e-14
+    assert rel(so.simulate_continuous(d, d['x0'], d['qc'], float(d['dtc'])), d['xc']) < 1e-14
+
+
 @pytest.mark.parametrize('name', ['c1_ungm_ukf', 'c5_pend_gpq', 'c3s_reentry_gpq'])
 def test_scores(name):
     g, c = golden('scores'), golden(name)
