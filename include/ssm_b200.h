@@ -57,9 +57,11 @@ extern "C" {
 #define SSM_DYN_REENTRY   3  /* ReentryVehicle2DTransition.dyn_fcn  ssmod.py:530-564  par[0] = dt                 */
 #define SSM_DYN_COORDTURN 4  /* CoordinatedTurnTransition.dyn_fcn   ssmod.py:675-690  par[0] = dt                 */
 #define SSM_DYN_REENTRY1D 5  /* ReentryVehicle1DTransition.dyn_fcn  ssmod.py:418-421  par[0] = dt                 */
+#define SSM_DYN_UNGMNA    6  /* UNGMNATransition.dyn_fcn (non-additive noise) ssmod.py:299-300                  */
 #define SSM_OBS_UNGM      1  /* UNGMMeasurement.meas_fcn            ssmod.py:1060-1061                            */
 #define SSM_OBS_PENDULUM  2  /* Pendulum2DMeasurement.meas_fcn      ssmod.py:1114-1115                            */
 #define SSM_OBS_RADAR     3  /* Radar2DMeasurement.meas_fcn         ssmod.py:1227-1252 par[0..1] = radar_loc      */
+#define SSM_OBS_UNGMNA    5  /* UNGMNAMeasurement.meas_fcn (non-additive noise) ssmod.py:1085-1086              */
 #define SSM_OBS_RANGE     4  /* RangeMeasurement.meas_fcn           ssmod.py:1146-1148 par[0..1] = (sx, sy)       */
 
 /* ---- moment-transform kinds ---------------------------------------------------------------- */
@@ -110,6 +112,15 @@ typedef struct ssm_desc {
     int32_t fixed_dof;
     int32_t reserved2;
     ssm_transform tf_dyn, tf_obs;
+    /* Non-additive noise (TransitionModel / MeasurementModel.noise_additive == False): the transform of that model
+     * works on the augmented vector [x; noise] (dim_in = dx + dq / dx + dy) with mean [m; q_mean] and covariance
+     * blockdiag(P, q_cov), ssinf.py:271-272, 282-283; GQG / R are not added for such a model (:278, :290).
+     * Ignored (may be NULL) for additive models. */
+    const double *q_mean;           /* (dq)                                                      */
+    const double *q_cov;            /* (dq, dq)                                                  */
+    const double *r_mean;           /* (dy)      measurement noise mean; its covariance is R     */
+    int32_t dq;                     /* process noise dimension                                   */
+    int32_t reserved3;
 } ssm_desc;
 
 /* ---- library info -------------------------------------------------------------------------- */

@@ -20,6 +20,7 @@ int filter_pendulum(const FilterLaunch &L);
 int filter_reentry(const FilterLaunch &L);
 int filter_coordturn(const FilterLaunch &L);
 int filter_reentry1d(const FilterLaunch &L);
+int filter_ungmna(const FilterLaunch &L);
 
 static bool tf_valid(const ssm_transform &t) {
     if (t.n_pts < 1 || !t.points || !t.wm || !t.Wc) return false;
@@ -43,7 +44,7 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
     if (!desc || !y || !status) { set_error("ssm_filter: desc, y and status must not be NULL"); return SSM_E_INVALID; }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_filter: bad sizes (n_traj=%lld n_steps=%d ld=%lld)", (long long)n_traj, n_steps, (long long)ld); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_filter: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
-    if (!desc->m0 || !desc->P0 || !desc->GQG || !desc->R) { set_error("ssm_filter: m0, P0, GQG, R must not be NULL"); return SSM_E_INVALID; }
+    if (!desc->m0 || !desc->P0 || !desc->R || (!desc->GQG && !desc->q_cov)) { set_error("ssm_filter: m0, P0, GQG (or q_cov), R must not be NULL"); return SSM_E_INVALID; }
     if ((init_mean == nullptr) != (init_cov == nullptr)) { set_error("ssm_filter: init_mean and init_cov go together"); return SSM_E_INVALID; }
     if (!tf_valid(desc->tf_dyn) || !tf_valid(desc->tf_obs)) { set_error("ssm_filter: incomplete transform description"); return SSM_E_INVALID; }
     if (desc->family != SSM_FAMILY_GAUSS && desc->family != SSM_FAMILY_STUDENT) { set_error("ssm_filter: unknown family %d", desc->family); return SSM_E_INVALID; }
@@ -68,6 +69,8 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
         rc = filter_coordturn(L);
     else if (dm == SSM_DYN_REENTRY1D && om == SSM_OBS_RANGE && desc->dx == 3 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
         rc = filter_reentry1d(L);
+    else if (dm == SSM_DYN_UNGMNA && om == SSM_OBS_UNGMNA && desc->dx == 1 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = filter_ungmna(L);
     else
         set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));

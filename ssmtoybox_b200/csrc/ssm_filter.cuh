@@ -307,8 +307,25 @@ struct FilterPar {
     double R[TriSize<DY>::value];
     double dof, x0_dof, q_dof, r_dof, s0;  // Student family
     int fixed_dof;
+    // non-additive noise: moments of the noise part of the augmented vector [x; noise] (ssinf.py:271-272, 282-283)
+    double q_mean[5], q_cov[TriSize<5>::value], r_mean[DY];
     FilterBuffers b;
 };
+
+// [m; nm], blockdiag(P, Nc) in packed lower storage: the augmented moments of a non-additive model
+template <int DX, int DN>
+SSM_DEV void augment(const double (&m)[DX], const double (&P)[TriSize<DX>::value], const double *nm, const double *Nc,
+                     double (&ma)[DX + DN], double (&Pa)[TriSize<DX + DN>::value]) {
+#pragma unroll
+    for (int i = 0; i < DX; ++i) ma[i] = m[i];
+#pragma unroll
+    for (int i = 0; i < DN; ++i) ma[DX + i] = nm[i];
+#pragma unroll
+    for (int r = 0; r < DX + DN; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c)
+            Pa[tri(r, c)] = (r < DX) ? P[tri(r, c)] : (c < DX ? 0.0 : Nc[tri(r - DX, c - DX)]);
+}
 
 // Element (c, k, t) of a bulk array = base + rk + c * cs with rk = k * ld + t (per thread, once per step) and the
 // kernel-uniform component stride cs = n_steps * ld: one 64-bit add per access instead of a 64-bit multiply chain.
@@ -455,18 +472,43 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         double mp[DX], Pp[TX];
         const bool want_xx = b.pr_xx != nullptr;
         double *q_xx = b.pr_xx ? row_ptr(b.pr_xx, rk) : nullptr;
-        bool ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT>(
-            p.tf_dyn, m, P,
-            [&](const double (&x)[DX], double (&o)[DX]) {
-                const double q0[Dyn::DQ] = {};
-                Dyn::template f<false>(p.dyn_par, x, q0, time, o);
-            },
-            mp, Pp, want_xx,
-            [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
+        bool ok;
+        if constexpr (Dyn::ADDITIVE) {
+            ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT>(
+                p.tf_dyn, m, P,
+                [&](const double (&x)[DX], double (&o)[DX]) {
+                    const double q0[Dyn::DQ] = {};
+                    Dyn::template f<false>(p.dyn_par, x, q0, time, o);
+                },
+                mp, Pp, want_xx,
+                [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
 #pragma unroll
-                for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
-            },
-            sfx);
+                    for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
+                },
+                sfx);
+        } else {
+            // non-additive process noise: transform of the augmented vector [x; q], cross-covariance trimmed to its
+            // first dx columns (ssinf.py:271-272, 294)
+            constexpr int DD = DX + Dyn::DQ;
+            double ma[DD], Pa[TriSize<DD>::value];
+            augment<DX, Dyn::DQ>(m, P, p.q_mean, p.q_cov, ma, Pa);
+            ok = moment_transform<DD, DX, PTS, NPTS, KIND, SMT>(
+                p.tf_dyn, ma, Pa,
+                [&](const double (&xq)[DD], double (&o)[DX]) {
+                    double x[DX], q[Dyn::DQ];
+#pragma unroll
+                    for (int i = 0; i < DX; ++i) x[i] = xq[i];
+#pragma unroll
+                    for (int i = 0; i < Dyn::DQ; ++i) q[i] = xq[DX + i];
+                    Dyn::template f<true>(p.dyn_par, x, q, time, o);
+                },
+                mp, Pp, want_xx,
+                [&](int a, const double (&row)[DD]) {
+#pragma unroll
+                    for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
+                },
+                sfx);
+        }
         if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
             if (b.pr_cov) {
@@ -478,26 +520,51 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 #pragma unroll
             for (int a = 0; a < TX; ++a) Pp[a] = fma(scale, Pp[a], p.s0 * p.GQG[a]);  // x_smat_pr, ssinf.py:672, 676
         } else {
+            if (Dyn::ADDITIVE) {
 #pragma unroll
-            for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:279
+                for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:278-279
+            }
             store_sym<DX>(b.pr_cov, cs, rk, Pp);
         }
         store_vec<DX>(b.pr_mean, cs, rk, mp);
 
         // ---- predictive measurement moments (ssinf.py:287-291 / 684-693) ------------------------
         double my[DY], Sy[TY], Syx[DY][DX];
-        ok = moment_transform<DX, DY, PTS, NPTS, KIND, SMT>(
-            p.tf_obs, mp, Pp,
-            [&](const double (&x)[DX], double (&o)[DY]) {
-                const double r0[DY] = {};
-                Obs::template h<false>(p.obs_par, x, r0, time, o);
-            },
-            my, Sy, true,
-            [&](int a, const double (&row)[DX]) {
+        if constexpr (Obs::ADDITIVE) {
+            ok = moment_transform<DX, DY, PTS, NPTS, KIND, SMT>(
+                p.tf_obs, mp, Pp,
+                [&](const double (&x)[DX], double (&o)[DY]) {
+                    const double r0[DY] = {};
+                    Obs::template h<false>(p.obs_par, x, r0, time, o);
+                },
+                my, Sy, true,
+                [&](int a, const double (&row)[DX]) {
 #pragma unroll
-                for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
-            },
-            sfx);
+                    for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
+                },
+                sfx);
+        } else {
+            // non-additive measurement noise: [x; r] (ssinf.py:282-283), cross-covariance trimmed (:293)
+            constexpr int DO = DX + DY;
+            double ma[DO], Pa[TriSize<DO>::value];
+            augment<DX, DY>(mp, Pp, p.r_mean, p.R, ma, Pa);
+            ok = moment_transform<DO, DY, PTS, NPTS, KIND, SMT>(
+                p.tf_obs, ma, Pa,
+                [&](const double (&xr)[DO], double (&o)[DY]) {
+                    double x[DX], r[DY];
+#pragma unroll
+                    for (int i = 0; i < DX; ++i) x[i] = xr[i];
+#pragma unroll
+                    for (int i = 0; i < DY; ++i) r[i] = xr[DX + i];
+                    Obs::template h<true>(p.obs_par, x, r, time, o);
+                },
+                my, Sy, true,
+                [&](int a, const double (&row)[DO]) {
+#pragma unroll
+                    for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
+                },
+                sfx);
+        }
         if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; continue; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
 #pragma unroll
@@ -506,9 +573,9 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             for (int a = 0; a < DY; ++a)
 #pragma unroll
                 for (int d = 0; d < DX; ++d) Syx[a][d] *= scale;
-        } else {
+        } else if (Obs::ADDITIVE) {
 #pragma unroll
-            for (int a = 0; a < TY; ++a) Sy[a] += p.R[a];
+            for (int a = 0; a < TY; ++a) Sy[a] += p.R[a];  // ssinf.py:290-291
         }
 
         // ---- measurement update (ssinf.py:321-323 / 724-736) -----------------------------------

@@ -24,8 +24,12 @@ template <class Dyn, class Obs, int THREADS, int MINB>
 int dispatch_filter_model(const FilterLaunch &L) {
     const ssm_desc &d = *L.desc;
     const ssm_transform &a = d.tf_dyn, &b = d.tf_obs;
-    if (a.dim_in != Dyn::DX || a.dim_out != Dyn::DX || b.dim_in != Dyn::DX || b.dim_out != Obs::DY) {
-        set_error("transform dimensions do not match the model (additive noise: dim_in = dim_state)");
+    // a model with non-additive noise is integrated over the augmented vector [x; noise] (ssinf.py:271-272, 282-283)
+    constexpr int DD = Dyn::ADDITIVE ? Dyn::DX : Dyn::DX + Dyn::DQ, DO = Obs::ADDITIVE ? Dyn::DX : Dyn::DX + Obs::DY;
+    if (a.dim_in != DD || a.dim_out != Dyn::DX || b.dim_in != DO || b.dim_out != Obs::DY) {
+        set_error("transform dimensions do not match the model (dim_in = dim_state, + dim_noise when the noise is non-additive): "
+                  "dynamics %d -> %d (expected %d -> %d), measurement %d -> %d (expected %d -> %d)",
+                  a.dim_in, a.dim_out, DD, Dyn::DX, b.dim_in, b.dim_out, DO, Obs::DY);
         return SSM_E_INVALID;
     }
     if (a.kind != b.kind) { set_error("dynamics and measurement transforms must be of the same kind"); return SSM_E_UNSUPPORTED; }
@@ -35,6 +39,13 @@ int dispatch_filter_model(const FilterLaunch &L) {
         set_error("Student family is implemented for sigma-point transforms only");
         return SSM_E_UNSUPPORTED;
     }
+    if constexpr (!Dyn::ADDITIVE || !Obs::ADDITIVE) {
+        // augmented transforms run on the runtime-N path (weights in global memory) only
+        if (fam == SSM_FAMILY_STUDENT) { set_error("non-additive noise is implemented for the Gaussian family only"); return SSM_E_UNSUPPORTED; }
+        if (!Dyn::ADDITIVE && (!d.q_mean || !d.q_cov || d.dq != Dyn::DQ)) { set_error("non-additive dynamics: q_mean, q_cov (dq = %d) required", Dyn::DQ); return SSM_E_INVALID; }
+        if (!Obs::ADDITIVE && !d.r_mean) { set_error("non-additive measurement model: r_mean required"); return SSM_E_INVALID; }
+        return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
+    } else {
     const bool same = id.pts == io.pts && a.n_pts == b.n_pts;
     if (!same || id.pts == PTS_GENERIC) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
 #define SSM_CASE(P, K, F)                                                        \
@@ -50,6 +61,7 @@ int dispatch_filter_model(const FilterLaunch &L) {
 #undef SSM_CASE
     set_error("unsupported transform kind %d / family %d", kind, fam);
     return SSM_E_UNSUPPORTED;
+    }
 }
 
 // ---- generic point sets: runtime N <= GEN_CAP, weights staged in device memory ------------------
@@ -80,8 +92,9 @@ inline int fill_tf_global(TfGlobal<D, E> &o, const ssm_transform &tf, const Host
 template <class Dyn, class Obs, int KIND, int FAMILY, int THREADS, int MINB>
 int launch_filter_global(const FilterLaunch &L) {
     constexpr int DX = Dyn::DX, DY = Obs::DY;
-    using TfD = TfGlobal<DX, DX>;
-    using TfO = TfGlobal<DX, DY>;
+    constexpr int DD = Dyn::ADDITIVE ? DX : DX + Dyn::DQ, DO = Obs::ADDITIVE ? DX : DX + DY;  // transform input dimensions
+    using TfD = TfGlobal<DD, DX>;
+    using TfO = TfGlobal<DO, DY>;
     using Par = FilterPar<DX, DY, TfD, TfO>;
     const ssm_desc &d = *L.desc;
     const int Na = d.tf_dyn.n_pts, Nb = d.tf_obs.n_pts;
@@ -89,7 +102,7 @@ int launch_filter_global(const FilterLaunch &L) {
         set_error("generic point sets support at most %d points (got %d / %d)", GEN_CAP, Na, Nb);
         return SSM_E_UNSUPPORTED;
     }
-    const size_t cnt = (size_t)(2 * Na + 2 * Na * Na + 2 * DX * Na) + (size_t)(2 * Nb + 2 * Nb * Nb + 2 * DX * Nb);
+    const size_t cnt = (size_t)(2 * Na + 2 * Na * Na + 2 * DD * Na) + (size_t)(2 * Nb + 2 * Nb * Nb + 2 * DO * Nb);
     double *host = (double *)malloc(cnt * sizeof(double));
     double *dev = nullptr;
     if (cudaMallocAsync(&dev, cnt * sizeof(double), L.stream) != cudaSuccess) { free(host); set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
@@ -106,6 +119,12 @@ int launch_filter_global(const FilterLaunch &L) {
     pack_lower<DX>(d.P0, p.P0);
     pack_lower<DX>(d.GQG, p.GQG);
     pack_lower<DY>(d.R, p.R);
+    if (!Dyn::ADDITIVE) {
+        for (int i = 0; i < Dyn::DQ; ++i) p.q_mean[i] = d.q_mean[i];
+        pack_lower<Dyn::DQ>(d.q_cov, p.q_cov);
+    }
+    if (!Obs::ADDITIVE)
+        for (int i = 0; i < DY; ++i) p.r_mean[i] = d.r_mean[i];
     p.dof = d.dof; p.x0_dof = d.x0_dof; p.q_dof = d.q_dof; p.r_dof = d.r_dof;
     p.s0 = (d.family == SSM_FAMILY_STUDENT) ? (d.dof - 2.0) / d.dof : 1.0;
     p.fixed_dof = d.fixed_dof;

@@ -1,0 +1,5 @@
+// forward-pass instantiations: UNGM with NON-additive process and measurement noise (augmented-state transforms)
+#include "ssm_filter_dispatch.cuh"
+namespace ssm {
+int filter_ungmna(const FilterLaunch &L) { return dispatch_filter_model<DynUngmNA, ObsUngmNA<1, 0>, 128, 4>(L); }
+}  // namespace ssm

@@ -10,6 +10,7 @@ namespace ssm {
 // ---- UNGMTransition.dyn_fcn, ssmod.py:268-269 -------------------------------------------------
 struct DynUngm {
     static constexpr int DX = 1, DQ = 1, ID = SSM_DYN_UNGM;
+    static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = false;
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
@@ -19,9 +20,23 @@ struct DynUngm {
     SSM_DEV static void fc(const double *, const double (&)[1], const double (&)[1], double, double (&o)[1]) { o[0] = 0.0; }
 };
 
+// ---- UNGMNATransition.dyn_fcn, ssmod.py:299-300: NON-additive noise 8 q cos(1.2 k) ------------------
+// The filter feeds it through the augmented state [x; q] (ssinf.py:271-272); f<NOISE = false> is the model with q = 0.
+struct DynUngmNA {
+    static constexpr int DX = 1, DQ = 1, ID = SSM_DYN_UNGMNA;
+    static constexpr bool ADDITIVE = false;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
+        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + 8.0 * (NOISE ? q[0] : 0.0) * cos(1.2 * t);
+    }
+    SSM_DEV static void fc(const double *, const double (&)[1], const double (&)[1], double, double (&o)[1]) { o[0] = 0.0; }
+};
+
 // ---- Pendulum2DTransition.dyn_fcn, ssmod.py:357-358; par[0] = dt, g = 9.81 (ssmod.py:351) ------
 struct DynPendulum {
     static constexpr int DX = 2, DQ = 2, ID = SSM_DYN_PENDULUM;
+    static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = false;
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[2], const double (&q)[2], double, double (&o)[2]) {
@@ -38,6 +53,7 @@ struct DynPendulum {
 // constants ssmod.py:523-526; the 3-dimensional noise enters components 2..4 (G = [0; I3], :527)
 struct DynReentry {
     static constexpr int DX = 5, DQ = 3, ID = SSM_DYN_REENTRY;
+    static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = true;
     SSM_DEV static void forces(const double (&x)[5], double &D, double &G) {
         const double R0 = 6374.0, H0 = 13.406, Gm0 = 3.9860e5, b0 = -0.59783;
@@ -84,6 +100,7 @@ struct DynReentry {
 // 0 * x, which is finite).  Rows 0 and 2 become NaN, exactly as below.
 struct DynCoordTurn {
     static constexpr int DX = 5, DQ = 5, ID = SSM_DYN_COORDTURN;
+    static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = false;
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[5], double, double (&o)[5]) {
@@ -114,6 +131,7 @@ struct DynCoordTurn {
 // state [altitude, velocity, ballistic coefficient], additive 3-D noise
 struct DynReentry1D {
     static constexpr int DX = 3, DQ = 3, ID = SSM_DYN_REENTRY1D;
+    static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = true;
     SSM_DEV static double drag(const double (&x)[3]) { return m_exp(-(1.0 / 6.096) * x[0]) * (x[1] * x[1]) * x[2]; }
     template <bool NOISE>
@@ -138,6 +156,7 @@ struct DynReentry1D {
 template <int DXS, int I0>
 struct ObsUngm {
     static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_UNGM;
+    static constexpr bool ADDITIVE = true;
     template <bool NOISE>
     SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
         o[0] = 0.05 * x[I0] * x[I0];
@@ -145,10 +164,22 @@ struct ObsUngm {
     }
 };
 
+// ---- UNGMNAMeasurement.meas_fcn, ssmod.py:1085-1086: NON-additive noise, z = 0.05 r x^2 --------------
+template <int DXS, int I0>
+struct ObsUngmNA {
+    static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_UNGMNA;
+    static constexpr bool ADDITIVE = false;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
+        o[0] = 0.05 * (NOISE ? r[0] : 0.0) * (x[I0] * x[I0]);
+    }
+};
+
 // ---- Pendulum2DMeasurement.meas_fcn, ssmod.py:1114-1115 ----------------------------------------
 template <int DXS, int I0>
 struct ObsPendulum {
     static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_PENDULUM;
+    static constexpr bool ADDITIVE = true;
     template <bool NOISE>
     SSM_DEV static void h(const double *, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
         o[0] = sin(x[I0]);
@@ -160,6 +191,7 @@ struct ObsPendulum {
 template <int DXS, int I0>
 struct ObsRange {
     static constexpr int DX = DXS, DY = 1, ID = SSM_OBS_RANGE;
+    static constexpr bool ADDITIVE = true;
     template <bool NOISE>
     SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[1], double, double (&o)[1]) {
         const double ey = x[I0] - par[1];
@@ -174,6 +206,7 @@ struct ObsRange {
 template <int DXS, int I0, int I1>
 struct ObsRadar {
     static constexpr int DX = DXS, DY = 2, ID = SSM_OBS_RADAR;
+    static constexpr bool ADDITIVE = true;
     template <bool NOISE>
     SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[2], double, double (&o)[2]) {
         const double ex = x[I0] - par[0], ey = x[I1] - par[1];

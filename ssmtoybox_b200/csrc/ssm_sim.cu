@@ -241,6 +241,8 @@ extern "C" int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mo
         rc = launch_sim<DynCoordTurn, ObsRadar<5, 0, 2>>(SSM_SIM_ARGS);
     else if (dm == SSM_DYN_REENTRY1D && om == SSM_OBS_RANGE && (nsi == 0 || (nsi == 1 && si[0] == 0)))
         rc = launch_sim<DynReentry1D, ObsRange<3, 0>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_UNGMNA && om == SSM_OBS_UNGMNA && (nsi == 0 || (nsi == 1 && si[0] == 0)))
+        rc = launch_sim<DynUngmNA, ObsUngmNA<1, 0>>(SSM_SIM_ARGS);
     else
         set_error("ssm_simulate: no device implementation for dyn_model=%d obs_model=%d", dm, om);
 #undef SSM_SIM_ARGS
