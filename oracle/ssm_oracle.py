@@ -359,6 +359,8 @@ def dyn_fcn(name, x, q, time, dt):
         q = [q] * 5
     if name == 'UNGMTransition':  # ssmod.py:268-269
         return (0.5 * xp[0] + 25 * (xp[0] / (1 + xp[0] ** 2)) + 8 * np.cos(1.2 * time))[None] + q[0]
+    if name == 'UNGMNATransition':  # ssmod.py:299-300: non-additive noise
+        return (0.5 * xp[0] + 25 * (xp[0] / (1 + xp[0] ** 2)) + 8 * q[0] * np.cos(1.2 * time))[None]
     if name == 'Pendulum2DTransition':  # ssmod.py:357-358
         return np.stack([xp[0] + xp[1] * dt + q[0], xp[1] - PEND_G * dt * np.sin(xp[0]) + q[1]])
     if name == 'ReentryVehicle2DTransition':  # ssmod.py:530-564 (noise enters components 2..4)
@@ -415,6 +417,8 @@ def meas_fcn(name, x, r, time, radar_loc=(0.0, 0.0)):
         r = [r] * 2
     if name == 'UNGMMeasurement':  # ssmod.py:1060-1061
         return (0.05 * x[0] ** 2 + r[0])[None]
+    if name == 'UNGMNAMeasurement':  # ssmod.py:1085-1086: non-additive noise
+        return (0.05 * r[0] * x[0] ** 2)[None]
     if name == 'Pendulum2DMeasurement':  # ssmod.py:1114-1115
         return (np.sin(x[0]) + r[0])[None]
     if name == 'RangeMeasurement':  # ssmod.py:1146-1148; (sx, sy) travels in radar_loc
@@ -426,15 +430,25 @@ def meas_fcn(name, x, r, time, radar_loc=(0.0, 0.0)):
     raise NotImplementedError(name)
 
 
+NONADDITIVE = {'UNGMNATransition', 'UNGMNAMeasurement'}   # noise_additive = False (ssmod.py:296, 1081)
+
+
 def _meas_eval(desc, x, time):
-    """meas_eval: select state_index, zero additive noise.                      ssmod.py:960-1009"""
+    """meas_eval: select state_index, zero additive noise; a non-additive model takes the augmented vector
+    [x; r] apart (state_index is None for the only such model).              ssmod.py:960-1009"""
+    if str(desc['obs_name']) in NONADDITIVE:
+        dr = np.asarray(desc['r_cov']).shape[0]
+        return meas_fcn(str(desc['obs_name']), x[:-dr], x[-dr:], time, desc['radar_loc'])
     si = np.asarray(desc['state_index']).astype(int)
     xs = x[si] if si.size else x
     return meas_fcn(str(desc['obs_name']), xs, 0.0, time, desc['radar_loc'])
 
 
 def _dyn_eval(desc, x, time):
-    """dyn_eval with zero additive noise.                                        ssmod.py:129-166"""
+    """dyn_eval with zero additive noise; [x; q] taken apart for a non-additive model.  ssmod.py:129-166"""
+    if str(desc['dyn_name']) in NONADDITIVE:
+        dq = np.asarray(desc['q_cov']).shape[0]
+        return dyn_fcn(str(desc['dyn_name']), x[:-dq], x[-dq:], time, float(desc['dyn_dt']))
     return dyn_fcn(str(desc['dyn_name']), x, 0.0, time, float(desc['dyn_dt']))
 
 
@@ -655,6 +669,20 @@ def _forward_batch(desc, y, la, dt, init=None, t0=None):
     dx = m0.shape[0]
     GQG, R = _noise_terms(desc, dt)
     tf_dyn, tf_obs = _tf(desc, 'dyn'), _tf(desc, 'obs')
+    # non-additive noise: the transform integrates over [x; noise] with blockdiag covariance (ssinf.py:271-272, 282-283)
+    dyn_na, obs_na = str(desc['dyn_name']) in NONADDITIVE, str(desc['obs_name']) in NONADDITIVE
+    q_cov = np.atleast_2d(np.asarray(desc['q_cov'], dtype=dt))
+    q_mean = np.asarray(desc['q_mean'], dtype=dt).reshape(-1) if 'q_mean' in desc else np.zeros(q_cov.shape[0], dtype=dt)
+    r_mean = np.asarray(desc['r_mean'], dtype=dt).reshape(-1) if 'r_mean' in desc else np.zeros(R.shape[0], dtype=dt)
+
+    def augment(mean, cov, nm, nc):
+        lead = mean.shape[:-1]
+        d, dn = mean.shape[-1], nm.shape[0]
+        ma = np.concatenate([mean, np.broadcast_to(nm, lead + (dn,))], axis=-1)
+        Pa = np.zeros(lead + (d + dn, d + dn), dtype=dt)
+        Pa[..., :d, :d] = cov
+        Pa[..., d:, d:] = nc
+        return ma, Pa
     batched = la.batched
     B = (M,) if batched else ()
     fi_mean = np.full((M, N + 1, dx), np.nan, dtype=dt)
@@ -683,16 +711,22 @@ def _forward_batch(desc, y, la, dt, init=None, t0=None):
         for k in range(1, N + 1):
             t = toff + (k - 1)                                                 # ssinf.py:104, 277, 288
             try:
-                mp, Pp, Pxx, ok = transform_apply(la, tf_dyn, lambda x: _dyn_eval(desc, x, t), m, P, FAIL_CHOL_DYN)
+                ma, Pa = augment(m, P, q_mean, q_cov) if dyn_na else (m, P)      # ssinf.py:271-272
+                mp, Pp, Pxx, ok = transform_apply(la, tf_dyn, lambda x: _dyn_eval(desc, x, t), ma, Pa, FAIL_CHOL_DYN)
+                Pxx = Pxx[..., :dx]                                            # ssinf.py:294
                 if batched:
                     fail(ok, k, FAIL_CHOL_DYN)
-                Pp = Pp + GQG                                                  # ssinf.py:278-279
+                if not dyn_na:
+                    Pp = Pp + GQG                                              # ssinf.py:278-279
                 if batched:  # keep dead trajectories harmless
                     Pp = np.where(alive[:, None, None], Pp, eye_x)
-                my, Py, Pyx, ok = transform_apply(la, tf_obs, lambda x: _meas_eval(desc, x, t), mp, Pp, FAIL_CHOL_OBS)
+                ma, Pa = augment(mp, Pp, r_mean, R) if obs_na else (mp, Pp)      # ssinf.py:282-283
+                my, Py, Pyx, ok = transform_apply(la, tf_obs, lambda x: _meas_eval(desc, x, t), ma, Pa, FAIL_CHOL_OBS)
+                Pyx = Pyx[..., :dx]                                            # ssinf.py:293
                 if batched:
                     fail(ok, k, FAIL_CHOL_OBS)
-                Py = Py + R                                                    # ssinf.py:290-291
+                if not obs_na:
+                    Py = Py + R                                                # ssinf.py:290-291
                 K, ok, fin = la.gain(Py, Pyx, FAIL_CHOL_GAIN)                  # ssinf.py:321
                 if batched:
                     fail(fin, k, FAIL_NONFINITE_GAIN)

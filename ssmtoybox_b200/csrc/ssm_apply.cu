@@ -10,16 +10,21 @@ namespace ssm {
 
 void set_error(const char *fmt, ...);
 
-struct FnDynUngm { static constexpr int D = 1, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { DynUngm::f<NZ>(p, x, n, t, o); } };
-struct FnDynPend { static constexpr int D = 2, E = 2, NQ = 2; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[2], double t, double (&o)[2]) { DynPendulum::f<NZ>(p, x, n, t, o); } };
-struct FnDynReentry { static constexpr int D = 5, E = 5, NQ = 3; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[3], double t, double (&o)[5]) { DynReentry::f<NZ>(p, x, n, t, o); } };
-struct FnDynCt { static constexpr int D = 5, E = 5, NQ = 5; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[5], double t, double (&o)[5]) { DynCoordTurn::f<NZ>(p, x, n, t, o); } };
-struct FnDynReentry1D { static constexpr int D = 3, E = 3, NQ = 3; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[3], double t, double (&o)[3]) { DynReentry1D::f<NZ>(p, x, n, t, o); } };
-struct FnObsRange { static constexpr int D = 3, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[1], double t, double (&o)[1]) { ObsRange<3, 0>::h<NZ>(p, x, n, t, o); } };
-struct FnObsUngm { static constexpr int D = 1, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { ObsUngm<1, 0>::h<NZ>(p, x, n, t, o); } };
-struct FnObsPend { static constexpr int D = 2, E = 1, NQ = 1; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[1], double t, double (&o)[1]) { ObsPendulum<2, 0>::h<NZ>(p, x, n, t, o); } };
-struct FnObsRadar01 { static constexpr int D = 5, E = 2, NQ = 2; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<5, 0, 1>::h<NZ>(p, x, n, t, o); } };
-struct FnObsRadar02 { static constexpr int D = 5, E = 2, NQ = 2; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<5, 0, 2>::h<NZ>(p, x, n, t, o); } };
+struct FnDynUngm { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { DynUngm::f<NZ>(p, x, n, t, o); } };
+struct FnDynPend { static constexpr int D = 2, E = 2, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[2], double t, double (&o)[2]) { DynPendulum::f<NZ>(p, x, n, t, o); } };
+struct FnDynReentry { static constexpr int D = 5, E = 5, NQ = 3; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[3], double t, double (&o)[5]) { DynReentry::f<NZ>(p, x, n, t, o); } };
+struct FnDynCt { static constexpr int D = 5, E = 5, NQ = 5; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[5], double t, double (&o)[5]) { DynCoordTurn::f<NZ>(p, x, n, t, o); } };
+struct FnDynReentry1D { static constexpr int D = 3, E = 3, NQ = 3; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[3], double t, double (&o)[3]) { DynReentry1D::f<NZ>(p, x, n, t, o); } };
+struct FnObsRange { static constexpr int D = 3, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[1], double t, double (&o)[1]) { ObsRange<3, 0>::h<NZ>(p, x, n, t, o); } };
+// non-additive models: plain (state, noise) form for ssm_model_eval, augmented form [x; noise] for ssm_transform_apply
+struct FnDynUngmNA { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { DynUngmNA::f<NZ>(p, x, n, t, o); } };
+struct FnObsUngmNA { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { ObsUngmNA<1, 0>::h<NZ>(p, x, n, t, o); } };
+struct FnDynUngmNAaug { static constexpr int D = 2, E = 1, NQ = 1; static constexpr bool EXACT = true; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&xq)[2], const double (&)[1], double t, double (&o)[1]) { const double x[1] = {xq[0]}, q[1] = {xq[1]}; DynUngmNA::f<true>(p, x, q, t, o); } };
+struct FnObsUngmNAaug { static constexpr int D = 2, E = 1, NQ = 1; static constexpr bool EXACT = true; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&xr)[2], const double (&)[1], double t, double (&o)[1]) { const double x[1] = {xr[0]}, r[1] = {xr[1]}; ObsUngmNA<1, 0>::h<true>(p, x, r, t, o); } };
+struct FnObsUngm { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { ObsUngm<1, 0>::h<NZ>(p, x, n, t, o); } };
+struct FnObsPend { static constexpr int D = 2, E = 1, NQ = 1; static constexpr bool EXACT = true; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[2], const double (&n)[1], double t, double (&o)[1]) { ObsPendulum<2, 0>::h<NZ>(p, x, n, t, o); } };
+struct FnObsRadar01 { static constexpr int D = 5, E = 2, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<5, 0, 1>::h<NZ>(p, x, n, t, o); } };
+struct FnObsRadar02 { static constexpr int D = 5, E = 2, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<5, 0, 2>::h<NZ>(p, x, n, t, o); } };
 
 template <int D, int E>
 struct ApplyPar {
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) P[tri(r, c)] = p.cov[(long long)(r * D + c) * p.ld + t];
-    const bool ok = moment_transform<D, E, PTS_GENERIC, 0, KIND, 0>(
+    const bool ok = moment_transform<D, E, PTS_GENERIC, 0, KIND, 0, Fn::EXACT>(
         p.tf, m, P,
         [&](const double (&x)[D], double (&o)[E]) {
             const double z[Fn::NQ] = {};
@@ -168,7 +173,9 @@ extern "C" int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_sta
     cudaStream_t s = (cudaStream_t)stream;
     int rc = SSM_OK;
 #define CALL(FN) rc = apply_kind<FN>(*tf, par, time, mean, cov, mean_f, cov_f, cov_fx, status, n, ld, s);
-    SSM_FN_DISPATCH(CALL)
+    if (which == 0 && model == SSM_DYN_UNGMNA) { CALL(FnDynUngmNAaug) }          // mean / cov of [x; q] (ssmod.py:158-160)
+    else if (which == 1 && model == SSM_OBS_UNGMNA && dim_state == 1) { CALL(FnObsUngmNAaug) }
+    else SSM_FN_DISPATCH(CALL)
 #undef CALL
     if (rc == SSM_E_CUDA) set_error("ssm_transform_apply: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
@@ -183,7 +190,9 @@ extern "C" int ssm_model_eval(int32_t which, int32_t model, int32_t dim_state, i
     Par4 p4;
     for (int i = 0; i < 4; ++i) p4.v[i] = par ? par[i] : 0.0;
 #define CALL(FN) eval_kernel_v<FN><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p4, time, x, noise, out, (long long)n, (long long)ld);
-    SSM_FN_DISPATCH(CALL)
+    if (which == 0 && model == SSM_DYN_UNGMNA) { CALL(FnDynUngmNA) }
+    else if (which == 1 && model == SSM_OBS_UNGMNA && dim_state == 1) { CALL(FnObsUngmNA) }
+    else SSM_FN_DISPATCH(CALL)
 #undef CALL
     if (cudaGetLastError() != cudaSuccess) { set_error("ssm_model_eval: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError())); return SSM_E_CUDA; }
     return SSM_OK;

@@ -126,7 +126,12 @@ struct FxStore<E, NCAP, 0> {  // registers
 // The cross-covariance is handed out row by row through `sink(a, row)` (row = Cov(f_a, x), D values) so that the
 // caller decides where it lives: the measurement transform keeps it in registers for the gain, the dynamics
 // transform streams it straight to HBM (no 25-double live array between the transform and the stores).
-template <int D, int E, int PTS, int NPTS, int KIND, int SMT, class Tf, class F, class Sink>
+// EXACT: mean and centred cross-covariance sums with separately rounded products (no FMA).  The reference's models
+// with non-additive noise rely on EXACT cancellation between mirrored sigma points: z = 0.05 r x^2 at the +r / -r
+// points must sum to a mean of exactly 0 and a state cross-covariance of exactly 0, because the measurement covariance
+// is ~m^4 (1e-60 while the mean is still at rounding level) and K = Pxy / Py turns any 1e-17 residue of a fused
+// multiply-add into O(1) garbage.  numpy's small dot products round every product before adding, so they cancel.
+template <int D, int E, int PTS, int NPTS, int KIND, int SMT, bool EXACT, class Tf, class F, class Sink>
 SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (&P)[TriSize<D>::value], F f,
                               double (&mf)[E], double (&Cf)[TriSize<E>::value], const bool want_cross, Sink sink,
                               double *sfx) {
@@ -150,7 +155,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
     for (int a = 0; a < E; ++a) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) s = fma(fx(a, i), tf.wm(i), s);
+        for (int i = 0; i < n; ++i) s = EXACT ? __dadd_rn(s, __dmul_rn(fx(a, i), tf.wm(i))) : fma(fx(a, i), tf.wm(i), s);
         mf[a] = s;
     }
 #pragma unroll
@@ -190,7 +195,8 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                     if (r < j0) continue;  // structurally zero
                     const double dxr = x[r] - m[r];  // (x - mean), mtran.py:148
 #pragma unroll
-                    for (int a = 0; a < E; ++a) Cfx[a][r] = fma(fx(a, i) * w, dxr, Cfx[a][r]);
+                    for (int a = 0; a < E; ++a)
+                        Cfx[a][r] = EXACT ? __dadd_rn(Cfx[a][r], __dmul_rn(__dmul_rn(fx(a, i), w), dxr)) : fma(fx(a, i) * w, dxr, Cfx[a][r]);
                 }
             }
 #pragma unroll
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     double *sfx = SMEM_FX ? ssm_dyn_smem + threadIdx.x : nullptr;
     constexpr int DX = Dyn::DX, DY = Obs::DY;
     constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
+    constexpr bool NA = !Dyn::ADDITIVE || !Obs::ADDITIVE;  // non-additive noise somewhere: exact-cancellation sums
     const FilterBuffers &b = p.b;
     const int N = b.n_steps;
     const long long ld = b.ld;
@@ -474,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         double *q_xx = b.pr_xx ? row_ptr(b.pr_xx, rk) : nullptr;
         bool ok;
         if constexpr (Dyn::ADDITIVE) {
-            ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT>(
+            ok = moment_transform<DX, DX, PTS, NPTS, KIND, SMT, NA>(
                 p.tf_dyn, m, P,
                 [&](const double (&x)[DX], double (&o)[DX]) {
                     const double q0[Dyn::DQ] = {};
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             constexpr int DD = DX + Dyn::DQ;
             double ma[DD], Pa[TriSize<DD>::value];
             augment<DX, Dyn::DQ>(m, P, p.q_mean, p.q_cov, ma, Pa);
-            ok = moment_transform<DD, DX, PTS, NPTS, KIND, SMT>(
+            ok = moment_transform<DD, DX, PTS, NPTS, KIND, SMT, NA>(
                 p.tf_dyn, ma, Pa,
                 [&](const double (&xq)[DD], double (&o)[DX]) {
                     double x[DX], q[Dyn::DQ];
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         // ---- predictive measurement moments (ssinf.py:287-291 / 684-693) ------------------------
         double my[DY], Sy[TY], Syx[DY][DX];
         if constexpr (Obs::ADDITIVE) {
-            ok = moment_transform<DX, DY, PTS, NPTS, KIND, SMT>(
+            ok = moment_transform<DX, DY, PTS, NPTS, KIND, SMT, NA>(
                 p.tf_obs, mp, Pp,
                 [&](const double (&x)[DX], double (&o)[DY]) {
                     const double r0[DY] = {};
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             constexpr int DO = DX + DY;
             double ma[DO], Pa[TriSize<DO>::value];
             augment<DX, DY>(mp, Pp, p.r_mean, p.R, ma, Pa);
-            ok = moment_transform<DO, DY, PTS, NPTS, KIND, SMT>(
+            ok = moment_transform<DO, DY, PTS, NPTS, KIND, SMT, NA>(
                 p.tf_obs, ma, Pa,
                 [&](const double (&xr)[DO], double (&o)[DY]) {
                     double x[DX], r[DY];

@@ -84,7 +84,8 @@ def lower(d):
     R = _c(d['r_cov'])
     dy = R.shape[0]
     G = _c(d['G'])
-    GQG = _c(G.dot(_c(d['q_cov'])).dot(G.T))  # ssinf.py:279
+    q_cov = np.atleast_2d(_c(d['q_cov']))
+    GQG = _c(G.dot(q_cov).dot(G.T))  # ssinf.py:279
     keep += [m0, P0, R, GQG]
     s = _lib.SsmDesc()
     s.dyn_model, s.obs_model, s.dx, s.dy = _lib.DYN_IDS[dyn_name], _lib.OBS_IDS[obs_name], dx, dy
@@ -96,6 +97,13 @@ def lower(d):
     for i, v in enumerate(si):
         s.state_index[i] = int(v)
     s.m0, s.P0, s.GQG, s.R = _ptr(m0), _ptr(P0), _ptr(GQG), _ptr(R)
+    # noise moments for models with non-additive noise (augmented transforms, ssinf.py:271-272, 282-283)
+    dq = q_cov.shape[0]
+    q_mean = _c(np.asarray(d.get('q_mean', np.zeros(dq)), dtype=np.float64).reshape(-1))
+    r_mean = _c(np.asarray(d.get('r_mean', np.zeros(dy)), dtype=np.float64).reshape(-1))
+    q_cov = _c(q_cov)
+    keep += [q_mean, r_mean, q_cov]
+    s.q_mean, s.q_cov, s.r_mean, s.dq = _ptr(q_mean), _ptr(q_cov), _ptr(r_mean), dq
     if 'dof' in d:
         s.family = _lib.FAMILY_STUDENT
         s.dof, s.x0_dof = float(d['dof']), float(d['x0_dof'])

@@ -32,11 +32,12 @@ from .ssmod import TransitionModel, MeasurementModel
 from .utils import StudentRV
 
 _DEFAULT_OBS = {1: ('UNGMMeasurement', []), 2: ('Pendulum2DMeasurement', []), 3: ('Radar2DMeasurement', []),
-                4: ('Radar2DMeasurement', [0, 2]), 5: ('RangeMeasurement', [])}
+                4: ('Radar2DMeasurement', [0, 2]), 5: ('RangeMeasurement', []), 6: ('UNGMNAMeasurement', [])}
 _DEFAULT_DYN = {('UNGMMeasurement', ()): ('UNGMTransition', 1, 1), ('Pendulum2DMeasurement', ()): ('Pendulum2DTransition', 2, 2),
                 ('Radar2DMeasurement', ()): ('ReentryVehicle2DTransition', 5, 3),
                 ('Radar2DMeasurement', (0, 1)): ('ReentryVehicle2DTransition', 5, 3),
                 ('Radar2DMeasurement', (0, 2)): ('CoordinatedTurnTransition', 5, 5),
+                ('UNGMNAMeasurement', ()): ('UNGMNATransition', 1, 1),
                 ('RangeMeasurement', ()): ('ReentryVehicle1DTransition', 3, 3),
                 ('RangeMeasurement', (0,)): ('ReentryVehicle1DTransition', 3, 3)}
 

@@ -65,7 +65,7 @@ class TransitionModel(metaclass=ABCMeta):
         d = {'dyn_name': type(self).__name__, 'dyn_dt': float(getattr(self, 'dt', 0.0)), 'G': self.noise_gain}
         st = self.init_rv.get_stats()
         d['m0'], d['P0'] = st[0], st[1]
-        d['q_cov'] = self.noise_rv.get_stats()[1]
+        d['q_mean'], d['q_cov'] = self.noise_rv.get_stats()[:2]
         if len(st) == 3:
             d['x0_dof'], d['q_dof'] = float(st[2]), float(self.noise_rv.dof)
         return d
@@ -81,8 +81,11 @@ class TransitionModel(metaclass=ABCMeta):
         if dx:
             raise NotImplementedError('Jacobians are not part of the device hot path')
         xq = np.asarray(xq, dtype=np.float64)
-        assert xq.shape[0] == self.dim_state
-        return self.dyn_fcn(xq, self.zero_q, time)
+        if self.noise_additive:
+            assert xq.shape[0] == self.dim_state
+            return self.dyn_fcn(xq, self.zero_q, time)
+        assert xq.shape[0] == self.dim_state + self.dim_noise      # ssmod.py:158-160
+        return self.dyn_fcn(xq[:self.dim_state], xq[-self.dim_noise:], time)
 
     # -- simulation ---------------------------------------------------------------------------------
     def _sim_low(self, obs=None):
@@ -115,6 +118,17 @@ class UNGMTransition(TransitionModel):
 
     def __init__(self, init_rv, noise_rv):
         super(UNGMTransition, self).__init__(init_rv, noise_rv)
+
+
+class UNGMNATransition(TransitionModel):
+    """UNGM with non-additive process noise, x' = 0.5 x + 25 x / (1 + x^2) + 8 q cos(1.2 k) (ssmod.py:278-306)."""
+    dim_state = 1
+    dim_noise = 1
+    noise_additive = False
+    _device_id = 6
+
+    def __init__(self, init_rv, noise_rv):
+        super(UNGMNATransition, self).__init__(init_rv, noise_rv)
 
 
 class Pendulum2DTransition(TransitionModel):
@@ -196,7 +210,7 @@ class MeasurementModel(metaclass=ABCMeta):
         return (int(si[0]), int(si[1]) if len(si) > 1 else 0)
 
     def _desc(self):
-        d = {'obs_name': type(self).__name__, 'r_cov': self.noise_rv.get_stats()[1],
+        d = {'obs_name': type(self).__name__, 'r_mean': self.noise_rv.get_stats()[0], 'r_cov': self.noise_rv.get_stats()[1],
              'state_index': [] if self.state_index is None else list(self.state_index),
              'radar_loc': np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64)}
         if isinstance(self.noise_rv, StudentRV):
@@ -218,7 +232,11 @@ class MeasurementModel(metaclass=ABCMeta):
         if dx:
             raise NotImplementedError('Jacobians are not part of the device hot path')
         xr = np.asarray(xr, dtype=np.float64)
-        return _eval(1, self._device_id, self.dim_state, self._si(), self._par(), time, xr, self.zero_r, self.dim_out)
+        if self.noise_additive:
+            return _eval(1, self._device_id, self.dim_state, self._si(), self._par(), time, xr, self.zero_r, self.dim_out)
+        assert xr.shape[0] == self.dim_state + self.dim_noise      # ssmod.py:999-1001 (state_index = None)
+        return _eval(1, self._device_id, self.dim_state, self._si(), self._par(), time, xr[:self.dim_state],
+                     xr[-self.dim_noise:], self.dim_out)
 
     def simulate_measurements(self, x, device_out=False):
         """y[:, k, i] = h(x[state_index, k, i], r[:, k, i], k+1) (ssmod.py:1011-1039)."""
@@ -245,6 +263,18 @@ class UNGMMeasurement(MeasurementModel):
 
     def __init__(self, noise_rv, dim_state, state_index=None):
         super(UNGMMeasurement, self).__init__(noise_rv, dim_state, state_index)
+
+
+class UNGMNAMeasurement(MeasurementModel):
+    """z = 0.05 r x^2, non-additive measurement noise (ssmod.py:1067-1089)."""
+    dim_substate = 1
+    dim_out = 1
+    dim_noise = 1
+    noise_additive = False
+    _device_id = 5
+
+    def __init__(self, noise_rv, dim_state, state_index=None):
+        super(UNGMNAMeasurement, self).__init__(noise_rv, dim_state, state_index)
 
 
 class Pendulum2DMeasurement(MeasurementModel):

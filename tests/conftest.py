@@ -38,16 +38,23 @@ def golden_filter_cases():
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, 'c*.npz')))
 
 
-def relstep(a, b):
-    """max over (step, trajectory) of the max-norm relative error; time axis -2, trajectory axis -1."""
+def relstep(a, b, floor=0.0):
+    """max over (step, trajectory) of the max-norm relative error; time axis -2, trajectory axis -1.
+    floor: lower bound of the normalisation (see MEAN_FLOOR)."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     ax = tuple(range(a.ndim - 2))
     ok = np.isfinite(b).all(axis=ax)
     if not ok.any():
         return 0.0
     num = np.abs(a - b).max(axis=ax)[ok]
-    den = np.abs(b).max(axis=ax)[ok]
+    den = np.maximum(np.abs(b).max(axis=ax)[ok], floor)
     return float(np.max(num / den))
+
+
+# UNGM with non-additive noise (c7_*): the measurement 0.05 r x^2 is uncorrelated with the state, so no filter ever
+# corrects the mean; under some rules (GH-4) it decays to 0 and ends as rounding noise around exact zeros.  These means
+# are compared absolutely (normalised by >= 1; the state's standard deviation is ~20), the covariances relatively.
+MEAN_FLOOR = {'c7_ungmna_ukf': 1.0, 'c7_ungmna_ckf': 1.0, 'c7_ungmna_ghkf': 1.0, 'c7_ungmna_gpq': 1.0}
 
 
 def rel(a, b):
@@ -80,6 +87,7 @@ FULL_TOL = {
     'c4_ct_tpq': 1e-8, 'c4_ct_gpq': 1e-9, 'c4_ct_ukf': 1e-9, 'c4_ct_bsq': None,
     'c4_ct_fsstudent': 1e-9, 'c4_ct_fsstudent_incdof': 1e-9, 'c4_ct_fsstudent_deg5': 1e-9,
     'c6_reentry1d_gpq': 1e-8, 'c6_reentry1d_ukf': 1e-9,
+    'c7_ungmna_ukf': 1e-8, 'c7_ungmna_ckf': 1e-8, 'c7_ungmna_ghkf': 1e-8, 'c7_ungmna_gpq': 1e-7,
     'c5_pend_ukf': 1e-9, 'c5_pend_gpq': 1e-9, 'c5_pend_tpq': 1e-9, 'c5_pend_bsq': None, 'c5_pend_ghkf3': 1e-9,
 }
 for _i in range(11):
