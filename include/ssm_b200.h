@@ -338,6 +338,13 @@ int ssm_memcpy2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, u
  * The caller times it with CUDA events. */
 int ssm_fp64_peak_kernel(int32_t n_blocks, int32_t n_iters, double *sink, double *flops, void *stream);
 
+/* ---- device math probe -----------------------------------------------------------------------------
+ * Evaluates the library's own fp64 routines at n points (device arrays): which = 0 exp(a), 1 sqrt(a), 2 1/sqrt(a),
+ * 3 a / b, 4 atan2(a, b).  b is read for which >= 3 only.  Test hook: the forward pass calls these routines out of
+ * line (one shared copy each) -- the parity suite measures their error in ulp against
+ * numpy over the whole argument range. */
+int ssm_math_probe(int32_t which, const double *a, const double *b, double *out, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

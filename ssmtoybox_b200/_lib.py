@@ -82,6 +82,8 @@ def _load():
     lib.ssm_scores_phase2_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_bootstrap_var.restype = C.c_int
     lib.ssm_bootstrap_var.argtypes = [vp, i64, i32, C.c_uint64, vp, vp, vp]
+    lib.ssm_math_probe.restype = C.c_int
+    lib.ssm_math_probe.argtypes = [i32, vp, vp, vp, i64, vp]
     lib.ssm_smooth.restype = C.c_int
     lib.ssm_smooth.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, vp]
     lib.ssm_fp64_peak_kernel.restype = C.c_int

@@ -79,3 +79,28 @@ extern "C" int ssm_bootstrap_var(const double *data, int64_t n, int32_t n_boot, 
     }
     return SSM_OK;
 }
+
+// ---- device math probe (test hook, include/ssm_b200.h) --------------------------------------------------------------
+namespace ssm {
+__global__ void math_probe_kernel(int which, const double *a, const double *b, double *out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = a[i], y = (which >= 3) ? b[i] : 0.0;
+    double r;
+    switch (which) {
+        case 0: r = m_exp(x); break;
+        case 1: r = m_sqrt(x); break;
+        case 2: r = m_rsqrt(x); break;
+        case 3: r = m_div(x, y); break;
+        default: r = m_atan2(x, y); break;
+    }
+    out[i] = r;
+}
+}  // namespace ssm
+
+extern "C" int ssm_math_probe(int32_t which, const double *a, const double *b, double *out, int64_t n, void *stream) {
+    if (!a || !out || (which >= 3 && !b) || which < 0 || which > 4 || n < 0) { set_error("ssm_math_probe: bad arguments"); return SSM_E_INVALID; }
+    if (n == 0) return SSM_OK;
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, a, b, out, (long long)n);
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}

@@ -467,3 +467,33 @@ def test_c3_filter_with_device_weights_runs_and_matches_oracle():
     assert relstep(N_(o['fi_cov']), ref['fi_cov']) < 2e-5
     # and the filter tracks much better than with the reference's noise weights (golden: 0.48)
     assert np.abs(N_(o['fi_mean'])[:2] - g['x'][:2]).mean() < 0.2
+
+
+def test_math_probe():
+    """the device.s out-of-line fp64 routines against numpy, in ulp"""
+    from ssmtoybox_b200._lib import lib, check
+    from ssmtoybox_b200.device import _p, _stream
+
+    def probe(which, a, b=None):
+        ta = T(a)
+        tb = T(b) if b is not None else None
+        out = torch.empty_like(ta)
+        check(lib.ssm_math_probe(which, _p(ta), _p(tb), _p(out), ta.numel(), _stream()), 'ssm_math_probe')
+        return N_(out)
+
+    def ulps(got, ref):
+        return np.abs(got - ref) / np.spacing(np.abs(ref))
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.uniform(-700, 700, 200000), rs.uniform(-30, 5, 200000), rs.uniform(-1, 1, 100000) * 1e-3,
+                        np.array([0.0, -0.0, 699.999, -699.999, 0.34657359, -0.34657359, 1.0, -1.0])])
+    u = ulps(probe(0, x), np.exp(x))
+    assert u.max() <= 1.0, u.max()                     # numpy's exp is itself within 1 ulp of the true value
+    assert (u == 0).mean() > 0.8
+    edge = np.array([np.nan, np.inf, -np.inf, 710.0, -746.0, 800.0, -800.0, 700.0, -700.0])     # libm path
+    with np.errstate(over='ignore'):
+        assert np.array_equal(probe(0, edge), np.exp(edge), equal_nan=True)
+    a, b = rs.uniform(1e-6, 1e8, 100000), rs.uniform(-1e4, 1e4, 100000)
+    assert ulps(probe(1, a), np.sqrt(a)).max() == 0
+    assert ulps(probe(2, a), 1.0 / np.sqrt(a)).max() <= 1.0
+    assert ulps(probe(3, b, a), b / a).max() == 0
+    assert ulps(probe(4, b, a - 5e7), np.arctan2(b, a - 5e7)).max() <= 2.0
