@@ -83,7 +83,7 @@ static int launch_apply(const ssm_transform &tf, const double *par, double time,
     if (N < 1 || N > GEN_CAP) { set_error("ssm_transform_apply: at most %d points", GEN_CAP); return SSM_E_UNSUPPORTED; }
     const size_t cnt = (size_t)(2 * N + 2 * N * N + 2 * D * N);
     double *host = (double *)malloc(cnt * sizeof(double)), *dev = nullptr;
-    if (cudaMallocAsync(&dev, cnt * sizeof(double), s) != cudaSuccess) { free(host); return SSM_E_CUDA; }
+    if (scratch_alloc((void **)&dev, cnt * sizeof(double), s) != cudaSuccess) { free(host); return SSM_E_CUDA; }
     ApplyPar<D, E> p;
     memset(&p, 0, sizeof(p));
     size_t off = 0;

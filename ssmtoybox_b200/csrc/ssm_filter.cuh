@@ -822,7 +822,7 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     if (want_ticket && CHUNK > 0 && cap > 0 && blocks > cap && win >= 2 * CHUNK) {
         const size_t n_int = ((size_t)blocks + 2 + 1) / 2 * 2;  // ticket, done[blocks], wait counter; doubles stay 8-byte aligned
         const size_t bytes = n_int * sizeof(int) + (size_t)blocks * THREADS * (DX + TriSize<DX>::value + 2) * sizeof(double);
-        if (cudaMallocAsync(&work, bytes, L.stream) != cudaSuccess) { delete pp; set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
+        if (scratch_alloc((void **)&work, bytes, L.stream) != cudaSuccess) { delete pp; set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
         cudaMemsetAsync(work, 0, n_int * sizeof(int), L.stream);
         p.b.sched = (int *)work;
         p.b.state = (double *)((int *)work + n_int);

@@ -105,7 +105,7 @@ int launch_filter_global(const FilterLaunch &L) {
     const size_t cnt = (size_t)(2 * Na + 2 * Na * Na + 2 * DD * Na) + (size_t)(2 * Nb + 2 * Nb * Nb + 2 * DO * Nb);
     double *host = (double *)malloc(cnt * sizeof(double));
     double *dev = nullptr;
-    if (cudaMallocAsync(&dev, cnt * sizeof(double), L.stream) != cudaSuccess) { free(host); set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
+    if (scratch_alloc((void **)&dev, cnt * sizeof(double), L.stream) != cudaSuccess) { free(host); set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }
     Par p;
     memset(&p, 0, sizeof(p));
     size_t off = 0;

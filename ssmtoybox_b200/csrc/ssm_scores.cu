@@ -147,7 +147,7 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
     double *partial = nullptr;
-    if (cudaMallocAsync(&partial, (size_t)n_cta * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    if (scratch_alloc((void **)&partial, (size_t)n_cta * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, nll_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * W;
     scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, n_cta, WLEN, DX);
@@ -162,7 +162,7 @@ static int run_phase2(const double *x, const double *mean, const double *cov, co
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
     double *partial = nullptr;
-    if (cudaMallocAsync(&partial, (size_t)n_cta * WLEN * 2 * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    if (scratch_alloc((void **)&partial, (size_t)n_cta * WLEN * 2 * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, mse, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * 2;
     scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);

@@ -217,7 +217,7 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
     const long long tail_blocks = (rem + SC_THREADS - 1) / SC_THREADS;
     constexpr int W = ScoreRow<DX>::WP;
     double *partial = nullptr;
-    if (x_truth && cudaMallocAsync(&partial, (size_t)(n_full + tail_blocks) * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    if (x_truth && scratch_alloc((void **)&partial, (size_t)(n_full + tail_blocks) * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     a.partial = partial;
     cudaError_t e = cudaSuccess;
     if (n_full) e = x_truth ? launch_tma<DX, true>(a, n_full, s) : launch_tma<DX, false>(a, n_full, s);

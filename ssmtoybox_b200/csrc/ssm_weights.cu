@@ -473,7 +473,7 @@ extern "C" int ssm_bq_weights(int32_t dim, int32_t n_pts, int32_t n_par, const d
     const long long work_stride = work_elems * (precision ? 2 : 1);   // in doubles; dd = 2 doubles per element
     const size_t bytes = (n_in + (size_t)work_stride * n_par) * sizeof(double) + (size_t)(D * Q + 2) * sizeof(int);
     double *dev = nullptr;
-    if (cudaMallocAsync(&dev, bytes, s) != cudaSuccess) { set_error("ssm_bq_weights: cudaMallocAsync failed"); return SSM_E_CUDA; }
+    if (scratch_alloc((void **)&dev, bytes, s) != cudaSuccess) { set_error("ssm_bq_weights: cudaMallocAsync failed"); return SSM_E_CUDA; }
     std::vector<double> host(n_in);
     size_t off = 0;
     WeightsPar p;
@@ -584,7 +584,7 @@ extern "C" int ssm_rbf_eval(int32_t dim, int32_t n1, int32_t n2, const double *p
     memcpy(host.data() + dim + 1, x1, (size_t)dim * n1 * sizeof(double));
     memcpy(host.data() + dim + 1 + (size_t)dim * n1, x2, (size_t)dim * n2 * sizeof(double));
     double *dev = nullptr;
-    if (cudaMallocAsync(&dev, cnt * sizeof(double), s) != cudaSuccess) { set_error("ssm_rbf_eval: cudaMallocAsync failed"); return SSM_E_CUDA; }
+    if (scratch_alloc((void **)&dev, cnt * sizeof(double), s) != cudaSuccess) { set_error("ssm_rbf_eval: cudaMallocAsync failed"); return SSM_E_CUDA; }
     cudaMemcpyAsync(dev, host.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, s);
     RbfPar p{dim, n1, n2, scaling, dev, dev + dim + 1, dev + dim + 1 + (size_t)dim * n1, K, nullptr, nullptr, nullptr, nullptr};
     const int total = n1 * n2;
@@ -604,7 +604,7 @@ extern "C" int ssm_rbf_expectations(int32_t dim, int32_t n_pts, const double *pa
     memcpy(host.data(), par, (dim + 1) * sizeof(double));
     memcpy(host.data() + dim + 1, points, (size_t)dim * n_pts * sizeof(double));
     double *dev = nullptr;
-    if (cudaMallocAsync(&dev, cnt * sizeof(double), s) != cudaSuccess) { set_error("ssm_rbf_expectations: cudaMallocAsync failed"); return SSM_E_CUDA; }
+    if (scratch_alloc((void **)&dev, cnt * sizeof(double), s) != cudaSuccess) { set_error("ssm_rbf_expectations: cudaMallocAsync failed"); return SSM_E_CUDA; }
     cudaMemcpyAsync(dev, host.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, s);
     RbfPar p{dim, n_pts, n_pts, scaling, dev, dev + dim + 1, dev + dim + 1, nullptr, q, R, Q, kbar};
     rbf_expect_kernel<<<1, 128, 0, s>>>(p);

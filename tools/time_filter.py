@@ -25,8 +25,8 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); dv.filter_forward(low, y, store_pred=sp, out=o); e1.record(); e1.synchronize()
             ts.append(e0.elapsed_time(e1))
-        ms = float(np.median(ts))
-        print('%s M=%d N=%d store_pred=%s: %.2f ms  %.3e traj-steps/s  %.2f TFLOP/s(alg 5756)  fails=%d' % (name, M, N, sp, ms, M * N / ms * 1e3, M * N * 5756 / ms * 1e-9, int((o['status'] != 0).sum())))
+        ms = float(np.median(ts)); mn = float(np.min(ts))
+        print('%s M=%d N=%d store_pred=%s: %.2f ms (min %.2f)  %.3e traj-steps/s  %.2f TFLOP/s(alg 5756)  fails=%d' % (name, M, N, sp, ms, mn, M * N / ms * 1e3, M * N * 5756 / ms * 1e-9, int((o['status'] != 0).sum())))
         del o
 
 if __name__ == '__main__':
