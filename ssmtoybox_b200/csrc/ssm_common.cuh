@@ -66,10 +66,10 @@ SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 #define SSM_MATH_FN static __device__ __forceinline__
 #endif
 // exp stays libm's.  Measured alternatives on the reentry forward pass (16 calls per step, 64 instructions each of which
-// 22 are UMOV halves of immediates; 125 000 x 500, filter only): own 2^k exp(r) with the coefficients in a constant-bank
-// table (37 instructions per call) 16.0 -> 22.1 ms -- the LDCU latency in front of every call costs more than the saved
-// issue slots; own Estrin-scheme evaluation with immediates (5-deep instead of 14-deep DFMA chain) 17.2 ms -- the wider
-// callee clobbers more registers around every call site.  Both were within 1 ulp (tests/...::test_math_probe).
+// 22 are UMOV halves of immediates; 125 000 x 500, filter only / with predictive moments, libm 15.75 / 20.28 ms):
+// own 2^k exp(r) with the coefficients in a constant-bank table (37 instructions per call, -430 per step) 16.14 / 20.45;
+// own Estrin-scheme evaluation with immediates (5-deep instead of 14-deep DFMA chain) 15.92 / 20.31.  Neither the issue
+// slots nor the chain latency of exp are what bounds the kernel; both were within 1 ulp of numpy.
 SSM_MATH_FN double m_exp(double x) { return exp(x); }
 SSM_MATH_FN double m_sqrt(double x) { return sqrt(x); }
 SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
