@@ -59,21 +59,37 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
     if (nll_acc && t < n_traj) nll_acc[t] = live ? nll_sum : qnan();
 }
 
-__global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= row) return;
+// Both finalise kernels: blockDim = (32, FIN_GROUPS); thread (x, y) adds the partial rows y, y + FIN_GROUPS, ... of
+// element x in ascending order, then the groups are combined in ascending y: a fixed order for a given row count, and
+// FIN_GROUPS times the memory-level parallelism of one thread per element (the sums run over ~1000 rows of 90 MB).
+SSM_DEV double finalize_sum(const double *__restrict__ p, long long stride, int n_rows, double (*sm)[33]) {
     double s = 0.0;
-    for (int c = 0; c < n_cta; ++c) s += partial[(long long)c * row + i];
-    stats[i] = s;
+    for (int c = threadIdx.y; c < n_rows; c += FIN_GROUPS) s += p[(long long)c * stride];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.y == 0)
+        for (int g = 0; g < FIN_GROUPS; ++g) tot += sm[g][threadIdx.x];
+    return tot;
+}
+
+__global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row) {
+    __shared__ double sm[FIN_GROUPS][33];
+    const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+    const long long ic = i < row ? i : row - 1;
+    const double s = finalize_sum(partial + ic, row, n_cta, sm);
+    if (threadIdx.y == 0 && i < row) stats[i] = s;
 }
 
 __global__ void scores_finalize_packed_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, int n_steps, int dx) {
+    __shared__ double sm[FIN_GROUPS][33];
     const int tx = dx * (dx + 1) / 2, wp = dx + tx + 3, w = dx + dx * dx + 3;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n_steps * wp) return;
+    const long long n = (long long)n_steps * wp;
+    const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+    const long long ic = i < n ? i : n - 1;
+    const double s = finalize_sum(partial + ic, n, n_cta, sm);   // partial[(c * n_steps + k) * wp + j] = partial[c * n + i]
+    if (threadIdx.y != 0 || i >= n) return;
     const int k = (int)(i / wp), j = (int)(i % wp);
-    double s = 0.0;
-    for (int c = 0; c < n_cta; ++c) s += partial[((long long)c * n_steps + k) * wp + j];
     double *row = stats + (long long)k * w;
     if (j < dx) row[j] = s;
     else if (j < dx + tx) {
@@ -85,13 +101,34 @@ __global__ void scores_finalize_packed_kernel(const double *__restrict__ partial
     } else row[dx + dx * dx + (j - dx - tx)] = s;
 }
 
+// Cholesky factor of the per-step MSE matrix, once per step instead of once per trajectory-step: row k of `tab` =
+// [ packed lower factor (TX) | reciprocal pivots (DX) | ok ]
+template <int DX>
+__global__ void phase2_prepare_kernel(const double *__restrict__ mse, double *__restrict__ tab, int N, int k_lo, int k_hi) {
+    constexpr int TX = TriSize<DX>::value, TW = TX + DX + 1;
+    const int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_hi) return;
+    double S[TX], Ls[TX], inv[DX];
+#pragma unroll
+    for (int r = 0; r < DX; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) S[tri(r, c)] = mse[(long long)(r * DX + c) * N + k];
+    const bool ok = chol_lower<DX>(S, Ls, inv);
+    double *row = tab + (long long)(k - k_lo) * TW;
+#pragma unroll
+    for (int i = 0; i < TX; ++i) row[i] = Ls[i];
+#pragma unroll
+    for (int i = 0; i < DX; ++i) row[TX + i] = inv[i];
+    row[TX + DX] = ok ? 1.0 : 0.0;
+}
+
 template <int DX>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
-                                                                   const double *__restrict__ mse, double *__restrict__ partial,
+                                                                   const double *__restrict__ tab, double *__restrict__ partial,
                                                                    double *__restrict__ lcr_acc,
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
-    constexpr int TX = TriSize<DX>::value;
+    constexpr int TX = TriSize<DX>::value, TW = TX + DX + 1;
     const int WLEN = k_hi - k_lo;
     __shared__ double smem[BlockReduce<2>::SIZE];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,7 +139,7 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
     for (int k = k_lo; k < k_hi; ++k) {
         double v[2] = {0.0, 0.0};
         if (live) {
-            double d[DX], P[TX], S[TX], L[TX], Ls[TX];
+            double d[DX], P[TX], L[TX], inv[DX];
             const long long rk = (long long)k * ld + t;
             const double *qx = row_ptr(x, rk), *qm = row_ptr(mean, rk), *qc = row_ptr(cov, rk);
 #pragma unroll
@@ -110,12 +147,12 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) {
-                    P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
-                    S[tri(r, c)] = __ldg(mse + (long long)(r * DX + c) * N + k);
-                }
-            // log_cred_ratio, utils.py:113-120: both quadratic forms through Cholesky factors
-            const bool ok = chol_lower<DX>(P, L) & chol_lower<DX>(S, Ls);
+                for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
+            // log_cred_ratio, utils.py:113-120: both quadratic forms through Cholesky factors; the factor of the MSE
+            // matrix comes from the per-step table (one address per warp: broadcast loads), substitutions multiply by
+            // the reciprocal pivots the factorisations already have
+            const double *ts = tab + (long long)(k - k_lo) * TW;
+            const bool ok = chol_lower<DX>(P, L, inv) & (__ldg(ts + TX + DX) != 0.0);
             double qa = 0.0, qb = 0.0, za[DX], zb[DX];
 #pragma unroll
             for (int i = 0; i < DX; ++i) {
@@ -123,10 +160,10 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
 #pragma unroll
                 for (int c = 0; c < i; ++c) {
                     sa = fma(-L[tri(i, c)], za[c], sa);
-                    sb = fma(-Ls[tri(i, c)], zb[c], sb);
+                    sb = fma(-__ldg(ts + tri(i, c)), zb[c], sb);
                 }
-                za[i] = sa / L[tri(i, i)];
-                zb[i] = sb / Ls[tri(i, i)];
+                za[i] = sa * inv[i];
+                zb[i] = sb * __ldg(ts + TX + i);
                 qa = fma(za[i], za[i], qa);
                 qb = fma(zb[i], zb[i], qb);
             }
@@ -150,7 +187,7 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
     if (scratch_alloc((void **)&partial, (size_t)n_cta * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, nll_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * W;
-    scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, n_cta, WLEN, DX);
+    scores_finalize_packed_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, n_cta, WLEN, DX);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
@@ -159,13 +196,16 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
 template <int DX>
 static int run_phase2(const double *x, const double *mean, const double *cov, const int32_t *status, const double *mse,
                       double *lcr, double *lcr_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+    constexpr int TW = TriSize<DX>::value + DX + 1;
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
-    double *partial = nullptr;
-    if (scratch_alloc((void **)&partial, (size_t)n_cta * WLEN * 2 * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
-    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, mse, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
+    double *partial = nullptr;  // [n_cta][WLEN][2] partial rows, then the [WLEN][TW] table of MSE factors
+    if (scratch_alloc((void **)&partial, ((size_t)n_cta * WLEN * 2 + (size_t)WLEN * TW) * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    double *tab = partial + (size_t)n_cta * WLEN * 2;
+    phase2_prepare_kernel<DX><<<(WLEN + 63) / 64, 64, 0, s>>>(mse, tab, N, k_lo, k_hi);
+    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, tab, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * 2;
-    scores_finalize_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);
+    scores_finalize_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;

@@ -92,6 +92,7 @@ SSM_DEV void block_reduce_store(const double (&v)[W], double *smem /* [BlockRedu
     }
 }
 
+constexpr int FIN_GROUPS = 8;  // blockDim.y of the finalise kernels (ssm_scores.cu)
 // stats[i] = sum over CTAs (fixed order) of partial[cta][i]
 __global__ void scores_finalize_kernel(const double *__restrict__ partial, double *__restrict__ stats, int n_cta, long long row);
 // same, expanding packed rows (width WP) into public rows (width W) with the symmetric matrix mirrored

@@ -236,7 +236,7 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
     }
     if (x_truth) {
         const long long row = (long long)WLEN * W;
-        scores_finalize_packed_kernel<<<(unsigned)((row + 255) / 256), 256, 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W,
+        scores_finalize_packed_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W,
                                                                                     (int)(n_full + tail_blocks), WLEN, DX);
         if (e == cudaSuccess) e = cudaGetLastError();
         cudaFreeAsync(partial, s);
