@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 2
+#define SSM_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define SSM_OK             0
