@@ -319,6 +319,13 @@ int ssm_rbf_eval(int32_t dim, int32_t n1, int32_t n2, const double *par, const d
 int ssm_rbf_expectations(int32_t dim, int32_t n_pts, const double *par, const double *points, int32_t scaling,
                          double *q, double *R, double *Q, double *kbar, void *stream);
 
+/* Monte-Carlo counterpart for a standard Student-t density (RBFStudent, bq/bqkern.py:457-536; 2 * 10^6 samples in
+ * the reference): q (N), R (D, N), Q (N, N), kbar (1) of the UNSCALED kernel from n_samples draws of t_dof(0, I),
+ * Philox-keyed by (seed, sample index).  dim <= 8, n_pts <= 32. */
+int ssm_rbf_student_expectations(int32_t dim, int32_t n_pts, const double *par, const double *points, double dof,
+                                 int64_t n_samples, uint64_t seed, double *q, double *R, double *Q, double *kbar,
+                                 void *stream);
+
 /* ---- stand-alone sampler ---------------------------------------------------------------------
  * Replaces GaussRV.sample / StudentRV.sample (utils.py:618-619, 670-671): out (dim, ld) =
  * mean + F z (dof = 0) or mean + F z / sqrt(gamma(dof/2, 2/dof)) (dof > 0), Philox-keyed by

@@ -397,6 +397,27 @@ def gen_ungmna():
     save('simulation_ungmna', **d)
 
 
+def gen_student_bq():
+    """Student filters with BQ transforms whose kernel expectations are Monte-Carlo integrals under a Student density
+    (RBFStudent, bq/bqkern.py:457-536): StudentProcessStudent (TPQSF, ssinf.py:778-833) and the GPQ Student filter of
+    research/tpq/tpq_base.py:41-91, on the heavy-tailed coordinated-turn model.  The Monte-Carlo weights (numpy MT19937,
+    2e6 samples) are stored: the device filter is checked with them assigned, its own Monte-Carlo weights statistically."""
+    np.random.seed(3)
+    dyn_s, obs_s, x, y = coordinated_turn(60, 3, student=True)
+    par_dyn = np.array([[1.0, 1, 1, 1, 1, 1]])
+    par_obs = np.array([[1.0, 1, 1e2, 1, 1e2, 1e2]])
+    np.random.seed(21)
+    alg = ssinf.StudentProcessStudent(dyn_s, obs_s, par_dyn, par_obs, dof=6.0)
+    extra = {'kern_par_dyn': par_dyn, 'kern_par_obs': par_obs,
+             'dyn_q': alg.tf_dyn.model.q, 'dyn_Q': alg.tf_dyn.model.Q, 'obs_q': alg.tf_obs.model.q, 'obs_Q': alg.tf_obs.model.Q}
+    filter_case('c4_ct_fsstudent_tpq', alg, x, y, smooth=False, extra=extra)
+    # GPQStudent of tpq_base.py: GaussianProcessTransform(dim_in, kern_par, 'rbf-student', 'fs', {'dof': q_dof})
+    t_dyn = bqmtran.GaussianProcessTransform(5, 5, par_dyn, 'rbf-student', 'fs', {'dof': dyn_s.noise_rv.dof})
+    t_obs = bqmtran.GaussianProcessTransform(5, 2, par_obs, 'rbf-student', 'fs', {'dof': obs_s.noise_rv.dof})
+    alg = ssinf.StudentianInference(dyn_s, obs_s, t_dyn, t_obs, 6.0, True)
+    filter_case('c4_ct_fsstudent_gpq', alg, x[..., :2], y[..., :2], smooth=False)
+
+
 def gen_weights():
     """BQ weights and kernel expectations (bqmod.py:495-523, 893-992; bqkern.py:329-424)."""
     cases = []
@@ -518,7 +539,7 @@ def gen_scores():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'weights': gen_weights, 'simulation': gen_simulation,
+    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'weights': gen_weights, 'simulation': gen_simulation,
             'scores': gen_scores}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

@@ -217,6 +217,81 @@ def rbf_exp_xy_kxy(par):
     return alpha ** 2 * np.linalg.det(2 * sil ** 2 + np.eye(sil.shape[0])) ** -0.5
 
 
+# ----------------------------------------------------------------------------------------------
+# RBF kernel expectations under a standard Student-t density               bq/bqkern.py:457-536
+# ----------------------------------------------------------------------------------------------
+def _gamma_mix_nodes(dof, n=400):
+    """Nodes / weights of the Gamma(dof/2, scale 2/dof) mixing variable u of x = z / sqrt(u), z ~ N(0, I)
+    (utils.py:349-382): Gauss-Legendre in the probability variable is inaccurate at the u -> 0 end, so the
+    integral over u in (0, inf) is done as Gauss-Legendre in t = log u on a range that leaves < 1e-18 outside."""
+    from scipy.special import gammaln
+    k, th = 0.5 * dof, 2.0 / dof
+    t, w = np.polynomial.legendre.leggauss(n)
+    # log-density in t is k (t - e^t) + const for the unit-mean Gamma: 40 below its maximum at both ends
+    lo, hi = -(40.0 / k + np.sqrt(80.0 / k)), np.log1p(40.0 / k + np.sqrt(80.0 / k))
+    t = 0.5 * (hi - lo) * t + 0.5 * (hi + lo)
+    w = 0.5 * (hi - lo) * w
+    u = np.exp(t)
+    logpdf = (k - 1) * t - u / th - gammaln(k) - k * np.log(th)
+    return u, w * np.exp(logpdf + t)
+
+
+def rbf_student_expectations(par, x, dof, n=400):
+    """What RBFStudent estimates by 2 * 10^6-sample Monte Carlo (bq/bqkern.py:475-536), computed to quadrature
+    accuracy: a standard Student-t variable is a Gaussian scale mixture, x | u ~ N(0, I / u), and under a Gaussian the
+    RBF expectations are closed-form (bqkern.py:345-424 with I replaced by I / u), so each expectation is a 1-D
+    integral over u (2-D for the pair expectation).  Unscaled kernel (scaling=False, as bq_weights calls it,
+    bqmod.py:508-511).  Returns q (N), R (D, N), Q (N, N), kbar = E[k(x, x')] for independent x, x'."""
+    par = np.atleast_2d(np.asarray(par, dtype=float))
+    l2 = par[0, 1:] ** 2                                        # squared lengthscales (D,)
+    u, w = _gamma_mix_nodes(dof, n)
+    s2 = 1.0 / u                                                # conditional variance
+    D, N = x.shape
+    # q_i(u) = prod_d (1 + s2 / l2_d)^-1/2 exp(-1/2 x_id^2 / (l2_d + s2))
+    den = l2[None, :] + s2[:, None]                             # (n, D)
+    c1 = np.prod(l2[None, :] / den, axis=1) ** 0.5              # (n,)
+    qi = c1[:, None] * np.exp(-0.5 * np.einsum('di,nd->ni', x ** 2, 1.0 / den))
+    q = w.dot(qi)
+    # R_di(u) = q_i(u) x_id s2 / (l2_d + s2)
+    R = np.einsum('n,ni,nd,di->di', w, qi, s2[:, None] / den, x)
+    # Q_ij(u) = exp(-|x_i - x_j|^2_l / 4) prod_d (1 + 2 s2 / l2_d)^-1/2 exp(-1/2 c_d^2 / (l2_d / 2 + s2)), c = (x_i + x_j) / 2
+    diff = x[:, :, None] - x[:, None, :]
+    cen = 0.5 * (x[:, :, None] + x[:, None, :])
+    pref = np.exp(-0.25 * np.einsum('dij,d->ij', diff ** 2, 1.0 / l2))
+    den2 = 0.5 * l2[None, :] + s2[:, None]
+    c2 = np.prod(0.5 * l2[None, :] / den2, axis=1) ** 0.5
+    Qu = c2[:, None, None] * np.exp(-0.5 * np.einsum('dij,nd->nij', cen ** 2, 1.0 / den2))
+    Q = pref * np.einsum('n,nij->ij', w, Qu)
+    # kbar: x - x' | u, u' ~ N(0, (1/u + 1/u') I)
+    ss = s2[:, None] + s2[None, :]
+    kb = np.prod(l2[None, None, :] / (l2[None, None, :] + ss[:, :, None]), axis=2) ** 0.5
+    kbar = w.dot(kb).dot(w)
+    return q, R, Q, float(kbar)
+
+
+def rbf_student_exp_xy_kxy_reference(par, kbar, num_samples=2e6):
+    """The value RBFStudent.exp_xy_kxy converges to (bq/bqkern.py:527-535): it sums the FULL 200 x 200 kernel matrix
+    of each of its 10^4 batches (diagonal included, scaling on) and divides by num_samples instead of by the number
+    of pairs, i.e. it returns (2e6 / num_samples) alpha^2 (199 kbar + 1), not kbar."""
+    alpha2 = float(np.atleast_2d(par)[0, 0]) ** 2
+    batch = int(2e6 // 10000)
+    return 2e6 / float(num_samples) * alpha2 * ((batch - 1) * kbar + 1.0)
+
+
+def student_bq_weights(par, points, dof=4.0):
+    """bq_weights (bqmod.py:495-523) with the RBFStudent expectations in the limit of infinitely many samples."""
+    par = np.atleast_2d(np.asarray(par, dtype=float))
+    p1 = par.copy()
+    p1[0, 0] = 1.0
+    iK = rbf_inv(p1, points)
+    q, R, Q, kbar = rbf_student_expectations(par, points, dof)
+    Wc = iK.dot(Q).dot(iK)
+    if not np.array_equal(Wc, Wc.T):
+        Wc = 0.5 * (Wc + Wc.T)
+    return dict(wm=q.dot(iK), Wc=Wc, Wcc=R.dot(iK), iK=iK, q=q, Q=Q, R=R, model_var=par[0, 0] ** 2 * (1 - np.trace(Q.dot(iK))),
+                integral_var=rbf_student_exp_xy_kxy_reference(par, kbar) - q.dot(iK).dot(q))
+
+
 # ==============================================================================================
 # Bayesian-quadrature weights                                      bq/bqmod.py:495-523, 893-992
 # ==============================================================================================

@@ -101,3 +101,52 @@ class RBFGauss(Kernel):
     def exp_xy_kxy(self, par):
         x = np.zeros((self.dim, 1))
         return self._expect(par, x, False)[3]
+
+
+class RBFStudent(RBFGauss):
+    """RBF kernel with expectations under a standard Student-t density, by Monte Carlo on the device (mirror of
+    bqkern.py:457-536).  One launch (ssm_rbf_student_expectations) draws num_samples multivariate-t samples and
+    accumulates all expectations from them; the result is cached per (parameters, points), so the three methods
+    bq_weights calls in a row share one set of samples (the reference draws a fresh set for each)."""
+    supports_parameter_estimation = False
+
+    def __init__(self, dim, par, jitter=1e-8, dof=4.0, num_samples=2e6, num_batches=1000, seed=0):
+        self.mean = np.zeros((dim, ))
+        self.scale_mat = np.eye(dim)
+        self.dof = dof
+        self.num_samples = int(num_samples)
+        self.num_batches = int(num_batches)          # kept for signature compatibility; the device needs no batches
+        self.batch_size = int(num_samples // num_batches)
+        self.seed = seed
+        self._cache = {}
+        super(RBFStudent, self).__init__(dim, par, jitter)
+
+    def _expect(self, par, x, scaling):
+        x = dv._c(x)
+        D, N = x.shape
+        p = self._par1(par)
+        key = (p.tobytes(), x.tobytes())
+        if key not in self._cache:
+            kw = dict(dtype=torch.float64, device='cuda')
+            q, R, Q, kbar = torch.empty(N, **kw), torch.empty((D, N), **kw), torch.empty((N, N), **kw), torch.empty(1, **kw)
+            rc = lib.ssm_rbf_student_expectations(D, N, dv._ptr(p), dv._ptr(x), float(self.dof), self.num_samples,
+                                                  int(self.seed) & 0xFFFFFFFFFFFFFFFF, dv._p(q), dv._p(R), dv._p(Q), dv._p(kbar),
+                                                  dv._stream())
+            _lib.check(rc, 'ssm_rbf_student_expectations')
+            self._cache = {key: (q.cpu().numpy(), R.cpu().numpy(), Q.cpu().numpy(), float(kbar.cpu().numpy()[0]))}
+        q, R, Q, kbar = self._cache[key]
+        a2 = float(p[0]) ** 2 if scaling else 1.0      # scaling multiplies every kernel evaluation by alpha^2
+        return q * a2, R * a2, Q * a2 * a2, kbar * a2
+
+    def exp_xy_kxy(self, par):
+        """Mirrors what the reference RETURNS, not the pair expectation kbar = E[k(x, x')] (bqkern.py:527-535): the
+        reference sums the full 200 x 200 kernel matrix (diagonal included, scaling on) of each of its 10^4 batches and
+        divides by num_samples, which converges to (2e6 / num_samples) alpha^2 (199 kbar + 1).  Only integral_var
+        reads it."""
+        kbar = next(iter(self._cache.values()))[3] if self._cache else self._expect(par, np.zeros((self.dim, 1)), False)[3]
+        batch = int(2e6 // 10000)
+        return 2e6 / float(self.num_samples) * self.exp_x_kxx(par) * ((batch - 1) * kbar + 1.0)
+
+    def exp_xy_kxy_pairs(self, par):
+        """kbar = E[k(x, x')], x, x' independent standard Student-t (what exp_xy_kxy is meant to estimate)."""
+        return self._expect(par, np.zeros((self.dim, 1)), False)[3]

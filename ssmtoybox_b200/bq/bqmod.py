@@ -7,7 +7,7 @@ import numpy as np
 
 from .. import device as dv
 from ..mtran import SphericalRadialTransform, UnscentedTransform, GaussHermiteTransform, FullySymmetricStudentTransform
-from .bqkern import RBFGauss
+from .bqkern import RBFGauss, RBFStudent
 
 
 def n_sum_k(n, k):
@@ -31,7 +31,7 @@ def n_sum_k(n, k):
 class Model(object):
     """Kernel + point set (bqmod.py:15-106)."""
     _supported_points_ = ['sr', 'ut', 'gh', 'fs']
-    _supported_kernels_ = ['rbf']
+    _supported_kernels_ = ['rbf', 'rbf-student']
 
     def __init__(self, dim, kern_par, kern_str, point_str, point_par, estimate_par):
         self.kernel = Model.get_kernel(dim, kern_str, kern_par)
@@ -63,18 +63,44 @@ class Model(object):
 
     @staticmethod
     def get_kernel(dim, kernel, par):
-        """(bqmod.py:384-423); 'rbf-student' (Monte-Carlo expectations) and 'rq' are not on the hot path."""
+        """(bqmod.py:384-423); 'rq' is not on the hot path."""
         kernel = kernel.lower()
+        if kernel == 'rbf-student':
+            return RBFStudent(dim, par)     # dof is the class default 4.0, as in the reference (bqmod.py:421)
         if kernel != 'rbf':
-            raise NotImplementedError("kernel '{}' has no device implementation (only 'rbf')".format(kernel))
+            raise NotImplementedError("kernel '{}' has no device implementation ('rbf', 'rbf-student')".format(kernel))
         return RBFGauss(dim, par)
 
     def _weights(self, par, mulind=None):
         par = self.kernel.get_parameters(par)
+        if isinstance(self.kernel, RBFStudent):
+            return self._weights_mc(par)
         w = dv.bq_weights(par[:1], self.points, mulind)
         if int(w['info'][0]) != 0:
             raise np.linalg.LinAlgError('kernel matrix is not positive definite (info = {})'.format(int(w['info'][0])))
         return w
+
+
+def _weights_mc(self, par):
+    """bq_weights (bqmod.py:495-523) from Monte-Carlo kernel expectations: the inverse kernel matrix comes from the
+    weights kernel (double-double), q / Q / R / kbar from ssm_rbf_student_expectations, the products are the
+    reference's own numpy expressions."""
+    k = self.kernel
+    p1 = np.array(par[:1], dtype=np.float64)
+    p1[0, 0] = 1.0
+    iK = dv.bq_weights(p1, self.points)['iK'][0]                        # eval_inv_dot(par, x, scaling=False)
+    q, Q, R = k.exp_x_kx(par, self.points), k.exp_x_kxkx(par, par, self.points), k.exp_x_xkx(par, self.points)
+    w_c = iK.dot(Q).dot(iK)
+    if not np.array_equal(w_c, w_c.T):
+        w_c = 0.5 * (w_c + w_c.T)
+    model_var = k.exp_x_kxx(par) * (1 - np.trace(Q.dot(iK)))
+    integral_var = k.exp_xy_kxy(par) - q.T.dot(iK).dot(q)
+    self.q, self.Q, self.R = q, Q, R
+    return dict(wm=q.dot(iK)[None], Wc=w_c[None], Wcc=R.dot(iK)[None], iK=iK[None], model_var=np.array([model_var]),
+                integral_var=np.array([integral_var]), info=np.zeros(1, dtype=np.int32))
+
+
+Model._weights_mc = _weights_mc
 
 
 class GaussianProcessModel(Model):

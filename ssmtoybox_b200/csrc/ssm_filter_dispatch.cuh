@@ -35,10 +35,6 @@ int dispatch_filter_model(const FilterLaunch &L) {
     if (a.kind != b.kind) { set_error("dynamics and measurement transforms must be of the same kind"); return SSM_E_UNSUPPORTED; }
     const HostTfInfo id = classify_points(a), io = classify_points(b);
     const int kind = a.kind, fam = d.family;
-    if (fam == SSM_FAMILY_STUDENT && kind != SSM_TF_SP) {
-        set_error("Student family is implemented for sigma-point transforms only");
-        return SSM_E_UNSUPPORTED;
-    }
     if constexpr (!Dyn::ADDITIVE || !Obs::ADDITIVE) {
         // augmented transforms run on the runtime-N path (weights in global memory) only
         if (fam == SSM_FAMILY_STUDENT) { set_error("non-additive noise is implemented for the Gaussian family only"); return SSM_E_UNSUPPORTED; }
@@ -58,6 +54,11 @@ int dispatch_filter_model(const FilterLaunch &L) {
     SSM_CASE(PTS_AXIS, SSM_TF_TP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_STUDENT)
     SSM_CASE(PTS_AXIS, SSM_TF_SP, SSM_FAMILY_STUDENT)
+    // Student filters with BQ transforms on fully-symmetric degree-3 points: GPQStudent (research/tpq/tpq_base.py:41-91),
+    // StudentProcessStudent (ssinf.py:778-833); other point sets take the runtime-N path
+    SSM_CASE(PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_STUDENT)
+    SSM_CASE(PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_STUDENT)
+    if (fam == SSM_FAMILY_STUDENT) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
 #undef SSM_CASE
     set_error("unsupported transform kind %d / family %d", kind, fam);
     return SSM_E_UNSUPPORTED;
@@ -139,7 +140,13 @@ int launch_filter_global(const FilterLaunch &L) {
 
 template <class Dyn, class Obs, int THREADS, int MINB>
 int launch_filter_generic(const FilterLaunch &L, int kind, int family) {
-    if (family == SSM_FAMILY_STUDENT) return launch_filter_global<Dyn, Obs, SSM_TF_SP, SSM_FAMILY_STUDENT, THREADS, MINB>(L);
+    if (family == SSM_FAMILY_STUDENT) {
+        if (kind == SSM_TF_SP) return launch_filter_global<Dyn, Obs, SSM_TF_SP, SSM_FAMILY_STUDENT, THREADS, MINB>(L);
+        if (kind == SSM_TF_BQ) return launch_filter_global<Dyn, Obs, SSM_TF_BQ, SSM_FAMILY_STUDENT, THREADS, MINB>(L);
+        if (kind == SSM_TF_TP) return launch_filter_global<Dyn, Obs, SSM_TF_TP, SSM_FAMILY_STUDENT, THREADS, MINB>(L);
+        set_error("unsupported transform kind %d", kind);
+        return SSM_E_UNSUPPORTED;
+    }
     if (kind == SSM_TF_SP) return launch_filter_global<Dyn, Obs, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB>(L);
     if (kind == SSM_TF_BQ) return launch_filter_global<Dyn, Obs, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB>(L);
     if (kind == SSM_TF_TP) return launch_filter_global<Dyn, Obs, SSM_TF_TP, SSM_FAMILY_GAUSS, THREADS, MINB>(L);

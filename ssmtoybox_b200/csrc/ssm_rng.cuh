@@ -34,4 +34,62 @@ SSM_DEV double u01(uint32_t lo, uint32_t hi) {
     return ((double)(v >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// per-trajectory (or per-sample) generator: normals by Box-Muller, Gamma by Marsaglia-Tsang, Gaussian / Student draws
+struct Rng {
+    Philox ph;
+    uint32_t t_lo, t_hi;
+    // two standard normals for (step, stream, call) by Box-Muller
+    SSM_DEV void normal2(uint32_t step, uint32_t stream, uint32_t call, double &z0, double &z1) const {
+        uint32_t r[4];
+        ph.gen(t_lo, t_hi, step, (stream << 16) | call, r);
+        const double u = u01(r[0], r[1]), v = u01(r[2], r[3]);
+        const double rad = sqrt(-2.0 * log(u));
+        double s, c;
+        sincospi(2.0 * v, &s, &c);
+        z0 = rad * c;
+        z1 = rad * s;
+    }
+    template <int DIM>
+    SSM_DEV void normals(uint32_t step, uint32_t stream, double (&z)[DIM]) const {
+#pragma unroll
+        for (int i = 0; i < DIM; i += 2) {
+            double a, b;
+            normal2(step, stream, i / 2, a, b);
+            z[i] = a;
+            if (i + 1 < DIM) z[i + 1] = b;
+        }
+    }
+    // Gamma(shape a >= 1, scale 1) by Marsaglia-Tsang; calls >= 64 are reserved for it
+    SSM_DEV double gamma(uint32_t step, uint32_t stream, double a) const {
+        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (uint32_t it = 0; it < 64; ++it) {
+            uint32_t r[4];
+            double x, unused;
+            normal2(step, stream, 64 + 2 * it, x, unused);
+            ph.gen(t_lo, t_hi, step, (stream << 16) | (65 + 2 * it), r);
+            const double u = u01(r[0], r[1]);
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+        }
+        return d;
+    }
+    // DIM-variate draw  F z  (Gaussian) or  F z / sqrt(g), g ~ Gamma(nu/2, 2/nu)  (Student, utils.py:380-382)
+    template <int DIM>
+    SSM_DEV void draw(uint32_t step, uint32_t stream, const double *F, double dof, double (&o)[DIM]) const {
+        double z[DIM];
+        normals<DIM>(step, stream, z);
+        double sc = 1.0;
+        if (dof > 0.0) sc = rsqrt(gamma(step, stream, 0.5 * dof) * (2.0 / dof));
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) s = fma(F[i * DIM + j], z[j], s);
+            o[i] = s * sc;
+        }
+    }
+};
+
 }  // namespace ssm

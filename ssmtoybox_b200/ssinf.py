@@ -360,6 +360,24 @@ class StudentianInference(StateSpaceInference):
         super(StudentianInference, self).reset()
 
 
+class StudentProcessStudent(StudentianInference):
+    """Student's t-process quadrature Student filter (TPQSF) on fully-symmetric points (ssinf.py:778-833).  The
+    kernel expectations under the Student density come from the device Monte-Carlo kernel (bq.bqkern.RBFStudent)."""
+
+    def __init__(self, dyn, obs, kern_par_dyn, kern_par_obs, point_par=None, dof=4.0, fixed_dof=True, dof_tp=4.0):
+        assert isinstance(dyn.init_rv, StudentRV) and isinstance(dyn.noise_rv, StudentRV)
+        q_dof, r_dof = dyn.noise_rv.dof, obs.noise_rv.dof
+        if point_par is None:
+            point_par = dict()
+        point_par_dyn = point_par.copy()
+        point_par_obs = point_par.copy()
+        point_par_dyn.update({'dof': q_dof})
+        point_par_obs.update({'dof': r_dof})
+        t_dyn = StudentTProcessTransform(dyn.dim_in, 1, kern_par_dyn, 'rbf-student', 'fs', point_par_dyn, nu=dof_tp)
+        t_obs = StudentTProcessTransform(obs.dim_in, 1, kern_par_obs, 'rbf-student', 'fs', point_par_obs, nu=dof_tp)
+        super(StudentProcessStudent, self).__init__(dyn, obs, t_dyn, t_obs, dof, fixed_dof)
+
+
 class FullySymmetricStudent(StudentianInference):
     """Student filter with fully-symmetric rules ("Student-t UKF", ssinf.py:743-775)."""
 

@@ -86,6 +86,7 @@ FULL_TOL = {
     'c3_reentry_bsq': None, 'c3_reentry_gpq_fail': 1e-9, 'c3s_reentry_gpq': 2e-6,
     'c4_ct_tpq': 1e-8, 'c4_ct_gpq': 1e-9, 'c4_ct_ukf': 1e-9, 'c4_ct_bsq': None,
     'c4_ct_fsstudent': 1e-9, 'c4_ct_fsstudent_incdof': 1e-9, 'c4_ct_fsstudent_deg5': 1e-9,
+    'c4_ct_fsstudent_gpq': 1e-9, 'c4_ct_fsstudent_tpq': 1e-8,
     'c6_reentry1d_gpq': 1e-8, 'c6_reentry1d_ukf': 1e-9,
     'c7_ungmna_ukf': 1e-8, 'c7_ungmna_ckf': 1e-8, 'c7_ungmna_ghkf': 1e-8, 'c7_ungmna_gpq': 1e-7,
     'c5_pend_ukf': 1e-9, 'c5_pend_gpq': 1e-9, 'c5_pend_tpq': 1e-9, 'c5_pend_bsq': None, 'c5_pend_ghkf3': 1e-9,

@@ -394,3 +394,77 @@ def test_mc_filter_scores_streaming_matches_reference_scores():
     r2 = U.evaluate_performance(torch.as_tensor(x, device='cuda'), ms, Ps, status=alg.status)
     assert rel(r1['rmse'], r2['rmse']) < 1e-12 and abs(r1['nll'] - r2['nll']) < 1e-11 * abs(r2['nll'])
     assert abs(r1['nci'] - r2['nci']) < 1e-10 * abs(r2['nci']) + 1e-12
+
+
+def test_rbf_student_monte_carlo_kernel():
+    """ssm_rbf_student_expectations (device Monte Carlo, Philox) against the scale-mixture quadrature of the oracle:
+    inside 6 standard errors element-wise; deterministic for a seed; ragged sample counts."""
+    from ssmtoybox_b200.bq.bqkern import RBFStudent
+    g = golden('c4_ct_fsstudent_tpq')
+    for w, dof in (('dyn', 4.0), ('obs', 4.0), ('obs', 7.5)):
+        par, x = g[w + '_kern_par'], g[w + '_points']
+        n = 2000000
+        k = RBFStudent(5, par, dof=dof, num_samples=n, seed=11)
+        q, R, Q = k.exp_x_kx(par, x), k.exp_x_xkx(par, x), k.exp_x_kxkx(par, par, x)
+        kbar = k.exp_xy_kxy_pairs(par)
+        eq, eR, eQ, ekbar = so.rbf_student_expectations(par, x, dof)
+        assert np.all(np.abs(q - eq) < 6 * np.sqrt(eq / n))
+        assert np.all(np.abs(Q - eQ) < 6 * np.sqrt(eQ / n) + 1e-12) and np.array_equal(Q, Q.T)
+        # Var[x_d k] <= E[x_d^2 k] <= sqrt(E[x_d^4 ...]) is heavy-tailed for small dof: use the sample-free bound
+        # E[x_d^2 k^2] <= max_x x^2 exp(-(|x| - |x_i|)^2 / l^2) ... simply 6 sigma with sigma^2 <= E[x_d^2] = dof / (dof - 2)
+        assert np.all(np.abs(R - eR) < 6 * np.sqrt(dof / (dof - 2) / n))
+        assert abs(kbar - ekbar) < 6 * np.sqrt(ekbar / (n / 2))
+        assert abs(k.exp_xy_kxy(par) - so.rbf_student_exp_xy_kxy_reference(par, ekbar)) < 199 * 6 * np.sqrt(ekbar / (n / 2))
+        k2 = RBFStudent(5, par, dof=dof, num_samples=n, seed=11)
+        assert np.array_equal(k2.exp_x_kxkx(par, par, x), Q)                    # same seed -> same bits
+        k3 = RBFStudent(5, par, dof=dof, num_samples=n, seed=12)
+        assert not np.array_equal(k3.exp_x_kx(par, x), q)
+    for n in (1, 127, 129, 1000):                                                # ragged tiles
+        k = RBFStudent(5, par, dof=4.0, num_samples=n, seed=3)
+        q = k.exp_x_kx(par, x)
+        assert np.isfinite(q).all() and np.all(q >= 0) and np.all(q <= 1)
+    # 1-D, 3 points (UNGM size)
+    par1, x1 = np.array([[1.0, 0.7]]), np.array([[0.0, 1.3, -1.3]])
+    k = RBFStudent(1, par1, dof=5.0, num_samples=500000, seed=1)
+    eq, eR, eQ, ekbar = so.rbf_student_expectations(par1, x1, 5.0)
+    assert np.all(np.abs(k.exp_x_kx(par1, x1) - eq) < 6 * np.sqrt(eq / 5e5))
+    assert np.all(np.abs(k.exp_x_kxkx(par1, par1, x1) - eQ) < 6 * np.sqrt(eQ / 5e5))
+
+
+def test_student_filters_with_bq_transforms():
+    """StudentProcessStudent (TPQSF, ssinf.py:778-833) and the GPQ Student filter of research/tpq/tpq_base.py:41-91.
+    The reference's weights are Monte-Carlo estimates from numpy's MT19937 stream, which cannot be reproduced: filter
+    parity is established with the reference's weights assigned (as research code does, tpq_ungm.py:114-124); the
+    device's own Monte-Carlo weights are checked against the exact expectations at the Monte-Carlo noise level."""
+    from ssmtoybox_b200.ssinf import StudentProcessStudent, StudentianInference
+    from ssmtoybox_b200.bq.bqmtran import GaussianProcessTransform
+    dyn_s, obs_s = coordinated_turn(student=True)
+    g = golden('c4_ct_fsstudent_tpq')
+    par_dyn, par_obs = g['kern_par_dyn'], g['kern_par_obs']
+    alg = StudentProcessStudent(dyn_s, obs_s, par_dyn, par_obs, dof=6.0)
+    for tf, w in ((alg.tf_dyn, 'dyn'), (alg.tf_obs, 'obs')):
+        assert np.array_equal(tf.model.points, g[w + '_points'])
+        e = so.student_bq_weights(g[w + '_kern_par'], g[w + '_points'], 4.0)
+        n = 2e6
+        assert np.all(np.abs(tf.model.q - e['q']) < 6 * np.sqrt(e['q'] / n))
+        assert np.all(np.abs(tf.model.Q - e['Q']) < 6 * np.sqrt(e['Q'] / n) + 1e-12)
+        assert abs(tf.model.model_var - e['model_var']) < 3e-3 and abs(tf.model.integral_var / e['integral_var'] - 1) < 3e-3
+        assert rel(tf.model.iK, g[w + '_iK']) < 1e-7      # cond(K) ~ 1e7: the float64 inverse of the reference carries ~1e-9
+        tf.wm, tf.Wc, tf.Wcc = g[w + '_wm'], g[w + '_Wc'], g[w + '_Wcc']
+        tf.model.model_var = float(g[w + '_model_var'])
+    check(alg, 'c4_ct_fsstudent_tpq', 1e-8, smooth=False)
+    # own Monte-Carlo weights: the filter runs and tracks like the reference's (means within a fraction of the
+    # posterior standard deviation)
+    alg = StudentProcessStudent(dyn_s, obs_s, par_dyn, par_obs, dof=6.0)
+    m, P = alg.forward_pass(g['y'])
+    assert np.isfinite(m).all() and (np.asarray(alg.status) == 0).all()
+    sd = np.sqrt(np.einsum('iikm->ikm', g['fi_cov']))
+    assert np.median(np.abs(m - g['fi_mean']) / sd) < 0.25
+    g = golden('c4_ct_fsstudent_gpq')
+    t_dyn = GaussianProcessTransform(5, 5, par_dyn, 'rbf-student', 'fs', {'dof': 6.0})
+    t_obs = GaussianProcessTransform(5, 2, par_obs, 'rbf-student', 'fs', {'dof': 6.0})
+    alg = StudentianInference(dyn_s, obs_s, t_dyn, t_obs, 6.0, True)
+    for tf, w in ((alg.tf_dyn, 'dyn'), (alg.tf_obs, 'obs')):
+        tf.wm, tf.Wc, tf.Wcc = g[w + '_wm'], g[w + '_Wc'], g[w + '_Wcc']
+        tf.model.model_var = float(g[w + '_model_var'])
+    check(alg, 'c4_ct_fsstudent_gpq', 1e-9, smooth=False)

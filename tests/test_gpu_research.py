@@ -3,6 +3,8 @@ outputs of the reference's own drivers on the same data (tests/golden/research_*
 The drivers replay the reference's data through the optional x / z arguments; everything else -- algorithm lists,
 kernel parameters, batched passes, device reductions -- is the shipped code path."""
 import numpy as np
+
+import ssm_oracle as so
 import pytest
 import torch
 
@@ -130,6 +132,29 @@ def test_tpq_base_scores():
     np.testing.assert_allclose(r2[:, 0], g['rmse_avg'][:, 0], rtol=1e-7)
     # TPQ: the package's double-double weights against the reference's float64 weights
     np.testing.assert_allclose(r2[:, 1], g['rmse_avg'][:, 1], rtol=1e-3)
+
+
+def test_tpq_base_student_filters():
+    """GPQStudent / FSQStudent / rbf_student_mc_weights of research/tpq/tpq_base.py:41-151."""
+    from test_gpu_facade import coordinated_turn, check
+    from ssmtoybox_b200.research import tpq_base
+    from ssmtoybox_b200.bq.bqkern import RBFStudent
+    dyn_s, obs_s = coordinated_turn(student=True)
+    g = golden('c4_ct_fsstudent_gpq')
+    par_dyn, par_obs = np.array([[1.0, 1, 1, 1, 1, 1]]), np.array([[1.0, 1, 1e2, 1, 1e2, 1e2]])
+    alg = tpq_base.GPQStudent(dyn_s, obs_s, par_dyn, par_obs, dof=6.0)
+    for tf, w in ((alg.tf_dyn, 'dyn'), (alg.tf_obs, 'obs')):
+        assert np.array_equal(tf.model.points, g[w + '_points'])
+        tf.wm, tf.Wc, tf.Wcc = g[w + '_wm'], g[w + '_Wc'], g[w + '_Wcc']
+        tf.model.model_var = float(g[w + '_model_var'])
+    check(alg, 'c4_ct_fsstudent_gpq', 1e-9, smooth=False)
+    check(tpq_base.FSQStudent(dyn_s, obs_s, dof=6.0), 'c4_ct_fsstudent', 1e-9, smooth=False)   # same dofs -> same filter
+    x = g['dyn_points']
+    wm, Wc, Wcc, Q = tpq_base.rbf_student_mc_weights(x, RBFStudent(5, par_dyn, dof=4.0), 1000000, 1000)
+    e = so.student_bq_weights(par_dyn, x, 4.0)
+    assert np.all(np.abs(Q - e['Q']) < 6 * np.sqrt(e['Q'] / 1e6) + 1e-12)
+    assert wm.shape == (11,) and Wc.shape == (11, 11) and Wcc.shape == (5, 11)
+    assert np.abs(wm - e['wm']).max() < 5e-3 and np.abs(Wcc - e['Wcc']).max() < 5e-3
 
 
 def test_gpq_tracking_demos():

@@ -187,3 +187,26 @@ def test_scores(name):
     assert rel(e['lcr_km'][1:], g[name + '_lcr'][1:]) < 1e-8
     assert abs(e['nci'] - g[name + '_nci_f'].ravel()[0]) < 1e-9 * abs(e['nci']) + 1e-12
     assert abs(e['nll'] - g[name + '_nll_f'].ravel()[0]) < 1e-11 * abs(e['nll'])
+
+
+def test_rbf_student_expectations_vs_reference_monte_carlo():
+    """The scale-mixture quadrature of the oracle against the reference's own 2 * 10^6-sample Monte-Carlo estimates
+    stored in the golden file (bq/bqkern.py:475-536): agreement at the Monte-Carlo noise level, and the value
+    exp_xy_kxy converges to (full-batch sum, SURVEY.md f2 / DESIGN.md)."""
+    g = golden('c4_ct_fsstudent_tpq')
+    for w in ('dyn', 'obs'):
+        par, x = g[w + '_kern_par'], g[w + '_points']
+        q, R, Q, kbar = so.rbf_student_expectations(par, x, 4.0)
+        n = 2e6
+        assert np.all(np.abs(q - g[w + '_q']) < 6 * np.sqrt(q / n))                  # Var[k] <= E[k] since 0 <= k <= 1
+        assert np.all(np.abs(Q - g[w + '_Q']) < 6 * np.sqrt(Q / n) + 1e-12)
+        q2 = so.rbf_student_expectations(par, x, 4.0, n=800)
+        assert rel(q2[0], q) < 1e-12 and rel(q2[2], Q) < 1e-12 and abs(q2[3] - kbar) < 1e-12   # quadrature converged
+        W = so.student_bq_weights(par, x, 4.0)
+        assert abs(W['integral_var'] / float(g[w + '_integral_var']) - 1) < 2e-3
+        assert abs(W['model_var'] - float(g[w + '_model_var'])) < 2e-3
+    # Gaussian limit: dof -> inf reproduces the closed forms of RBFGauss (bqkern.py:345-424)
+    par, x = g['dyn_kern_par'], g['dyn_points']
+    q, R, Q, kbar = so.rbf_student_expectations(par, x, 4e6, n=200)
+    assert rel(q, so.rbf_exp_x_kx(par, x)) < 1e-5 and rel(R, so.rbf_exp_x_xkx(par, x)) < 1e-5
+    assert rel(Q, so.rbf_exp_x_kxkx(par, par, x)) < 1e-5 and abs(kbar - so.rbf_exp_xy_kxy(par)) < 1e-6
