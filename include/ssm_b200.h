@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 3
+#define SSM_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define SSM_OK             0
@@ -58,10 +58,13 @@ extern "C" {
 #define SSM_DYN_COORDTURN 4  /* CoordinatedTurnTransition.dyn_fcn   ssmod.py:675-690  par[0] = dt                 */
 #define SSM_DYN_REENTRY1D 5  /* ReentryVehicle1DTransition.dyn_fcn  ssmod.py:418-421  par[0] = dt                 */
 #define SSM_DYN_UNGMNA    6  /* UNGMNATransition.dyn_fcn (non-additive noise) ssmod.py:299-300                  */
+#define SSM_DYN_CONSTVEL  7  /* ConstantVelocity.dyn_fcn            ssmod.py:839-846  par[0] = dt                 */
+#define SSM_DYN_CTRS      8  /* ConstantTurnRateSpeed.dyn_fcn (non-additive noise) ssmod.py:755-774 par[0] = dt   */
 #define SSM_OBS_UNGM      1  /* UNGMMeasurement.meas_fcn            ssmod.py:1060-1061                            */
 #define SSM_OBS_PENDULUM  2  /* Pendulum2DMeasurement.meas_fcn      ssmod.py:1114-1115                            */
 #define SSM_OBS_RADAR     3  /* Radar2DMeasurement.meas_fcn         ssmod.py:1227-1252 par[0..1] = radar_loc      */
 #define SSM_OBS_UNGMNA    5  /* UNGMNAMeasurement.meas_fcn (non-additive noise) ssmod.py:1085-1086              */
+#define SSM_OBS_BEARING   6  /* BearingMeasurement.meas_fcn, 4 sensors ssmod.py:1189-1195 par[2i], par[2i+1] = sensor i */
 #define SSM_OBS_RANGE     4  /* RangeMeasurement.meas_fcn           ssmod.py:1146-1148 par[0..1] = (sx, sy)       */
 
 /* ---- moment-transform kinds ---------------------------------------------------------------- */
@@ -299,7 +302,7 @@ int ssm_bootstrap_var(const double *data, int64_t n, int32_t n_boot, uint64_t se
  * mean_f (E, ld), cov_f (E*E, ld), cov_fx (E*D, ld).  The integrand is a device model function:
  * which = 0 -> TransitionModel.dyn_eval of model SSM_DYN_*, which = 1 -> MeasurementModel.meas_eval of
  * model SSM_OBS_* with state_index (si0, si1) (ssmod.py:129-166, 960-1009).  par = model parameters
- * (host, 4 doubles), time = the integrand's time argument.
+ * (host, 8 doubles), time = the integrand's time argument.
  * ssm_model_eval evaluates dyn_fcn / meas_fcn themselves at n points x (D, ld) with optional noise
  * (DQ, ld) (ssmod.py:268-269, 357-358, 530-564, 675-690, 1060-1061, 1114-1115, 1227-1252). */
 int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,

@@ -98,6 +98,8 @@ def model_dict(dyn, obs):
     d['G'] = dyn.noise_gain
     d['state_index'] = np.asarray(obs.state_index if obs.state_index is not None else [], dtype=np.int64)
     d['radar_loc'] = np.asarray(getattr(obs, 'radar_loc', [0.0, 0.0]), dtype=float)
+    if hasattr(obs, 'sensor_pos'):  # BearingMeasurement: sensor positions (4, 2), flattened, in the same slot
+        d['radar_loc'] = np.asarray(obs.sensor_pos, dtype=float).reshape(-1)
     if hasattr(obs, 'sx'):  # RangeMeasurement: the sensor position (ssmod.py:1143-1144) travels in the same slot
         d['radar_loc'] = np.array([float(obs.sx), float(obs.sy)])
     st = dyn.init_rv.get_stats()
@@ -418,6 +420,79 @@ def gen_student_bq():
     filter_case('c4_ct_fsstudent_gpq', alg, x[..., :2], y[..., :2], smooth=False)
 
 
+def gen_more_models():
+    """C8-C10: the remaining models of ssmod.py on the set-ups of the reference's own tests (tests/test_ssinf.py:66-93,
+    227-244): ConstantVelocity + radar (Gaussian and Student noise), CoordinatedTurn + 4 bearing sensors,
+    ConstantTurnRateSpeed (non-additive noise) + radar.  Filters, smoothers and the simulators with injected noise."""
+    rng = np.random.RandomState(31)
+
+    def sims(tag, dyn, obs, steps=40, mc=3, x0_sd=0.1):
+        dx, dq, dr = dyn.dim_state, dyn.dim_noise, obs.dim_noise
+        qc, rc = dyn.noise_rv.get_stats()[1], obs.noise_rv.get_stats()[1]
+        x0 = dyn.init_rv.get_stats()[0][:, None] + rng.randn(dx, mc) * x0_sd
+        q = rng.randn(dq, steps, mc) * np.sqrt(np.diag(qc))[:, None, None]
+        r = rng.randn(dr, steps, mc) * np.sqrt(np.diag(rc))[:, None, None]
+        irv, qrv, rrv = dyn.init_rv, dyn.noise_rv, obs.noise_rv
+        dyn.init_rv, dyn.noise_rv, obs.noise_rv = InjectedRV(irv, [x0]), InjectedRV(qrv, [q]), InjectedRV(rrv, [r])
+        x = dyn.simulate_discrete(steps, mc_sims=mc)
+        d = {'x0': x0, 'q': q, 'r': r, 'x': x, 'y': obs.simulate_measurements(x)}
+        d.update(model_dict(dyn, obs))
+        dyn.init_rv, dyn.noise_rv, obs.noise_rv = irv, qrv, rrv
+        save('simulation_' + tag, **d)
+
+    # C8: constant velocity + radar on the leading two state components (state_index None), tests/test_ssinf.py:227-244
+    m0, P0 = np.array([10175, 295, 980, -35.0]), np.diag([10000, 100, 10000, 100.0])
+    Q, R = np.diag([50, 5.0]), np.diag([50, 0.4e-6])
+    np.random.seed(41)
+    dyn = ssmod.ConstantVelocity(GaussRV(4, m0, P0), GaussRV(2, cov=Q), dt=0.5)
+    obs = ssmod.Radar2DMeasurement(GaussRV(2, cov=R), 4)
+    x = dyn.simulate_discrete(100, mc_sims=3)
+    y = obs.simulate_measurements(x)
+    filter_case('c8_cv_ukf', ssinf.UnscentedKalman(dyn, obs), x, y)
+    filter_case('c8_cv_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :1], y[..., :1])
+    kp = np.array([[1.0, 3, 3, 3, 3]])
+    filter_case('c8_cv_gpq', ssinf.GaussianProcessKalman(dyn, obs, kp, kp, points='ut'), x[..., :2], y[..., :2])
+    obs02 = ssmod.Radar2DMeasurement(GaussRV(2, cov=R), 4, state_index=[0, 2])
+    y02 = obs02.simulate_measurements(x)
+    filter_case('c8_cv02_ukf', ssinf.UnscentedKalman(dyn, obs02), x[..., :2], y02[..., :2])
+    sims('cv', dyn, obs)
+    dyn_s = ssmod.ConstantVelocity(StudentRV(4, m0, P0, 1000.0), StudentRV(2, scale=Q, dof=1000.0), dt=0.5)
+    obs_s = ssmod.Radar2DMeasurement(StudentRV(2, scale=R, dof=4.0), 4)
+    filter_case('c8_cv_fsstudent', ssinf.FullySymmetricStudent(dyn_s, obs_s), x[..., :2], y[..., :2], smooth=False)
+
+    # C9: coordinated turn + bearings from 4 sensors, tests/test_ssinf.py:66-82
+    np.random.seed(42)
+    dyn, _, x, _ = coordinated_turn(100, 3)
+    sen = np.vstack((1000 * np.eye(2), -1000 * np.eye(2))).astype(float)
+    obs = ssmod.BearingMeasurement(GaussRV(4, cov=10e-3 * np.eye(4)), 5, state_index=[0, 2], sensor_pos=sen)
+    y = obs.simulate_measurements(x)
+    filter_case('c9_ctb_ukf', ssinf.UnscentedKalman(dyn, obs), x, y)
+    filter_case('c9_ctb_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :1], y[..., :1])
+    kp = np.array([[1.0, 3, 3, 3, 3, 3]])
+    filter_case('c9_ctb_gpq', ssinf.GaussianProcessKalman(dyn, obs, kp, kp, points='ut'), x[..., :2], y[..., :2])
+    sims('ctb', dyn, obs)
+
+    # C10: constant turn rate and speed (non-additive noise) + radar, tests/test_ssinf.py:84-93.  The fixture's zero
+    # initial mean puts the central sigma point on the x[4] == 0 branch and the object on top of the radar; a moving
+    # object away from the origin is the main case, the fixture is kept as c10_ctrs_fixture_ukf.
+    np.random.seed(43)
+    q, r = GaussRV(2, cov=np.diag([0.1, 0.1 * np.pi])), GaussRV(2, cov=np.diag([0.3, 0.03]))
+    dyn = ssmod.ConstantTurnRateSpeed(GaussRV(5, np.array([10.0, 20, 5, 0.3, 0.1]), 0.1 * np.eye(5)), q)
+    obs = ssmod.Radar2DMeasurement(r, 5)
+    x = dyn.simulate_discrete(100, mc_sims=3)
+    y = obs.simulate_measurements(x)
+    filter_case('c10_ctrs_ukf', ssinf.UnscentedKalman(dyn, obs), x, y)
+    filter_case('c10_ctrs_ckf', ssinf.CubatureKalman(dyn, obs), x[..., :1], y[..., :1])
+    kpd, kpo = np.array([[1.0, 3, 3, 3, 3, 3, 3, 3]]), np.array([[1.0, 3, 3, 3, 3, 3]])
+    filter_case('c10_ctrs_gpq', ssinf.GaussianProcessKalman(dyn, obs, kpd, kpo, points='ut'), x[..., :2], y[..., :2])
+    sims('ctrs', dyn, obs)
+    np.random.seed(44)
+    dyn0 = ssmod.ConstantTurnRateSpeed(GaussRV(5, cov=0.1 * np.eye(5)), q)
+    x = dyn0.simulate_discrete(100, mc_sims=2)
+    y = obs.simulate_measurements(x)
+    filter_case('c10_ctrs_fixture_ukf', ssinf.UnscentedKalman(dyn0, obs), x, y)
+
+
 def gen_weights():
     """BQ weights and kernel expectations (bqmod.py:495-523, 893-992; bqkern.py:329-424)."""
     cases = []
@@ -539,7 +614,7 @@ def gen_scores():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'weights': gen_weights, 'simulation': gen_simulation,
+    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'weights': gen_weights, 'simulation': gen_simulation,
             'scores': gen_scores}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

@@ -62,4 +62,11 @@ def install():
         scipy.special.factorial2 = factorial2
     if REFERENCE_PATH not in sys.path:
         sys.path.insert(0, REFERENCE_PATH)
+    # 5. BearingMeasurement sets dim_noise = None at class level and MeasurementModel.__init__ calls
+    #    np.zeros(self.dim_noise) before the subclass assigns it (ssmod.py:901, 1176, 1186-1187): numpy >= 1.20 rejects
+    #    None as a shape.  The class default is set to the 4 sensors of the default set-up; the instance attribute is
+    #    still assigned by the reference's own constructor.
+    from ssmtoybox import ssmod
+    if ssmod.BearingMeasurement.dim_noise is None:
+        ssmod.BearingMeasurement.dim_noise = 4
     install._done = True

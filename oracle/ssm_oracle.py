@@ -468,6 +468,19 @@ def dyn_fcn(name, x, q, time, dt):
             r3 = z * xp[0] + a * xp[1] + z * xp[2] + b * xp[3] + z * xp[4]
             r4 = z * xp[0] + z * xp[1] + z * xp[2] + z * xp[3] + 1 * xp[4]
         return np.stack([r0 + q[0], r1 + q[1], r2 + q[2], r3 + q[3], r4 + q[4]])
+    if name == 'ConstantVelocity':  # ssmod.py:839-846, noise gain :833-836
+        h = dt ** 2 / 2
+        return np.stack([xp[0] + dt * xp[1] + h * q[0], xp[1] + dt * q[0], xp[2] + dt * xp[3] + h * q[1], xp[3] + dt * q[1]])
+    if name == 'ConstantTurnRateSpeed':  # ssmod.py:755-774: non-additive noise; restated as written (heading += dt * x[3])
+        with np.errstate(all='ignore'):
+            zero = xp[4] == 0
+            c = xp[2] / np.where(zero, 1.0, xp[4])
+            f0 = np.where(zero, dt * xp[2] * np.cos(xp[3]),
+                          c * (np.sin(xp[3] + xp[4] * dt) - np.sin(xp[3])) + 0.5 * dt ** 2 * np.cos(xp[3]) * q[0])
+            f1 = np.where(zero, dt * xp[2] * np.sin(xp[3]),
+                          c * (-np.cos(xp[3] + xp[4] * dt) + np.cos(xp[3])) + 0.5 * dt ** 2 * np.sin(xp[3]) * q[0])
+        return np.stack([xp[0] + f0, xp[1] + f1, xp[2] + dt * q[0], xp[3] + (dt * xp[3] + 0.5 * dt ** 2 * q[1]),
+                         xp[4] + dt * q[1]])
     raise NotImplementedError(name)
 
 
@@ -489,7 +502,7 @@ def dyn_fcn_cont(name, x, q, time):
 def meas_fcn(name, x, r, time, radar_loc=(0.0, 0.0)):
     """Measurement function y_k = h(x_k[state_index], r_k); x is already index-selected."""
     if np.isscalar(r):
-        r = [r] * 2
+        r = [r] * 4
     if name == 'UNGMMeasurement':  # ssmod.py:1060-1061
         return (0.05 * x[0] ** 2 + r[0])[None]
     if name == 'UNGMNAMeasurement':  # ssmod.py:1085-1086: non-additive noise
@@ -502,10 +515,15 @@ def meas_fcn(name, x, r, time, radar_loc=(0.0, 0.0)):
         rng = np.sqrt((x[0] - radar_loc[0]) ** 2 + (x[1] - radar_loc[1]) ** 2)
         theta = np.arctan2((x[1] - radar_loc[1]), (x[0] - radar_loc[0]))
         return np.stack([rng + r[0], theta + r[1]])
+    if name == 'BearingMeasurement':  # ssmod.py:1189-1195; sensor_pos (4, 2) travels flattened in radar_loc
+        sp = np.asarray(radar_loc, dtype=float).reshape(-1, 2)
+        if np.isscalar(r) or len(r) < len(sp):
+            r = [r if np.isscalar(r) else r[0]] * len(sp)
+        return np.stack([np.arctan2(x[1] - sp[i, 1], x[0] - sp[i, 0]) + r[i] for i in range(len(sp))])
     raise NotImplementedError(name)
 
 
-NONADDITIVE = {'UNGMNATransition', 'UNGMNAMeasurement'}   # noise_additive = False (ssmod.py:296, 1081)
+NONADDITIVE = {'UNGMNATransition', 'UNGMNAMeasurement', 'ConstantTurnRateSpeed'}   # noise_additive = False (ssmod.py:296, 751, 1081)
 
 
 def _meas_eval(desc, x, time):

@@ -17,10 +17,11 @@ c_int32_p = C.POINTER(C.c_int32)
 SSM_OK, SSM_E_INVALID, SSM_E_UNSUPPORTED, SSM_E_CUDA = 0, -1, -2, -3
 FAIL_CHOL_DYN, FAIL_CHOL_OBS, FAIL_CHOL_GAIN, FAIL_NONFINITE_GAIN, FAIL_CHOL_SMOOTH = 1, 2, 3, 4, 5
 DYN_IDS = {'UNGMTransition': 1, 'Pendulum2DTransition': 2, 'ReentryVehicle2DTransition': 3,
-           'CoordinatedTurnTransition': 4, 'ReentryVehicle1DTransition': 5, 'UNGMNATransition': 6}
+           'CoordinatedTurnTransition': 4, 'ReentryVehicle1DTransition': 5, 'UNGMNATransition': 6,
+           'ConstantVelocity': 7, 'ConstantTurnRateSpeed': 8}
 OBS_IDS = {'UNGMMeasurement': 1, 'Pendulum2DMeasurement': 2, 'Radar2DMeasurement': 3, 'RangeMeasurement': 4,
-           'UNGMNAMeasurement': 5}
-NONADDITIVE = {'UNGMNATransition', 'UNGMNAMeasurement'}   # models integrated over the augmented vector [x; noise]
+           'UNGMNAMeasurement': 5, 'BearingMeasurement': 6}
+NONADDITIVE = {'UNGMNATransition', 'UNGMNAMeasurement', 'ConstantTurnRateSpeed'}   # models integrated over the augmented vector [x; noise]
 TF_SP, TF_BQ, TF_TP = 1, 2, 3
 FAMILY_GAUSS, FAMILY_STUDENT = 1, 2
 SIM_DISCRETE, SIM_CONTINUOUS, SIM_MEASURE = 1, 2, 3

@@ -21,6 +21,10 @@ int filter_reentry(const FilterLaunch &L);
 int filter_coordturn(const FilterLaunch &L);
 int filter_reentry1d(const FilterLaunch &L);
 int filter_ungmna(const FilterLaunch &L);
+int filter_constvel01(const FilterLaunch &L);
+int filter_constvel02(const FilterLaunch &L);
+int filter_coordturn_bearing(const FilterLaunch &L);
+int filter_ctrs(const FilterLaunch &L);
 
 static bool tf_valid(const ssm_transform &t) {
     if (t.n_pts < 1 || !t.points || !t.wm || !t.Wc) return false;
@@ -71,6 +75,14 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
         rc = filter_reentry1d(L);
     else if (dm == SSM_DYN_UNGMNA && om == SSM_OBS_UNGMNA && desc->dx == 1 && desc->dy == 1 && (nsi == 0 || (nsi == 1 && si[0] == 0)))
         rc = filter_ungmna(L);
+    else if (dm == SSM_DYN_CONSTVEL && om == SSM_OBS_RADAR && desc->dx == 4 && desc->dy == 2 && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = filter_constvel01(L);
+    else if (dm == SSM_DYN_CONSTVEL && om == SSM_OBS_RADAR && desc->dx == 4 && desc->dy == 2 && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = filter_constvel02(L);
+    else if (dm == SSM_DYN_COORDTURN && om == SSM_OBS_BEARING && desc->dx == 5 && desc->dy == 4 && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = filter_coordturn_bearing(L);
+    else if (dm == SSM_DYN_CTRS && om == SSM_OBS_RADAR && desc->dx == 5 && desc->dy == 2 && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = filter_ctrs(L);
     else
         set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));

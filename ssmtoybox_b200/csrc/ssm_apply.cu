@@ -16,6 +16,12 @@ struct FnDynReentry { static constexpr int D = 5, E = 5, NQ = 3; static constexp
 struct FnDynCt { static constexpr int D = 5, E = 5, NQ = 5; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[5], double t, double (&o)[5]) { DynCoordTurn::f<NZ>(p, x, n, t, o); } };
 struct FnDynReentry1D { static constexpr int D = 3, E = 3, NQ = 3; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[3], double t, double (&o)[3]) { DynReentry1D::f<NZ>(p, x, n, t, o); } };
 struct FnObsRange { static constexpr int D = 3, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[3], const double (&n)[1], double t, double (&o)[1]) { ObsRange<3, 0>::h<NZ>(p, x, n, t, o); } };
+struct FnDynCv { static constexpr int D = 4, E = 4, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[4], const double (&n)[2], double t, double (&o)[4]) { DynConstVel::f<NZ>(p, x, n, t, o); } };
+struct FnObsRadar4_01 { static constexpr int D = 4, E = 2, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[4], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<4, 0, 1>::h<NZ>(p, x, n, t, o); } };
+struct FnObsRadar4_02 { static constexpr int D = 4, E = 2, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[4], const double (&n)[2], double t, double (&o)[2]) { ObsRadar<4, 0, 2>::h<NZ>(p, x, n, t, o); } };
+struct FnObsBearing02 { static constexpr int D = 5, E = 4, NQ = 4; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[4], double t, double (&o)[4]) { ObsBearing4<5, 0, 2>::h<NZ>(p, x, n, t, o); } };
+struct FnDynCtrs { static constexpr int D = 5, E = 5, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[5], const double (&n)[2], double t, double (&o)[5]) { DynCtrs::f<NZ>(p, x, n, t, o); } };
+struct FnDynCtrsAug { static constexpr int D = 7, E = 5, NQ = 2; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&xq)[7], const double (&)[2], double t, double (&o)[5]) { const double x[5] = {xq[0], xq[1], xq[2], xq[3], xq[4]}, q[2] = {xq[5], xq[6]}; DynCtrs::f<true>(p, x, q, t, o); } };
 // non-additive models: plain (state, noise) form for ssm_model_eval, augmented form [x; noise] for ssm_transform_apply
 struct FnDynUngmNA { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { DynUngmNA::f<NZ>(p, x, n, t, o); } };
 struct FnObsUngmNA { static constexpr int D = 1, E = 1, NQ = 1; static constexpr bool EXACT = false; template <bool NZ> SSM_DEV static void ev(const double *p, const double (&x)[1], const double (&n)[1], double t, double (&o)[1]) { ObsUngmNA<1, 0>::h<NZ>(p, x, n, t, o); } };
@@ -29,7 +35,7 @@ struct FnObsRadar02 { static constexpr int D = 5, E = 2, NQ = 2; static constexp
 template <int D, int E>
 struct ApplyPar {
     TfGlobal<D, E> tf;
-    double par[4];
+    double par[8];
     double time;
     const double *mean, *cov;
     double *mean_f, *cov_f, *cov_fx;
@@ -105,7 +111,7 @@ static int launch_apply(const ssm_transform &tf, const double *par, double time,
         put(tf.points, (size_t)D * N, o.U_);
     }
     cudaMemcpyAsync(dev, host, off * sizeof(double), cudaMemcpyHostToDevice, s);
-    for (int i = 0; i < 4; ++i) p.par[i] = par ? par[i] : 0.0;
+    for (int i = 0; i < 8; ++i) p.par[i] = par ? par[i] : 0.0;
     p.time = time; p.mean = mean; p.cov = cov; p.mean_f = mean_f; p.cov_f = cov_f; p.cov_fx = cov_fx; p.status = status;
     p.n = n; p.ld = ld;
     apply_kernel<Fn, KIND><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(p);
@@ -127,7 +133,7 @@ static int apply_kind(const ssm_transform &tf, const double *par, double time, c
     return SSM_E_INVALID;
 }
 
-struct Par4 { double v[4]; };
+struct Par4 { double v[8]; };
 template <class Fn>
 __global__ void eval_kernel_v(const Par4 par, double time, const double *x, const double *noise, double *out, long long n, long long ld) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,6 +161,10 @@ using namespace ssm;
     else if (which == 0 && model == SSM_DYN_REENTRY1D) { CALL(FnDynReentry1D) }                        \
     else if (which == 1 && model == SSM_OBS_RANGE && dim_state == 3 && si0 == 0) { CALL(FnObsRange) }  \
     else if (which == 1 && model == SSM_OBS_UNGM && dim_state == 1) { CALL(FnObsUngm) }                \
+    else if (which == 0 && model == SSM_DYN_CONSTVEL) { CALL(FnDynCv) }                                \
+    else if (which == 1 && model == SSM_OBS_RADAR && dim_state == 4 && si0 == 0 && si1 == 1) { CALL(FnObsRadar4_01) } \
+    else if (which == 1 && model == SSM_OBS_RADAR && dim_state == 4 && si0 == 0 && si1 == 2) { CALL(FnObsRadar4_02) } \
+    else if (which == 1 && model == SSM_OBS_BEARING && dim_state == 5 && si0 == 0 && si1 == 2) { CALL(FnObsBearing02) } \
     else if (which == 1 && model == SSM_OBS_PENDULUM && dim_state == 2) { CALL(FnObsPend) }            \
     else if (which == 1 && model == SSM_OBS_RADAR && dim_state == 5 && si0 == 0 && si1 == 1) { CALL(FnObsRadar01) } \
     else if (which == 1 && model == SSM_OBS_RADAR && dim_state == 5 && si0 == 0 && si1 == 2) { CALL(FnObsRadar02) } \
@@ -174,6 +184,7 @@ extern "C" int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_sta
     int rc = SSM_OK;
 #define CALL(FN) rc = apply_kind<FN>(*tf, par, time, mean, cov, mean_f, cov_f, cov_fx, status, n, ld, s);
     if (which == 0 && model == SSM_DYN_UNGMNA) { CALL(FnDynUngmNAaug) }          // mean / cov of [x; q] (ssmod.py:158-160)
+    else if (which == 0 && model == SSM_DYN_CTRS) { CALL(FnDynCtrsAug) }
     else if (which == 1 && model == SSM_OBS_UNGMNA && dim_state == 1) { CALL(FnObsUngmNAaug) }
     else SSM_FN_DISPATCH(CALL)
 #undef CALL
@@ -188,9 +199,10 @@ extern "C" int ssm_model_eval(int32_t which, int32_t model, int32_t dim_state, i
     if (n <= 0) return SSM_OK;
     cudaStream_t s = (cudaStream_t)stream;
     Par4 p4;
-    for (int i = 0; i < 4; ++i) p4.v[i] = par ? par[i] : 0.0;
+    for (int i = 0; i < 8; ++i) p4.v[i] = par ? par[i] : 0.0;
 #define CALL(FN) eval_kernel_v<FN><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p4, time, x, noise, out, (long long)n, (long long)ld);
     if (which == 0 && model == SSM_DYN_UNGMNA) { CALL(FnDynUngmNA) }
+    else if (which == 0 && model == SSM_DYN_CTRS) { CALL(FnDynCtrs) }
     else if (which == 1 && model == SSM_OBS_UNGMNA && dim_state == 1) { CALL(FnObsUngmNA) }
     else SSM_FN_DISPATCH(CALL)
 #undef CALL

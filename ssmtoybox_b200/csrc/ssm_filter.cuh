@@ -306,7 +306,7 @@ template <int DX, int DY, class TfD, class TfO>
 struct FilterPar {
     TfD tf_dyn;
     TfO tf_obs;
-    double dyn_par[4], obs_par[4];
+    double dyn_par[4], obs_par[8];
     double m0[DX];
     double P0[TriSize<DX>::value];
     double GQG[TriSize<DX>::value];
@@ -783,7 +783,8 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     memset(pp, 0, sizeof(Par));
     fill_tf(p.tf_dyn, d.tf_dyn, id);
     fill_tf(p.tf_obs, d.tf_obs, io);
-    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d.dyn_par[i]; p.obs_par[i] = d.obs_par[i]; }
+    for (int i = 0; i < 4; ++i) p.dyn_par[i] = d.dyn_par[i];
+    for (int i = 0; i < 8; ++i) p.obs_par[i] = d.obs_par[i];
     for (int i = 0; i < DX; ++i) p.m0[i] = d.m0[i];
     pack_lower<DX>(d.P0, p.P0);
     pack_lower<DX>(d.GQG, p.GQG);

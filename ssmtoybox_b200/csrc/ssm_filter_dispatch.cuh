@@ -115,7 +115,8 @@ int launch_filter_global(const FilterLaunch &L) {
     fill_tf_global(p.tf_obs, d.tf_obs, gi, dev, host, off);
     // pageable-source async copy: staged before the call returns, so `host` can be freed below
     cudaMemcpyAsync(dev, host, off * sizeof(double), cudaMemcpyHostToDevice, L.stream);
-    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d.dyn_par[i]; p.obs_par[i] = d.obs_par[i]; }
+    for (int i = 0; i < 4; ++i) p.dyn_par[i] = d.dyn_par[i];
+    for (int i = 0; i < 8; ++i) p.obs_par[i] = d.obs_par[i];
     for (int i = 0; i < DX; ++i) p.m0[i] = d.m0[i];
     pack_lower<DX>(d.P0, p.P0);
     pack_lower<DX>(d.GQG, p.GQG);

@@ -152,6 +152,68 @@ struct DynReentry1D {
     }
 };
 
+// ---- ConstantVelocity.dyn_fcn, ssmod.py:831-846; par[0] = dt -------------------------------------
+// state [x, vx, y, vy]; the 2-D noise enters through the gain [[dt^2/2, 0], [dt, 0], [0, dt^2/2], [0, dt]] (:833-836)
+struct DynConstVel {
+    static constexpr int DX = 4, DQ = 2, ID = SSM_DYN_CONSTVEL;
+    static constexpr bool ADDITIVE = true;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[4], const double (&q)[2], double, double (&o)[4]) {
+        const double dt = par[0], h = 0.5 * dt * dt;
+        o[0] = x[0] + dt * x[1];
+        o[1] = x[1];
+        o[2] = x[2] + dt * x[3];
+        o[3] = x[3];
+        if (NOISE) {
+            o[0] += h * q[0];
+            o[1] += dt * q[0];
+            o[2] += h * q[1];
+            o[3] += dt * q[1];
+        }
+    }
+    SSM_DEV static void fc(const double *, const double (&)[4], const double (&)[2], double, double (&o)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = 0.0;
+    }
+};
+
+// ---- ConstantTurnRateSpeed.dyn_fcn, ssmod.py:755-774; par[0] = dt: NON-additive noise ----------------
+// state [x, y, speed, heading, yaw rate], noise [acceleration, yaw acceleration].  Restated as written, including
+// the heading increment dt * x[3] (not dt * x[4]) of both branches and the noise-free position of the x[4] == 0 branch.
+struct DynCtrs {
+    static constexpr int DX = 5, DQ = 2, ID = SSM_DYN_CTRS;
+    static constexpr bool ADDITIVE = false;
+    static constexpr bool HAS_CONT = false;
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[2], double, double (&o)[5]) {
+        const double dt = par[0], h = 0.5 * dt * dt;
+        const double q0 = NOISE ? q[0] : 0.0, q1 = NOISE ? q[1] : 0.0;
+        double s3, c3;
+        sincos(x[3], &s3, &c3);
+        double f0, f1;
+        if (x[4] == 0.0) {
+            f0 = dt * x[2] * c3;
+            f1 = dt * x[2] * s3;
+        } else {
+            const double c = m_div(x[2], x[4]);
+            double s34, c34;
+            sincos(x[3] + x[4] * dt, &s34, &c34);
+            f0 = c * (s34 - s3) + h * c3 * q0;
+            f1 = c * (-c34 + c3) + h * s3 * q0;
+        }
+        o[0] = x[0] + f0;
+        o[1] = x[1] + f1;
+        o[2] = x[2] + dt * q0;
+        o[3] = x[3] + (dt * x[3] + h * q1);
+        o[4] = x[4] + dt * q1;
+    }
+    SSM_DEV static void fc(const double *, const double (&)[5], const double (&)[2], double, double (&o)[5]) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o[i] = 0.0;
+    }
+};
+
 // ---- UNGMMeasurement.meas_fcn, ssmod.py:1060-1061 ----------------------------------------------
 template <int DXS, int I0>
 struct ObsUngm {
@@ -214,6 +276,21 @@ struct ObsRadar {
         if (NOISE) o[0] += r[0];
         o[1] = m_atan2(ey, ex);
         if (NOISE) o[1] += r[1];
+    }
+};
+
+// ---- BearingMeasurement.meas_fcn, ssmod.py:1189-1195; 4 sensors, par[2 i], par[2 i + 1] = position of sensor i ------
+template <int DXS, int I0, int I1>
+struct ObsBearing4 {
+    static constexpr int DX = DXS, DY = 4, ID = SSM_OBS_BEARING;
+    static constexpr bool ADDITIVE = true;
+    template <bool NOISE>
+    SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[4], double, double (&o)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[i] = m_atan2(x[I1] - par[2 * i + 1], x[I0] - par[2 * i]);
+            if (NOISE) o[i] += r[i];
+        }
     }
 };
 

@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...);
 
 template <int DX, int DQ, int DY>
 struct SimPar {
-    double dyn_par[4], obs_par[4];
+    double dyn_par[4], obs_par[8];
     double x0_mean[DX], x0_F[DX * DX], q_F[DQ * DQ], r_F[DY * DY];
     double x0_dof, q_dof, r_dof;
     unsigned long long seed;
@@ -125,7 +125,8 @@ static int launch_sim(const ssm_desc *d, const ssm_rng *rng, int mode, double dt
     }
     SimPar<DX, DQ, DY> p;
     memset(&p, 0, sizeof(p));
-    for (int i = 0; i < 4; ++i) { p.dyn_par[i] = d->dyn_par[i]; p.obs_par[i] = d->obs_par[i]; }
+    for (int i = 0; i < 4; ++i) p.dyn_par[i] = d->dyn_par[i];
+    for (int i = 0; i < 8; ++i) p.obs_par[i] = d->obs_par[i];
     const bool meas_only = mode == SSM_SIM_MEASURE;
     const bool need_rng = meas_only ? !r_inj : (!x0_inj || !q_inj || (y && !r_inj));
     if (need_rng && meas_only) {
@@ -186,6 +187,14 @@ extern "C" int ssm_simulate(const ssm_desc *desc, const ssm_rng *rng, int32_t mo
         rc = launch_sim<DynReentry1D, ObsRange<3, 0>>(SSM_SIM_ARGS);
     else if (dm == SSM_DYN_UNGMNA && om == SSM_OBS_UNGMNA && (nsi == 0 || (nsi == 1 && si[0] == 0)))
         rc = launch_sim<DynUngmNA, ObsUngmNA<1, 0>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_CONSTVEL && om == SSM_OBS_RADAR && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = launch_sim<DynConstVel, ObsRadar<4, 0, 1>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_CONSTVEL && om == SSM_OBS_RADAR && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = launch_sim<DynConstVel, ObsRadar<4, 0, 2>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_COORDTURN && om == SSM_OBS_BEARING && nsi == 2 && si[0] == 0 && si[1] == 2)
+        rc = launch_sim<DynCoordTurn, ObsBearing4<5, 0, 2>>(SSM_SIM_ARGS);
+    else if (dm == SSM_DYN_CTRS && om == SSM_OBS_RADAR && (nsi == 0 || (nsi == 2 && si[0] == 0 && si[1] == 1)))
+        rc = launch_sim<DynCtrs, ObsRadar<5, 0, 1>>(SSM_SIM_ARGS);
     else
         set_error("ssm_simulate: no device implementation for dyn_model=%d obs_model=%d", dm, om);
 #undef SSM_SIM_ARGS

@@ -91,7 +91,8 @@ def lower(d):
     s.dyn_model, s.obs_model, s.dx, s.dy = _lib.DYN_IDS[dyn_name], _lib.OBS_IDS[obs_name], dx, dy
     s.dyn_par[0] = float(d.get('dyn_dt', 0.0))
     rl = np.asarray(d.get('radar_loc', [0.0, 0.0]), dtype=np.float64).reshape(-1)
-    s.obs_par[0], s.obs_par[1] = float(rl[0]), float(rl[1])
+    for i, v in enumerate(rl[:8]):      # radar_loc (2) / RangeMeasurement sensor (2) / BearingMeasurement sensor_pos (4, 2)
+        s.obs_par[i] = float(v)
     si = np.asarray(d.get('state_index', []), dtype=np.int64).reshape(-1)
     s.n_state_index = len(si)
     for i, v in enumerate(si):

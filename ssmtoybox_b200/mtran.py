@@ -47,7 +47,7 @@ def _apply_device(tf_dict, f, mean, cov, fcn_pars):
     mf, cf, cfx = torch.empty((dim_out, n), **kw), torch.empty((dim_out, dim_out, n), **kw), torch.empty((dim_out, D, n), **kw)
     status = torch.empty((n,), dtype=torch.int32, device='cuda')
     time = float(np.asarray(fcn_pars).reshape(-1)[0]) if fcn_pars is not None and np.size(fcn_pars) else 0.0
-    p = (C.c_double * 4)(*par)
+    p = (C.c_double * 8)(*(list(par) + [0.0] * (8 - len(par))))
     rc = lib.ssm_transform_apply(which, model_id, dim_state, si[0], si[1], p, C.byref(t), time, dv._p(mt), dv._p(ct),
                                  dv._p(mf), dv._p(cf), dv._p(cfx), dv._p(status), n, n, dv._stream())
     _lib.check(rc, 'ssm_transform_apply')

@@ -32,11 +32,17 @@ from .ssmod import TransitionModel, MeasurementModel
 from .utils import StudentRV
 
 _DEFAULT_OBS = {1: ('UNGMMeasurement', []), 2: ('Pendulum2DMeasurement', []), 3: ('Radar2DMeasurement', []),
-                4: ('Radar2DMeasurement', [0, 2]), 5: ('RangeMeasurement', []), 6: ('UNGMNAMeasurement', [])}
+                4: ('Radar2DMeasurement', [0, 2]), 5: ('RangeMeasurement', []), 6: ('UNGMNAMeasurement', []),
+                7: ('Radar2DMeasurement', []), 8: ('Radar2DMeasurement', [])}
+# (measurement model, state_index[, dim_state]) -> (transition model, dx, dq); the entry with dim_state wins
 _DEFAULT_DYN = {('UNGMMeasurement', ()): ('UNGMTransition', 1, 1), ('Pendulum2DMeasurement', ()): ('Pendulum2DTransition', 2, 2),
                 ('Radar2DMeasurement', ()): ('ReentryVehicle2DTransition', 5, 3),
                 ('Radar2DMeasurement', (0, 1)): ('ReentryVehicle2DTransition', 5, 3),
                 ('Radar2DMeasurement', (0, 2)): ('CoordinatedTurnTransition', 5, 5),
+                ('Radar2DMeasurement', (), 4): ('ConstantVelocity', 4, 2),
+                ('Radar2DMeasurement', (0, 1), 4): ('ConstantVelocity', 4, 2),
+                ('Radar2DMeasurement', (0, 2), 4): ('ConstantVelocity', 4, 2),
+                ('BearingMeasurement', (0, 2)): ('CoordinatedTurnTransition', 5, 5),
                 ('UNGMNAMeasurement', ()): ('UNGMNATransition', 1, 1),
                 ('RangeMeasurement', ()): ('ReentryVehicle1DTransition', 3, 3),
                 ('RangeMeasurement', (0,)): ('ReentryVehicle1DTransition', 3, 3)}
@@ -62,8 +68,10 @@ def lower_models(dyn, obs):
         d.update({'obs_name': name, 'state_index': si, 'radar_loc': [0.0, 0.0], 'r_cov': np.eye(dy)})
     if dyn is None:
         key = (type(obs).__name__, tuple(obs.state_index) if obs.state_index is not None else ())
+        if key + (obs.dim_state,) in _DEFAULT_DYN:
+            key = key + (obs.dim_state,)
         if key not in _DEFAULT_DYN:
-            raise NotImplementedError('no device implementation for {} with state_index {}'.format(*key))
+            raise NotImplementedError('no device implementation for {} with state_index {}'.format(*key[:2]))
         name, dx, dq = _DEFAULT_DYN[key]
         d.update({'dyn_name': name, 'dyn_dt': 0.1, 'G': np.eye(dx, dq), 'm0': np.zeros(dx), 'P0': np.eye(dx),
                   'q_cov': np.eye(dq)})

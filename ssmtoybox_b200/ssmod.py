@@ -31,7 +31,7 @@ def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
         nz = np.array(np.broadcast_to(nz.reshape(nz.shape[0], -1), (nz.shape[0], n)), dtype=np.float64, order='C')
         nt = torch.as_tensor(nz, device='cuda')
     out = torch.empty((dim_out, n), dtype=torch.float64, device='cuda')
-    p = (C.c_double * 4)(*par)
+    p = (C.c_double * 8)(*(list(par) + [0.0] * (8 - len(par))))
     t = float(np.asarray(time).reshape(-1)[0]) if time is not None else 0.0
     rc = lib.ssm_model_eval(which, model_id, dim_state, si[0], si[1], p, t, dv._p(xt), dv._p(nt), dv._p(out), n, n,
                             dv._stream())
@@ -186,6 +186,33 @@ class CoordinatedTurnTransition(TransitionModel):
         self.dt = dt
 
 
+class ConstantTurnRateSpeed(TransitionModel):
+    """Constant turn-rate and speed model, state [x, y, speed, heading, yaw rate], NON-additive 2-D noise
+    (ssmod.py:699-781); the filters integrate it over the augmented vector [x; q]."""
+    dim_state = 5
+    dim_noise = 2
+    noise_additive = False
+    _device_id = 8
+
+    def __init__(self, init_rv, noise_rv, dt=0.05):
+        super(ConstantTurnRateSpeed, self).__init__(init_rv, noise_rv)
+        self.dt = dt
+
+
+class ConstantVelocity(TransitionModel):
+    """Constant velocity model, state [x, vx, y, vy], 2-D acceleration noise through the gain
+    [[dt^2/2, 0], [dt, 0], [0, dt^2/2], [0, dt]] (ssmod.py:783-855)."""
+    dim_state = 4
+    dim_noise = 2
+    noise_additive = True
+    _device_id = 7
+
+    def __init__(self, init_rv, noise_rv, dt=0.1):
+        self.dt = dt
+        noise_gain = np.array([[self.dt ** 2 / 2, 0], [self.dt, 0], [0, self.dt ** 2 / 2], [0, self.dt]])
+        super(ConstantVelocity, self).__init__(init_rv, noise_rv, noise_gain)
+
+
 class MeasurementModel(metaclass=ABCMeta):
     """Measurement model (ssmod.py:858-1039)."""
     dim_substate = None
@@ -202,8 +229,8 @@ class MeasurementModel(metaclass=ABCMeta):
         self.dim_state = dim_state
 
     def _par(self):
-        rl = np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64)
-        return [float(rl[0]), float(rl[1]), 0.0, 0.0]
+        rl = np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64).reshape(-1)
+        return [float(v) for v in rl] + [0.0] * (8 - rl.size)
 
     def _si(self):
         si = list(self.state_index) if self.state_index is not None else list(range(self.dim_substate))
@@ -319,3 +346,28 @@ class Radar2DMeasurement(MeasurementModel):
         if radar_loc is None:
             radar_loc = np.array([0, 0])
         self.radar_loc = radar_loc
+
+
+class BearingMeasurement(MeasurementModel):
+    """Bearings from the sensors at sensor_pos (n_sensors, 2) to the object (ssmod.py:1155-1198).  The device
+    implementation covers 4 sensors (the default and the reference's test set-up, tests/test_ssinf.py:77-79); the
+    sensor positions travel in the radar_loc slot of the descriptor (obs_par[0..7])."""
+    dim_substate = 2
+    dim_out = 4
+    dim_noise = 4
+    noise_additive = True
+    _device_id = 6
+
+    def __init__(self, noise_rv, dim_state, state_index=None, sensor_pos=None):
+        super(BearingMeasurement, self).__init__(noise_rv, dim_state, state_index)
+        if sensor_pos is None:
+            sensor_pos = np.vstack((np.eye(2), -np.eye(2)))
+        self.sensor_pos = sensor_pos
+        self.dim_out = len(self.sensor_pos)
+        self.dim_noise = self.dim_out
+        self.zero_r = np.zeros(self.dim_noise)
+        if self.dim_out != 4:
+            raise NotImplementedError('BearingMeasurement runs on the device with 4 sensors (got {})'.format(self.dim_out))
+
+    radar_loc = property(lambda self: np.asarray(self.sensor_pos, dtype=np.float64).reshape(-1))
+

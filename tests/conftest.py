@@ -88,6 +88,13 @@ FULL_TOL = {
     'c4_ct_fsstudent': 1e-9, 'c4_ct_fsstudent_incdof': 1e-9, 'c4_ct_fsstudent_deg5': 1e-9,
     'c4_ct_fsstudent_gpq': 1e-9, 'c4_ct_fsstudent_tpq': 1e-8,
     'c6_reentry1d_gpq': 1e-8, 'c6_reentry1d_ukf': 1e-9,
+    'c8_cv_ukf': 1e-9, 'c8_cv_ckf': 1e-9, 'c8_cv_gpq': 1e-9, 'c8_cv02_ukf': 1e-9, 'c8_cv_fsstudent': 1e-9,
+    'c9_ctb_ukf': 1e-9, 'c9_ctb_ckf': 1e-9, 'c9_ctb_gpq': 1e-9,
+    'c10_ctrs_ukf': 1e-8, 'c10_ctrs_ckf': 1e-9, 'c10_ctrs_gpq': 1e-9,
+    # the reference's own test fixture (zero initial mean): the object starts on top of the radar, the sign of the
+    # ~1e-18 rounding residue of the predicted position decides the bearing of the central sigma point (0 or pi) and
+    # the recursion amplifies it to O(1) (the oracle's two back-ends differ by 1e-4 as well)
+    'c10_ctrs_fixture_ukf': None,
     'c7_ungmna_ukf': 1e-8, 'c7_ungmna_ckf': 1e-8, 'c7_ungmna_ghkf': 1e-8, 'c7_ungmna_gpq': 1e-7,
     'c5_pend_ukf': 1e-9, 'c5_pend_gpq': 1e-9, 'c5_pend_tpq': 1e-9, 'c5_pend_bsq': None, 'c5_pend_ghkf3': 1e-9,
 }

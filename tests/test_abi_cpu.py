@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_lib.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), 'symbol {} declared in include/ssm_b200.h is not exported'.format(s)
-    assert _lib.lib.ssm_abi_version() == 3
+    assert _lib.lib.ssm_abi_version() == 4
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -85,7 +85,14 @@ def test_lowering_from_golden_description():
     low = dv.lower(g)
     assert low.desc.family == _lib.FAMILY_STUDENT and low.desc.dof == 6.0 and low.desc.fixed_dof == 1
     with pytest.raises(NotImplementedError):
-        dv.lower(dict(g, dyn_name='ConstantVelocity'))
+        dv.lower(dict(g, dyn_name='NoSuchTransition'))
+    g = golden('c9_ctb_ukf')                                             # 4 bearing sensors: positions in obs_par[0..7]
+    low = dv.lower(g)
+    assert (low.desc.dyn_model, low.desc.obs_model, low.desc.dx, low.desc.dy) == (4, 6, 5, 4)
+    assert list(low.desc.obs_par) == [1000.0, 0, 0, 1000.0, -1000.0, 0, 0, -1000.0]
+    g = golden('c10_ctrs_ukf')                                           # non-additive: transform over [x; q], 7-D
+    low = dv.lower(g)
+    assert (low.desc.dyn_model, low.desc.dq, low.desc.tf_dyn.dim_in, low.desc.tf_dyn.n_pts, low.desc.tf_obs.dim_in) == (8, 2, 7, 15, 5)
 
 
 def test_product_package_never_imports_the_oracle():

@@ -312,6 +312,24 @@ def test_simulation_reentry1d_vs_reference():
     assert rel(N_(xc), d['xc']) < 1e-13
 
 
+@pytest.mark.parametrize('tag,dim_in', [('cv', 4), ('ctb', 5), ('ctrs', 7)])
+def test_simulation_more_models_vs_reference(tag, dim_in):
+    """ConstantVelocity + radar, CoordinatedTurn + 4 bearing sensors, ConstantTurnRateSpeed (non-additive) + radar:
+    simulate_discrete / simulate_measurements with the reference's noise injected (ssmod.py:168-199, 1011-1039)."""
+    from ssmtoybox_b200 import device as dv
+    d = dict(golden('simulation_' + tag))
+    dx = d['x0'].shape[0]
+    for pfx, dim in (('dyn_', dim_in), ('obs_', dx)):
+        pts, wm, Wc = so.classical_rule('ut', dim)
+        d.update({pfx + 'kind': 'sp', pfx + 'points': pts, pfx + 'wm': wm, pfx + 'Wc': Wc})
+    low = dv.lower(d)
+    M, N = d['x0'].shape[1], d['q'].shape[1]
+    x, y = dv.simulate(low, M, N, x0=T(d['x0']), q=T(d['q']), r=T(d['r']))
+    assert rel(N_(x), d['x']) < 1e-13 and rel(N_(y), d['y']) < 1e-13
+    y2 = dv.simulate_measurements(low, T(d['x']), r=T(d['r']))
+    assert rel(N_(y2), d['y']) < 1e-13
+
+
 @pytest.mark.parametrize('name', ['ungm', 'reentry', 'ct'])
 def test_simulation_philox_statistics_and_shard_invariance(name):
     from ssmtoybox_b200 import device as dv
