@@ -329,6 +329,20 @@ int ssm_rbf_student_expectations(int32_t dim, int32_t n_pts, const double *par, 
                                  int64_t n_samples, uint64_t seed, double *q, double *R, double *Q, double *kbar,
                                  void *stream);
 
+/* ---- K5c: marginal likelihood of the integrand model (hyper-parameter fitting) -------------------
+ * Replaces GaussianProcessModel.neg_log_marginal_likelihood (bq/bqmod.py:537-596; nu = 0) and
+ * StudentTProcessModel.neg_log_marginal_likelihood (bq/bqmod.py:1191-1245; nu > 2) with RBFGauss.der_par
+ * (bq/bqkern.py:426-436), the objective of Model.optimize (bq/bqmod.py:250-285), for n_par kernel LOG-parameter
+ * vectors at once (optimiser restarts / parameter grids; one CTA each).
+ *   log_par (n_par, D+1) host  log [alpha, l_1..l_D];  x_obs (D, N) host;  fcn_obs (N, E) host;
+ *   jitter (N, N) host, added to the kernel matrix (the reference passes 1e-8 I), nullable.
+ * Outputs (device): nlml (n_par), grad (n_par, D+1) -- as the reference defines it (der_par: alpha-derivative for
+ * column 0, log-lengthscale derivatives for the others), info (n_par) int32 = 1 where the kernel matrix is not
+ * positive definite (nlml / grad = NaN; numpy.linalg.LinAlgError in the reference).  dim <= 8, N <= 32, E <= 8. */
+int ssm_gp_nlml(int32_t dim, int32_t n_pts, int32_t n_out, int32_t n_par, const double *log_par,
+                const double *x_obs, const double *fcn_obs, const double *jitter, double nu, double *nlml,
+                double *grad, int32_t *info, void *stream);
+
 /* ---- stand-alone sampler ---------------------------------------------------------------------
  * Replaces GaussRV.sample / StudentRV.sample (utils.py:618-619, 670-671): out (dim, ld) =
  * mean + F z (dof = 0) or mean + F z / sqrt(gamma(dof/2, 2/dof)) (dof > 0), Philox-keyed by

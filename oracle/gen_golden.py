@@ -493,6 +493,54 @@ def gen_more_models():
     filter_case('c10_ctrs_fixture_ukf', ssinf.UnscentedKalman(dyn0, obs), x, y)
 
 
+def gen_nlml():
+    """Hyper-parameter fitting: neg_log_marginal_likelihood of the GP and the Student-t process model
+    (bq/bqmod.py:537-596, 1191-1245) on the set-ups of tests/test_bqmod.py:51-56, 86-96, 160-176, for batches of
+    log-parameter vectors, and the optimum Model.optimize (bq/bqmod.py:250-285) finds with BFGS."""
+    rs = np.random.RandomState(17)
+    d = {}
+    cases = []
+
+    def add(tag, model, y, lps):
+        x = model.points
+        jit = 1e-8 * np.eye(model.num_pts)
+        vals, grads = [], []
+        for lp in lps:
+            f, df = model.neg_log_marginal_likelihood(lp, y, x, jit)
+            vals.append(f), grads.append(df)
+        d.update({tag + '_x': x, tag + '_y': y, tag + '_log_par': np.array(lps), tag + '_nlml': np.array(vals),
+                  tag + '_grad': np.array(grads), tag + '_nu': np.asarray(float(getattr(model, 'nu', 0.0)) if isinstance(model, bqmod.StudentTProcessModel) else 0.0)})
+        cases.append(tag)
+
+    f1 = lambda x: 0.05 * x ** 2                                             # tests/test_bqmod.py:18
+    for cls, nm in ((bqmod.GaussianProcessModel, 'gp'), (bqmod.StudentTProcessModel, 'tp')):
+        m = cls(1, np.array([[1.0, 3.0]]), 'rbf', 'ut', {'alpha': 1.0})
+        add(nm + '_1d_ut', m, f1(m.points).T, [np.log([1.0, 3.0])] + [rs.uniform(-1, 1.5, 2) for _ in range(7)])
+        m = cls(1, np.array([[1.0, 3.0]]), 'rbf', 'gh', {'degree': 15})
+        add(nm + '_1d_gh15', m, f1(m.points).T, [np.log([1.0, 0.5])] + [rs.uniform(-0.5, 1.0, 2) for _ in range(7)])
+        # 5-D, 5 outputs: coordinated-turn dynamics at the sigma points (tests/test_bqmod.py:139-157)
+        m0 = np.array([1000, 300, 1000, 0, np.deg2rad(-3)])
+        dyn = ssmod.CoordinatedTurnTransition(GaussRV(5, m0, np.diag([100, 10, 100, 10, 0.1])), GaussRV(5))
+        m = cls(5, np.array([[1.0, 3, 3, 3, 3, 3]]), 'rbf', 'ut', {'alpha': 1.0})
+        x = m0[:, None] + m.points
+        y = np.apply_along_axis(dyn.dyn_eval, 0, x, None)
+        y = y - y.mean(axis=1, keepdims=True)                                # keep the fit well scaled
+        add(nm + '_5d_ut', m, y.T, [np.log([1.0] + 5 * [3.0])] + [rs.uniform(0.0, 2.0, 6) for _ in range(7)])
+    # optimum of the 1-D GH-15 case (tests/test_bqmod.py:160-176 without the constraint, which BFGS ignores)
+    # (the Student-t process objective sends unbounded BFGS into parameters where the kernel matrix is not PD -- the
+    # reference raises LinAlgError there --, so that model is fitted with bounds, as tests/test_bqmtran.py:196-207 does)
+    bounds = ((np.log(0.5), np.log(2.0)), (np.log(0.2), np.log(5.0)))
+    for cls, nm, kw in ((bqmod.GaussianProcessModel, 'gp', dict(method='BFGS')),
+                        (bqmod.StudentTProcessModel, 'tp', dict(method='L-BFGS-B', bounds=bounds))):
+        m = cls(1, np.array([[1.0, 3.0]]), 'rbf', 'gh', {'degree': 15})
+        # 1-D x0: scipy >= 1.11 rejects the (1, 2) array of tests/test_bqmod.py:167
+        res = m.optimize(np.log([1.0, 0.5]), f1(m.points).T, m.points, **kw)
+        d.update({nm + '_opt_x': res.x, nm + '_opt_fun': np.asarray(res.fun), nm + '_opt_nit': np.asarray(res.nit)})
+    d['opt_bounds'] = np.array(bounds)
+    d['cases'] = np.array(cases)
+    save('nlml', **d)
+
+
 def gen_weights():
     """BQ weights and kernel expectations (bqmod.py:495-523, 893-992; bqkern.py:329-424)."""
     cases = []
@@ -614,7 +662,7 @@ def gen_scores():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'weights': gen_weights, 'simulation': gen_simulation,
+    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'weights': gen_weights, 'simulation': gen_simulation,
             'scores': gen_scores}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

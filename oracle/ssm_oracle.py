@@ -314,6 +314,41 @@ def gp_weights(par, points):
     return dict(wm=wm, Wc=Wc, Wcc=Wcc, model_var=model_var, integral_var=integral_var, iK=iK, q=q, Q=Q, R=R)
 
 
+def rbf_der_par(par, x):
+    """dK/dalpha = 2 K / alpha and, for each lengthscale, K_ij (x_di - x_dj)^2 / l_d^2, as written in
+    RBFGauss.der_par.                                                          bqkern.py:426-436"""
+    par = np.asarray(par, dtype=float).squeeze()
+    alpha, el = par[0], par[1:]
+    K = rbf_eval(par, x)
+    d_alpha = 2 * alpha ** -1 * K
+    d_el = (x[:, None, :] - x[:, :, None]) ** 2 * (el ** -2)[:, None, None] * K[None, :, :]
+    return np.concatenate((d_alpha[..., None], d_el.T), axis=2)
+
+
+def gp_nlml(log_par, fcn_obs, x_obs, jitter, nu=None):
+    """Negative log marginal likelihood and gradient of the GP (nu None; bqmod.py:537-596) or Student-t process
+    (bqmod.py:1191-1245) regression model.  fcn_obs (N, E), x_obs (D, N), jitter (N, N)."""
+    from scipy.special import gammaln
+    par = np.exp(np.asarray(log_par, dtype=float))
+    N, E = fcn_obs.shape
+    K = rbf_eval(par, x_obs) + jitter
+    L = cho_factor(K)
+    a = cho_solve(L, fcn_obs)
+    yda = np.einsum('ij,ij->j', fcn_obs, a)
+    hl = np.sum(np.log(np.diag(L[0])))
+    dK = rbf_der_par(par, x_obs)
+    iK = cho_solve(L, np.eye(N))
+    if nu is None:
+        nlml = E * hl + 0.5 * (yda.sum() + E * N * np.log(2 * np.pi))
+        aoa = a.dot(a.T)
+    else:
+        const = (N / 2) * np.log((nu - 2) * np.pi) - gammaln((nu + N) / 2) + gammaln(nu / 2)
+        nlml = 0.5 * (nu + N) * np.log(1 + yda / (nu - 2)).sum() + E * (hl + const)
+        aoa = (a * ((nu + N) / (nu + yda - 2))[None, :]).dot(a.T)
+    grad = 0.5 * np.einsum('ij,jip->p', E * iK - aoa, dK)
+    return nlml, grad
+
+
 def _fact2(n):
     """Double factorial with (-1)!! = 0!! = 1 (the convention bqmod.py:656-661 relies on)."""
     n = int(n)

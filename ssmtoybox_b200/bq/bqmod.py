@@ -1,10 +1,16 @@
 """Integrand models of Bayesian quadrature (mirror of ssmtoybox/bq/bqmod.py: Model :15-106, 340-423,
 GaussianProcessModel :426-523, BayesSardModel :599-992, StudentTProcessModel :1055-1160).
 
-bq_weights runs on the GPU (ssm_bq_weights, one CTA per kernel-parameter vector).  Hyper-parameter
-fitting (optimize / neg_log_marginal_likelihood), predict and plotting are outside the hot path."""
-import numpy as np
+bq_weights runs on the GPU (ssm_bq_weights, one CTA per kernel-parameter vector), and so does the objective of the
+hyper-parameter fit (neg_log_marginal_likelihood -> ssm_gp_nlml, batched over log-parameter vectors); the optimiser
+itself is scipy.optimize.minimize on the host, as in the reference (bqmod.py:250-285).  predict and plotting are
+outside the hot path."""
+import ctypes as C
 
+import numpy as np
+import torch
+
+from .. import _lib
 from .. import device as dv
 from ..mtran import SphericalRadialTransform, UnscentedTransform, GaussHermiteTransform, FullySymmetricStudentTransform
 from .bqkern import RBFGauss, RBFStudent
@@ -101,6 +107,71 @@ def _weights_mc(self, par):
 
 
 Model._weights_mc = _weights_mc
+
+
+def _nlml_batch(self, log_par, fcn_obs, x_obs, jitter=None):
+    """Negative log marginal likelihood and its gradient for a BATCH of kernel log-parameter vectors in one launch
+    (ssm_gp_nlml): log_par (n_par, D+1) -> nlml (n_par,), grad (n_par, D+1), info (n_par,).  The batched form of
+    neg_log_marginal_likelihood (bqmod.py:537-596 / 1191-1245); not positive-definite kernel matrices give NaN and
+    info = 1 instead of an exception."""
+    lp = dv._c(np.atleast_2d(log_par))
+    x = dv._c(x_obs)
+    y = dv._c(np.asarray(fcn_obs, dtype=np.float64).reshape(x.shape[1], -1))
+    D, N = x.shape
+    E, n_par = y.shape[1], lp.shape[0]
+    if lp.shape[1] != D + 1:
+        raise ValueError('log_par must have {} columns (log alpha, log l_1..l_D)'.format(D + 1))
+    jit = None if jitter is None else dv._c(np.broadcast_to(np.asarray(jitter, dtype=np.float64), (N, N)))
+    kw = dict(dtype=torch.float64, device='cuda')
+    nlml, grad = torch.empty(n_par, **kw), torch.empty((n_par, D + 1), **kw)
+    info = torch.empty(n_par, dtype=torch.int32, device='cuda')
+    nu = float(self.nu) if isinstance(self, StudentTProcessModel) else 0.0
+    rc = _lib.lib.ssm_gp_nlml(D, N, E, n_par, dv._ptr(lp), dv._ptr(x), dv._ptr(y), dv._ptr(jit) if jit is not None else None, nu,
+                              dv._p(nlml), dv._p(grad), dv._p(info), dv._stream())
+    _lib.check(rc, 'ssm_gp_nlml')
+    return nlml.cpu().numpy(), grad.cpu().numpy(), info.cpu().numpy()
+
+
+def _neg_log_marginal_likelihood(self, log_par, fcn_obs, x_obs, jitter):
+    """-> (nlml, gradient) for one log-parameter vector (bqmod.py:537-596; Student-t process: :1191-1245)."""
+    v, g, info = self.nlml_batch(np.asarray(log_par, dtype=np.float64).reshape(1, -1), fcn_obs, x_obs, jitter)
+    if info[0] != 0:
+        raise np.linalg.LinAlgError('kernel matrix is not positive definite')     # scipy cho_factor, bqmod.py:578
+    return float(v[0]), g[0]
+
+
+def _optimize(self, log_par_0, fcn_obs, x_obs, method='BFGS', **kwargs):
+    """Model.optimize (bqmod.py:250-285): scipy.optimize.minimize over the kernel log-parameters with the device
+    objective and gradient."""
+    from scipy.optimize import minimize
+    jitter = 1e-8 * np.eye(np.asarray(x_obs).shape[1])
+    return minimize(self.neg_log_marginal_likelihood, np.asarray(log_par_0, dtype=np.float64).reshape(-1),
+                    args=(fcn_obs, x_obs, jitter), method=method, jac=True, **kwargs)
+
+
+def _optimize_multistart(self, log_par_0, fcn_obs, x_obs, method='BFGS', **kwargs):
+    """Batched extension: the objective of EVERY start in log_par_0 (n_start, D+1) is evaluated in one launch, the
+    starts are ranked, and the best `n_refine` (default 1) are refined with optimize().  Returns the best result and
+    the initial objective values."""
+    n_refine = int(kwargs.pop('n_refine', 1))
+    lp0 = np.atleast_2d(np.asarray(log_par_0, dtype=np.float64))
+    jitter = 1e-8 * np.eye(np.asarray(x_obs).shape[1])
+    v0, _, info = self.nlml_batch(lp0, fcn_obs, x_obs, jitter)
+    v0 = np.where(info == 0, v0, np.inf)
+    best = None
+    for i in np.argsort(v0)[:n_refine]:
+        if not np.isfinite(v0[i]):
+            continue
+        r = self.optimize(lp0[i], fcn_obs, x_obs, method=method, **kwargs)
+        if best is None or r.fun < best.fun:
+            best = r
+    return best, v0
+
+
+Model.nlml_batch = _nlml_batch
+Model.neg_log_marginal_likelihood = _neg_log_marginal_likelihood
+Model.optimize = _optimize
+Model.optimize_multistart = _optimize_multistart
 
 
 class GaussianProcessModel(Model):

@@ -538,3 +538,61 @@ def test_remaining_models_of_ssmod():
     m, P = alg.forward_pass(g['y'])
     assert np.array_equal(np.asarray(alg.status) >> 8, g['status']) and np.isfinite(m).all()
     assert np.abs(alg.pr_mean[:, 1] - g['pr_mean'][:, 1]).max() < 1e-15 and rel(alg.pr_cov[:, :, 1], g['pr_cov'][:, :, 1]) < 1e-12
+
+
+def test_hyperparameter_fitting_on_device():
+    """neg_log_marginal_likelihood (batched, ssm_gp_nlml) and Model.optimize of the GP and the
+    Student-t process model against the reference's values (tests/golden/nlml.npz; set-ups of tests/test_bqmod.py)."""
+    from ssmtoybox_b200.bq.bqmod import GaussianProcessModel, StudentTProcessModel
+    g = golden('nlml')
+    models = {}
+    for nm, cls in (('gp', GaussianProcessModel), ('tp', StudentTProcessModel)):
+        models[nm + '_1d_ut'] = cls(1, np.array([[1.0, 3.0]]), 'rbf', 'ut', {'alpha': 1.0})
+        models[nm + '_1d_gh15'] = cls(1, np.array([[1.0, 3.0]]), 'rbf', 'gh', {'degree': 15})
+        models[nm + '_5d_ut'] = cls(5, np.array([[1.0, 3, 3, 3, 3, 3]]), 'rbf', 'ut', {'alpha': 1.0})
+    for c in map(str, g['cases']):
+        m, x, y = models[c], g[c + '_x'], g[c + '_y']
+        jit = 1e-8 * np.eye(x.shape[1])
+        v, gr, info = m.nlml_batch(g[c + '_log_par'], y, x, jit)                 # the whole batch in one launch
+        assert (info == 0).all()
+        tol_v, tol_g = (1e-7, 1e-5) if 'gh15' in c else (1e-11, 1e-9)            # 15 GH points: cond(K) ~ 1e8
+        assert np.all(np.abs(v - g[c + '_nlml']) <= tol_v * np.maximum(np.abs(g[c + '_nlml']), 1.0)), c
+        assert np.all(np.abs(gr - g[c + '_grad']).max(axis=1) <= tol_g * np.maximum(np.abs(g[c + '_grad']).max(axis=1), 1.0)), c
+        f, df = m.neg_log_marginal_likelihood(g[c + '_log_par'][0], y, x, jit)   # the reference's call
+        assert f == v[0] and np.array_equal(df, gr[0])
+    # finite-difference check of the gradient in the variables it is defined in (alpha, log l): tests/test_bqmod.py:86-96
+    m, c = models['gp_5d_ut'], 'gp_5d_ut'
+    x, y, lp = g[c + '_x'], g[c + '_y'], g[c + '_log_par'][1]
+    jit = 1e-8 * np.eye(11)
+    h = 1e-6
+    pert = np.tile(lp, (12, 1))
+    pert[0::2][0, 0] = np.log(np.exp(lp[0]) + h)
+    pert[1::2][0, 0] = np.log(np.exp(lp[0]) - h)
+    for d in range(1, 6):
+        pert[2 * d, d] += h
+        pert[2 * d + 1, d] -= h
+    v, _, _ = m.nlml_batch(pert, y, x, jit)
+    _, gr, _ = m.nlml_batch(lp[None], y, x, jit)
+    fd = (v[0::2] - v[1::2]) / (2 * h)
+    assert np.abs(fd - gr[0]).max() <= 1e-5 * np.abs(gr[0]).max()
+    # the optimum of the reference's fit
+    f1 = lambda xx: 0.05 * xx ** 2                                                # noqa: E731
+    m = models['gp_1d_gh15']
+    res = m.optimize(np.log([1.0, 0.5]), f1(m.points).T, m.points, method='BFGS')
+    assert abs(res.fun - float(g['gp_opt_fun'])) < 1e-4 * abs(float(g['gp_opt_fun'])) and np.abs(res.x - g['gp_opt_x']).max() < 1e-2
+    m = models['tp_1d_gh15']
+    b = tuple(map(tuple, g['opt_bounds']))
+    res = m.optimize(np.log([1.0, 0.5]), f1(m.points).T, m.points, method='L-BFGS-B', bounds=b)
+    assert abs(res.fun - float(g['tp_opt_fun'])) < 1e-6 * abs(float(g['tp_opt_fun'])) and np.abs(res.x - g['tp_opt_x']).max() < 1e-4
+    # multi-start: 64 starts ranked in one launch, the best refined
+    rs = np.random.RandomState(0)
+    m = models['gp_1d_gh15']
+    starts = np.c_[np.zeros(64), rs.uniform(-1.0, 1.5, 64)]
+    best, v0 = m.optimize_multistart(starts, f1(m.points).T, m.points, method='BFGS')
+    assert v0.shape == (64,) and best.fun <= float(g['gp_opt_fun']) + 1e-3 * abs(float(g['gp_opt_fun']))
+    # not positive definite: NaN + info in the batch, LinAlgError in the single call (scipy cho_factor in the reference)
+    bad = np.log([[1.0, 1e9]])                 # all kernel values are exactly 1: the second pivot is exactly 0
+    v, gr, info = m.nlml_batch(bad, f1(m.points).T, m.points, None)
+    assert info[0] == 1 and np.isnan(v[0])
+    with pytest.raises(np.linalg.LinAlgError):
+        m.neg_log_marginal_likelihood(bad[0], f1(m.points).T, m.points, np.zeros((15, 15)))

@@ -210,3 +210,15 @@ def test_rbf_student_expectations_vs_reference_monte_carlo():
     q, R, Q, kbar = so.rbf_student_expectations(par, x, 4e6, n=200)
     assert rel(q, so.rbf_exp_x_kx(par, x)) < 1e-5 and rel(R, so.rbf_exp_x_xkx(par, x)) < 1e-5
     assert rel(Q, so.rbf_exp_x_kxkx(par, par, x)) < 1e-5 and abs(kbar - so.rbf_exp_xy_kxy(par)) < 1e-6
+
+
+def test_nlml_vs_reference():
+    """neg_log_marginal_likelihood of the GP / Student-t process model and its gradient (bq/bqmod.py:537-596, 1191-1245)
+    against the reference's values for batches of log-parameter vectors."""
+    g = golden('nlml')
+    for c in map(str, g['cases']):
+        x, y, nu = g[c + '_x'], g[c + '_y'], float(g[c + '_nu'])
+        for lp, v, gr in zip(g[c + '_log_par'], g[c + '_nlml'], g[c + '_grad']):
+            f, df = so.gp_nlml(lp, y, x, 1e-8 * np.eye(x.shape[1]), nu if nu > 0 else None)
+            assert abs(f - v) <= 1e-12 * max(abs(v), 1.0)
+            assert np.abs(df - gr).max() <= 1e-8 * max(np.abs(gr).max(), 1.0)     # 15 GH points: cond(K) ~ 1e8
