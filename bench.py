@@ -307,7 +307,7 @@ def run_gpu_arm(args):
                            'time-windowed H2D (y forward in time, x backward) overlapped with forward pass + RTS smoother + '
                            'scores of the windows that have landed; scores and status read back',
                     'windows': args.windows},
-            'gpu_launches': 5 * args.steps,   # filter, smoother, finalize, scores phase 2, finalize
+            'gpu_launches': 6 * args.steps,   # filter, NaN fill of failed trajectories, smoother, finalize, scores phase 2, finalize
             'kernel_ms': {'filter_forward': k_filter, 'rts_smoother_with_phase1_scores': k_smooth, 'scores_phase2_incl_allreduce': k_scores},
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
             'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,

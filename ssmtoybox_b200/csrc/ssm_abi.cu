@@ -26,6 +26,34 @@ int filter_constvel02(const FilterLaunch &L);
 int filter_coordturn_bearing(const FilterLaunch &L);
 int filter_ctrs(const FilterLaunch &L);
 
+__global__ void __launch_bounds__(128) filter_nan_fill_kernel(const FilterBuffers b, int dx) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int from = 0x7fffffff;
+    if (t < b.n_traj) {
+        const int st = b.status[t];   // (failing step, 1-based) << 8 | code; failures of earlier windows start before k_lo
+        if (st != 0) from = max((st >> 8) - 1, b.k_lo);
+    }
+    const int first = __reduce_min_sync(0xffffffffu, from);
+    if (first >= b.k_hi) return;      // no failed trajectory in this warp
+    const long long cs = (long long)b.n_steps * b.ld;
+    const double q = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = first; k < b.k_hi; ++k) {
+        if (k < from) continue;
+        const long long rk = (long long)k * b.ld + t;
+        if (b.fi_mean) for (int c = 0; c < dx; ++c) b.fi_mean[c * cs + rk] = q;
+        if (b.pr_mean) for (int c = 0; c < dx; ++c) b.pr_mean[c * cs + rk] = q;
+        if (b.fi_cov) for (int c = 0; c < dx * dx; ++c) b.fi_cov[c * cs + rk] = q;
+        if (b.pr_cov) for (int c = 0; c < dx * dx; ++c) b.pr_cov[c * cs + rk] = q;
+        if (b.pr_xx) for (int c = 0; c < dx * dx; ++c) b.pr_xx[c * cs + rk] = q;
+    }
+}
+
+int filter_nan_fill(const FilterBuffers &b, int dx, cudaStream_t stream) {
+    if (b.n_traj <= 0) return SSM_OK;
+    filter_nan_fill_kernel<<<(unsigned)((b.n_traj + 127) / 128), 128, 0, stream>>>(b, dx);
+    return cudaGetLastError() == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
 static bool tf_valid(const ssm_transform &t) {
     if (t.n_pts < 1 || !t.points || !t.wm || !t.Wc) return false;
     if (t.kind != SSM_TF_SP && t.kind != SSM_TF_BQ && t.kind != SSM_TF_TP) return false;

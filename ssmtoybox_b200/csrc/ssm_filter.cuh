@@ -302,6 +302,14 @@ struct FilterBuffers {
     int k_lo, k_hi, resume;
 };
 
+// NaN-fill of the outputs of failed trajectories from their failing step on, launched behind every forward-pass
+// kernel (ssm_abi.cu).  All lanes of a warp walk the time steps together, so the failed lanes of a warp write the same
+// rows in the same iteration; warps without a failed trajectory exit after reading their status word.  (Filling the
+// tail from inside the forward pass cost the headline kernel 5-9 % through register allocation; a failed thread filling
+// its own tail at the end of the forward pass issued 85 scattered 8-byte stores per step in a serial loop -- with the
+// 35 % failures of the reference's TPQ weights on the coordinated-turn model that was 25 ms on top of a 35 ms pass.)
+int filter_nan_fill(const FilterBuffers &b, int dx, cudaStream_t stream);
+
 template <int DX, int DY, class TfD, class TfO>
 struct FilterPar {
     TfD tf_dyn;
@@ -351,12 +359,6 @@ SSM_DEV void store_sym(double *base, long long cs, long long rk, const double (&
 #pragma unroll
         for (int c = 0; c < D; ++c) st_stream(q + (r * D + c) * cs, P[sym(r, c)]);
 }
-SSM_DEV void fill_nan(double *base, int comps, long long n_steps, long long ld, int k_from, int k_to, long long t) {
-    if (!base) return;
-    for (int c = 0; c < comps; ++c)
-        for (int k = k_from; k < k_to; ++k) base[((long long)c * n_steps + k) * ld + t] = qnan();
-}
-
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -661,11 +663,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         if (threadIdx.x == 0) atomicExch(b.sched + 1 + blk, kc + 1);
     } else if (active) {
         if (fail) {
-            fill_nan(b.fi_mean, DX, N, ld, kfail, b.k_hi, t);
-            fill_nan(b.fi_cov, DX * DX, N, ld, kfail, b.k_hi, t);
-            fill_nan(b.pr_mean, DX, N, ld, kfail, b.k_hi, t);
-            fill_nan(b.pr_cov, DX * DX, N, ld, kfail, b.k_hi, t);
-            fill_nan(b.pr_xx, DX * DX, N, ld, kfail, b.k_hi, t);
+            // the NaN rows [kfail, k_hi) of the bulk outputs are written by filter_nan_fill() after this kernel
     #pragma unroll
             for (int a = 0; a < DX; ++a) m[a] = qnan();
     #pragma unroll
@@ -832,7 +830,8 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
         grid = cap;
     }
     kern<<<(unsigned)grid, THREADS, smem, L.stream>>>(p);
-    const cudaError_t err = cudaGetLastError();
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && filter_nan_fill(L.buf, DX, L.stream) != SSM_OK) err = cudaErrorUnknown;
     if (work && getenv("SSM_TICKET_DEBUG")) {
         int waits = 0;
         cudaMemcpyAsync(&waits, (int *)work + 1 + blocks, sizeof(int), cudaMemcpyDeviceToHost, L.stream);

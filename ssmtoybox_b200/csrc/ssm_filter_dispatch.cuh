@@ -6,6 +6,10 @@
 
 #include "ssm_filter.cuh"
 
+#ifndef SSM_TP_MINB
+#define SSM_TP_MINB 2
+#endif
+
 namespace ssm {
 
 void set_error(const char *fmt, ...);
@@ -44,8 +48,11 @@ int dispatch_filter_model(const FilterLaunch &L) {
     } else {
     const bool same = id.pts == io.pts && a.n_pts == b.n_pts;
     if (!same || id.pts == PTS_GENERIC) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
+    // TPQ carries K^-1 and the row products fx K^-1 next to everything a BQ transform holds: at the register budget
+    // of MINB = 3 (168) the 5-D instantiations spill ~3 KB per step; two CTAs per SM (255 registers) are faster
+    constexpr int MINB_TP = (Dyn::DX >= 4 && MINB > SSM_TP_MINB) ? SSM_TP_MINB : MINB;
 #define SSM_CASE(P, K, F)                                                        \
-    if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, MINB>(L, id, io);
+    if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, (K == SSM_TF_TP ? MINB_TP : MINB)>(L, id, io);
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_GAUSS)
@@ -133,7 +140,8 @@ int launch_filter_global(const FilterLaunch &L) {
     p.b = L.buf;
     const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
     filter_kernel<Dyn, Obs, PTS_GENERIC, 0, KIND, FAMILY, Par, THREADS, MINB, false><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
-    const cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && filter_nan_fill(L.buf, DX, L.stream) != SSM_OK) e = cudaErrorUnknown;
     cudaFreeAsync(dev, L.stream);
     free(host);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;

@@ -55,13 +55,13 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
         block_reduce_store<W>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
     };
     bool alive = in_range && status[t] == 0;
-    if (in_range && !alive) {  // the forward pass failed: nothing to smooth
-        for (int k = k_lo; k < k_hi; ++k) {
-            for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
-            for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
-        }
-        if (!SCORE) return;
-    }
+    // A trajectory whose forward pass failed (nothing to smooth) or whose smoother fails on the way gets NaN rows,
+    // written step by step inside the time loops next to the stores of the healthy lanes of the warp (a thread that
+    // fills its whole tail on its own issues 30 scattered 8-byte stores per step).
+    auto nan_row = [&](int k) {
+        for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
+        for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
+    };
     // The reference iterates k = N-2 .. 1 over arrays with N+1 slots (slot 0 = initial moments):
     // slots N and N-1 (indices N-1, N-2 here) keep their filtered values, and the recursion starts
     // from the filtered moments of slot N (ssinf.py:117, 137).
@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                     if (k == N - 1 && c <= r) Ps[tri(r, c)] = v;
                     st_stream(sm_cov + at(r * DX + c, k), v);
                 }
+        } else if (in_range) {
+            nan_row(k);
         }
         if (SCORE) score(k, alive, mk, Pk);
     }
@@ -175,19 +177,14 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
 #pragma unroll
             for (int c = 0; c < DX; ++c) st_stream(q_sc + (r * DX + c) * cs, Ps[sym(r, c)]);
       } while (0);
+        if (!alive && in_range) nan_row(k);
         if (SCORE) score(k, alive, ms, Ps);
     }
     if (SCORE && rmse_acc && in_range) {
 #pragma unroll
         for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = (alive && !fail) ? se_acc[a] : qnan();
     }
-    if (fail && in_range) {
-        for (int k = kfail; k >= k_lo; --k) {
-            for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
-            for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
-        }
-        status[t] = ((kfail + 1) << 8) | fail;
-    }
+    if (fail && in_range) status[t] = ((kfail + 1) << 8) | fail;
 }
 
 template <int DX, bool SCORE>
