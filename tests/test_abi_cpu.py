@@ -65,6 +65,29 @@ def test_argument_validation_needs_no_gpu():
         _lib.check(_lib.SSM_E_UNSUPPORTED, 'x')
 
 
+def test_setup_kernels_validate_arguments_without_a_gpu():
+    """ssm_rbf_student_expectations / ssm_gp_nlml: NULL pointers, sizes beyond the compiled capacities and bad
+    degrees of freedom are rejected before any CUDA call."""
+    import ctypes as C
+    from ssmtoybox_b200 import _lib
+    lib = _lib.lib
+    par = (C.c_double * 9)(*([1.0] * 9))
+    pts = (C.c_double * 512)()
+    buf = C.c_void_p(8)      # never dereferenced: validation comes first
+    assert lib.ssm_rbf_student_expectations(5, 11, None, pts, 4.0, 1000, 0, buf, buf, buf, buf, None) == _lib.SSM_E_INVALID
+    assert lib.ssm_rbf_student_expectations(9, 11, par, pts, 4.0, 1000, 0, buf, buf, buf, buf, None) == _lib.SSM_E_UNSUPPORTED
+    assert lib.ssm_rbf_student_expectations(5, 33, par, pts, 4.0, 1000, 0, buf, buf, buf, buf, None) == _lib.SSM_E_UNSUPPORTED
+    assert lib.ssm_rbf_student_expectations(5, 11, par, pts, 0.0, 1000, 0, buf, buf, buf, buf, None) == _lib.SSM_E_INVALID
+    assert lib.ssm_rbf_student_expectations(5, 11, par, pts, 4.0, 0, 0, buf, buf, buf, buf, None) == _lib.SSM_E_INVALID
+    assert b'dof' in lib.ssm_last_error()
+    assert lib.ssm_gp_nlml(5, 11, 5, 1, None, pts, pts, None, 0.0, buf, buf, buf, None) == _lib.SSM_E_INVALID
+    assert lib.ssm_gp_nlml(9, 11, 5, 1, par, pts, pts, None, 0.0, buf, buf, buf, None) == _lib.SSM_E_UNSUPPORTED
+    assert lib.ssm_gp_nlml(5, 33, 5, 1, par, pts, pts, None, 0.0, buf, buf, buf, None) == _lib.SSM_E_UNSUPPORTED
+    assert lib.ssm_gp_nlml(5, 11, 9, 1, par, pts, pts, None, 0.0, buf, buf, buf, None) == _lib.SSM_E_UNSUPPORTED
+    assert lib.ssm_gp_nlml(5, 11, 5, 1, par, pts, pts, None, 1.5, buf, buf, buf, None) == _lib.SSM_E_INVALID      # TP needs nu > 2
+    assert lib.ssm_gp_nlml(5, 11, 5, 0, par, pts, pts, None, 0.0, buf, buf, buf, None) == _lib.SSM_OK             # empty batch
+
+
 def test_lowering_from_golden_description():
     from ssmtoybox_b200 import _lib, device as dv
     g = golden('c3_reentry_gpq')
