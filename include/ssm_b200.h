@@ -350,6 +350,13 @@ int ssm_gp_nlml(int32_t dim, int32_t n_pts, int32_t n_out, int32_t n_par, const 
 int ssm_sample(int32_t dim, const double *mean, const double *factor, double dof, uint64_t seed, int64_t offset,
                double *out, int64_t n, int64_t ld, void *stream);
 
+/* Gaussian-mixture counterpart: utils.gauss_mixture (utils.py:261-301) and GaussianMixtureRV.sample
+ * (research/tpq/tpq_base.py:13-31), the heavy-tailed data generators of the TPQ experiments.  means (K, dim),
+ * factors (K, dim, dim) with F_k F_k^T = cov_k, alphas (K) host; out (dim, ld) device, idx (ld) int32 device
+ * (component of each sample, nullable).  dim <= 8, K <= 4. */
+int ssm_sample_mixture(int32_t dim, int32_t n_comp, const double *means, const double *factors, const double *alphas,
+                       uint64_t seed, int64_t offset, double *out, int32_t *idx, int64_t n, int64_t ld, void *stream);
+
 /* ---- strided copy of a trajectory range ---------------------------------------------------------
  * height rows of width bytes with row pitches dpitch / spitch (bytes): moves columns [a, b) of a host array laid
  * out [component][step][trajectory] into a compact device chunk (or back).  Asynchronous on the stream when the

@@ -113,6 +113,8 @@ def _load():
     lib.ssm_rbf_expectations.argtypes = [i32, i32, c_double_p, c_double_p, i32, vp, vp, vp, vp, vp]
     lib.ssm_rbf_student_expectations.restype = C.c_int
     lib.ssm_rbf_student_expectations.argtypes = [i32, i32, c_double_p, c_double_p, dbl, i64, C.c_uint64, vp, vp, vp, vp, vp]
+    lib.ssm_sample_mixture.restype = C.c_int
+    lib.ssm_sample_mixture.argtypes = [i32, i32, c_double_p, c_double_p, c_double_p, C.c_uint64, i64, vp, vp, i64, i64, vp]
     lib.ssm_gp_nlml.restype = C.c_int
     lib.ssm_gp_nlml.argtypes = [i32, i32, i32, i32, c_double_p, c_double_p, c_double_p, c_double_p, dbl, vp, vp, vp, vp]
     lib.ssm_sample.restype = C.c_int

@@ -248,3 +248,67 @@ extern "C" int ssm_sample(int32_t dim, const double *mean, const double *factor,
     if (cudaGetLastError() != cudaSuccess) { set_error("ssm_sample: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError())); return SSM_E_CUDA; }
     return SSM_OK;
 }
+
+// ---- Gaussian-mixture sampler: utils.gauss_mixture (utils.py:261-301), GaussianMixtureRV (research/tpq/tpq_base.py:13-31) ----
+// One thread per sample: component index from one uniform against the cumulative mixing proportions, then
+// mean_k + F_k z.  (The reference draws the component counts first, fills the components block by block and shuffles;
+// the joint distribution of (sample, index) is the same.)
+namespace ssm {
+constexpr int MIX_MAXK = 4;
+struct MixturePar {
+    int dim, n_comp;
+    double mean[MIX_MAXK][SAMPLE_MAXD], F[MIX_MAXK][SAMPLE_MAXD * SAMPLE_MAXD], cum[MIX_MAXK];
+    unsigned long long seed;
+    long long offset, n, ld;
+    double *out;
+    int32_t *idx;
+};
+__global__ void sample_mixture_kernel(const __grid_constant__ MixturePar p) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    Rng rng;
+    rng.ph.k0 = (uint32_t)p.seed;
+    rng.ph.k1 = (uint32_t)(p.seed >> 32);
+    const unsigned long long gt = (unsigned long long)(p.offset + t);
+    rng.t_lo = (uint32_t)gt;
+    rng.t_hi = (uint32_t)(gt >> 32);
+    uint32_t r[4];
+    rng.ph.gen(rng.t_lo, rng.t_hi, 0, (5u << 16) | 63u, r);
+    const double u = u01(r[0], r[1]);
+    int k = 0;
+    while (k < p.n_comp - 1 && u >= p.cum[k]) ++k;
+    double z[SAMPLE_MAXD];
+    rng.normals<SAMPLE_MAXD>(0, 5, z);
+    for (int i = 0; i < p.dim; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < p.dim; ++j) s = fma(p.F[k][i * p.dim + j], z[j], s);
+        p.out[(long long)i * p.ld + t] = p.mean[k][i] + s;
+    }
+    if (p.idx) p.idx[t] = k;
+}
+}  // namespace ssm
+
+extern "C" int ssm_sample_mixture(int32_t dim, int32_t n_comp, const double *means, const double *factors, const double *alphas,
+                                  uint64_t seed, int64_t offset, double *out, int32_t *idx, int64_t n, int64_t ld, void *stream) {
+    if (!means || !factors || !alphas || !out || dim < 1 || dim > SAMPLE_MAXD || n_comp < 1 || n_comp > MIX_MAXK || n < 0 || ld < n) {
+        set_error("ssm_sample_mixture: bad arguments (dim <= %d, components <= %d)", SAMPLE_MAXD, MIX_MAXK);
+        return SSM_E_INVALID;
+    }
+    if (n == 0) return SSM_OK;
+    MixturePar p;
+    memset(&p, 0, sizeof(p));
+    p.dim = dim; p.n_comp = n_comp;
+    double c = 0.0;
+    for (int k = 0; k < n_comp; ++k) {
+        if (!(alphas[k] >= 0.0)) { set_error("ssm_sample_mixture: negative mixing proportion"); return SSM_E_INVALID; }
+        for (int i = 0; i < dim; ++i) p.mean[k][i] = means[k * dim + i];
+        for (int i = 0; i < dim * dim; ++i) p.F[k][i] = factors[k * dim * dim + i];
+        c += alphas[k];
+        p.cum[k] = c;
+    }
+    if (!(fabs(c - 1.0) < 1e-9)) { set_error("ssm_sample_mixture: mixing proportions must sum to one (got %g)", c); return SSM_E_INVALID; }
+    p.seed = seed; p.offset = offset; p.n = n; p.ld = ld; p.out = out; p.idx = idx;
+    sample_mixture_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) { set_error("ssm_sample_mixture: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError())); return SSM_E_CUDA; }
+    return SSM_OK;
+}

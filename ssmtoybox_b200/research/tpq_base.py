@@ -1,11 +1,13 @@
 """research/tpq/tpq_base.py `run_filters` (:175-192) and `eval_perf_scores` (:154-172) as batched GPU workloads."""
 import numpy as np
+import torch
 
 from . import scoring
 from ..ssinf import StudentianInference
 from ..mtran import FullySymmetricStudentTransform
 from ..bq.bqmtran import GaussianProcessTransform
 from ..bq.bqkern import RBFStudent
+from ..utils import GaussianMixtureRV  # noqa: F401  (tpq_base.py:13-31)
 
 
 class GPQStudent(StudentianInference):
@@ -67,7 +69,10 @@ def eval_perf_scores(x, mf, Pf):
     mfs, Pfs = scoring._split_algs(mf, 4), scoring._split_algs(Pf, 5)
     rmse, lcr = [], []
     for m, P in zip(mfs, Pfs):
-        r = scoring.score_pass(xd, m, P, None, skip_first=False, reg=1e-6 * np.eye(xD))
+        # a trajectory whose filter failed (NaN-filled from the failing step on) is left out of the averages; the
+        # reference has no such case: its run_filters would have stopped with the exception
+        status = torch.isnan(m[0, -1]).to(torch.int32)
+        r = scoring.score_pass(xd, m, P, status if bool(status.any()) else None, skip_first=False, reg=1e-6 * np.eye(xD))
         rmse.append((r['stats'][:, xD + xD * xD + 1] / r['count']).cpu().numpy())
         lcr.append((r['lcr'][:, 0] / r['count']).cpu().numpy())
     return np.stack(rmse, axis=1), np.stack(lcr, axis=1)

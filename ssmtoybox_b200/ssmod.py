@@ -15,7 +15,7 @@ import torch
 
 from . import _lib, device as dv
 from ._lib import lib
-from .utils import StudentRV, next_stream_seed
+from .utils import GaussRV, StudentRV, next_stream_seed
 
 
 def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
@@ -38,6 +38,31 @@ def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
     _lib.check(rc, 'ssm_model_eval')
     o = out.cpu().numpy()
     return o[:, 0] if single else o
+
+
+def _replayed(rv):
+    """True for random variables the simulation kernel cannot draw itself (anything but GaussRV / StudentRV, e.g.
+    GaussianMixtureRV): their own sample() draws the noise and the kernel replays it (injected-noise mode)."""
+    return not isinstance(rv, (GaussRV, StudentRV))
+
+
+def _draw(rv, size):
+    """rv.sample(size) as a contiguous float64 CUDA tensor (dim,) + size."""
+    try:
+        s = rv.sample(size, device_out=True)
+    except TypeError:                      # user-defined RandomVariable with the reference's signature
+        s = rv.sample(size)
+    if not isinstance(s, torch.Tensor):
+        s = torch.as_tensor(np.ascontiguousarray(np.asarray(s, dtype=np.float64)), device='cuda')
+    return s.to(dtype=torch.float64).contiguous()
+
+
+def _moments(rv, dim):
+    """(mean, cov) for the descriptor; placeholders for replayed random variables (the descriptor of a simulation
+    never reads them)."""
+    if _replayed(rv):
+        return np.zeros(dim), np.eye(dim)
+    return rv.get_stats()[:2]
 
 
 class TransitionModel(metaclass=ABCMeta):
@@ -63,11 +88,10 @@ class TransitionModel(metaclass=ABCMeta):
 
     def _desc(self):
         d = {'dyn_name': type(self).__name__, 'dyn_dt': float(getattr(self, 'dt', 0.0)), 'G': self.noise_gain}
-        st = self.init_rv.get_stats()
-        d['m0'], d['P0'] = st[0], st[1]
-        d['q_mean'], d['q_cov'] = self.noise_rv.get_stats()[:2]
-        if len(st) == 3:
-            d['x0_dof'], d['q_dof'] = float(st[2]), float(self.noise_rv.dof)
+        d['m0'], d['P0'] = _moments(self.init_rv, self.dim_state)
+        d['q_mean'], d['q_cov'] = _moments(self.noise_rv, self.dim_noise)
+        if isinstance(self.init_rv, StudentRV):
+            d['x0_dof'], d['q_dof'] = float(self.init_rv.dof), float(self.noise_rv.dof)
         return d
 
     # -- function evaluation ------------------------------------------------------------------------
@@ -96,8 +120,12 @@ class TransitionModel(metaclass=ABCMeta):
         """x (dim_state, steps, mc_sims) with x[:, 0] ~ init_rv, x[:, k] = f(x[:, k-1], q[:, k-1], k-1)
         (ssmod.py:168-199), one GPU thread per trajectory."""
         low, d = self._sim_low()
-        rng = dv.make_rng(d, next_stream_seed())
-        x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='discrete', want_y=False)
+        if _replayed(self.init_rv) or _replayed(self.noise_rv):
+            x0, q = _draw(self.init_rv, mc_sims), _draw(self.noise_rv, (steps, mc_sims))
+            x, _ = dv.simulate(low, mc_sims, steps, mode='discrete', x0=x0, q=q, want_y=False)
+        else:
+            rng = dv.make_rng(d, next_stream_seed())
+            x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='discrete', want_y=False)
         return x if device_out else x.cpu().numpy()
 
     def simulate_continuous(self, duration, dt=0.1, mc_sims=1, device_out=False):
@@ -237,7 +265,7 @@ class MeasurementModel(metaclass=ABCMeta):
         return (int(si[0]), int(si[1]) if len(si) > 1 else 0)
 
     def _desc(self):
-        d = {'obs_name': type(self).__name__, 'r_mean': self.noise_rv.get_stats()[0], 'r_cov': self.noise_rv.get_stats()[1],
+        d = {'obs_name': type(self).__name__, 'r_mean': _moments(self.noise_rv, self.dim_noise)[0], 'r_cov': _moments(self.noise_rv, self.dim_noise)[1],
              'state_index': [] if self.state_index is None else list(self.state_index),
              'radar_loc': np.asarray(getattr(self, 'radar_loc', [0.0, 0.0]), dtype=np.float64)}
         if isinstance(self.noise_rv, StudentRV):
@@ -275,8 +303,11 @@ class MeasurementModel(metaclass=ABCMeta):
         if xt.shape[0] != self.dim_state:
             raise ValueError('state array must have dim_state = {} rows'.format(self.dim_state))
         low, d = lower_models(None, self)
-        rng = dv.make_rng(d, next_stream_seed())
-        y = dv.simulate_measurements(low, xt.contiguous(), rng=rng)
+        if _replayed(self.noise_rv):
+            y = dv.simulate_measurements(low, xt.contiguous(), r=_draw(self.noise_rv, tuple(xt.shape[1:])))
+        else:
+            rng = dv.make_rng(d, next_stream_seed())
+            y = dv.simulate_measurements(low, xt.contiguous(), rng=rng)
         return y if device_out else y.cpu().numpy()
 
 

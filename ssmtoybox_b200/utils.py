@@ -38,7 +38,7 @@ class RandomVariable(metaclass=ABCMeta):
     def get_stats(self):
         pass
 
-    def _sample(self, size, dof):
+    def _sample(self, size, dof, device_out=False):
         shape = (size,) if np.isscalar(size) else tuple(size)
         n = int(np.prod(shape))
         mean = dv._c(self.mean)
@@ -47,7 +47,8 @@ class RandomVariable(metaclass=ABCMeta):
         rc = lib.ssm_sample(self.dim, dv._ptr(mean), dv._ptr(factor), float(dof), C.c_uint64(next_stream_seed()), 0,
                             dv._p(out), n, n, dv._stream())
         _lib.check(rc, 'ssm_sample')
-        return out.cpu().numpy().reshape((self.dim,) + shape)
+        out = out.reshape((self.dim,) + shape)
+        return out if device_out else out.cpu().numpy()
 
 
 class GaussRV(RandomVariable):
@@ -64,8 +65,8 @@ class GaussRV(RandomVariable):
         self.mean = mean
         self.cov = cov
 
-    def sample(self, size):
-        return self._sample(size, 0.0)
+    def sample(self, size, device_out=False):
+        return self._sample(size, 0.0, device_out)
 
     def get_stats(self):
         return self.mean, self.cov
@@ -88,11 +89,70 @@ class StudentRV(RandomVariable):
         self.scale = scale
         self.dof = dof
 
-    def sample(self, size):
-        return self._sample(size, self.dof)
+    def sample(self, size, device_out=False):
+        return self._sample(size, self.dof, device_out)
 
     def get_stats(self):
         return self.mean, self.scale, self.dof
+
+
+class GaussianMixtureRV(RandomVariable):
+    """Gaussian-mixture random variable, the heavy-tailed data generator of the TPQ experiments (mirror of
+    research/tpq/tpq_base.py:13-31; its sample() breaks on tuple sizes in the reference because utils.gauss_mixture
+    returns a (samples, indexes) pair -- here sample(size) -> (dim,) + size for int and tuple sizes)."""
+
+    def __init__(self, dim, means, covs, alphas):
+        if len(means) != len(covs) or len(covs) != len(alphas):
+            raise ValueError('Same number of means, covariances and mixture weights needs to be supplied!')
+        if not np.isclose(np.sum(alphas), 1.0):
+            raise ValueError('Mixture weights must sum to unity!')
+        self.dim = dim
+        self.means = means
+        self.covs = covs
+        self.alphas = alphas
+
+    def sample(self, size, device_out=False):
+        shape = (size,) if np.isscalar(size) else tuple(size)
+        out, _ = _mixture(self.means, self.covs, self.alphas, int(np.prod(shape)), self.dim)
+        out = out.reshape((self.dim,) + shape)
+        return out if device_out else out.cpu().numpy()
+
+    def get_stats(self):
+        return self.means, self.covs, self.alphas
+
+
+def _mixture(means, covs, alphas, n, dim):
+    K = len(alphas)
+    mu = dv._c(np.stack([np.atleast_1d(np.asarray(m, dtype=np.float64)).reshape(dim) for m in means]))
+    F = dv._c(np.stack([dv._cov_factor(np.atleast_2d(c)) for c in covs]))
+    al = dv._c(np.asarray(alphas, dtype=np.float64).reshape(K))
+    out = torch.empty((dim, n), dtype=torch.float64, device='cuda')
+    idx = torch.empty((n,), dtype=torch.int32, device='cuda')
+    rc = lib.ssm_sample_mixture(dim, K, dv._ptr(mu), dv._ptr(F), dv._ptr(al), C.c_uint64(next_stream_seed()), 0,
+                                dv._p(out), dv._p(idx), n, n, dv._stream())
+    _lib.check(rc, 'ssm_sample_mixture')
+    return out, idx
+
+
+def gauss_mixture(means, covs, alphas, size):
+    """Samples of a Gaussian mixture and the component each one came from -> (n, dim), (n,) (utils.py:261-301)."""
+    if len(means) != len(covs) or len(covs) != len(alphas):
+        raise ValueError('means, covs and alphas need to have the same length.')
+    n = int(np.prod(size))
+    out, idx = _mixture(means, covs, alphas, n, len(np.atleast_1d(means[0])))
+    return out.T.cpu().numpy(), idx.cpu().numpy().astype(int)
+
+
+def multivariate_t(mean, scale, nu, size):
+    """Samples of a multivariate Student's t-distribution -> (size, dim) (utils.py:349-382)."""
+    mean = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    return StudentRV(mean.shape[0], mean, scale, nu).sample(int(size)).T
+
+
+def bootstrap_var(data, samples=1000):
+    """Bootstrap estimate of the variance of the sample mean (utils.py:223-244), resampled on the device."""
+    d = torch.as_tensor(np.ascontiguousarray(np.asarray(data, dtype=np.float64).squeeze()), device='cuda')
+    return float(dv.bootstrap_var(d, int(samples), seed=next_stream_seed()))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -596,3 +596,41 @@ def test_hyperparameter_fitting_on_device():
     assert info[0] == 1 and np.isnan(v[0])
     with pytest.raises(np.linalg.LinAlgError):
         m.neg_log_marginal_likelihood(bad[0], f1(m.points).T, m.points, np.zeros((15, 15)))
+
+
+def test_mixture_and_student_samplers_and_bootstrap():
+    """utils.gauss_mixture (utils.py:261-301), utils.multivariate_t (:349-382), utils.bootstrap_var (:223-244) and the
+    GaussianMixtureRV of research/tpq/tpq_base.py:13-31 on the device."""
+    from ssmtoybox_b200 import utils as U
+    from ssmtoybox_b200.ssmod import UNGMTransition, UNGMMeasurement
+    U.seed(3)
+    means = (np.array([0.0, 0.0]), np.array([5.0, -5.0]))
+    covs = (np.eye(2), np.array([[4.0, 1.0], [1.0, 2.0]]))
+    n = 400000
+    s, idx = U.gauss_mixture(means, covs, np.array([0.7, 0.3]), n)
+    assert s.shape == (n, 2) and idx.shape == (n,) and set(np.unique(idx)) == {0, 1}
+    assert abs((idx == 1).mean() - 0.3) < 5 * np.sqrt(0.21 / n)
+    for k in (0, 1):
+        sk = s[idx == k]
+        assert np.abs(sk.mean(axis=0) - means[k]).max() < 0.02 and np.abs(np.cov(sk.T) - covs[k]).max() < 0.05
+    U.seed(3)
+    s2, idx2 = U.gauss_mixture(means, covs, np.array([0.7, 0.3]), n)
+    assert np.array_equal(s, s2) and np.array_equal(idx, idx2)                  # same package seed -> same draws
+    with pytest.raises(ValueError):
+        U.gauss_mixture(means, covs, np.array([0.7, 0.2, 0.1]), 10)
+    t = U.multivariate_t(np.array([1.0, 2.0]), np.diag([1.0, 4.0]), 6.0, 300000)
+    assert t.shape == (300000, 2) and np.abs(t.mean(axis=0) - [1, 2]).max() < 0.03
+    assert np.abs(t.var(axis=0) / (6.0 / 4.0 * np.array([1.0, 4.0])) - 1).max() < 0.05
+    data = np.random.RandomState(0).randn(1, 500) * 2.0
+    v = U.bootstrap_var(data, 20000)
+    assert abs(v / (data.var() / 500) - 1) < 0.1
+    # replayed noise in the simulators: any RandomVariable works as a noise source
+    rv = U.GaussianMixtureRV(1, (np.zeros(1), np.zeros(1)), (np.atleast_2d(10.0), np.atleast_2d(100.0)), np.array([0.8, 0.2]))
+    q = rv.sample((50, 2000))
+    assert q.shape == (1, 50, 2000) and abs(q.var() / (0.8 * 10 + 0.2 * 100) - 1) < 0.05
+    dyn = UNGMTransition(U.GaussRV(1, cov=1.0), rv)
+    x = dyn.simulate_discrete(50, 2000)
+    z = UNGMMeasurement(U.GaussianMixtureRV(1, (np.zeros(1), np.zeros(1)), (np.atleast_2d(0.01), np.atleast_2d(1.0)), np.array([0.8, 0.2])), 1).simulate_measurements(x)
+    assert x.shape == (1, 50, 2000) and z.shape == (1, 50, 2000) and np.isfinite(z).all()
+    incr = x[0, 1:] - (0.5 * x[0, :-1] + 25 * x[0, :-1] / (1 + x[0, :-1] ** 2) + 8 * np.cos(1.2 * np.arange(49))[:, None])
+    assert abs(incr.var() / 28.0 - 1) < 0.05                                    # the process noise is the mixture

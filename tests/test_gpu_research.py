@@ -157,6 +157,35 @@ def test_tpq_base_student_filters():
     assert np.abs(wm - e['wm']).max() < 5e-3 and np.abs(Wcc - e['Wcc']).max() < 5e-3
 
 
+def test_tpq_ungm_demo_runs_end_to_end():
+    """research/tpq/tpq_ungm.py:39-174 -- the UNGM experiment of the TPQ paper (mixture-noise data, UKF / Student
+    filter / three TPQ Student filters sharing one set of Monte-Carlo weights).  The reference's driver itself no
+    longer runs (GaussianMixtureRV.sample, tpq_base.py:27-28), so the outputs are checked for consistency."""
+    from ssmtoybox_b200 import utils as U
+    from ssmtoybox_b200.research import tpq_ungm
+    U.seed(5)
+    o = tpq_ungm.ungm_demo(steps=60, mc_sims=400, mc_weight_samples=200000, num_bs_samples=2000)
+    assert o['labels'] == ['UnscentedKalman', 'FullySymmetricStudent'] + ['StudentProcessStudent'] * 3
+    assert o['rmse_avg'].shape == (60, 5) and o['lcr_avg'].shape == (60, 5) and o['table'].shape == (5, 4)
+    # the fully-symmetric Student filter diverges on a few outlier-hit trajectories (means ~ -5e4 in the oracle too) and
+    # its update P - K S K' then cancels to rounding noise of either sign (+-3.7e-9 on trajectory 219: the oracle
+    # continues, the device reports the non-PD covariance; tools/diag_tpq_ungm.py); eval_perf_scores leaves failed
+    # trajectories out of the averages
+    assert np.isfinite(o['table']).all() and (o['table'][:, 1] > 0).all() and max(o['n_failed']) <= 2
+    # heavy tails in the data: 20 % of the measurement noise has 100x the variance
+    x, z = o['x'].cpu().numpy(), o['z'].cpu().numpy()
+    r = z - 0.05 * x ** 2
+    assert abs(np.mean(np.abs(r) > 3 * 0.1) - 0.2 * 0.764) < 0.02           # P(|N(0, 1)| > 0.3) = 0.764; nominal part: 0.27 %
+    # every TPQSF got the same weights; the Student filters beat the Gaussian UKF on this data in RMSE
+    wm = o['weights']['tf_dyn'][0]
+    assert wm.shape == (3,) and abs(wm.sum() - 1) < 0.2
+    assert o['table'][1:, 0].min() < o['table'][0, 0]
+    # replaying the same data gives the same scores up to the Monte-Carlo noise of the weights
+    o2 = tpq_ungm.ungm_demo(steps=60, mc_sims=400, x=o['x'], z=o['z'], mc_weight_samples=200000, num_bs_samples=2000)
+    np.testing.assert_allclose(o2['table'][:2, 0], o['table'][:2, 0], rtol=1e-12)     # UKF and FS Student: no MC weights
+    np.testing.assert_allclose(o2['table'][2:, 0], o['table'][2:, 0], rtol=0.1)
+
+
 def test_gpq_tracking_demos():
     """research/gpq/gpq_tracking.py: both tracking experiments of the GPQ paper"""
     from ssmtoybox_b200.research import gpq_tracking
