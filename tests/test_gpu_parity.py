@@ -89,7 +89,9 @@ def test_bq_noise_floor(name):
 
 
 @pytest.mark.parametrize('name,M,N', [('c3_reentry_ukf', 2048, 60), ('c3_reentry_gpq', 1024, 60), ('c5_pend_tpq', 4096, 100),
-                                      ('c1_ungm_ukf', 4096, 40), ('c4_ct_ukf', 1024, 60), ('c4_ct_fsstudent', 1024, 60)])
+                                      ('c1_ungm_ukf', 4096, 40), ('c4_ct_ukf', 1024, 60), ('c4_ct_fsstudent', 1024, 60),
+                                      ('c8_cv_ukf', 1024, 60), ('c8_cv_fsstudent', 512, 60), ('c9_ctb_ukf', 512, 60), ('c9_ctb_gpq', 512, 60),
+                                      ('c10_ctrs_ukf', 512, 60), ('c10_ctrs_gpq', 256, 60), ('c4_ct_fsstudent_tpq', 512, 60)])
 def test_batched_vs_oracle_seeded(name, M, N):
     """Larger seeded batches vs the batched oracle (explicit-loop back-end)."""
     from ssmtoybox_b200 import device as dv
