@@ -541,6 +541,25 @@ def gen_nlml():
     save('nlml', **d)
 
 
+def gen_large_pointsets():
+    """Gauss-Hermite Kalman filters on the 5-D models: 3^5 = 243 points at the default degree (mtran.py:309-360), the
+    configuration the reference's own test runs on every model (tests/test_ssinf.py:135-149).  4-D constant velocity:
+    81 points; degree 5 on the 2-D pendulum: 25 points (below the streaming threshold, for comparison)."""
+    np.random.seed(2)
+    dyn, obs, x, y = reentry(60, 2)
+    filter_case('c3_reentry_ghkf3', ssinf.GaussHermiteKalman(dyn, obs), x, y)
+    np.random.seed(3)
+    dyn, obs, x, y = coordinated_turn(60, 2)
+    filter_case('c4_ct_ghkf3', ssinf.GaussHermiteKalman(dyn, obs), x, y)
+    np.random.seed(41)
+    m0, P0 = np.array([10175, 295, 980, -35.0]), np.diag([10000, 100, 10000, 100.0])
+    dyn = ssmod.ConstantVelocity(GaussRV(4, m0, P0), GaussRV(2, cov=np.diag([50, 5.0])), dt=0.5)
+    obs = ssmod.Radar2DMeasurement(GaussRV(2, cov=np.diag([50, 0.4e-6])), 4)
+    x = dyn.simulate_discrete(60, mc_sims=2)
+    y = obs.simulate_measurements(x)
+    filter_case('c8_cv_ghkf3', ssinf.GaussHermiteKalman(dyn, obs), x, y)
+
+
 def gen_weights():
     """BQ weights and kernel expectations (bqmod.py:495-523, 893-992; bqkern.py:329-424)."""
     cases = []
@@ -662,7 +681,7 @@ def gen_scores():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'weights': gen_weights, 'simulation': gen_simulation,
+    sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'large_pointsets': gen_large_pointsets, 'weights': gen_weights, 'simulation': gen_simulation,
             'scores': gen_scores}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

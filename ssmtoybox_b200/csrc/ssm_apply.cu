@@ -4,7 +4,7 @@
 // evaluations TransitionModel.dyn_fcn / dyn_eval and MeasurementModel.meas_fcn / meas_eval
 // (ssmod.py:129-166, 960-1009).  Uses the runtime-N code path of the filter kernel (weights in global
 // memory): these calls are latency-bound, the fused forward pass is the fast path.
-#include "ssm_filter.cuh"
+#include "ssm_filter_dispatch.cuh"
 
 namespace ssm {
 
@@ -85,31 +85,18 @@ static int launch_apply(const ssm_transform &tf, const double *par, double time,
                         double *mean_f, double *cov_f, double *cov_fx, int32_t *status, long long n, long long ld, cudaStream_t s) {
     constexpr int D = Fn::D, E = Fn::E;
     if (tf.dim_in != D || tf.dim_out != E) { set_error("ssm_transform_apply: transform is %dx%d, model function is %dx%d", tf.dim_in, tf.dim_out, D, E); return SSM_E_INVALID; }
-    const int N = tf.n_pts;
-    if (N < 1 || N > GEN_CAP) { set_error("ssm_transform_apply: at most %d points", GEN_CAP); return SSM_E_UNSUPPORTED; }
-    const size_t cnt = (size_t)(2 * N + 2 * N * N + 2 * D * N);
+    if (!tf_global_fits(tf)) {
+        set_error("ssm_transform_apply: at most %d points (sigma-point rules: %d), got %d", GEN_CAP, GEN_CAP_STREAM, tf.n_pts);
+        return SSM_E_UNSUPPORTED;
+    }
+    const size_t cnt = tf_global_count(tf, D);
     double *host = (double *)malloc(cnt * sizeof(double)), *dev = nullptr;
     if (scratch_alloc((void **)&dev, cnt * sizeof(double), s) != cudaSuccess) { free(host); return SSM_E_CUDA; }
     ApplyPar<D, E> p;
     memset(&p, 0, sizeof(p));
     size_t off = 0;
     HostTfInfo gi{PTS_GENERIC, 0.0};
-    // (same staging as the generic filter path)
-    {
-        TfGlobal<D, E> &o = p.tf;
-        fill_tf_common(o, tf, gi);
-        auto put = [&](const double *src, size_t c, const double *&dst) {
-            if (src) memcpy(host + off, src, c * sizeof(double)); else memset(host + off, 0, c * sizeof(double));
-            dst = dev + off; off += c;
-        };
-        put(tf.wm, N, o.wm_);
-        for (int i = 0; i < N; ++i) host[off + i] = tf.Wc[i * N + i];
-        o.wc_ = dev + off; off += N;
-        put(tf.Wc, (size_t)N * N, o.Wc_);
-        put(tf.kind != SSM_TF_SP ? tf.Wcc : nullptr, (size_t)D * N, o.Wcc_);
-        put(tf.kind == SSM_TF_TP ? tf.iK : nullptr, (size_t)N * N, o.iK_);
-        put(tf.points, (size_t)D * N, o.U_);
-    }
+    fill_tf_global(p.tf, tf, gi, dev, host, off);   // same staging as the generic filter path
     cudaMemcpyAsync(dev, host, off * sizeof(double), cudaMemcpyHostToDevice, s);
     for (int i = 0; i < 8; ++i) p.par[i] = par ? par[i] : 0.0;
     p.time = time; p.mean = mean; p.cov = cov; p.mean_f = mean_f; p.cov_f = cov_f; p.cov_fx = cov_fx; p.status = status;

@@ -20,7 +20,8 @@
 namespace ssm {
 
 enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
-constexpr int GEN_CAP = 64;  // capacity of the runtime-N (generic point set) path
+constexpr int GEN_CAP = 64;  // capacity of the runtime-N (generic point set) path with the function values kept per thread
+constexpr int GEN_CAP_STREAM = 4096;  // sigma-point rules beyond GEN_CAP points: two streaming passes, nothing stored
 
 // ------------------------------------------------------------------------------------------------
 // transform parameters, fast path: everything by value inside the kernel parameter block
@@ -131,6 +132,59 @@ struct FxStore<E, NCAP, 0> {  // registers
 // points must sum to a mean of exactly 0 and a state cross-covariance of exactly 0, because the measurement covariance
 // is ~m^4 (1e-60 while the mean is still at rounding level) and K = Pxy / Py turns any 1e-17 residue of a fused
 // multiply-add into O(1) garbage.  numpy's small dot products round every product before adding, so they cancel.
+// Sigma-point transform over a LARGE generic point set (Gauss-Hermite product rules: 3^5 = 243 points for the 5-D
+// models at the default degree, mtran.py:309-360): the function values do not fit a thread, so the rule is walked
+// twice -- mean first, then the centred covariance and cross-covariance with the function re-evaluated at every
+// point.  Loop nests and FMA order are those of the stored variant below, so the results are identical to it.
+template <int D, int E, bool EXACT, class Tf, class F, class Sink>
+SSM_DEV void sigma_point_transform_streamed(const Tf &tf, const int n, const double (&m)[D], const double (&L)[TriSize<D>::value], F f,
+                                            double (&mf)[E], double (&Cf)[TriSize<E>::value], const bool want_cross, Sink sink) {
+#pragma unroll
+    for (int a = 0; a < E; ++a) mf[a] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double x[D], o[E];
+        sigma_point<D, PTS_GENERIC>(tf, i, m, L, x);
+        f(x, o);
+        const double w = tf.wm(i);
+#pragma unroll
+        for (int a = 0; a < E; ++a) mf[a] = EXACT ? __dadd_rn(mf[a], __dmul_rn(o[a], w)) : fma(o[a], w, mf[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < TriSize<E>::value; ++a) Cf[a] = 0.0;
+    double Cfx[E][D];
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int r = 0; r < D; ++r) Cfx[a][r] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double x[D], o[E];
+        sigma_point<D, PTS_GENERIC>(tf, i, m, L, x);
+        f(x, o);
+        const double w = tf.wc(i);
+#pragma unroll
+        for (int a = 0; a < E; ++a) o[a] -= mf[a];
+#pragma unroll
+        for (int a = 0; a < E; ++a) {
+            const double t = o[a] * w;
+#pragma unroll
+            for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(t, o[b], Cf[tri(a, b)]);
+        }
+        if (want_cross) {
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                const double dxr = x[r] - m[r];
+#pragma unroll
+                for (int a = 0; a < E; ++a)
+                    Cfx[a][r] = EXACT ? __dadd_rn(Cfx[a][r], __dmul_rn(__dmul_rn(o[a], w), dxr)) : fma(o[a] * w, dxr, Cfx[a][r]);
+            }
+        }
+    }
+    if (want_cross) {
+#pragma unroll
+        for (int a = 0; a < E; ++a) sink(a, Cfx[a]);
+    }
+}
+
 template <int D, int E, int PTS, int NPTS, int KIND, int SMT, bool EXACT, class Tf, class F, class Sink>
 SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (&P)[TriSize<D>::value], F f,
                               double (&mf)[E], double (&Cf)[TriSize<E>::value], const bool want_cross, Sink sink,
@@ -139,6 +193,12 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
     const int n = (NPTS > 0) ? NPTS : tf.n;
     double L[TriSize<D>::value];
     const bool ok = chol_lower<D>(P, L);
+    if constexpr (KIND == SSM_TF_SP && PTS == PTS_GENERIC) {
+        if (n > NCAP) {
+            sigma_point_transform_streamed<D, E, EXACT>(tf, n, m, L, f, mf, Cf, want_cross, sink);
+            return ok;
+        }
+    }
 
     FxStore<E, NCAP, SMT> fxs(sfx);
 #define fx(a, i) fxs.get(a, i)

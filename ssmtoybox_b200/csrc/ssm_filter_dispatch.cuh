@@ -90,11 +90,27 @@ inline int fill_tf_global(TfGlobal<D, E> &o, const ssm_transform &tf, const Host
         o.wc_ = dev + off;
         off += N;
     }
-    put(tf.Wc, (size_t)N * N, o.Wc_);
-    put(tf.kind != SSM_TF_SP ? tf.Wcc : nullptr, (size_t)D * N, o.Wcc_);
-    put(tf.kind == SSM_TF_TP ? tf.iK : nullptr, (size_t)N * N, o.iK_);
+    // a sigma-point rule reads the diagonal of Wc only (staged above): no dense N x N copies for it (243^2 ... 3125^2 doubles)
+    if (tf.kind == SSM_TF_SP) { o.Wc_ = o.wc_; o.Wcc_ = o.wc_; o.iK_ = o.wc_; }
+    else {
+        put(tf.Wc, (size_t)N * N, o.Wc_);
+        put(tf.Wcc, (size_t)D * N, o.Wcc_);
+        put(tf.kind == SSM_TF_TP ? tf.iK : nullptr, (size_t)N * N, o.iK_);
+    }
     put(tf.points, (size_t)D * N, o.U_);
     return SSM_OK;
+}
+
+// doubles fill_tf_global stages for one transform
+inline size_t tf_global_count(const ssm_transform &tf, int D) {
+    const size_t N = (size_t)tf.n_pts;
+    return 2 * N + (tf.kind == SSM_TF_SP ? 0 : 2 * N * N + (size_t)D * N) + (size_t)D * N;
+}
+
+// capacity of the runtime-N path: BQ / TP transforms keep their function values per thread (GEN_CAP); sigma-point
+// rules beyond that are streamed (GEN_CAP_STREAM)
+inline bool tf_global_fits(const ssm_transform &tf) {
+    return tf.n_pts >= 1 && tf.n_pts <= (tf.kind == SSM_TF_SP ? GEN_CAP_STREAM : GEN_CAP);
 }
 
 template <class Dyn, class Obs, int KIND, int FAMILY, int THREADS, int MINB>
@@ -106,11 +122,11 @@ int launch_filter_global(const FilterLaunch &L) {
     using Par = FilterPar<DX, DY, TfD, TfO>;
     const ssm_desc &d = *L.desc;
     const int Na = d.tf_dyn.n_pts, Nb = d.tf_obs.n_pts;
-    if (Na > GEN_CAP || Nb > GEN_CAP || Na < 1 || Nb < 1) {
-        set_error("generic point sets support at most %d points (got %d / %d)", GEN_CAP, Na, Nb);
+    if (!tf_global_fits(d.tf_dyn) || !tf_global_fits(d.tf_obs)) {
+        set_error("generic point sets support at most %d points (sigma-point rules: %d); got %d / %d", GEN_CAP, GEN_CAP_STREAM, Na, Nb);
         return SSM_E_UNSUPPORTED;
     }
-    const size_t cnt = (size_t)(2 * Na + 2 * Na * Na + 2 * DD * Na) + (size_t)(2 * Nb + 2 * Nb * Nb + 2 * DO * Nb);
+    const size_t cnt = tf_global_count(d.tf_dyn, DD) + tf_global_count(d.tf_obs, DO);
     double *host = (double *)malloc(cnt * sizeof(double));
     double *dev = nullptr;
     if (scratch_alloc((void **)&dev, cnt * sizeof(double), L.stream) != cudaSuccess) { free(host); set_error("cudaMallocAsync failed"); return SSM_E_CUDA; }

@@ -89,6 +89,7 @@ FULL_TOL = {
     'c4_ct_fsstudent_gpq': 1e-9, 'c4_ct_fsstudent_tpq': 1e-8,
     'c6_reentry1d_gpq': 1e-8, 'c6_reentry1d_ukf': 1e-9,
     'c8_cv_ukf': 1e-9, 'c8_cv_ckf': 1e-9, 'c8_cv_gpq': 1e-9, 'c8_cv02_ukf': 1e-9, 'c8_cv_fsstudent': 1e-9,
+    'c3_reentry_ghkf3': 1e-9, 'c4_ct_ghkf3': 1e-9, 'c8_cv_ghkf3': 1e-9,     # 243 / 243 / 81 Gauss-Hermite points: streamed rule
     'c9_ctb_ukf': 1e-9, 'c9_ctb_ckf': 1e-9, 'c9_ctb_gpq': 1e-9,
     'c10_ctrs_ukf': 1e-8, 'c10_ctrs_ckf': 1e-9, 'c10_ctrs_gpq': 1e-9,
     # the reference's own test fixture (zero initial mean): the object starts on top of the radar, the sign of the

@@ -634,3 +634,40 @@ def test_mixture_and_student_samplers_and_bootstrap():
     assert x.shape == (1, 50, 2000) and z.shape == (1, 50, 2000) and np.isfinite(z).all()
     incr = x[0, 1:] - (0.5 * x[0, :-1] + 25 * x[0, :-1] / (1 + x[0, :-1] ** 2) + 8 * np.cos(1.2 * np.arange(49))[:, None])
     assert abs(incr.var() / 28.0 - 1) < 0.05                                    # the process noise is the mixture
+
+
+def test_gauss_hermite_filters_on_5d_models_streamed_rule():
+    """GaussHermiteKalman at the default degree on the 5-D / 4-D models: 243 / 81 points, above the 64 function values a
+    thread keeps -> two streaming passes over the rule (the set-up the reference's test runs on every model,
+    tests/test_ssinf.py:135-149).  Filter, smoother, stand-alone transform; capacity errors."""
+    from ssmtoybox_b200.utils import GaussRV
+    from ssmtoybox_b200.ssmod import ConstantVelocity, Radar2DMeasurement
+    from ssmtoybox_b200.ssinf import GaussHermiteKalman, GaussianProcessKalman
+    from ssmtoybox_b200.mtran import GaussHermiteTransform
+    dyn, obs = reentry()
+    alg = GaussHermiteKalman(dyn, obs)
+    assert alg.tf_dyn.unit_sp.shape == (5, 243)
+    check(alg, 'c3_reentry_ghkf3', 1e-9)
+    dyn, obs = coordinated_turn()
+    check(GaussHermiteKalman(dyn, obs), 'c4_ct_ghkf3', 1e-9)
+    m0, P0 = np.array([10175, 295, 980, -35.0]), np.diag([10000, 100, 10000, 100.0])
+    dyn = ConstantVelocity(GaussRV(4, m0, P0), GaussRV(2, cov=np.diag([50, 5.0])), dt=0.5)
+    obs = Radar2DMeasurement(GaussRV(2, cov=np.diag([50, 0.4e-6])), 4)
+    check(GaussHermiteKalman(dyn, obs), 'c8_cv_ghkf3', 1e-9)
+    # stand-alone transform with 243 points against the oracle
+    dyn, obs = reentry()
+    tf = GaussHermiteTransform(5)
+    m0, P0 = dyn.init_rv.get_stats()
+    mf, Cf, Cfx = tf.apply(dyn.dyn_eval, m0, P0, np.atleast_1d(0))
+    o = so.transform_apply(so._LA('lapack'), {'kind': 'sp', 'points': tf.unit_sp, 'wm': tf.wm, 'Wc': tf.Wc},
+                           lambda xx: so.dyn_fcn('ReentryVehicle2DTransition', xx, 0.0, 0, 0.1), m0, P0, 1)
+    assert rel(mf, o[0]) < 1e-13 and rel(Cf, o[1]) < 1e-9 and rel(Cfx, o[2]) < 1e-9
+    # degree 5 in 5-D: 3125 points, still inside the streamed capacity
+    alg = GaussHermiteKalman(dyn, obs, deg=5)
+    g = golden('c3_reentry_ghkf3')
+    m, P = alg.forward_pass(g['y'][:, :5])
+    assert alg.tf_dyn.unit_sp.shape == (5, 3125) and np.isfinite(m).all() and relstep(m, g['fi_mean'][:, :5]) < 1e-3
+    # BQ transforms keep their function values per thread: more than 64 points are refused, loudly
+    kp = np.array([[1.0, 3, 3, 3, 3, 3]])
+    with pytest.raises(NotImplementedError):
+        GaussianProcessKalman(dyn, obs, kp, kp, points='gh', point_hyp={'degree': 3}).forward_pass(g['y'][..., 0])

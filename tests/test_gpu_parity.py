@@ -165,8 +165,14 @@ def test_empty_inputs_and_bad_arguments():
     assert o['fi_mean'].shape == (2, 0, 4)
     with pytest.raises(ValueError):
         dv.filter_forward(low, torch.zeros((1, 5, 4), dtype=torch.float32, device='cuda'))
-    bad = dict(g, dyn_points=so.gh_points(2, 9), dyn_wm=so.gh_weights(2, 9), dyn_Wc=np.diag(so.gh_weights(2, 9)))
-    with pytest.raises(NotImplementedError):  # 81 points > capacity of the generic path: loud, no fallback
+    # 81 sigma points > the 64 function values a thread keeps: the rule is streamed (two passes), same result as the oracle
+    big_rule = dict(g, dyn_points=so.gh_points(2, 9), dyn_wm=so.gh_weights(2, 9), dyn_Wc=np.diag(so.gh_weights(2, 9)))
+    o = dv.filter_forward(dv.lower(big_rule), T(g['y'][:, :20]))
+    ref = so.forward_pass(big_rule, g['y'][:, :20], backend='loops')
+    assert relstep(N_(o['fi_mean']), ref['fi_mean']) < 1e-9 and relstep(N_(o['fi_cov']), ref['fi_cov']) < 1e-9
+    # 65^2 = 4225 points > capacity of the streamed path: loud, no fallback
+    bad = dict(g, dyn_points=so.gh_points(2, 65), dyn_wm=so.gh_weights(2, 65), dyn_Wc=np.diag(so.gh_weights(2, 65)))
+    with pytest.raises(NotImplementedError):
         dv.filter_forward(dv.lower(bad), torch.zeros((1, 5, 4), dtype=torch.float64, device='cuda'))
 
 
