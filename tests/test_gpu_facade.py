@@ -671,3 +671,66 @@ def test_gauss_hermite_filters_on_5d_models_streamed_rule():
     kp = np.array([[1.0, 3, 3, 3, 3, 3]])
     with pytest.raises(NotImplementedError):
         GaussianProcessKalman(dyn, obs, kp, kp, points='gh', point_hyp={'degree': 3}).forward_pass(g['y'][..., 0])
+
+
+def test_every_filter_on_every_model_like_the_reference_tests():
+    """The model x filter grid of the reference's own smoke tests (tests/test_ssinf.py:17-262): every combination has a
+    device implementation -- it either completes or stops with the numerical exception the reference would raise
+    (LinAlgError / ValueError); NotImplementedError (a missing instantiation) fails the test."""
+    from ssmtoybox_b200.utils import GaussRV, StudentRV
+    from ssmtoybox_b200 import ssmod as M, ssinf as F
+    ssm = {}
+    ssm['ungm'] = (M.UNGMTransition(GaussRV(1), GaussRV(1, cov=np.array([[10.0]]))), M.UNGMMeasurement(GaussRV(1), 1))
+    ssm['ungmna'] = (M.UNGMNATransition(GaussRV(1), GaussRV(1, cov=np.array([[10.0]]))), M.UNGMNAMeasurement(GaussRV(1), 1))
+    ssm['pend'] = pendulum()
+    m0 = np.array([6500.4, 349.14, -1.8093, -6.7967, 0.6932])
+    ssm['rer'] = (M.ReentryVehicle2DTransition(GaussRV(5, m0, np.diag([1e-6, 1e-6, 1e-6, 1e-6, 1])),
+                                               GaussRV(3, cov=np.diag([2.4064e-5, 2.4064e-5, 1e-6]))),
+                  M.Radar2DMeasurement(GaussRV(2, cov=np.diag([1e-6, 0.17e-6])), 5))
+    ct, _ = coordinated_turn()
+    sen = np.vstack((1000 * np.eye(2), -1000 * np.eye(2))).astype(float)
+    ssm['ctb'] = (ct, M.BearingMeasurement(GaussRV(4, cov=10e-3 * np.eye(4)), 5, state_index=[0, 2], sensor_pos=sen))
+    ssm['ctrs'] = (M.ConstantTurnRateSpeed(GaussRV(5, cov=0.1 * np.eye(5)), GaussRV(2, cov=np.diag([0.1, 0.1 * np.pi]))),
+                   M.Radar2DMeasurement(GaussRV(2, cov=np.diag([0.3, 0.03])), 5))
+    ran, stopped = [], []
+
+    def attempt(label, make, y, smooth=True):
+        try:
+            alg = make()
+            alg.forward_pass(y)
+            if smooth:
+                alg.backward_pass()
+            alg.reset()
+            ran.append(label)
+        except (np.linalg.LinAlgError, ValueError, AssertionError) as e:
+            stopped.append((label, type(e).__name__))
+
+    for name, (dyn, obs) in ssm.items():
+        y = obs.simulate_measurements(dyn.simulate_discrete(100))[..., 0]
+        assert y.shape == (obs.dim_out, 100)
+        ones = lambda d: np.atleast_2d(np.ones(d + 1))                                       # noqa: E731
+        attempt(name + ':ckf', lambda: F.CubatureKalman(dyn, obs), y)
+        attempt(name + ':ukf', lambda: F.UnscentedKalman(dyn, obs), y)
+        attempt(name + ':ghkf', lambda: F.GaussHermiteKalman(dyn, obs), y)
+        if name not in ('rer', 'ctb'):                                                       # tests/test_ssinf.py:156-158
+            attempt(name + ':gpq', lambda: F.GaussianProcessKalman(dyn, obs, ones(dyn.dim_in), ones(obs.dim_in)), y)
+            attempt(name + ':tpq', lambda: F.StudentProcessKalman(dyn, obs, ones(dyn.dim_in), ones(obs.dim_in)), y)
+        attempt(name + ':bsq', lambda: F.BayesSardKalman(dyn, obs, ones(dyn.dim_in), ones(obs.dim_in), MUL(dyn.dim_in), MUL(obs.dim_in)), y)
+    # Student filters on the Student SSMs of tests/test_ssinf.py:218-262
+    dyn = M.UNGMTransition(StudentRV(1), StudentRV(1, scale=np.array([[10.0]])))
+    obs = M.UNGMMeasurement(StudentRV(1), 1)
+    m_0, P_0 = np.array([10175, 295, 980, -35.0]), np.diag([10000, 100, 10000, 100.0])
+    cv = (M.ConstantVelocity(StudentRV(4, m_0, P_0, 1000.0), StudentRV(2, scale=np.diag([50, 5.0]), dof=1000.0), dt=0.5),
+          M.Radar2DMeasurement(StudentRV(2, scale=np.diag([50, 0.4e-6]), dof=4.0), 4))
+    data = {'ungm': (dyn, obs, M.UNGMMeasurement(GaussRV(1), 1).simulate_measurements(M.UNGMTransition(GaussRV(1), GaussRV(1, cov=np.array([[10.0]]))).simulate_discrete(100))[..., 0]),
+            'cv': (cv[0], cv[1], M.Radar2DMeasurement(GaussRV(2, cov=np.diag([50, 0.4e-6])), 4).simulate_measurements(
+                M.ConstantVelocity(GaussRV(4, m_0, P_0), GaussRV(2, cov=np.diag([50, 5.0])), dt=0.5).simulate_discrete(100))[..., 0])}
+    for name, (dyn, obs, y) in data.items():
+        ones = np.atleast_2d(np.ones(dyn.dim_state + 1))
+        attempt(name + ':fss', lambda: F.FullySymmetricStudent(dyn, obs), y, smooth=False)
+        attempt(name + ':tpqs', lambda: F.StudentProcessStudent(dyn, obs, ones, ones), y, smooth=False)
+    print('completed:', ran)
+    print('stopped numerically:', stopped)
+    assert len(ran) >= 24                   # the classical filters run everywhere; BQ filters with all-one kernel parameters may stop
+    for lab in ('ungm:ukf', 'pend:ukf', 'rer:ukf', 'ctb:ukf', 'ungm:ghkf', 'pend:ghkf', 'rer:ghkf', 'ctb:ghkf', 'ungm:fss', 'cv:fss', 'ungm:tpqs', 'cv:tpqs'):
+        assert lab in ran, lab
