@@ -199,10 +199,10 @@ def run_gpu_arm(args):
         if e: e[0].record()
         dv.filter_forward(low, y, store_pred=True, out=fwd)
         if e: e[1].record()
-        dv.smooth_backward(low.dx, fwd, out=sm, x_truth=x)      # RTS smoother + in-kernel phase-1 statistics
+        dv.smooth_backward(low.dx, fwd, out=sm, x_truth=x, want_quad=True)   # RTS smoother + in-kernel phase-1 statistics
         if e: e[2].record()
         sc = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], comm=comm, to_host=False,
-                                    phase1=(sm['stats'], sm['rmse_acc']))
+                                    phase1=(sm['stats'], sm['rmse_acc']), quad=sm['quad'])
         if e:
             e[3].record()
             timers.append(e)

@@ -197,6 +197,16 @@ int ssm_smooth_window(int32_t dx, const double *fi_mean, const double *fi_cov,
                       const double *x_truth, double *stats, double *rmse_acc,
                       int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
+/* Same pass with one more output for the two-phase scores: quad (n_steps, ld) receives d' P_s^-1 d of every scored
+ * (step, trajectory) -- the first quadratic form of the log credibility ratio (utils.py:113-120), which the in-kernel
+ * scoring computes anyway for the NLL -- so that ssm_scores_phase2_quad does not have to read the smoothed covariances
+ * again (NaN where the covariance is not positive definite).  quad needs x_truth; quad = NULL: ssm_smooth_window. */
+int ssm_smooth_quad(int32_t dx, const double *fi_mean, const double *fi_cov,
+                    const double *pr_mean, const double *pr_cov, const double *pr_xx_cov,
+                    double *sm_mean, double *sm_cov, int32_t *status,
+                    const double *x_truth, double *stats, double *rmse_acc, double *quad,
+                    int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+
 /* ---- K1: batched simulation -----------------------------------------------------------------
  * Replaces TransitionModel.simulate_discrete / simulate_continuous (ssmod.py:168-244),
  * MeasurementModel.simulate_measurements (ssmod.py:1011-1039) and the samplers
@@ -288,6 +298,12 @@ int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, cons
 int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov,
                            const int32_t *status, const double *mse, double *lcr, double *lcr_acc,
                            int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+/* Phase 2 from the quadratic forms stored by ssm_smooth_quad instead of the covariances: reads x, mean (2 dx doubles)
+ * and quad (1 double) per unit instead of 2 dx + dx (dx + 1) / 2; bitwise the same result as ssm_scores_phase2_traj on
+ * the smoothed moments. */
+int ssm_scores_phase2_quad(int32_t dx, const double *x, const double *mean, const double *quad, const int32_t *status,
+                           const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                           int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
 /* ---- bootstrap variance of a sample mean -------------------------------------------------------
  * Replaces utils.bootstrap_var (utils.py:223-244): var[0] = population variance of the means of n_boot resamples

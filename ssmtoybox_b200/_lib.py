@@ -79,6 +79,10 @@ def _load():
     lib.ssm_scores_phase2_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase1_traj.restype = C.c_int
     lib.ssm_scores_phase1_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_smooth_quad.restype = C.c_int
+    lib.ssm_smooth_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase2_quad.restype = C.c_int
+    lib.ssm_scores_phase2_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase2_traj.restype = C.c_int
     lib.ssm_scores_phase2_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_bootstrap_var.restype = C.c_int

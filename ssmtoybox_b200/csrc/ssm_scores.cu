@@ -122,7 +122,9 @@ __global__ void phase2_prepare_kernel(const double *__restrict__ mse, double *__
     row[TX + DX] = ok ? 1.0 : 0.0;
 }
 
-template <int DX>
+// QUAD: `cov` is not the covariance array but the (N, ld) array of d' P^-1 d that the smoother's in-kernel scoring
+// stored (ssm_smooth_quad): no covariance read (120 of 200 bytes per unit for dx = 5), no factorisation.
+template <int DX, bool QUAD>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    const double *__restrict__ tab, double *__restrict__ partial,
@@ -144,29 +146,37 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
             const double *qx = row_ptr(x, rk), *qm = row_ptr(mean, rk), *qc = row_ptr(cov, rk);
 #pragma unroll
             for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - ld_stream(qm + a * cs);
+            double q_given = 0.0;
+            if (QUAD) q_given = ld_stream(qc);
+            else {
 #pragma unroll
-            for (int r = 0; r < DX; ++r)
+                for (int r = 0; r < DX; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
+                    for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
+            }
             // log_cred_ratio, utils.py:113-120: both quadratic forms through Cholesky factors; the factor of the MSE
             // matrix comes from the per-step table (one address per warp: broadcast loads), substitutions multiply by
             // the reciprocal pivots the factorisations already have
             const double *ts = tab + (long long)(k - k_lo) * TW;
-            const bool ok = chol_lower<DX>(P, L, inv) & (__ldg(ts + TX + DX) != 0.0);
+            bool ok = __ldg(ts + TX + DX) != 0.0;
+            if (!QUAD) ok = chol_lower<DX>(P, L, inv) & ok;
             double qa = 0.0, qb = 0.0, za[DX], zb[DX];
 #pragma unroll
             for (int i = 0; i < DX; ++i) {
                 double sa = d[i], sb = d[i];
 #pragma unroll
                 for (int c = 0; c < i; ++c) {
-                    sa = fma(-L[tri(i, c)], za[c], sa);
+                    if (!QUAD) sa = fma(-L[tri(i, c)], za[c], sa);
                     sb = fma(-__ldg(ts + tri(i, c)), zb[c], sb);
                 }
-                za[i] = sa * inv[i];
+                if (!QUAD) {
+                    za[i] = sa * inv[i];
+                    qa = fma(za[i], za[i], qa);
+                }
                 zb[i] = sb * __ldg(ts + TX + i);
-                qa = fma(za[i], za[i], qa);
                 qb = fma(zb[i], zb[i], qb);
             }
+            if (QUAD) qa = q_given;   // NaN where the covariance was not positive definite
             const double g = ok ? 10.0 * (log10(qa) - log10(qb)) : qnan();
             v[0] = g;
             v[1] = fabs(g);
@@ -193,7 +203,7 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
-template <int DX>
+template <int DX, bool QUAD>
 static int run_phase2(const double *x, const double *mean, const double *cov, const int32_t *status, const double *mse,
                       double *lcr, double *lcr_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     constexpr int TW = TriSize<DX>::value + DX + 1;
@@ -203,7 +213,7 @@ static int run_phase2(const double *x, const double *mean, const double *cov, co
     if (scratch_alloc((void **)&partial, ((size_t)n_cta * WLEN * 2 + (size_t)WLEN * TW) * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     double *tab = partial + (size_t)n_cta * WLEN * 2;
     phase2_prepare_kernel<DX><<<(WLEN + 63) / 64, 64, 0, s>>>(mse, tab, N, k_lo, k_hi);
-    scores_phase2_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, tab, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
+    scores_phase2_kernel<DX, QUAD><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, tab, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * 2;
     scores_finalize_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);
     const cudaError_t e = cudaGetLastError();
@@ -249,24 +259,41 @@ extern "C" int ssm_scores_phase1(int32_t dx, const double *x, const double *mean
 }
 
 // lcr: (n_steps, 2) = per step [ sum of log credibility ratios | sum of their absolute values ]
-extern "C" int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
-                                      const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
-                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+static int scores_phase2_impl(bool quad, int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                              const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                              int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!x || !mean || !cov || !mse || !lcr) { set_error("ssm_scores_phase2: NULL buffer"); return SSM_E_INVALID; }
     if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase2: bad sizes"); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi <= k_lo || k_hi > n_steps) { set_error("ssm_scores_phase2: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = run_phase2<1>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 2: rc = run_phase2<2>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 3: rc = run_phase2<3>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 4: rc = run_phase2<4>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 5: rc = run_phase2<5>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 1: rc = quad ? run_phase2<1, true>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s)
+                        : run_phase2<1, false>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = quad ? run_phase2<2, true>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s)
+                        : run_phase2<2, false>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = quad ? run_phase2<3, true>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s)
+                        : run_phase2<3, false>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = quad ? run_phase2<4, true>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s)
+                        : run_phase2<4, false>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = quad ? run_phase2<5, true>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s)
+                        : run_phase2<5, false>(x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase2: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                      const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return scores_phase2_impl(false, dx, x, mean, cov, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, stream);
+}
+
+extern "C" int ssm_scores_phase2_quad(int32_t dx, const double *x, const double *mean, const double *quad, const int32_t *status,
+                                      const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return scores_phase2_impl(true, dx, x, mean, quad, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, stream);
 }
 
 extern "C" int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,

@@ -19,7 +19,8 @@ struct ScoreRow {
 // packed row: [ squared error (DX) | lower triangle of d d^T (DX(DX+1)/2) | NLL | |d| | 1 ]; the finalise kernel
 // mirrors the triangle into the public full-matrix layout (a third fewer shuffles in the per-step reduction)
 template <int DX>
-SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::value], double (&v)[ScoreRow<DX>::WP], double (&se)[DX]) {
+SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::value], double (&v)[ScoreRow<DX>::WP], double (&se)[DX],
+                        double *quad_out = nullptr) {
     constexpr int TX = TriSize<DX>::value;
     double sse = 0.0;
 #pragma unroll
@@ -51,6 +52,9 @@ SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::va
     }
     const double logdet = log(pdiag);
     v[DX + TX] = ok ? 0.5 * (2.0 * logdet + quad + DX * 1.8378770664093453) : qnan();
+    // d' P^-1 d, the first quadratic form of the log credibility ratio (utils.py:113-120): identical arithmetic to
+    // scores_phase2_kernel, so a pass that keeps it saves phase 2 the covariance read and its factorisation
+    if (quad_out) *quad_out = ok ? quad : qnan();
     v[DX + TX + 1] = sqrt(sse);  // per-trajectory error norm, bsq_tracking.py:331
     v[DX + TX + 2] = 1.0;
 }

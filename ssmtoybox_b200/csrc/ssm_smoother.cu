@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                                                               const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
                                                               double *__restrict__ sm_cov, int32_t *__restrict__ status,
                                                               const double *__restrict__ x_truth, double *__restrict__ partial,
-                                                              double *__restrict__ rmse_acc, long long n_traj, int N, int k_lo, int k_hi,
-                                                              long long ld) {
+                                                              double *__restrict__ rmse_acc, double *__restrict__ quad, long long n_traj, int N,
+                                                              int k_lo, int k_hi, long long ld) {
     // Time window [k_lo, k_hi) of the N slots (ssm_smooth_window): a window with k_hi < N continues the recursion
     // from the smoothed moments the later window left in sm_mean / sm_cov (same stream => ordered), so walking the
     // windows from the last to the first reproduces the one-pass result bit for bit.
@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
             double d[DX], se[DX];
 #pragma unroll
             for (int a = 0; a < DX; ++a) d[a] = ld_stream(x_truth + at(a, k)) - ms_[a];
-            score_step<DX>(d, Ps_, v, se);
+            double qf;
+            score_step<DX>(d, Ps_, v, se, &qf);
+            if (quad) st_stream(quad + row(k), qf);
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
@@ -204,12 +206,12 @@ static cudaError_t launch_tma(const SmootherArgs &a, long long n_full, cudaStrea
 template <int DX>
 static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
                            const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, const double *x_truth,
-                           double *stats, double *rmse_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+                           double *stats, double *rmse_acc, double *quad, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     const int WLEN = k_hi - k_lo;
-    SmootherArgs a{fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, nullptr, rmse_acc, ld, N, k_lo, k_hi};
+    SmootherArgs a{fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, nullptr, rmse_acc, ld, N, k_lo, k_hi, quad};
     // TMA path: warp-CTAs over the full blocks of 32 trajectories; the ragged tail (and unaligned problems) take the
     // per-thread ld/st kernel.  Both write partial statistics rows that one finalise kernel sums in block order.
-    const long long n_full = smoother_tma_eligible(a, n_traj) ? n_traj / 32 : 0;
+    const long long n_full = (!quad && smoother_tma_eligible(a, n_traj)) ? n_traj / 32 : 0;
     const long long t_tail = n_full * 32, rem = n_traj - t_tail;
     const long long tail_blocks = (rem + SC_THREADS - 1) / SC_THREADS;
     constexpr int W = ScoreRow<DX>::WP;
@@ -224,11 +226,11 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
         if (x_truth)
             smoother_kernel<DX, true><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                 off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
-                off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), rem, N, k_lo, k_hi, ld);
+                off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), rem, N, k_lo, k_hi, ld);
         else
             smoother_kernel<DX, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                 off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
-                nullptr, nullptr, nullptr, rem, N, k_lo, k_hi, ld);
+                nullptr, nullptr, nullptr, nullptr, rem, N, k_lo, k_hi, ld);
         e = cudaGetLastError();
     }
     if (x_truth) {
@@ -245,10 +247,11 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
 
 using namespace ssm;
 
-extern "C" int ssm_smooth_window(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
-                                 const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
-                                 int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
-                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+extern "C" int ssm_smooth_quad(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                               const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
+                               int32_t *status, const double *x_truth, double *stats, double *rmse_acc, double *quad,
+                               int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    if (quad && !x_truth) { set_error("ssm_smooth: quad needs x_truth"); return SSM_E_INVALID; }
     if (!fi_mean || !fi_cov || !pr_mean || !pr_cov || !pr_xx_cov || !sm_mean || !sm_cov || !status) {
         set_error("ssm_smooth: NULL buffer");
         return SSM_E_INVALID;
@@ -260,15 +263,23 @@ extern "C" int ssm_smooth_window(int32_t dx, const double *fi_mean, const double
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 3: rc = launch_smoother<3>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 4: rc = launch_smoother<4>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 1: rc = launch_smoother<1>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = launch_smoother<2>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = launch_smoother<3>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = launch_smoother<4>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = launch_smoother<5>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_smooth: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_smooth_window(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                                 const double *pr_cov, const double *pr_xx_cov, double *sm_mean, double *sm_cov,
+                                 int32_t *status, const double *x_truth, double *stats, double *rmse_acc,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return ssm_smooth_quad(dx, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, sm_mean, sm_cov, status, x_truth, stats, rmse_acc, nullptr,
+                           n_traj, n_steps, k_lo, k_hi, ld, stream);
 }
 
 extern "C" int ssm_smooth(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,

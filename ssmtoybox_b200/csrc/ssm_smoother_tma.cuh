@@ -57,6 +57,7 @@ struct SmootherArgs {
     double *partial, *rmse_acc;
     long long ld;
     int N, k_lo, k_hi;
+    double *quad;   // (N, ld) d' P_s^-1 d per (step, trajectory), nullable (per-thread kernel only)
 };
 
 template <int DX, bool SCORE>

@@ -197,12 +197,13 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     return o
 
 
-def smooth_backward(dx, fwd, out=None, x_truth=None, window=None):
+def smooth_backward(dx, fwd, out=None, x_truth=None, window=None, want_quad=False):
     """Run the RTS smoother (ssm_smooth) over the arrays stored by filter_forward(store_pred=True).
     window = (k_lo, k_hi): smooth only those steps (ssm_smooth_window); windows must be walked from the last to the
     first with the same `out` (the first call, k_hi == N, copies the forward-pass status).
     With x_truth (dx, N, M) the kernel also accumulates the phase-1 score statistics of the smoothed moments:
-    out['stats'] (N, W) and out['rmse_acc'] (dx, M), identical to scores_phase1(x_truth, sm_mean, sm_cov, status)."""
+    out['stats'] (N, W) and out['rmse_acc'] (dx, M), identical to scores_phase1(x_truth, sm_mean, sm_cov, status);
+    want_quad: also out['quad'] (N, M) = d' P_s^-1 d per unit for scores_phase2(..., quad=...) (ssm_smooth_quad)."""
     _, N, M = fwd['fi_mean'].shape
     o = out if out is not None else {}
     if 'sm_mean' not in o:
@@ -224,10 +225,19 @@ def smooth_backward(dx, fwd, out=None, x_truth=None, window=None):
         if 'stats' not in o:
             o['stats'] = torch.empty((N, W), dtype=torch.float64, device=fwd['fi_mean'].device)
             o['rmse_acc'] = torch.empty((dx, M), dtype=torch.float64, device=fwd['fi_mean'].device)
-    rc = lib.ssm_smooth_window(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
-                               _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']),
-                               _p(x_truth), _p(o.get('stats') if x_truth is not None else None),
-                               _p(o.get('rmse_acc') if x_truth is not None else None), M, N, k_lo, k_hi, ld, _stream())
+    quad = None
+    if want_quad:
+        if x_truth is None:
+            raise ValueError('want_quad needs x_truth')
+        if ld != M:
+            raise ValueError('want_quad is not supported on trajectory-range views')
+        if 'quad' not in o:
+            o['quad'] = torch.empty((N, M), dtype=torch.float64, device=fwd['fi_mean'].device)
+        quad = o['quad']
+    rc = lib.ssm_smooth_quad(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
+                             _p(fwd['pr_xx_cov']), _p(o['sm_mean']), _p(o['sm_cov']), _p(o['status']),
+                             _p(x_truth), _p(o.get('stats') if x_truth is not None else None),
+                             _p(o.get('rmse_acc') if x_truth is not None else None), _p(quad), M, N, k_lo, k_hi, ld, _stream())
     _lib.check(rc, 'ssm_smooth')
     return o
 
@@ -358,13 +368,17 @@ def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, ou
     return stats, acc
 
 
-def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None, lcr_acc=None):
+def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None, lcr_acc=None, quad=None):
     """Per-step sums of the log credibility ratio and of its absolute value: (N, 2).  mse (dx, dx, N).
     window = (k_lo, k_hi) fills only those rows of out (N, 2) and reads only those columns of mse.
     lcr_acc (M,): optional per-trajectory time-sum of the ratio (continued, not reset, when k_lo > 0)."""
     dx, N, M = x.shape
     lcr = out if out is not None else torch.empty((N, 2), dtype=torch.float64, device=x.device)
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    if quad is not None:   # d' P^-1 d stored by smooth_backward(..., want_quad=True): the covariances are not read (cov may be None)
+        rc = lib.ssm_scores_phase2_quad(dx, _p(x), _p(mean), _p(quad), _p(status), _p(mse.contiguous()), _p(lcr), _p(lcr_acc), M, N, k_lo, k_hi, M, _stream())
+        _lib.check(rc, 'ssm_scores_phase2')
+        return lcr
     rc = lib.ssm_scores_phase2_traj(dx, _p(x), _p(mean), _p(cov), _p(status), _p(mse.contiguous()), _p(lcr), _p(lcr_acc), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase2')
     return lcr

@@ -99,13 +99,13 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
     mse = torch.empty((dx * dx, N), **kw)
     lcr = torch.empty((N, 2), **kw)
 
-    def second_phase(k0, k1, mean, cov, status):
+    def second_phase(k0, k1, mean, cov, status, quad=None):
         """stats rows [k0, k1) are complete on this rank: all-reduce them, form the MSE matrices, second phase"""
         rows = stats[k0:k1]
         if comm is not None:
             comm.allreduce_sum(rows)
         mse[:, k0:k1] = (rows[:, dx:dx + dx * dx] / rows[:, -1:]).T
-        dv.scores_phase2(xd, mean, cov, mse, status, window=(k0, k1), out=lcr)
+        dv.scores_phase2(xd, mean, cov, mse, status, window=(k0, k1), out=lcr, quad=quad)
 
     # ---- forward pass, window by window --------------------------------------------------------------
     fwd = {}
@@ -130,8 +130,8 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
             k0, k1 = wins[c]
             if ev_x[c] is not None:
                 comp.wait_event(ev_x[c])
-            dv.smooth_backward(dx, fwd, out=sm, x_truth=xd, window=(k0, k1))
-            second_phase(k0, k1, sm['sm_mean'], sm['sm_cov'], sm['status'])
+            dv.smooth_backward(dx, fwd, out=sm, x_truth=xd, window=(k0, k1), want_quad=True)
+            second_phase(k0, k1, sm['sm_mean'], sm['sm_cov'], sm['status'], quad=sm['quad'])
         mean, cov, st = sm['sm_mean'], sm['sm_cov'], sm['status']
         # trajectories that failed INSIDE the smoother were still alive in the rows of later steps
         n_bad = ((st != 0).sum() - (fwd['status'] != 0).sum()).to(torch.float64)

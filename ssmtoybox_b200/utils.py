@@ -204,7 +204,7 @@ def log_cred_ratio(x, m, P, MSE):
     return float(lcr.cpu().numpy()[0, 0])
 
 
-def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, phase1=None):
+def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, phase1=None, quad=None):
     """Batched RMSE / NCI / NLL of one filter over all trajectories, aggregated exactly like
     research/gpq/icinco_demo.py:17-52 (RMSE = trajectory-mean of sqrt(time-mean SE); NCI and NLL skip
     k = 0 but divide by N), computed on the device in two reduction phases.
@@ -213,6 +213,8 @@ def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, pha
     packed statistics are all-reduced (one NCCL call per phase).
     phase1: optional (stats, rmse_acc) already accumulated in-kernel by the smoother (device.smooth_backward(...,
     x_truth=x)); the first reduction pass over the arrays is then skipped.
+    quad: optional (N, M) array of d' P^-1 d stored by the same call with want_quad=True; the second phase then does not
+    read the covariances again.
     Returns dict(rmse (dx,), nci, nll, inc (inclination), mse (dx,dx,N), rmse_vs_time (N,), n_ok); device
     tensors instead of numpy / floats when to_host=False (no synchronisation)."""
     xd, md, Pd = _dev(x), _dev(mean), _dev(cov)
@@ -230,7 +232,7 @@ def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, pha
     cnt = st[:, -1]
     n_ok = cnt[0]
     mse = (st[:, dx:dx + dx * dx] / cnt[:, None]).T.reshape(dx, dx, N).contiguous()
-    lcr = dv.scores_phase2(xd, md, Pd, mse, status)
+    lcr = dv.scores_phase2(xd, md, Pd, mse, status, quad=quad)
     if comm is not None:
         lcr = comm.allreduce_sum(lcr)
     out = dict(rmse=(rm / n_ok), nll=st[1:, dx + dx * dx].sum() / (N * n_ok), inc=lcr[1:, 0].sum() / (N * n_ok),

@@ -251,6 +251,18 @@ def test_full_size_smoother_and_scores(big):
     assert torch.equal(sm2['sm_mean'], sm['sm_mean']) and torch.equal(sm2['sm_cov'], sm['sm_cov'])
     assert torch.equal(sm2['stats'], s_sep)                       # same CTA partition, same reduction order
     assert torch.allclose(sm2['rmse_acc'], acc_sep, rtol=1e-13, atol=0)   # time sum runs backwards: order differs
+    # second phase from the quadratic forms d' P^-1 d kept by the smoother == second phase from the covariances
+    sm3 = dv.smooth_backward(low.dx, o, x_truth=x, want_quad=True)
+    assert torch.equal(sm3['sm_cov'], sm['sm_cov']) and torch.equal(sm3['stats'], s_sep) and sm3['quad'].shape == x.shape[1:]
+    cnt = s_sep[:, -1]
+    mse = (s_sep[:, 5:30] / cnt[:, None]).T.reshape(5, 5, -1).contiguous()
+    acc_c, acc_q = torch.zeros(x.shape[-1], dtype=torch.float64, device='cuda'), torch.zeros(x.shape[-1], dtype=torch.float64, device='cuda')
+    l_cov = dv.scores_phase2(x, sm['sm_mean'], sm['sm_cov'], mse, sm['status'], lcr_acc=acc_c)
+    l_quad = dv.scores_phase2(x, sm['sm_mean'], None, mse, sm['status'], lcr_acc=acc_q, quad=sm3['quad'])
+    assert torch.equal(l_cov, l_quad) and torch.equal(acc_c, acc_q)
+    e_cov = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], phase1=(sm2['stats'], sm2['rmse_acc']))
+    e_quad = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], phase1=(sm3['stats'], sm3['rmse_acc']), quad=sm3['quad'])
+    assert e_cov['nci'] == e_quad['nci'] and e_cov['nll'] == e_quad['nll']
     # checksum of checksums: statistics of the two halves add up to the statistics of the whole
     s_all, _ = dv.scores_phase1(x, o['fi_mean'], o['fi_cov'], o['status'])
     h = y.shape[-1] // 2
