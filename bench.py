@@ -45,7 +45,7 @@ TRAJ_PER_GPU = 125000           # 10^6 / 8
 FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filter, reentry N=11
 FLOP_SMOOTH = 902.0
 BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
-BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 25)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write sm_*
+BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 25 + 1)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write sm_*, quad
 METRIC = 'filtered trajectory-steps/sec (fp64)'
 UNIT = 'trajectory-steps/s'
 CONFIG = {'workload': 'C3: reentry 5-D + radar, GPQ (RBF, UT) filter + RTS smoother + scores, '
