@@ -295,6 +295,10 @@ int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, co
 int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, const double *cov,
                            const int32_t *status, double *stats, double *rmse_acc, double *nll_acc,
                            int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+/* ... and with quad (n_steps, ld, nullable) = d' P^-1 d of every scored unit kept for ssm_scores_phase2_quad. */
+int ssm_scores_phase1_quad(int32_t dx, const double *x, const double *mean, const double *cov,
+                           const int32_t *status, double *stats, double *rmse_acc, double *nll_acc, double *quad,
+                           int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, const double *cov,
                            const int32_t *status, const double *mse, double *lcr, double *lcr_acc,
                            int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);

@@ -79,6 +79,8 @@ def _load():
     lib.ssm_scores_phase2_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase1_traj.restype = C.c_int
     lib.ssm_scores_phase1_traj.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase1_quad.restype = C.c_int
+    lib.ssm_scores_phase1_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_smooth_quad.restype = C.c_int
     lib.ssm_smooth_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase2_quad.restype = C.c_int

@@ -18,7 +18,7 @@ template <int DX>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    double *__restrict__ partial, double *__restrict__ rmse_acc,
-                                                                   double *__restrict__ nll_acc,
+                                                                   double *__restrict__ nll_acc, double *__restrict__ quad,
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     const int WLEN = k_hi - k_lo;
@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase1_kernel(const double 
             for (int r = 0; r < DX; ++r)
 #pragma unroll
                 for (int c = 0; c <= r; ++c) P[tri(r, c)] = ld_stream(qc + (r * DX + c) * cs);
-            score_step<DX>(d, P, v, se);
+            double qf;
+            score_step<DX>(d, P, v, se, &qf);
+            if (quad) st_stream(quad + rk, qf);   // d' P^-1 d for ssm_scores_phase2_quad
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
             nll_sum += v[DX + TX];
@@ -189,13 +191,13 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
 
 template <int DX>
 static int run_phase1(const double *x, const double *mean, const double *cov, const int32_t *status, double *stats,
-                      double *rmse_acc, double *nll_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+                      double *rmse_acc, double *nll_acc, double *quad, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     constexpr int W = ScoreRow<DX>::WP;
     const int n_cta = (int)((n_traj + SC_THREADS - 1) / SC_THREADS);
     const int WLEN = k_hi - k_lo;
     double *partial = nullptr;
     if (scratch_alloc((void **)&partial, (size_t)n_cta * WLEN * W * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
-    scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, nll_acc, n_traj, N, k_lo, k_hi, ld);
+    scores_phase1_kernel<DX><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, partial, rmse_acc, nll_acc, quad, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * W;
     scores_finalize_packed_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, stats + (long long)k_lo * ScoreRow<DX>::W, n_cta, WLEN, DX);
     const cudaError_t e = cudaGetLastError();
@@ -227,8 +229,8 @@ using namespace ssm;
 
 extern "C" int32_t ssm_scores_width(int32_t dx) { return dx + dx * dx + 3; }
 
-extern "C" int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
-                                      double *stats, double *rmse_acc, double *nll_acc, int64_t n_traj, int32_t n_steps,
+extern "C" int ssm_scores_phase1_quad(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                      double *stats, double *rmse_acc, double *nll_acc, double *quad, int64_t n_traj, int32_t n_steps,
                                       int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     if (!x || !mean || !cov || !stats) { set_error("ssm_scores_phase1: NULL buffer"); return SSM_E_INVALID; }
     if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase1: bad sizes"); return SSM_E_INVALID; }
@@ -236,15 +238,21 @@ extern "C" int ssm_scores_phase1_traj(int32_t dx, const double *x, const double 
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (dx) {
-        case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 3: rc = run_phase1<3>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 4: rc = run_phase1<4>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
-        case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, nll_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 1: rc = run_phase1<1>(x, mean, cov, status, stats, rmse_acc, nll_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 2: rc = run_phase1<2>(x, mean, cov, status, stats, rmse_acc, nll_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 3: rc = run_phase1<3>(x, mean, cov, status, stats, rmse_acc, nll_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 4: rc = run_phase1<4>(x, mean, cov, status, stats, rmse_acc, nll_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+        case 5: rc = run_phase1<5>(x, mean, cov, status, stats, rmse_acc, nll_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s); break;
         default: set_error("ssm_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_scores_phase1: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_scores_phase1_traj(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,
+                                      double *stats, double *rmse_acc, double *nll_acc, int64_t n_traj, int32_t n_steps,
+                                      int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return ssm_scores_phase1_quad(dx, x, mean, cov, status, stats, rmse_acc, nll_acc, nullptr, n_traj, n_steps, k_lo, k_hi, ld, stream);
 }
 
 extern "C" int ssm_scores_phase1_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,

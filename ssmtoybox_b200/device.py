@@ -350,11 +350,12 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
 # ------------------------------------------------------------------------------------------------
 # K6: scores
 # ------------------------------------------------------------------------------------------------
-def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None, nll_acc=None):
+def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None, nll_acc=None, quad=None):
     """Per-step packed statistics over trajectories: stats (N, W), W = dx + dx*dx + 3:
     [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE.
     window = (k_lo, k_hi) fills only those rows of out = (stats, rmse_acc) (walk the windows first to last).
-    nll_acc (M,): optional per-trajectory time-sum of the NLL (continued, not reset, when k_lo > 0)."""
+    nll_acc (M,): optional per-trajectory time-sum of the NLL (continued, not reset, when k_lo > 0).
+    quad (N, M): optional output, d' P^-1 d of every scored unit, for scores_phase2(..., quad=quad)."""
     dx, N, M = x.shape
     W = lib.ssm_scores_width(dx)
     if out is not None:
@@ -363,7 +364,7 @@ def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, ou
         stats = torch.empty((N, W), dtype=torch.float64, device=x.device)
         acc = torch.empty((dx, M), dtype=torch.float64, device=x.device) if want_rmse_acc else None
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
-    rc = lib.ssm_scores_phase1_traj(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), _p(nll_acc), M, N, k_lo, k_hi, M, _stream())
+    rc = lib.ssm_scores_phase1_quad(dx, _p(x), _p(mean), _p(cov), _p(status), _p(stats), _p(acc), _p(nll_acc), _p(quad), M, N, k_lo, k_hi, M, _stream())
     _lib.check(rc, 'ssm_scores_phase1')
     return stats, acc
 

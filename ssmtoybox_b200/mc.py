@@ -117,10 +117,12 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
         if not do_smooth:
             if ev_x[c] is not None:
                 comp.wait_event(ev_x[c])
-            dv.scores_phase1(xd, fwd['fi_mean'], fwd['fi_cov'], fwd['status'], window=(k0, k1), out=(stats, acc))
+            if c == 0:
+                quad_f = torch.empty((N, M), **kw)
+            dv.scores_phase1(xd, fwd['fi_mean'], fwd['fi_cov'], fwd['status'], window=(k0, k1), out=(stats, acc), quad=quad_f)
             if c == 0:
                 cnt0 = stats[0, -1].clone()      # trajectories of this rank alive after the first window
-            second_phase(k0, k1, fwd['fi_mean'], fwd['fi_cov'], fwd['status'])
+            second_phase(k0, k1, fwd['fi_mean'], fwd['fi_cov'], fwd['status'], quad=quad_f)
     mean, cov, st = fwd['fi_mean'], fwd['fi_cov'], fwd['status']
     n_bad = torch.zeros((), **kw)
     # ---- RTS smoother + scores, walking the windows backwards ------------------------------------------

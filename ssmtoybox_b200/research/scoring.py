@@ -55,15 +55,16 @@ def score_pass(x, m, P, status=None, mse=None, skip_first=True, reg=None):
     k1 = 1 if skip_first else 0
     if k1:
         dv.scores_phase1(x, m, P, status, window=(0, 1), out=(stats, acc))
+    quad = torch.empty((N, M), **kw)       # d' P^-1 d per unit, kept by the first pass for the second one
     if N > k1:
-        dv.scores_phase1(x, m, P, status, window=(k1, N), out=(stats, acc), nll_acc=nll)
+        dv.scores_phase1(x, m, P, status, window=(k1, N), out=(stats, acc), nll_acc=nll, quad=quad)
     cnt = stats[:, -1]
     own = (stats[:, dx:dx + dx * dx] / cnt[:, None]).T.reshape(dx, dx, N).contiguous()
     used = own if mse is None else mse
     if reg is not None:
         used = used + to_device(reg)[:, :, None]
     if N > k1:
-        dv.scores_phase2(x, m, P, used, status, window=(k1, N), out=lcr, lcr_acc=nci)
+        dv.scores_phase2(x, m, P, used, status, window=(k1, N), out=lcr, lcr_acc=nci, quad=quad)
     ok = torch.ones(M, dtype=torch.bool, device=x.device) if status is None else (status == 0)
     return dict(stats=stats, lcr=lcr, mse=own, rmse_data=torch.sqrt(acc / N), nll_data=nll / N, nci_data=nci / N, ok=ok,
                 count=cnt)

@@ -219,7 +219,11 @@ def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, pha
     tensors instead of numpy / floats when to_host=False (no synchronisation)."""
     xd, md, Pd = _dev(x), _dev(mean), _dev(cov)
     dx, N, M = xd.shape
-    stats, acc = phase1 if phase1 is not None else dv.scores_phase1(xd, md, Pd, status)
+    if phase1 is not None:
+        stats, acc = phase1
+    else:   # the first pass keeps d' P^-1 d per unit, so the second one does not read the covariances again
+        quad = torch.empty((N, M), dtype=torch.float64, device=xd.device)
+        stats, acc = dv.scores_phase1(xd, md, Pd, status, quad=quad)
     ok = torch.ones(M, dtype=torch.bool, device=xd.device) if status is None else (status == 0)
     # per-trajectory sqrt(time-mean SE), summed over the trajectories that completed
     rm = torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)
