@@ -117,10 +117,42 @@ def run_reference_arm(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  Primary: an NVML polling thread inside this
+    process (no start-up latency; the handle is looked up by the PCI bus id of the CUDA device, so
+    CUDA_VISIBLE_DEVICES re-mappings do not matter).  Fallback: `nvidia-smi -lms 20` as a child process (the recipe's
+    clocks line) -- on a busy 8-GPU box its first sample can arrive after a 170 ms timed region has ended."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
+        self.p, self.f, self.thread, self.rows = None, None, None, []
+        try:
+            import threading
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+            self.stop_flag = threading.Event()
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        r = int(get_reasons(h))
+                        self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, [k for k, b in bits.items() if r & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
@@ -129,6 +161,13 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+                    'power_w_max': max([r[1] for r in self.rows] or [0.0]), 'samples': len(self.rows),
+                    'reasons': sorted({k for r in self.rows for k in r[2]}), 'source': 'nvml'}
         if self.p is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -145,7 +184,7 @@ class ClockSampler:
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(rows[0][1]) if rows else None,
                 'power_w_max': max([float(r[2]) for r in rows if r[2].replace('.', '').isdigit()] or [0.0]),
-                'samples': len(rows), 'reasons': sorted(reasons)}
+                'samples': len(rows), 'reasons': sorted(reasons), 'source': 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------------
