@@ -78,7 +78,7 @@ struct TfGlobal {
 // ------------------------------------------------------------------------------------------------
 template <int D, int PTS, class Tf>
 SSM_DEV void sigma_point(const Tf &tf, int i, const double (&m)[D], const double (&L)[TriSize<D>::value], double (&x)[D]) {
-    if (PTS == PTS_GENERIC) {
+    if constexpr (PTS == PTS_GENERIC) {
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             double s = 0.0;

@@ -1,4 +1,5 @@
 // forward-pass instantiations: coordinated turn (5-D state) + radar on state_index = [0, 2]
+#define SSM_PAIR_MODEL 1
 #include "ssm_filter_dispatch.cuh"
 namespace ssm {
 int filter_coordturn(const FilterLaunch &L) { return dispatch_filter_model<DynCoordTurn, ObsRadar<5, 0, 2>, 128, 3>(L); }

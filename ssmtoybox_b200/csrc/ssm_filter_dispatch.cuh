@@ -5,14 +5,36 @@
 #include <string.h>
 
 #include "ssm_filter.cuh"
+#ifdef SSM_PAIR_MODEL
+#include "ssm_filter_pair.cuh"
+#endif
 
 #ifndef SSM_TP_MINB
 #define SSM_TP_MINB 2
 #endif
 
+#ifndef SSM_PAIR_TPB
+#define SSM_PAIR_TPB 64      // trajectories per CTA of the warp-pair kernel (CTA = 2 x TPB threads)
+#endif
+#ifndef SSM_PAIR_MINB
+#define SSM_PAIR_MINB 4
+#endif
+#ifndef SSM_PAIR_MINB_TP
+#define SSM_PAIR_MINB_TP 3
+#endif
+#ifndef SSM_PAIR_DEFAULT
+#define SSM_PAIR_DEFAULT 0
+#endif
+
 namespace ssm {
 
 void set_error(const char *fmt, ...);
+
+// SSM_PAIR=0 / 1 selects the forward-pass mapping at run time (developer switch for A/B measurements)
+inline bool pair_enabled() {
+    const char *e = getenv("SSM_PAIR");
+    return e ? atoi(e) != 0 : (SSM_PAIR_DEFAULT != 0);
+}
 
 template <class Dyn, class Obs, int PTS, int KIND, int FAMILY, int THREADS, int MINB>
 int dispatch_npts(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo &io) {
@@ -51,6 +73,14 @@ int dispatch_filter_model(const FilterLaunch &L) {
     // TPQ carries K^-1 and the row products fx K^-1 next to everything a BQ transform holds: at the register budget
     // of MINB = 3 (168) the 5-D instantiations spill ~3 KB per step; two CTAs per SM (255 registers) are faster
     constexpr int MINB_TP = (Dyn::DX >= 4 && MINB > SSM_TP_MINB) ? SSM_TP_MINB : MINB;
+#ifdef SSM_PAIR_MODEL
+    // warp pair per 32 trajectories (ssm_filter_pair.cuh): UT-type point sets, BQ / TP transforms, Gaussian family
+    if (id.pts == PTS_AXIS_C && fam == SSM_FAMILY_GAUSS && (kind == SSM_TF_BQ || kind == SSM_TF_TP) && pair_enabled()) {
+        const int rc = (kind == SSM_TF_BQ) ? launch_filter_pair<Dyn, Obs, SSM_TF_BQ, SSM_PAIR_TPB, SSM_PAIR_MINB>(L, id, io)
+                                           : launch_filter_pair<Dyn, Obs, SSM_TF_TP, SSM_PAIR_TPB, SSM_PAIR_MINB_TP>(L, id, io);
+        if (rc != SSM_E_UNSUPPORTED) return rc;
+    }
+#endif
 #define SSM_CASE(P, K, F)                                                        \
     if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, (K == SSM_TF_TP ? MINB_TP : MINB)>(L, id, io);
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS)

@@ -1,4 +1,5 @@
 // forward-pass instantiations: reentry vehicle (5-D state) + radar on the leading two components
+#define SSM_PAIR_MODEL 1
 #include "ssm_filter_dispatch.cuh"
 #ifndef SSM_MINB_5D
 #define SSM_MINB_5D 3

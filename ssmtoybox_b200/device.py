@@ -221,6 +221,8 @@ def smooth_backward(dx, fwd, out=None, x_truth=None, window=None, want_quad=Fals
     if x_truth is not None:
         if bulk_ld(x_truth) != ld and M > 1:
             raise ValueError('x_truth must share the leading dimension of the other bulk arrays')
+        if ld != M:   # rmse_acc (dx, M) is indexed with the bulk leading dimension inside the kernel
+            raise ValueError('in-kernel scoring (x_truth) is not supported on trajectory-range views')
         W = lib.ssm_scores_width(dx)
         if 'stats' not in o:
             o['stats'] = torch.empty((N, W), dtype=torch.float64, device=fwd['fi_mean'].device)
@@ -278,8 +280,8 @@ def make_rng(d, seed, traj_offset=0):
     r = _lib.SsmRng()
     r.seed, r.traj_offset = int(seed) & 0xFFFFFFFFFFFFFFFF, int(traj_offset)
     r.x0_mean, r.x0_factor, r.q_factor, r.r_factor = (_ptr(a) for a in keep)
-    if d.get('sample_student', False):
-        r.x0_dof, r.q_dof, r.r_dof = float(d['x0_dof']), float(d['q_dof']), float(d['r_dof'])
+    if d.get('sample_student', False):   # per random variable; 0 (absent) = Gaussian draws with the factor of its covariance
+        r.x0_dof, r.q_dof, r.r_dof = float(d.get('x0_dof', 0.0)), float(d.get('q_dof', 0.0)), float(d.get('r_dof', 0.0))
     r.dq = keep[2].shape[0]
     return r, keep
 
@@ -350,6 +352,14 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
 # ------------------------------------------------------------------------------------------------
 # K6: scores
 # ------------------------------------------------------------------------------------------------
+def _check_score_layout(x, mean, cov, quad):
+    """The score kernels are launched with ld = M: every bulk argument must be a dense (..., N, M) array."""
+    M = x.shape[-1]
+    for name, t in (('x', x), ('mean', mean), ('cov', cov), ('quad', quad)):
+        if t is not None and M > 1 and bulk_ld(t) != M:
+            raise ValueError('scores: {} must be C-contiguous (trajectory-range views are not supported)'.format(name))
+
+
 def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, out=None, nll_acc=None, quad=None):
     """Per-step packed statistics over trajectories: stats (N, W), W = dx + dx*dx + 3:
     [sum SE | sum d d^T | sum NLL | sum |d| | count]; rmse_acc (dx, M) per-trajectory time-sums of SE.
@@ -357,6 +367,7 @@ def scores_phase1(x, mean, cov, status=None, want_rmse_acc=True, window=None, ou
     nll_acc (M,): optional per-trajectory time-sum of the NLL (continued, not reset, when k_lo > 0).
     quad (N, M): optional output, d' P^-1 d of every scored unit, for scores_phase2(..., quad=quad)."""
     dx, N, M = x.shape
+    _check_score_layout(x, mean, cov, quad)
     W = lib.ssm_scores_width(dx)
     if out is not None:
         stats, acc = out
@@ -374,6 +385,7 @@ def scores_phase2(x, mean, cov, mse, status=None, window=None, out=None, lcr_acc
     window = (k_lo, k_hi) fills only those rows of out (N, 2) and reads only those columns of mse.
     lcr_acc (M,): optional per-trajectory time-sum of the ratio (continued, not reset, when k_lo > 0)."""
     dx, N, M = x.shape
+    _check_score_layout(x, mean, cov if quad is None else None, quad)
     lcr = out if out is not None else torch.empty((N, 2), dtype=torch.float64, device=x.device)
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
     if quad is not None:   # d' P^-1 d stored by smooth_backward(..., want_quad=True): the covariances are not read (cov may be None)

@@ -58,7 +58,14 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
     per_traj = 8 * N * ((0 if y.is_cuda else dy) + (0 if x.is_cuda else dx) + (dx + dx * dx)
                         + ((2 * dx + 3 * dx * dx) if do_smooth else 0))
     free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
-    if n_chunks is not None or per_traj * M > 0.85 * free or N < 4:
+    # cudaMemcpy2DAsync pitches are limited (cudaDevAttrMaxPitch, 2 GiB): very long rows take the chunked path
+    pitch_ok = (y.is_cuda and x.is_cuda) or N * M * 8 <= 2 ** 31 - 1
+    chunked = n_chunks is not None or per_traj * M > 0.85 * free or N < 4 or not pitch_ok
+    if comm is not None:
+        # the two paths issue different numbers of all-reduces: every rank must take the same one
+        flag = comm.allreduce_sum(torch.tensor([1.0 if chunked else 0.0], dtype=torch.float64, device=dev))
+        chunked = bool(flag.item() > 0.0)
+    if chunked:
         return _filter_scores_chunked(alg, y, x, smooth=smooth, n_chunks=n_chunks or 8, comm=comm, keep=keep)
     for src in (y, x):
         if not src.is_cuda and (src.dtype != torch.float64 or not src.is_contiguous()):
@@ -205,6 +212,12 @@ def _filter_scores_chunked(alg, y, x, smooth=True, n_chunks=8, comm=None, keep=F
             ev.record(copy)
         return ys, xs, ev
 
+    # CUDA sources (e.g. simulate(..., device_out=True) just before) are sliced on the copy stream: it must not run
+    # ahead of the kernels that produce them
+    copy.wait_stream(comp)
+    for src in (y, x):
+        if src.is_cuda:
+            src.record_stream(copy)
     nxt = stage(0)
     for c in range(len(bounds)):
         ys, xs, ev = nxt

@@ -78,7 +78,8 @@ def lower_models(dyn, obs):
     dx = np.asarray(d['m0']).shape[0]
     d.update(_sp_stub(dx, 'dyn_'))
     d.update(_sp_stub(dx, 'obs_'))
-    d.pop('x0_dof', None), d.pop('q_dof', None), d.pop('r_dof', None)
+    # StudentRV models: the simulators draw multivariate-t noise (make_rng reads the per-variable dofs)
+    d['sample_student'] = any(k in d for k in ('x0_dof', 'q_dof', 'r_dof'))
     return dv.lower(d), d
 
 

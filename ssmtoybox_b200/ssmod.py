@@ -40,10 +40,15 @@ def _eval(which, model_id, dim_state, si, par, time, x, noise, dim_out):
     return o[:, 0] if single else o
 
 
-def _replayed(rv):
+def _replayed(rv, noise=False):
     """True for random variables the simulation kernel cannot draw itself (anything but GaussRV / StudentRV, e.g.
-    GaussianMixtureRV): their own sample() draws the noise and the kernel replays it (injected-noise mode)."""
-    return not isinstance(rv, (GaussRV, StudentRV))
+    GaussianMixtureRV): their own sample() draws the noise and the kernel replays it (injected-noise mode).
+    The kernel draws process / measurement noise as F z without a mean (ssm_rng carries the mean of x0 only), so a
+    NOISE variable with a non-zero mean is replayed too: its sample() includes the mean like the reference's
+    noise_rv.sample() (ssmod.py:193, 1033)."""
+    if not isinstance(rv, (GaussRV, StudentRV)):
+        return True
+    return bool(noise and np.any(np.asarray(rv.mean) != 0.0))
 
 
 def _draw(rv, size):
@@ -90,8 +95,12 @@ class TransitionModel(metaclass=ABCMeta):
         d = {'dyn_name': type(self).__name__, 'dyn_dt': float(getattr(self, 'dt', 0.0)), 'G': self.noise_gain}
         d['m0'], d['P0'] = _moments(self.init_rv, self.dim_state)
         d['q_mean'], d['q_cov'] = _moments(self.noise_rv, self.dim_noise)
+        # degrees of freedom per random variable (0 = Gaussian): the simulators draw multivariate-t samples for
+        # StudentRV like init_rv.sample() / noise_rv.sample() of the reference (utils.py:349-382, 668-671)
         if isinstance(self.init_rv, StudentRV):
-            d['x0_dof'], d['q_dof'] = float(self.init_rv.dof), float(self.noise_rv.dof)
+            d['x0_dof'] = float(self.init_rv.dof)
+        if isinstance(self.noise_rv, StudentRV):
+            d['q_dof'] = float(self.noise_rv.dof)
         return d
 
     # -- function evaluation ------------------------------------------------------------------------
@@ -120,7 +129,7 @@ class TransitionModel(metaclass=ABCMeta):
         """x (dim_state, steps, mc_sims) with x[:, 0] ~ init_rv, x[:, k] = f(x[:, k-1], q[:, k-1], k-1)
         (ssmod.py:168-199), one GPU thread per trajectory."""
         low, d = self._sim_low()
-        if _replayed(self.init_rv) or _replayed(self.noise_rv):
+        if _replayed(self.init_rv) or _replayed(self.noise_rv, noise=True):
             x0, q = _draw(self.init_rv, mc_sims), _draw(self.noise_rv, (steps, mc_sims))
             x, _ = dv.simulate(low, mc_sims, steps, mode='discrete', x0=x0, q=q, want_y=False)
         else:
@@ -132,8 +141,12 @@ class TransitionModel(metaclass=ABCMeta):
         """Euler-Maruyama SDE simulation, returns x[:, 1:] (ssmod.py:201-244)."""
         low, d = self._sim_low()
         steps = int(np.floor(duration / dt))
-        rng = dv.make_rng(d, next_stream_seed())
-        x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='continuous', dt=dt, sub=1, want_y=False)
+        if _replayed(self.init_rv) or _replayed(self.noise_rv, noise=True):
+            x0, q = _draw(self.init_rv, mc_sims), _draw(self.noise_rv, (steps, mc_sims))
+            x, _ = dv.simulate(low, mc_sims, steps, mode='continuous', dt=dt, sub=1, x0=x0, q=q, want_y=False)
+        else:
+            rng = dv.make_rng(d, next_stream_seed())
+            x, _ = dv.simulate(low, mc_sims, steps, rng=rng, mode='continuous', dt=dt, sub=1, want_y=False)
         return x if device_out else x.cpu().numpy()
 
 
@@ -303,7 +316,7 @@ class MeasurementModel(metaclass=ABCMeta):
         if xt.shape[0] != self.dim_state:
             raise ValueError('state array must have dim_state = {} rows'.format(self.dim_state))
         low, d = lower_models(None, self)
-        if _replayed(self.noise_rv):
+        if _replayed(self.noise_rv, noise=True):
             y = dv.simulate_measurements(low, xt.contiguous(), r=_draw(self.noise_rv, tuple(xt.shape[1:])))
         else:
             rng = dv.make_rng(d, next_stream_seed())

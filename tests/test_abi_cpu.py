@@ -52,6 +52,29 @@ def test_struct_layout_matches_header(tmp_path):
     assert got == want
 
 
+def test_integration_md_struct_sketch_matches_header(tmp_path):
+    """The ctypes structs a maintainer would copy out of INTEGRATION.md have the size and field offsets the C header
+    gives them (an undersized sketch hands the library a short buffer)."""
+    import subprocess
+    md = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = re.search(r'```python\n(.*?)```', md, flags=re.S).group(1)
+    # only the struct definitions of the sketch: no library load, no torch
+    keep = ['import ctypes as C', 'P = C.POINTER(C.c_double)']
+    keep += re.findall(r'^class Ssm\w+\(C\.Structure\):.*?\n(?=\S)', block, flags=re.S | re.M)
+    ns = {}
+    exec('\n'.join(keep), ns)
+    src = tmp_path / 'layout.c'
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "ssm_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ssm_transform), sizeof(ssm_desc), '
+        'offsetof(ssm_desc, tf_obs), offsetof(ssm_desc, q_mean), offsetof(ssm_desc, r_mean), offsetof(ssm_desc, dq)); return 0; }\n')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    T, D = ns['SsmTransform'], ns['SsmDesc']
+    assert got == [C.sizeof(T), C.sizeof(D), D.tf_obs.offset, D.q_mean.offset, D.r_mean.offset, D.dq.offset]
+
+
 def test_argument_validation_needs_no_gpu():
     from ssmtoybox_b200 import _lib
     lib = _lib.lib
