@@ -45,7 +45,7 @@ TRAJ_PER_GPU = 125000           # 10^6 / 8
 FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filter, reentry N=11
 FLOP_SMOOTH = 902.0
 BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
-BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 25 + 1)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write sm_*, quad
+BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 1)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write d = x - m_s, quad (score-only mode)
 METRIC = 'filtered trajectory-steps/sec (fp64)'
 UNIT = 'trajectory-steps/s'
 CONFIG = {'workload': 'C3: reentry 5-D + radar, GPQ (RBF, UT) filter + RTS smoother + scores, '
@@ -238,10 +238,9 @@ def run_gpu_arm(args):
         if e: e[0].record()
         dv.filter_forward(low, y, store_pred=True, out=fwd)
         if e: e[1].record()
-        dv.smooth_backward(low.dx, fwd, out=sm, x_truth=x, want_quad=True)   # RTS smoother + in-kernel phase-1 statistics
+        dv.smooth_scores(low.dx, fwd, x, out=sm)   # RTS smoother, score-only mode: in-kernel phase-1 statistics, no sm_* stores
         if e: e[2].record()
-        sc = U.evaluate_performance(x, sm['sm_mean'], sm['sm_cov'], status=sm['status'], comm=comm, to_host=False,
-                                    phase1=(sm['stats'], sm['rmse_acc']), quad=sm['quad'])
+        sc = U.evaluate_scored(sm, comm=comm, to_host=False)
         if e:
             e[3].record()
             timers.append(e)
@@ -328,7 +327,7 @@ def run_gpu_arm(args):
                 'hbm': {'achieved': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': M * N * BYTES_FILTER / (k_filter * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_FILTER,
                         'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s'}}
-    roofline_smoother = {'kernel': 'smoother_kernel<5, SCORE> (RTS smoother + in-kernel phase-1 score accumulation)', 'bound': 'hbm',
+    roofline_smoother = {'kernel': 'smoother_kernel<5, SCORE, KEEP=false> (RTS smoother, score-only mode: in-kernel phase-1 score accumulation, no smoothed arrays stored)', 'bound': 'hbm',
                          'achieved': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': M * N * BYTES_SMOOTH / (k_smooth * 1e-3) / 1e9 / hbm_peak, 'bytes_per_unit': BYTES_SMOOTH,
                          'launch_ms': k_smooth, 'traffic': prof.get('smoother_kernel_dram_bytes_per_launch')}

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SSM_ABI_VERSION 4
+#define SSM_ABI_VERSION 5
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define SSM_OK             0
@@ -172,6 +172,20 @@ int ssm_filter_window(const ssm_desc *desc, const double *y,
                       int32_t *status, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld,
                       void *stream);
 
+/* Scoring forward pass: ssm_filter_window with the error statistics of the FILTERED moments accumulated in-kernel, so a
+ * filter-only Monte-Carlo run keeps no per-trajectory moment arrays (the loops of research/gpq/icinco_demo.py:115-125 and
+ * research/bsq/bsq_tracking.py:300-337 keep none either): fi_mean / fi_cov may be NULL.  x_truth (dx, n_steps, ld);
+ * stats rows [k_lo, k_hi) of (n_steps, ssm_scores_width(dx)) and rmse_acc (dx, ld) exactly as ssm_scores_phase1 on the
+ * stored moments would fill them (bitwise); quad (n_steps, ld) = d' P^-1 d and dres (dx, n_steps, ld) = d = x - m per
+ * scored unit for ssm_scores_phase2_res (both nullable).  No predictive moments (no smoother behind it).
+ * Compiled for additive models, [0 | cI | -cI] point sets (UT, fully-symmetric degree 3) and the Gaussian family;
+ * SSM_E_UNSUPPORTED otherwise (score the stored moments with ssm_scores_phase1 instead). */
+int ssm_filter_scores(const ssm_desc *desc, const double *y, const double *x_truth, double *fi_mean, double *fi_cov,
+                      double *stats, double *rmse_acc, double *quad, double *dres,
+                      const double *init_mean, const double *init_cov, double *last_mean, double *last_cov,
+                      const int32_t *t_offset, int32_t k0, int32_t *status,
+                      int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+
 /* ---- K3: RTS smoother -----------------------------------------------------------------------
  * Replaces StateSpaceInference.backward_pass + GaussianInference._smoothing_update
  * (ssinf.py:120-147, 325-344), including the reference's index range (slots N and N-1 are never
@@ -206,6 +220,17 @@ int ssm_smooth_quad(int32_t dx, const double *fi_mean, const double *fi_cov,
                     double *sm_mean, double *sm_cov, int32_t *status,
                     const double *x_truth, double *stats, double *rmse_acc, double *quad,
                     int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+
+/* Score-only smoother: the same recursion and in-kernel phase-1 statistics, but the smoothed moments are NOT stored
+ * (nothing reads them when only RMSE / NCI / NLL are wanted: the Monte-Carlo loops of research/gpq/icinco_demo.py:115-125
+ * keep no per-trajectory arrays either).  Outputs per scored unit: quad (n_steps, ld) = d' P_s^-1 d and
+ * dres (dx, n_steps, ld) = d = x - m_s, the two inputs of ssm_scores_phase2_res (both nullable).  Time windows walk
+ * from the last to the first and hand the recursion over through carry (dx + dx (dx + 1) / 2, ld) (required when the
+ * window is not the whole range).  status as in ssm_smooth.  Results bitwise equal to ssm_smooth_quad's statistics. */
+int ssm_smooth_scores(int32_t dx, const double *fi_mean, const double *fi_cov,
+                      const double *pr_mean, const double *pr_cov, const double *pr_xx_cov, int32_t *status,
+                      const double *x_truth, double *stats, double *rmse_acc, double *quad, double *dres, double *carry,
+                      int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
 /* ---- K1: batched simulation -----------------------------------------------------------------
  * Replaces TransitionModel.simulate_discrete / simulate_continuous (ssmod.py:168-244),
@@ -308,6 +333,12 @@ int ssm_scores_phase2_traj(int32_t dx, const double *x, const double *mean, cons
 int ssm_scores_phase2_quad(int32_t dx, const double *x, const double *mean, const double *quad, const int32_t *status,
                            const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
                            int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
+
+/* Phase 2 from the stored errors d = x - m (dres, ssm_smooth_scores / ssm_filter_scores) and quadratic forms: dx + 1
+ * doubles per unit; bitwise the same result as ssm_scores_phase2_quad. */
+int ssm_scores_phase2_res(int32_t dx, const double *dres, const double *quad, const int32_t *status,
+                          const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                          int32_t k_lo, int32_t k_hi, int64_t ld, void *stream);
 
 /* ---- bootstrap variance of a sample mean -------------------------------------------------------
  * Replaces utils.bootstrap_var (utils.py:223-244): var[0] = population variance of the means of n_boot resamples

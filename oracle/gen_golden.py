@@ -679,9 +679,105 @@ def gen_scores():
     save('scores', **d)
 
 
+def gen_c5_sweep():
+    """Configuration C5: Bayes-Sard filters with the expected model variance assigned from outside
+    (research/bsq/bsq_tracking.py:276-281) on the pendulum (tests/test_ssinf.py:42-51) and the coordinated turn +
+    radar, scored like research/gpq/icinco_demo.py:17-52.  The files carry x, y, the reference's weights and its
+    scores (RMSE / NCI / NLL, per-step MSE and credibility-ratio sums), and the filtered moments of the first 4
+    trajectories; the moments of all trajectories would be 10x larger and are not needed: the score path is pinned
+    by the aggregates."""
+    sys.path.insert(0, os.path.join(ref_shim.REFERENCE_PATH, 'research', 'gpq'))
+    import types
+    if 'tqdm' not in sys.modules:
+        try:
+            import tqdm  # noqa: F401
+        except ImportError:
+            sys.modules['tqdm'] = types.ModuleType('tqdm')
+            sys.modules['tqdm'].trange = range
+    import icinco_demo
+    for name, fixture, M, mv, seed in (('sweep_c5_pend_bsq_mv', pendulum, 200, 1e-2, 11), ('sweep_c5_ct_bsq_mv', coordinated_turn, 100, 1e-2, 12)):
+        np.random.seed(seed)
+        dyn, obs, x, y = fixture(100, M)
+        d = dyn.dim_in
+        kp = np.ones((1, d + 1))
+        alg = ssinf.BayesSardKalman(dyn, obs, kp, kp, MUL_UT(d), MUL_UT(d))
+        alg.tf_dyn.model.model_var = mv * np.eye(dyn.dim_state)
+        alg.tf_obs.model.model_var = 0.0 * np.eye(obs.dim_out)
+        out = run_filter(alg, y, smooth=False)
+        mf, Pf = out['fi_mean'], out['fi_cov']
+        assert (out['status'] == 0).all(), out['status']
+        sc = icinco_demo.evaluate_performance(x, mf[..., None], Pf[..., None], mf[..., None], Pf[..., None], bootstrap_variance=False)
+        N = x.shape[1]
+        mse = np.stack([utils.mse_matrix(x[:, k, :], mf[:, k, :]) for k in range(N)], axis=-1)
+        lcr = np.array([[utils.log_cred_ratio(x[:, k, i], mf[:, k, i], Pf[:, :, k, i], mse[..., k]) for i in range(M)] for k in range(N)])
+        e = {'x': x, 'y': y, 'fi_mean4': mf[..., :4], 'fi_cov4': Pf[..., :4], 'status': out['status'],
+             'rmse': np.asarray(sc[0]), 'nci': np.asarray(sc[1]), 'nll': np.asarray(sc[2]), 'mse': mse, 'lcr_sum': lcr.sum(axis=1),
+             'alg_name': np.asarray('BayesSardKalman'), 'assigned_model_var': np.asarray(mv)}
+        e.update(model_dict(dyn, obs))
+        e.update(transform_dict(alg.tf_dyn, 'dyn_'))
+        e.update(transform_dict(alg.tf_obs, 'obs_'))
+        save(name, **e)
+
+
+def gen_weight_envelope(n_var=16, mc=32, steps=100):
+    """Row a9: how far can float64 BQ weights of the C3 kernels move under perturbations the reference itself cannot
+    exclude?  The obs-transform kernel matrix of research/gpq/gpq_tracking.py:41-44 has cond ~ 1e9, so
+    Wc = iK Q iK carries rounding errors of order eps * cond^2.  The ensemble: the reference's own bq_weights
+    (bq/bqmod.py:495-523) with Kernel._cho_inv (bq/bqkern.py:38-64) fed a kernel matrix perturbed by +-1 ulp per entry
+    (symmetric), half of the members also solving with numpy.linalg.inv instead of cho_solve -- everything else is the
+    reference's code.  Each member's filter (the reference's forward_pass) runs on the same seeded data.  The file holds
+    the unperturbed weights, the members' weights and, per member and trajectory, the failure step and the time-mean
+    squared error: the envelope a float64 re-implementation is measured against."""
+    np.random.seed(21)
+    dyn, obs, x, y = reentry(steps, mc)
+    hdyn = np.array([[1.0, 25, 25, 25, 25, 25]])
+    hobs = np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
+    orig = bqkern.Kernel._cho_inv
+    eps = np.finfo(float).eps
+
+    def member(alg):
+        out = run_filter(alg, y, smooth=False)
+        se = ((out['fi_mean'] - x) ** 2).mean(axis=1)          # (dx, mc), NaN for failed trajectories
+        return {'wm_dyn': alg.tf_dyn.wm, 'Wc_dyn': alg.tf_dyn.Wc, 'Wcc_dyn': alg.tf_dyn.Wcc, 'mv_dyn': np.asarray(alg.tf_dyn.model.model_var),
+                'wm_obs': alg.tf_obs.wm, 'Wc_obs': alg.tf_obs.Wc, 'Wcc_obs': alg.tf_obs.Wcc, 'mv_obs': np.asarray(alg.tf_obs.model.model_var),
+                'status': out['status'], 'mse_time': se}
+
+    base_alg = ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut')
+    base = member(base_alg)
+    members = []
+    try:
+        for p in range(n_var):
+            rs = np.random.RandomState(1000 + p)
+
+            def pert(A, b=None, rs=rs, use_inv=(p % 2 == 1)):
+                b = np.eye(A.shape[0]) if b is None else b
+                E = np.triu(rs.randint(-1, 2, size=A.shape).astype(float))
+                E = E + np.triu(E, 1).T
+                A2 = A * (1.0 + eps * E)
+                iA = np.linalg.inv(A2).dot(b) if use_inv else scipy.linalg.cho_solve(scipy.linalg.cho_factor(A2), b)
+                return 0.5 * (iA + iA.T)
+            bqkern.Kernel._cho_inv = staticmethod(pert)
+            members.append(member(ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut')))
+    finally:
+        bqkern.Kernel._cho_inv = orig
+    d = {'x': x, 'y': y}
+    d.update(model_dict(dyn, obs))
+    d.update(transform_dict(base_alg.tf_dyn, 'dyn_'))
+    d.update(transform_dict(base_alg.tf_obs, 'obs_'))
+    for k, v in base.items():
+        d['base_' + k] = np.asarray(v)
+    for k in base:
+        d['ens_' + k] = np.stack([np.asarray(m[k]) for m in members])
+    save('weight_envelope_c3', **d)
+    fails = [int((m['status'] != 0).sum()) for m in members]
+    print('  base failures', int((base['status'] != 0).sum()), ' ensemble failures', fails)
+    print('  max |Wc_obs - base| over members', max(np.abs(m['Wc_obs'] - base['Wc_obs']).max() for m in members),
+          ' |base Wc_obs|max', np.abs(base['Wc_obs']).max())
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'large_pointsets': gen_large_pointsets, 'weights': gen_weights, 'simulation': gen_simulation,
-            'scores': gen_scores}
+            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

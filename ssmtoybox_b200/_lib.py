@@ -71,6 +71,8 @@ def _load():
     lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
     lib.ssm_filter_window.restype = C.c_int
     lib.ssm_filter_window.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_filter_scores.restype = C.c_int
+    lib.ssm_filter_scores.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_smooth_window.restype = C.c_int
     lib.ssm_smooth_window.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase1_window.restype = C.c_int
@@ -83,6 +85,10 @@ def _load():
     lib.ssm_scores_phase1_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_smooth_quad.restype = C.c_int
     lib.ssm_smooth_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_smooth_scores.restype = C.c_int
+    lib.ssm_smooth_scores.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_scores_phase2_res.restype = C.c_int
+    lib.ssm_scores_phase2_res.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase2_quad.restype = C.c_int
     lib.ssm_scores_phase2_quad.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_scores_phase2_traj.restype = C.c_int

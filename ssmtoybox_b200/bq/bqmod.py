@@ -16,6 +16,45 @@ from ..mtran import SphericalRadialTransform, UnscentedTransform, GaussHermiteTr
 from .bqkern import RBFGauss, RBFStudent
 
 
+# ------------------------------------------------------------------------------------------------
+# arithmetic of the quadrature weights
+# ------------------------------------------------------------------------------------------------
+# 'dd' (default): double-double evaluation rounded once -- the correctly rounded value of the reference's FORMULAS for
+#   every conditioning;  'float64': the reference's own arithmetic (float64 kernel matrix, Cholesky inverse, products).
+# Where K is well conditioned the two agree to rounding.  For cond(K) ~ 1e9 (the reference's reentry tracking
+# hyper-parameters, research/gpq/gpq_tracking.py:41-44) the float64 covariance weights are dominated by rounding noise
+# (eps * cond^2 = O(1)): 'float64' then reproduces the reference's arithmetic, not its bits -- only assigning tf.wm / Wc /
+# Wcc from a reference run does that (tests/test_gpu_weights_envelope.py bounds the difference).
+_PRECISION = [__import__('os').environ.get('SSM_BQ_PRECISION', 'dd')]
+
+
+def set_weight_precision(precision):
+    """Package-level switch for every bq_weights evaluation that follows: 'dd' or 'float64'.  Returns the old value."""
+    if precision not in ('dd', 'float64'):
+        raise ValueError("weight precision must be 'dd' or 'float64'")
+    old, _PRECISION[0] = _PRECISION[0], precision
+    return old
+
+
+def get_weight_precision():
+    return _PRECISION[0]
+
+
+class weight_precision(object):
+    """with weight_precision('float64'): alg = GaussianProcessKalman(...)   # weights in the reference's arithmetic"""
+
+    def __init__(self, precision):
+        self.precision = precision
+
+    def __enter__(self):
+        self.old = set_weight_precision(self.precision)
+        return self
+
+    def __exit__(self, *exc):
+        set_weight_precision(self.old)
+        return False
+
+
 def n_sum_k(n, k):
     """All n-tuples of non-negative integers summing to k, in the reference's column order (utils.py:459-475)."""
     assert k >= 0
@@ -81,7 +120,7 @@ class Model(object):
         par = self.kernel.get_parameters(par)
         if isinstance(self.kernel, RBFStudent):
             return self._weights_mc(par)
-        w = dv.bq_weights(par[:1], self.points, mulind)
+        w = dv.bq_weights(par[:1], self.points, mulind, precision=get_weight_precision())
         if int(w['info'][0]) != 0:
             raise np.linalg.LinAlgError('kernel matrix is not positive definite (info = {})'.format(int(w['info'][0])))
         return w
@@ -94,7 +133,7 @@ def _weights_mc(self, par):
     k = self.kernel
     p1 = np.array(par[:1], dtype=np.float64)
     p1[0, 0] = 1.0
-    iK = dv.bq_weights(p1, self.points)['iK'][0]                        # eval_inv_dot(par, x, scaling=False)
+    iK = dv.bq_weights(p1, self.points, precision=get_weight_precision())['iK'][0]    # eval_inv_dot(par, x, scaling=False)
     q, Q, R = k.exp_x_kx(par, self.points), k.exp_x_kxkx(par, par, self.points), k.exp_x_xkx(par, self.points)
     w_c = iK.dot(Q).dot(iK)
     if not np.array_equal(w_c, w_c.T):

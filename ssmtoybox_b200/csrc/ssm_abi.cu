@@ -69,10 +69,16 @@ using namespace ssm;
 extern "C" int ssm_abi_version(void) { return SSM_ABI_VERSION; }
 extern "C" const char *ssm_last_error(void) { return g_err; }
 
-extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
-                                 double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
-                                 double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
-                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+struct ScoreOut {
+    const double *x_truth;
+    double *stats, *rmse_acc, *quad, *dres;
+};
+
+static int filter_window_impl(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                              double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                              double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                              int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream,
+                              const ScoreOut *sc) {
     if (!desc || !y || !status) { set_error("ssm_filter: desc, y and status must not be NULL"); return SSM_E_INVALID; }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_filter: bad sizes (n_traj=%lld n_steps=%d ld=%lld)", (long long)n_traj, n_steps, (long long)ld); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_filter: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
@@ -87,6 +93,10 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
     L.buf = FilterBuffers{y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
                           t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0, nullptr, nullptr, 0, 0,
                           k_lo, k_hi, k_lo > 0 ? 1 : 0};
+    if (sc) {
+        L.buf.x_truth = sc->x_truth; L.buf.rmse_acc = sc->rmse_acc; L.buf.quad = sc->quad; L.buf.dres = sc->dres;
+        L.stats = sc->stats;
+    }
     const int dm = desc->dyn_model, om = desc->obs_model;
     const int nsi = desc->n_state_index;
     const int32_t *si = desc->state_index;
@@ -115,6 +125,25 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
         set_error("ssm_filter: no device implementation for dyn_model=%d obs_model=%d dx=%d dy=%d state_index(n=%d)", dm, om, desc->dx, desc->dy, nsi);
     if (rc == SSM_E_CUDA) set_error("ssm_filter: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
+}
+
+extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                                 double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                                 double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return filter_window_impl(desc, y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
+                              t_offset, k0, status, n_traj, n_steps, k_lo, k_hi, ld, stream, nullptr);
+}
+
+extern "C" int ssm_filter_scores(const ssm_desc *desc, const double *y, const double *x_truth, double *fi_mean, double *fi_cov,
+                                 double *stats, double *rmse_acc, double *quad, double *dres,
+                                 const double *init_mean, const double *init_cov, double *last_mean, double *last_cov,
+                                 const int32_t *t_offset, int32_t k0, int32_t *status,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    if (!x_truth || !stats) { set_error("ssm_filter_scores: x_truth and stats must not be NULL"); return SSM_E_INVALID; }
+    const ScoreOut sc{x_truth, stats, rmse_acc, quad, dres};
+    return filter_window_impl(desc, y, fi_mean, fi_cov, nullptr, nullptr, nullptr, init_mean, init_cov, last_mean, last_cov,
+                              t_offset, k0, status, n_traj, n_steps, k_lo, k_hi, ld, stream, &sc);
 }
 
 extern "C" int ssm_filter(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,

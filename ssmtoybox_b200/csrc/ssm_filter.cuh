@@ -16,10 +16,14 @@
 #include <stdlib.h>
 
 #include "ssm_models.cuh"
+#include "ssm_scores.cuh"
 
 namespace ssm {
 
 enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
+#ifndef SSM_WEIGHT_VIEWS
+#define SSM_WEIGHT_VIEWS 0
+#endif
 constexpr int GEN_CAP = 64;  // capacity of the runtime-N (generic point set) path with the function values kept per thread
 constexpr int GEN_CAP_STREAM = 4096;  // sigma-point rules beyond GEN_CAP points: two streaming passes, nothing stored
 
@@ -43,6 +47,18 @@ struct TfConst {
     double mv_[E][E];
     double iK_[NK][NCAP];
     double U_[DU][NCAP];
+    int zero_[8];  // always 0, but only known at run time: see row_view
+    // The weights as seen from output row a of an unrolled loop: the same table behind an offset the compiler cannot
+    // fold.  Without it the loads of every weight W(i, j) are merged across the E unrolled rows: ~130 weights stay live
+    // in uniform registers, get copied to vector registers (IMAD.U32 R, RZ, RZ, UR) and spilled; with it each use is one
+    // LDCU.64 c[0x0][UR + imm] next to its DFMA.
+    SSM_DEV const TfConst &row_view(int a) const {
+#if SSM_WEIGHT_VIEWS
+        return *(const TfConst *)((const char *)this + (size_t)((a + 1) & zero_[a & 7]) * 16);
+#else
+        return *this;
+#endif
+    }
     SSM_DEV double wm(int i) const { return wm_[i]; }
     SSM_DEV double wc(int i) const { return wc_[i]; }
     SSM_DEV double Wc(int i, int j) const { return Wc_[i][j]; }
@@ -61,6 +77,7 @@ struct TfGlobal {
     double tp_a, tp_b;
     const double *wm_, *wc_, *Wc_, *Wcc_, *iK_, *U_;
     double mv_[E][E];
+    SSM_DEV const TfGlobal &row_view(int) const { return *this; }
     SSM_DEV double wm(int i) const { return __ldg(wm_ + i); }
     SSM_DEV double wc(int i) const { return __ldg(wc_ + i); }
     SSM_DEV double Wc(int i, int j) const { return __ldg(Wc_ + i * n + j); }
@@ -213,9 +230,10 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
     // mean_f = fx . wm                                          mtran.py:143, bqmtran.py:175
 #pragma unroll
     for (int a = 0; a < E; ++a) {
+        const Tf &tw = tf.row_view(a);
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) s = EXACT ? __dadd_rn(s, __dmul_rn(fx(a, i), tf.wm(i))) : fma(fx(a, i), tf.wm(i), s);
+        for (int i = 0; i < n; ++i) s = EXACT ? __dadd_rn(s, __dmul_rn(fx(a, i), tw.wm(i))) : fma(fx(a, i), tw.wm(i), s);
         mf[a] = s;
     }
 #pragma unroll
@@ -267,6 +285,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
         if (want_cross) {
 #pragma unroll
             for (int a = 0; a < E; ++a) {
+                const Tf &tw = tf.row_view(a);
                 double T[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) T[d] = 0.0;
@@ -274,7 +293,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 for (int i = 0; i < n; ++i) {  // same summation order over i for every T[d]
                     const double v = fx(a, i);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) T[d] = fma(v, tf.Wcc(d, i), T[d]);
+                    for (int d = 0; d < D; ++d) T[d] = fma(v, tw.Wcc(d, i), T[d]);
                 }
                 double crow[D];
 #pragma unroll
@@ -289,6 +308,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
         }
 #pragma unroll
         for (int a = 0; a < E; ++a) {
+            const Tf &tw = tf.row_view(a);
             double row[NCAP];
 #pragma unroll
             for (int j = 0; j < n; ++j) row[j] = 0.0;
@@ -296,7 +316,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
             for (int i = 0; i < n; ++i) {
                 const double v = fx(a, i);
 #pragma unroll
-                for (int j = 0; j < n; ++j) row[j] = fma(v, tf.Wc(i, j), row[j]);
+                for (int j = 0; j < n; ++j) row[j] = fma(v, tw.Wc(i, j), row[j]);
             }
 #pragma unroll
             for (int b = 0; b <= a; ++b) {
@@ -311,6 +331,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
             const double mv0 = tf.mv(0, 0);
 #pragma unroll
             for (int a = 0; a < E; ++a) {
+                const Tf &tw = tf.row_view(a);
                 double row[NCAP];
 #pragma unroll
                 for (int j = 0; j < n; ++j) row[j] = 0.0;
@@ -318,7 +339,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 for (int i = 0; i < n; ++i) {
                     const double v = fx(a, i);
 #pragma unroll
-                    for (int j = 0; j < n; ++j) row[j] = fma(v, tf.iK(i, j), row[j]);
+                    for (int j = 0; j < n; ++j) row[j] = fma(v, tw.iK(i, j), row[j]);
                 }
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
@@ -360,6 +381,11 @@ struct FilterBuffers {
     // time window [k_lo, k_hi) of the n_steps slots to process (ssm_filter_window); resume: trajectories whose
     // status is already non-zero (failed in an earlier window) stay failed and keep their status
     int k_lo, k_hi, resume;
+    // in-kernel phase-1 scoring of the FILTERED moments (filter_kernel<..., SCORE = true>, ssm_filter_scores): truth,
+    // partial statistics rows [trajectory block][step of the window][ScoreRow::WP], per-trajectory time-sums of the
+    // squared error (dx, ld), and per scored unit d' P^-1 d (n_steps, ld) and d = x - m (dx, n_steps, ld), nullable
+    const double *x_truth;
+    double *partial, *rmse_acc, *quad, *dres;
 };
 
 // NaN-fill of the outputs of failed trajectories from their failing step on, launched behind every forward-pass
@@ -435,7 +461,11 @@ SSM_DEV void store_sym(double *base, long long cs, long long rk, const double (&
 #define SSM_SMEM_FX_MIN_DX 99  // state dimension from which the function evaluations move to shared memory
                                // (measured on B200: registers win for dx = 5, 21.2 vs 27.1 ms; kept as an option)
 #endif
-template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, class Par, int THREADS, int MINB, bool SMEM_FX>
+// SCORE: the filtered moments of every step are scored against x_truth while they are in registers (squared error, error
+// outer product, NLL, d' P^-1 d: score_step of ssm_scores.cuh, reduced over the CTA once per step like the smoother's
+// in-kernel scoring), so a filter-only Monte-Carlo run keeps no per-trajectory moment arrays at all
+// (research/gpq/icinco_demo.py:115-125 keeps none either).  Separate instantiation: the plain kernel is unchanged.
+template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, class Par, int THREADS, int MINB, bool SMEM_FX, bool SCORE = false>
 __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_constant__ Par p) {
     constexpr bool SYNC_STEPS = SSM_SYNC_STEPS != 0;
     constexpr int SMT = SMEM_FX ? THREADS : 0;
@@ -449,6 +479,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     const long long ld = b.ld;
     const long long cs = (long long)N * ld;  // component stride of the [component][step][trajectory] arrays
     constexpr int NSTATE = DX + TX + 2;
+    constexpr int WS = ScoreRow<DX>::WP;
+    static_assert(!SCORE || THREADS == SC_THREADS, "the CTA reduction of the scores is laid out for SC_THREADS threads");
+    static_assert(!SCORE || FAMILY == SSM_FAMILY_GAUSS, "in-kernel scoring reads the filtered COVARIANCE (Gaussian family)");
+    __shared__ double s_score[SCORE ? BlockReduce<WS>::SIZE : 1];
     __shared__ int s_ticket;
     // Ticket scheduling.  A trajectory is a 500-step serial recursion, so a plain launch is quantised in waves of
     // (resident CTAs x THREADS) whole trajectories: 125 000 trajectories = 2.2 waves cost 3 (measured -14 %).  With
@@ -513,13 +547,25 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     double ynext[DY];
 #pragma unroll
     for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + ((long long)k_begin * ld + t));
+    double se_acc[SCORE ? DX : 1];
+    if (SCORE) {   // per-trajectory time-sum of the squared error: continued across time chunks and windows
+#pragma unroll
+        for (int a = 0; a < DX; ++a) se_acc[a] = (b.rmse_acc && k_begin > 0) ? __ldcg(b.rmse_acc + (long long)a * ld + t) : 0.0;
+    }
 
     for (int k = k_begin; k < k_end; ++k) {
         // The fully unrolled step body is ~140 KB of SASS, far beyond the instruction caches.  Re-aligning
         // the warps of the CTA once per step makes them stream the body together, so one instruction fetch
         // from L2 serves all of them instead of one per warp (profiles/: stall_no_inst, fetch-bound).
         if (SYNC_STEPS) __syncthreads();
-        if (fail) continue;
+        double sv[SCORE ? WS : 1];
+        if (SCORE) {
+#pragma unroll
+            for (int i = 0; i < WS; ++i) sv[i] = 0.0;
+        }
+      // ONE exit of the step body: with SCORE every thread of the CTA must reach the reduction behind it
+      do {
+        if (fail) break;
         const long long rk = (long long)k * ld + t;  // row offset of step k (see store_vec)
         double yk[DY];
 #pragma unroll
@@ -578,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 },
                 sfx);
         }
-        if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; continue; }
+        if (!ok) { fail = SSM_FAIL_CHOL_DYN; kfail = k; break; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
             if (b.pr_cov) {
                 double Cp[TX];
@@ -634,7 +680,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 },
                 sfx);
         }
-        if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; continue; }
+        if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; break; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
 #pragma unroll
             for (int a = 0; a < TY; ++a) Sy[a] = fma(scale, Sy[a], p.s0 * p.R[a]);
@@ -655,10 +701,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         for (int a = 0; a < DY; ++a)
 #pragma unroll
             for (int d = 0; d < DX; ++d) fin = fin && finite_d(Syx[a][d]);
-        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; continue; }
+        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; break; }
         double K[DX][DY], Ls[TY];
         ok = spd_gain<DY, DX>(Sy, Syx, K, Ls);
-        if (!ok) { fail = SSM_FAIL_CHOL_GAIN; kfail = k; continue; }
+        if (!ok) { fail = SSM_FAIL_CHOL_GAIN; kfail = k; break; }
         double e[DY];
 #pragma unroll
         for (int a = 0; a < DY; ++a) e[a] = yk[a] - my[a];
@@ -706,6 +752,32 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             const double sc = (p.dof + dd) / (p.dof + (double)DY);
 #pragma unroll
             for (int a = 0; a < TX; ++a) P[a] *= sc;
+        }
+        if constexpr (SCORE) {
+            if (active) {   // score (m, P) of step k: utils.py:18-148 via score_step
+                double d[DX], se[DX], qf;
+                const double *qx = row_ptr(b.x_truth, rk);
+#pragma unroll
+                for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - m[a];
+                score_step<DX>(d, P, sv, se, &qf);
+                if (b.quad) st_stream(b.quad + rk, qf);
+                if (b.dres) {
+                    double *qd = row_ptr(b.dres, rk);
+#pragma unroll
+                    for (int a = 0; a < DX; ++a) st_stream(qd + a * cs, d[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
+            }
+        }
+      } while (0);
+        if constexpr (SCORE)
+            block_reduce_store<WS>(sv, s_score, k, b.partial + ((long long)blk * (b.k_hi - b.k_lo) + (k - b.k_lo)) * WS);
+    }
+    if constexpr (SCORE) {
+        if (b.rmse_acc && active) {
+#pragma unroll
+            for (int a = 0; a < DX; ++a) __stcg(b.rmse_acc + (long long)a * ld + t, (fail && k_end >= b.k_hi) ? qnan() : se_acc[a]);
         }
     }
 
@@ -825,10 +897,11 @@ struct FilterLaunch {
     const ssm_desc *desc;
     FilterBuffers buf;
     cudaStream_t stream;
+    double *stats = nullptr;  // scoring launches (buf.x_truth != NULL): rows [k_lo, k_hi) of the (n_steps, ScoreRow::W) statistics
 };
 
 // fast path launcher (all weights in the parameter block)
-template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, int THREADS, int MINB>
+template <class Dyn, class Obs, int PTS, int NPTS, int KIND, int FAMILY, int THREADS, int MINB, bool SCORE = false>
 int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo &io) {
     constexpr int DX = Dyn::DX, DY = Obs::DY;
     using TfD = TfConst<DX, DX, NPTS, KIND, PTS>;
@@ -853,7 +926,15 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     p.b = L.buf;
     const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
     constexpr bool SMEM_FX = (DX >= SSM_SMEM_FX_MIN_DX);
-    auto kern = filter_kernel<Dyn, Obs, PTS, NPTS, KIND, FAMILY, Par, THREADS, MINB, SMEM_FX>;
+    auto kern = filter_kernel<Dyn, Obs, PTS, NPTS, KIND, FAMILY, Par, THREADS, MINB, SMEM_FX, SCORE>;
+    double *partial = nullptr;
+    const int WLEN = L.buf.k_hi - L.buf.k_lo;
+    if (SCORE) {   // one partial statistics row per (trajectory block, step of the window)
+        if (scratch_alloc((void **)&partial, (size_t)blocks * WLEN * ScoreRow<DX>::WP * sizeof(double), L.stream) != cudaSuccess) {
+            delete pp; set_error("cudaMallocAsync failed"); return SSM_E_CUDA;
+        }
+        p.b.partial = partial;
+    }
     const size_t smem = SMEM_FX ? sizeof(double) * DX * NPTS * THREADS : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // multi-wave launches: persistent grid + ticket scheduler over (trajectory block, time chunk) items
@@ -892,6 +973,13 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     kern<<<(unsigned)grid, THREADS, smem, L.stream>>>(p);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && filter_nan_fill(L.buf, DX, L.stream) != SSM_OK) err = cudaErrorUnknown;
+    if (SCORE) {
+        const long long row = (long long)WLEN * ScoreRow<DX>::WP;
+        scores_finalize_packed_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, L.stream>>>(
+            partial, L.stats + (long long)L.buf.k_lo * ScoreRow<DX>::W, (int)blocks, WLEN, DX);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        cudaFreeAsync(partial, L.stream);
+    }
     if (work && getenv("SSM_TICKET_DEBUG")) {
         int waits = 0;
         cudaMemcpyAsync(&waits, (int *)work + 1 + blocks, sizeof(int), cudaMemcpyDeviceToHost, L.stream);

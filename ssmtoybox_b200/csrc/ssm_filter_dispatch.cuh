@@ -36,11 +36,11 @@ inline bool pair_enabled() {
     return e ? atoi(e) != 0 : (SSM_PAIR_DEFAULT != 0);
 }
 
-template <class Dyn, class Obs, int PTS, int KIND, int FAMILY, int THREADS, int MINB>
+template <class Dyn, class Obs, int PTS, int KIND, int FAMILY, int THREADS, int MINB, bool SCORE = false>
 int dispatch_npts(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo &io) {
     constexpr int D = Dyn::DX;
     constexpr int N = (PTS == PTS_AXIS_C) ? 2 * D + 1 : 2 * D;
-    return launch_filter_const<Dyn, Obs, PTS, N, KIND, FAMILY, THREADS, MINB>(L, id, io);
+    return launch_filter_const<Dyn, Obs, PTS, N, KIND, FAMILY, THREADS, MINB, SCORE>(L, id, io);
 }
 
 template <class Dyn, class Obs, int THREADS, int MINB>
@@ -61,6 +61,20 @@ int dispatch_filter_model(const FilterLaunch &L) {
     if (a.kind != b.kind) { set_error("dynamics and measurement transforms must be of the same kind"); return SSM_E_UNSUPPORTED; }
     const HostTfInfo id = classify_points(a), io = classify_points(b);
     const int kind = a.kind, fam = d.family;
+    if (L.buf.x_truth) {
+        // scoring forward pass (ssm_filter_scores): instantiated for additive models, UT-type point sets ([0 | cI | -cI]),
+        // Gaussian family; everything else reports SSM_E_UNSUPPORTED and the caller scores the stored moments instead
+        if constexpr (Dyn::ADDITIVE && Obs::ADDITIVE) {
+            if (id.pts == PTS_AXIS_C && io.pts == PTS_AXIS_C && a.n_pts == b.n_pts && fam == SSM_FAMILY_GAUSS) {
+                constexpr int MINB_TPS = (Dyn::DX >= 4 && MINB > SSM_TP_MINB) ? SSM_TP_MINB : MINB;
+                if (kind == SSM_TF_SP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
+                if (kind == SSM_TF_BQ) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
+                if (kind == SSM_TF_TP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_GAUSS, THREADS, MINB_TPS, true>(L, id, io);
+            }
+        }
+        set_error("ssm_filter_scores: in-kernel scoring is compiled for additive models, [0 | cI | -cI] point sets and the Gaussian family");
+        return SSM_E_UNSUPPORTED;
+    }
     if constexpr (!Dyn::ADDITIVE || !Obs::ADDITIVE) {
         // augmented transforms run on the runtime-N path (weights in global memory) only
         if (fam == SSM_FAMILY_STUDENT) { set_error("non-additive noise is implemented for the Gaussian family only"); return SSM_E_UNSUPPORTED; }

@@ -126,7 +126,9 @@ __global__ void phase2_prepare_kernel(const double *__restrict__ mse, double *__
 
 // QUAD: `cov` is not the covariance array but the (N, ld) array of d' P^-1 d that the smoother's in-kernel scoring
 // stored (ssm_smooth_quad): no covariance read (120 of 200 bytes per unit for dx = 5), no factorisation.
-template <int DX, bool QUAD>
+// RES (with QUAD): `x` is the array of errors d = x - m the score-only smoother stored (ssm_smooth_scores), `mean` is not
+// read: 48 instead of 88 bytes per unit for dx = 5.
+template <int DX, bool QUAD, bool RES = false>
 __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double *__restrict__ x, const double *__restrict__ mean,
                                                                    const double *__restrict__ cov, const int32_t *__restrict__ status,
                                                                    const double *__restrict__ tab, double *__restrict__ partial,
@@ -145,9 +147,9 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
         if (live) {
             double d[DX], P[TX], L[TX], inv[DX];
             const long long rk = (long long)k * ld + t;
-            const double *qx = row_ptr(x, rk), *qm = row_ptr(mean, rk), *qc = row_ptr(cov, rk);
+            const double *qx = row_ptr(x, rk), *qm = RES ? nullptr : row_ptr(mean, rk), *qc = row_ptr(cov, rk);
 #pragma unroll
-            for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - ld_stream(qm + a * cs);
+            for (int a = 0; a < DX; ++a) d[a] = RES ? ld_stream(qx + a * cs) : ld_stream(qx + a * cs) - ld_stream(qm + a * cs);
             double q_given = 0.0;
             if (QUAD) q_given = ld_stream(qc);
             else {
@@ -205,7 +207,7 @@ static int run_phase1(const double *x, const double *mean, const double *cov, co
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
-template <int DX, bool QUAD>
+template <int DX, bool QUAD, bool RES = false>
 static int run_phase2(const double *x, const double *mean, const double *cov, const int32_t *status, const double *mse,
                       double *lcr, double *lcr_acc, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
     constexpr int TW = TriSize<DX>::value + DX + 1;
@@ -215,7 +217,7 @@ static int run_phase2(const double *x, const double *mean, const double *cov, co
     if (scratch_alloc((void **)&partial, ((size_t)n_cta * WLEN * 2 + (size_t)WLEN * TW) * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
     double *tab = partial + (size_t)n_cta * WLEN * 2;
     phase2_prepare_kernel<DX><<<(WLEN + 63) / 64, 64, 0, s>>>(mse, tab, N, k_lo, k_hi);
-    scores_phase2_kernel<DX, QUAD><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, tab, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
+    scores_phase2_kernel<DX, QUAD, RES><<<n_cta, SC_THREADS, 0, s>>>(x, mean, cov, status, tab, partial, lcr_acc, n_traj, N, k_lo, k_hi, ld);
     const long long row = (long long)WLEN * 2;
     scores_finalize_kernel<<<(unsigned)((row + 31) / 32), dim3(32, FIN_GROUPS), 0, s>>>(partial, lcr + (long long)k_lo * 2, n_cta, row);
     const cudaError_t e = cudaGetLastError();
@@ -302,6 +304,24 @@ extern "C" int ssm_scores_phase2_quad(int32_t dx, const double *x, const double 
                                       const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
                                       int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     return scores_phase2_impl(true, dx, x, mean, quad, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, stream);
+}
+
+extern "C" int ssm_scores_phase2_res(int32_t dx, const double *dres, const double *quad, const int32_t *status,
+                                     const double *mse, double *lcr, double *lcr_acc, int64_t n_traj, int32_t n_steps,
+                                     int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    if (!dres || !quad || !mse || !lcr) { set_error("ssm_scores_phase2_res: NULL buffer"); return SSM_E_INVALID; }
+    if (n_traj <= 0 || n_steps <= 0 || ld < n_traj) { set_error("ssm_scores_phase2_res: bad sizes"); return SSM_E_INVALID; }
+    if (k_lo < 0 || k_hi <= k_lo || k_hi > n_steps) { set_error("ssm_scores_phase2_res: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+#define SSM_P2R_CASE(D) case D: rc = run_phase2<D, true, true>(dres, nullptr, quad, status, mse, lcr, lcr_acc, n_traj, n_steps, k_lo, k_hi, ld, s); break;
+    switch (dx) {
+        SSM_P2R_CASE(1) SSM_P2R_CASE(2) SSM_P2R_CASE(3) SSM_P2R_CASE(4) SSM_P2R_CASE(5)
+        default: set_error("ssm_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
+    }
+#undef SSM_P2R_CASE
+    if (rc == SSM_E_CUDA) set_error("ssm_scores_phase2_res: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
 }
 
 extern "C" int ssm_scores_phase2_window(int32_t dx, const double *x, const double *mean, const double *cov, const int32_t *status,

@@ -25,10 +25,12 @@ SSM_DEV void score_step(const double (&d)[DX], const double (&P)[TriSize<DX>::va
     double sse = 0.0;
 #pragma unroll
     for (int a = 0; a < DX; ++a) {
-        const double s = d[a] * d[a];
+        // rounded product: the callers add it to running sums, and a multiply-add contracted in one kernel but not in
+        // another would break the bitwise equality of the scoring passes (stand-alone, in-smoother, in-filter)
+        const double s = __dmul_rn(d[a], d[a]);
         v[a] = s;
         se[a] = s;
-        sse += s;
+        sse = __dadd_rn(sse, s);
     }
 #pragma unroll
     for (int r = 0; r < DX; ++r)

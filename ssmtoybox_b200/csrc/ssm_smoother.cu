@@ -13,21 +13,28 @@ void set_error(const char *fmt, ...);
 // SCORE: also accumulate the phase-1 error statistics of the SMOOTHED moments against the truth x while they are
 // in registers (same per-CTA reduction and row layout as scores_phase1_kernel, so the finalised statistics are
 // identical), which saves one full read pass over sm_mean / sm_cov.
-template <int DX, bool SCORE>
-__global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
-                                                              const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
-                                                              const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
-                                                              double *__restrict__ sm_cov, int32_t *__restrict__ status,
-                                                              const double *__restrict__ x_truth, double *__restrict__ partial,
-                                                              double *__restrict__ rmse_acc, double *__restrict__ quad, long long n_traj, int N,
-                                                              int k_lo, int k_hi, long long ld) {
+// KEEP = false (score-only mode, ssm_smooth_scores): the smoothed moments are scored while they are in registers and
+// never stored -- nothing downstream reads them when only the scores are wanted (200 of the 808 bytes per unit for
+// dx = 5).  The second score phase gets the error d = x - m_s itself (dres) next to d' P_s^-1 d (quad), and the
+// recursion crosses time windows through a (dx + dx (dx + 1) / 2, ld) carry buffer instead of the sm arrays.
+template <int DX, bool SCORE, bool KEEP>
+SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
+                           const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
+                           const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
+                           double *__restrict__ sm_cov, int32_t *__restrict__ status,
+                           const double *__restrict__ x_truth, double *__restrict__ partial,
+                           double *__restrict__ rmse_acc, double *__restrict__ quad,
+                           double *__restrict__ dres, double *__restrict__ carry, long long n_traj, int N,
+                           const int k_lo0, const int k_hi0, long long ld, const long long blk, const int k_lo, const int k_hi,
+                           double *smem) {
     // Time window [k_lo, k_hi) of the N slots (ssm_smooth_window): a window with k_hi < N continues the recursion
     // from the smoothed moments the later window left in sm_mean / sm_cov (same stream => ordered), so walking the
-    // windows from the last to the first reproduces the one-pass result bit for bit.
+    // windows from the last to the first reproduces the one-pass result bit for bit.  [k_lo0, k_hi0) is the window of
+    // the whole launch (row index of the partial statistics); they differ when the ticket kernel below runs one of
+    // its time chunks.
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
-    const int WLEN = k_hi - k_lo;
-    __shared__ double smem[SCORE ? BlockReduce<W>::SIZE : 1];
-    const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int WLEN = k_hi0 - k_lo0;
+    const long long t_raw = blk * blockDim.x + threadIdx.x;
     const bool in_range = t_raw < n_traj;
     if (!SCORE && !in_range) return;
     const long long t = in_range ? t_raw : n_traj - 1;   // idle lanes of the last CTA only take part in the reductions
@@ -38,7 +45,7 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     auto at = [&](int c, int k) { return c * cs + row(k); };
     double se_acc[DX];
 #pragma unroll
-    for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? rmse_acc[(long long)a * ld + t] : 0.0;
+    for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? __ldcg(rmse_acc + (long long)a * ld + t) : 0.0;
     // score the smoothed moments (ms, Ps) of step k; every thread of the CTA calls this once per step
     auto score = [&](int k, bool live, const double (&ms_)[DX], const double (&Ps_)[TX]) {
         double v[W];
@@ -51,16 +58,21 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
             double qf;
             score_step<DX>(d, Ps_, v, se, &qf);
             if (quad) st_stream(quad + row(k), qf);
+            if (dres) {
+#pragma unroll
+                for (int a = 0; a < DX; ++a) st_stream(dres + at(a, k), d[a]);
+            }
 #pragma unroll
             for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
         }
-        block_reduce_store<W>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * W);
+        block_reduce_store<W>(v, smem, k, partial + (blk * WLEN + (k - k_lo0)) * W);
     };
-    bool alive = in_range && status[t] == 0;
+    bool alive = in_range && __ldcg(status + t) == 0;
     // A trajectory whose forward pass failed (nothing to smooth) or whose smoother fails on the way gets NaN rows,
     // written step by step inside the time loops next to the stores of the healthy lanes of the warp (a thread that
     // fills its whole tail on its own issues 30 scattered 8-byte stores per step).
     auto nan_row = [&](int k) {
+        if (!KEEP) return;
         for (int c = 0; c < DX; ++c) sm_mean[at(c, k)] = qnan();
         for (int c = 0; c < DX * DX; ++c) sm_cov[at(c, k)] = qnan();
     };
@@ -70,12 +82,26 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
     double ms[DX], Ps[TX];
     if (k_hi < N && alive) {
         const int ki = (k_hi >= N - 2) ? N - 1 : k_hi;   // slots N-1, N-2 hold filtered values; the recursion starts from slot N-1
+        if (KEEP) {
 #pragma unroll
-        for (int a = 0; a < DX; ++a) ms[a] = ld_stream(sm_mean + at(a, ki));
+            for (int a = 0; a < DX; ++a) ms[a] = ld_stream(sm_mean + at(a, ki));
 #pragma unroll
-        for (int r = 0; r < DX; ++r)
+            for (int r = 0; r < DX; ++r)
 #pragma unroll
-            for (int c = 0; c <= r; ++c) Ps[tri(r, c)] = ld_stream(sm_cov + at(r * DX + c, ki));
+                for (int c = 0; c <= r; ++c) Ps[tri(r, c)] = ld_stream(sm_cov + at(r * DX + c, ki));
+        } else if (k_hi >= N - 2) {   // = the filtered moments of the last slot
+#pragma unroll
+            for (int a = 0; a < DX; ++a) ms[a] = ld_stream(fi_mean + at(a, ki));
+#pragma unroll
+            for (int r = 0; r < DX; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) Ps[tri(r, c)] = ld_stream(fi_cov + at(r * DX + c, ki));
+        } else {                      // smoothed moments of step k_hi, left by the window behind this one
+#pragma unroll
+            for (int a = 0; a < DX; ++a) ms[a] = __ldcg(carry + (long long)a * ld + t);
+#pragma unroll
+            for (int a = 0; a < TX; ++a) Ps[a] = __ldcg(carry + (long long)(DX + a) * ld + t);
+        }
     }
     for (int k = k_hi - 1; k >= k_lo && k >= N - 2; --k) {
         double mk[DX], Pk[TX];
@@ -85,16 +111,17 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                 const double v = ld_stream(fi_mean + at(a, k));
                 mk[a] = v;
                 if (k == N - 1) ms[a] = v;
-                st_stream(sm_mean + at(a, k), v);
+                if (KEEP) st_stream(sm_mean + at(a, k), v);
             }
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
                 for (int c = 0; c < DX; ++c) {
+                    if (!KEEP && c > r) continue;
                     const double v = ld_stream(fi_cov + at(r * DX + c, k));
                     if (c <= r) Pk[tri(r, c)] = v;
                     if (k == N - 1 && c <= r) Ps[tri(r, c)] = v;
-                    st_stream(sm_cov + at(r * DX + c, k), v);
+                    if (KEEP) st_stream(sm_cov + at(r * DX + c, k), v);
                 }
         } else if (in_range) {
             nan_row(k);
@@ -171,13 +198,15 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
                 for (int e = 0; e < DX; ++e) s = fma(T[r][e], Dg[c][e], s);
                 Ps[tri(r, c)] = Pf[tri(r, c)] + s;
             }
-        double *q_sm = row_ptr(sm_mean, rk), *q_sc = row_ptr(sm_cov, rk);
+        if (KEEP) {
+            double *q_sm = row_ptr(sm_mean, rk), *q_sc = row_ptr(sm_cov, rk);
 #pragma unroll
-        for (int a = 0; a < DX; ++a) st_stream(q_sm + a * cs, ms[a]);
+            for (int a = 0; a < DX; ++a) st_stream(q_sm + a * cs, ms[a]);
 #pragma unroll
-        for (int r = 0; r < DX; ++r)
+            for (int r = 0; r < DX; ++r)
 #pragma unroll
-            for (int c = 0; c < DX; ++c) st_stream(q_sc + (r * DX + c) * cs, Ps[sym(r, c)]);
+                for (int c = 0; c < DX; ++c) st_stream(q_sc + (r * DX + c) * cs, Ps[sym(r, c)]);
+        }
       } while (0);
         if (!alive && in_range) nan_row(k);
         if (SCORE) score(k, alive, ms, Ps);
@@ -186,7 +215,79 @@ __global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__re
 #pragma unroll
         for (int a = 0; a < DX; ++a) rmse_acc[(long long)a * ld + t] = (alive && !fail) ? se_acc[a] : qnan();
     }
+    if (!KEEP && carry && k_lo > 0 && in_range) {   // hand the recursion to the window in front of this one
+#pragma unroll
+        for (int a = 0; a < DX; ++a) carry[(long long)a * ld + t] = ms[a];
+#pragma unroll
+        for (int a = 0; a < TX; ++a) carry[(long long)(DX + a) * ld + t] = Ps[a];
+    }
     if (fail && in_range) status[t] = ((kfail + 1) << 8) | fail;
+}
+
+template <int DX, bool SCORE, bool KEEP>
+__global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
+                                                              const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
+                                                              const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
+                                                              double *__restrict__ sm_cov, int32_t *__restrict__ status,
+                                                              const double *__restrict__ x_truth, double *__restrict__ partial,
+                                                              double *__restrict__ rmse_acc, double *__restrict__ quad,
+                                                              double *__restrict__ dres, double *__restrict__ carry, long long n_traj, int N,
+                                                              int k_lo, int k_hi, long long ld) {
+    __shared__ double smem[SCORE ? BlockReduce<ScoreRow<DX>::WP>::SIZE : 1];
+    smoother_body<DX, SCORE, KEEP>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, partial, rmse_acc, quad,
+                                   dres, carry, n_traj, N, k_lo, k_hi, ld, blockIdx.x, k_lo, k_hi, smem);
+}
+
+// Ticket scheduling of the score-only smoother (opt-in, see launch_smoother: measured and rejected).  A trajectory is a serial recursion, so a plain launch is quantised in
+// waves of (resident CTAs x 128) whole trajectories -- 125 000 trajectories = 3.3 waves cost 4.  The persistent grid
+// draws (trajectory block, time chunk) items from an atomic ticket in chunk-major order, chunks counted from the END of
+// the window; a chunk is just a time window of its own, so the recursion crosses chunks exactly as it crosses windows
+// (carry, rmse_acc, status in global memory) and the results stay bitwise equal.  Item (blk, kc) waits for
+// done[blk] >= kc, published by a CTA that drew an earlier ticket and is therefore running: no deadlock.
+// The chunk body is an out-of-line call: inlined into the ticket loop it loses 25 % (255 registers + spills; measured
+// 12.5 ms against 10.0 ms for the same plain launch).
+template <int DX>
+__device__ __noinline__ void smoother_chunk(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
+                                            const double *pr_xx, int32_t *status, const double *x_truth, double *partial,
+                                            double *rmse_acc, double *quad, double *dres, double *carry, long long n_traj, int N,
+                                            int k_lo0, int k_hi0, long long ld, long long blk, int k_lo, int k_hi, double *smem) {
+    smoother_body<DX, true, false>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, nullptr, nullptr, status, x_truth, partial, rmse_acc, quad,
+                                   dres, carry, n_traj, N, k_lo0, k_hi0, ld, blk, k_lo, k_hi, smem);
+}
+
+template <int DX>
+__global__ void __launch_bounds__(SC_THREADS) smoother_ticket_kernel(const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                                                                     const double *pr_cov, const double *pr_xx, int32_t *status,
+                                                                     const double *x_truth, double *partial, double *rmse_acc,
+                                                                     double *quad, double *dres, double *carry, long long n_traj, int N,
+                                                                     int k_lo0, int k_hi0, long long ld, int *sched, int chunk, int n_blocks) {
+    __shared__ double smem[BlockReduce<ScoreRow<DX>::WP>::SIZE];
+    __shared__ int s_ticket;
+    const long long n_items = (long long)n_blocks * ((k_hi0 - k_lo0 + chunk - 1) / chunk);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(sched, 1);
+        __syncthreads();
+        const long long tk = s_ticket;
+        if (tk >= n_items) break;
+        const int kc = (int)(tk / n_blocks);
+        const long long blk = tk % n_blocks;
+        const int k_hi = k_hi0 - kc * chunk, k_lo = max(k_lo0, k_hi - chunk);
+        if (kc > 0) {
+            if (threadIdx.x == 0) {
+                while (atomicAdd(sched + 1 + blk, 0) < kc) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        smoother_chunk<DX>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, status, x_truth, partial, rmse_acc, quad, dres, carry, n_traj, N,
+                           k_lo0, k_hi0, ld, blk, k_lo, k_hi, smem);
+        if (k_lo > k_lo0) {   // publish: the chunk in front of this one may start
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(sched + 1 + (int)blk, kc + 1);
+        }
+    }
 }
 
 template <int DX, bool SCORE>
@@ -206,12 +307,13 @@ static cudaError_t launch_tma(const SmootherArgs &a, long long n_full, cudaStrea
 template <int DX>
 static int launch_smoother(const double *fi_mean, const double *fi_cov, const double *pr_mean, const double *pr_cov,
                            const double *pr_xx, double *sm_mean, double *sm_cov, int32_t *status, const double *x_truth,
-                           double *stats, double *rmse_acc, double *quad, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s) {
+                           double *stats, double *rmse_acc, double *quad, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s,
+                           bool keep = true, double *dres = nullptr, double *carry = nullptr) {
     const int WLEN = k_hi - k_lo;
     SmootherArgs a{fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, nullptr, rmse_acc, ld, N, k_lo, k_hi, quad};
     // TMA path: warp-CTAs over the full blocks of 32 trajectories; the ragged tail (and unaligned problems) take the
     // per-thread ld/st kernel.  Both write partial statistics rows that one finalise kernel sums in block order.
-    const long long n_full = (!quad && smoother_tma_eligible(a, n_traj)) ? n_traj / 32 : 0;
+    const long long n_full = (keep && !quad && smoother_tma_eligible(a, n_traj)) ? n_traj / 32 : 0;
     const long long t_tail = n_full * 32, rem = n_traj - t_tail;
     const long long tail_blocks = (rem + SC_THREADS - 1) / SC_THREADS;
     constexpr int W = ScoreRow<DX>::WP;
@@ -223,14 +325,44 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
     if (rem && e == cudaSuccess) {
         auto off = [&](const double *p) { return p ? p + t_tail : nullptr; };
         auto offw = [&](double *p) { return p ? p + t_tail : nullptr; };
-        if (x_truth)
-            smoother_kernel<DX, true><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
+        if (!keep) {
+            // multi-wave launches: persistent grid + ticket scheduler over (trajectory block, time chunk) items
+            auto kern = smoother_ticket_kernel<DX>;
+            int occ = 0, dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, 0);
+            const long long cap = (long long)occ * sms;
+            const char *env_on = getenv("SSM_SMOOTH_TICKET"), *env_chunk = getenv("SSM_SMOOTH_CHUNK");
+            const int CHUNK = env_chunk ? atoi(env_chunk) : 25;
+            // opt-in (SSM_SMOOTH_TICKET=1): measured SLOWER than the plain launch on B200 (125 000 x 500: 11.4 ms against
+            // 10.1 ms; chunks of 10 / 25 / 50 / 100 steps 11.6 / 11.4 / 11.4 / 11.5 ms) -- the last, partial wave of this
+            // HBM-latency-bound kernel runs at low occupancy and therefore fast, so the tail costs less than the hand-over
+            if (env_on && atoi(env_on) == 1 && CHUNK > 0 && cap > 0 && tail_blocks > cap && WLEN >= 2 * CHUNK && rmse_acc) {
+                void *work = nullptr;
+                const size_t n_int = ((size_t)tail_blocks + 1 + 1) / 2 * 2;
+                const size_t bytes = n_int * sizeof(int) + (carry ? 0 : (size_t)(DX + TriSize<DX>::value) * ld * sizeof(double));
+                if (scratch_alloc(&work, bytes, s) != cudaSuccess) return SSM_E_CUDA;
+                cudaMemsetAsync(work, 0, n_int * sizeof(int), s);
+                double *carry_w = carry ? carry : (double *)((int *)work + n_int);
+                kern<<<(unsigned)cap, SC_THREADS, 0, s>>>(
+                    off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), status + t_tail, off(x_truth),
+                    partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), offw(dres), offw(carry_w), rem, N, k_lo, k_hi, ld,
+                    (int *)work, CHUNK, (int)tail_blocks);
+                cudaFreeAsync(work, s);
+            } else {
+                smoother_kernel<DX, true, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
+                    off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), nullptr, nullptr, status + t_tail,
+                    off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), offw(dres), offw(carry), rem, N, k_lo, k_hi, ld);
+            }
+        } else if (x_truth)
+            smoother_kernel<DX, true, true><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                 off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
-                off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), rem, N, k_lo, k_hi, ld);
+                off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), nullptr, nullptr, rem, N, k_lo, k_hi, ld);
         else
-            smoother_kernel<DX, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
+            smoother_kernel<DX, false, true><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                 off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), offw(sm_mean), offw(sm_cov), status + t_tail,
-                nullptr, nullptr, nullptr, nullptr, rem, N, k_lo, k_hi, ld);
+                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rem, N, k_lo, k_hi, ld);
         e = cudaGetLastError();
     }
     if (x_truth) {
@@ -271,6 +403,30 @@ extern "C" int ssm_smooth_quad(int32_t dx, const double *fi_mean, const double *
         default: set_error("ssm_smooth: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
     }
     if (rc == SSM_E_CUDA) set_error("ssm_smooth: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}
+
+extern "C" int ssm_smooth_scores(int32_t dx, const double *fi_mean, const double *fi_cov, const double *pr_mean,
+                                 const double *pr_cov, const double *pr_xx_cov, int32_t *status, const double *x_truth,
+                                 double *stats, double *rmse_acc, double *quad, double *dres, double *carry,
+                                 int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    if (!fi_mean || !fi_cov || !pr_mean || !pr_cov || !pr_xx_cov || !status || !x_truth || !stats) {
+        set_error("ssm_smooth_scores: NULL buffer");
+        return SSM_E_INVALID;
+    }
+    if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_smooth_scores: bad sizes"); return SSM_E_INVALID; }
+    if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_smooth_scores: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
+    if ((k_lo > 0 || k_hi < n_steps) && !carry) { set_error("ssm_smooth_scores: time windows need the carry buffer"); return SSM_E_INVALID; }
+    if (n_traj == 0 || k_hi == k_lo) return SSM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+#define SSM_SS_CASE(D) case D: rc = launch_smoother<D>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, nullptr, nullptr, status, x_truth, stats, rmse_acc, quad, n_traj, n_steps, k_lo, k_hi, ld, s, false, dres, carry); break;
+    switch (dx) {
+        SSM_SS_CASE(1) SSM_SS_CASE(2) SSM_SS_CASE(3) SSM_SS_CASE(4) SSM_SS_CASE(5)
+        default: set_error("ssm_smooth_scores: state dimension %d has no device implementation (1 .. 5)", dx); return SSM_E_UNSUPPORTED;
+    }
+#undef SSM_SS_CASE
+    if (rc == SSM_E_CUDA) set_error("ssm_smooth_scores: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
 }
 

@@ -197,6 +197,52 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     return o
 
 
+def filter_scored(low, y, x_truth, out=None, window=None, init_mean=None, init_cov=None, t_offset=None, k0=0,
+                  want_res=True, keep_moments=False):
+    """Scoring forward pass (ssm_filter_scores): the filter of filter_forward with the phase-1 error statistics of the
+    filtered moments accumulated in-kernel; no moment arrays are stored unless keep_moments.  Returns / fills
+    out['stats'] (N, W), out['rmse_acc'] (dx, M), out['quad'] (N, M), out['dres'] (dx, N, M) (want_res), out['status'],
+    out['last_mean' / 'last_cov'] -- the inputs of utils.evaluate_scored.  Raises NotImplementedError for filters
+    without a scoring instantiation (non-additive noise, generic point sets, Student family)."""
+    dy, N, M = y.shape
+    dx = low.dx
+    dev = y.device
+    ld = bulk_ld(y)
+    if ld != M and M > 1:
+        raise ValueError('filter_scored is not supported on trajectory-range views')
+    if bulk_ld(x_truth) != ld and M > 1:
+        raise ValueError('x_truth must share the leading dimension of y')
+    kw = dict(dtype=torch.float64, device=dev)
+    o = out if out is not None else {}
+    if 'stats' not in o:
+        o['stats'] = torch.empty((N, lib.ssm_scores_width(dx)), **kw)
+        o['rmse_acc'] = torch.empty((dx, M), **kw)
+    if 'quad' not in o:
+        o['quad'] = torch.empty((N, M), **kw)
+    if want_res and 'dres' not in o:
+        o['dres'] = torch.empty((dx, N, M), **kw)
+    if keep_moments and 'fi_mean' not in o:
+        o['fi_mean'] = torch.empty((dx, N, M), **kw)
+        o['fi_cov'] = torch.empty((dx, dx, N, M), **kw)
+    if 'last_mean' not in o:
+        o['last_mean'] = torch.empty((dx, M), **kw)
+        o['last_cov'] = torch.empty((dx, dx, M), **kw)
+    if 'status' not in o:
+        o['status'] = torch.empty((M,), dtype=torch.int32, device=dev)
+    if M == 0 or N == 0:
+        o['status'].zero_()
+        return o
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    if init_mean is not None:
+        init_mean, init_cov = init_mean.contiguous(), init_cov.contiguous()
+    rc = lib.ssm_filter_scores(C.byref(low.desc), _p(y), _p(x_truth), _p(o.get('fi_mean') if keep_moments else None),
+                               _p(o.get('fi_cov') if keep_moments else None), _p(o['stats']), _p(o['rmse_acc']), _p(o['quad']),
+                               _p(o.get('dres') if want_res else None), _p(init_mean), _p(init_cov), _p(o['last_mean']),
+                               _p(o['last_cov']), _p(t_offset), int(k0), _p(o['status']), M, N, k_lo, k_hi, ld, _stream())
+    _lib.check(rc, 'ssm_filter_scores')
+    return o
+
+
 def smooth_backward(dx, fwd, out=None, x_truth=None, window=None, want_quad=False):
     """Run the RTS smoother (ssm_smooth) over the arrays stored by filter_forward(store_pred=True).
     window = (k_lo, k_hi): smooth only those steps (ssm_smooth_window); windows must be walked from the last to the
@@ -242,6 +288,55 @@ def smooth_backward(dx, fwd, out=None, x_truth=None, window=None, want_quad=Fals
                              _p(o.get('rmse_acc') if x_truth is not None else None), _p(quad), M, N, k_lo, k_hi, ld, _stream())
     _lib.check(rc, 'ssm_smooth')
     return o
+
+
+def smooth_scores(dx, fwd, x_truth, out=None, window=None, want_res=True):
+    """Score-only RTS smoother (ssm_smooth_scores): the recursion of smooth_backward with the phase-1 statistics
+    accumulated in-kernel and NO smoothed arrays stored.  out['stats'] (N, W), out['rmse_acc'] (dx, M), out['quad']
+    (N, M) = d' P_s^-1 d, out['dres'] (dx, N, M) = x - m_s (want_res) -- the inputs of scores_phase2_res --,
+    out['status'].  window = (k_lo, k_hi): walk the windows from the last to the first with the same `out`."""
+    _, N, M = fwd['fi_mean'].shape
+    o = out if out is not None else {}
+    dev = fwd['fi_mean'].device
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    if k_hi == N or 'status' not in o:
+        if 'status' in o and o['status'].shape == fwd['status'].shape:
+            o['status'].copy_(fwd['status'])
+        else:
+            o['status'] = fwd['status'].clone()
+    ld = bulk_ld(fwd['fi_mean'])
+    if ld != M and M > 1:
+        raise ValueError('smooth_scores is not supported on trajectory-range views')
+    if any(bulk_ld(t) != ld for t in (fwd['fi_cov'], fwd['pr_mean'], fwd['pr_cov'], fwd['pr_xx_cov'], x_truth)) and M > 1:
+        raise ValueError('all bulk arrays of one ssm_smooth_scores call must share the leading dimension')
+    kw = dict(dtype=torch.float64, device=dev)
+    if 'stats' not in o:
+        o['stats'] = torch.empty((N, lib.ssm_scores_width(dx)), **kw)
+        o['rmse_acc'] = torch.empty((dx, M), **kw)
+    if 'quad' not in o:
+        o['quad'] = torch.empty((N, M), **kw)
+    if want_res and 'dres' not in o:
+        o['dres'] = torch.empty((dx, N, M), **kw)
+    if (k_lo > 0 or k_hi < N) and 'carry' not in o:
+        o['carry'] = torch.empty((dx + dx * (dx + 1) // 2, M), **kw)
+    rc = lib.ssm_smooth_scores(dx, _p(fwd['fi_mean']), _p(fwd['fi_cov']), _p(fwd['pr_mean']), _p(fwd['pr_cov']),
+                               _p(fwd['pr_xx_cov']), _p(o['status']), _p(x_truth), _p(o['stats']), _p(o['rmse_acc']),
+                               _p(o['quad']), _p(o.get('dres') if want_res else None), _p(o.get('carry')),
+                               M, N, k_lo, k_hi, ld, _stream())
+    _lib.check(rc, 'ssm_smooth_scores')
+    return o
+
+
+def scores_phase2_res(dres, quad, mse, status=None, window=None, out=None, lcr_acc=None):
+    """Second score phase from the stored errors d = x - m (dx, N, M) and quadratic forms d' P^-1 d (N, M)
+    (ssm_scores_phase2_res): per-step sums of the log credibility ratio and of its absolute value, (N, 2)."""
+    dx, N, M = dres.shape
+    _check_score_layout(dres, None, None, quad)
+    lcr = out if out is not None else torch.empty((N, 2), dtype=torch.float64, device=dres.device)
+    k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
+    rc = lib.ssm_scores_phase2_res(dx, _p(dres), _p(quad), _p(status), _p(mse.contiguous()), _p(lcr), _p(lcr_acc), M, N, k_lo, k_hi, M, _stream())
+    _lib.check(rc, 'ssm_scores_phase2_res')
+    return lcr
 
 
 def fp64_peak(n_blocks=148 * 8, n_iters=4096, reps=5, mode=0):

@@ -41,12 +41,14 @@ def _windows(N, n):
     return [(a, min(a + w, N)) for a in range(0, N, w)]
 
 
-def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n_chunks=None):
+def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n_chunks=None, reduce_every=4):
     """RMSE / NCI / NLL of filter `alg` on measurements y (dy, N, M) against the truth x (dx, N, M).
     y, x: numpy arrays, CPU torch tensors (pinned for full copy speed) or CUDA tensors.
     Returns the dict of ssmtoybox_b200.utils.evaluate_performance (+ 'status' (M,) int32 on the host, and the
     device arrays under 'arrays' when keep=True).  n_windows: time windows of the streaming pipeline;
-    n_chunks forces the trajectory-chunked fallback."""
+    n_chunks forces the trajectory-chunked fallback.  keep=False (default) runs the RTS smoother in its score-only mode
+    (ssm_smooth_scores): the smoothed moments are scored in registers and never stored.  reduce_every: smoother
+    windows whose statistics rows share one all-reduce (and one second-phase launch)."""
     y, x = _as_host_or_device(y), _as_host_or_device(x)
     dy, N, M = y.shape
     dx = x.shape[0]
@@ -135,13 +137,29 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
     # ---- RTS smoother + scores, walking the windows backwards ------------------------------------------
     if do_smooth:
         sm = {'stats': stats, 'rmse_acc': acc}
+        pending = []
         for c in range(len(wins) - 1, -1, -1):
             k0, k1 = wins[c]
             if ev_x[c] is not None:
                 comp.wait_event(ev_x[c])
-            dv.smooth_backward(dx, fwd, out=sm, x_truth=xd, window=(k0, k1), want_quad=True)
-            second_phase(k0, k1, sm['sm_mean'], sm['sm_cov'], sm['status'], quad=sm['quad'])
-        mean, cov, st = sm['sm_mean'], sm['sm_cov'], sm['status']
+            if keep:
+                dv.smooth_backward(dx, fwd, out=sm, x_truth=xd, window=(k0, k1), want_quad=True)
+            else:
+                dv.smooth_scores(dx, fwd, xd, out=sm, window=(k0, k1))
+            pending.append((k0, k1))
+            if len(pending) >= max(1, int(reduce_every)) or c == 0:
+                # adjacent windows: one all-reduce of their statistics rows, one second-phase launch
+                a, b = pending[-1][0], pending[0][1]
+                if keep:
+                    second_phase(a, b, sm['sm_mean'], sm['sm_cov'], sm['status'], quad=sm['quad'])
+                else:
+                    rows = stats[a:b]
+                    if comm is not None:
+                        comm.allreduce_sum(rows)
+                    mse[:, a:b] = (rows[:, dx:dx + dx * dx] / rows[:, -1:]).T
+                    dv.scores_phase2_res(sm['dres'], sm['quad'], mse, sm['status'], window=(a, b), out=lcr)
+                pending = []
+        mean, cov, st = (sm['sm_mean'], sm['sm_cov'], sm['status']) if keep else (None, None, sm['status'])
         # trajectories that failed INSIDE the smoother were still alive in the rows of later steps
         n_bad = ((st != 0).sum() - (fwd['status'] != 0).sum()).to(torch.float64)
     else:
@@ -158,6 +176,8 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
     res = {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}
     if res.pop('n_bad') != 0.0:
         # rare: some trajectories failed after they had contributed to some rows -> exact two-pass recomputation
+        if mean is None:   # score-only smoother kept no arrays: run again with them
+            return filter_scores(alg, yd, xd, smooth=smooth, n_windows=n_windows, comm=comm, keep=True, reduce_every=reduce_every)
         from . import utils as U
         res = U.evaluate_performance(xd, mean, cov, status=st, comm=comm)
     res['status'] = st.cpu().numpy()
@@ -259,3 +279,80 @@ def _filter_scores_chunked(alg, y, x, smooth=True, n_chunks=8, comm=None, keep=F
     if keep:
         res['chunks'] = kept
     return res
+
+
+def monte_carlo_scores(alg, n_traj, n_steps, truth=None, sim='discrete', dt=0.0, sub=1, seed=0, chunk=131072, smooth=False,
+                       comm=None, to_host=True):
+    """Generator-driven Monte-Carlo experiment with nothing materialised per trajectory but the two score inputs:
+    for every chunk of trajectories  simulate (Philox, keyed by the GLOBAL trajectory index) -> filter [-> RTS smoother]
+    with the phase-1 error statistics accumulated IN the filter / smoother kernel; the states, measurements and filter
+    arrays of a chunk are dropped when the chunk is done -- like the reference's loops, which keep one trajectory at a
+    time (research/gpq/icinco_demo.py:115-125, research/bsq/bsq_tracking.py:300-306).  Per scored unit only
+    d = x - m (dx doubles) and d' P^-1 d (1 double) stay resident: the log credibility ratio needs the GLOBAL per-step
+    MSE matrix first (research/gpq/icinco_demo.py:34-40), so its second phase runs after the last chunk.
+
+    alg: a Gaussian-family filter of ssmtoybox_b200.ssinf.  truth: dict(m0, P0, q_cov, r_cov[, x0_dof, q_dof, r_dof])
+    of the data-generating system (default: the filter's own model), sim / dt / sub as device.simulate.
+    With a Communicator every rank runs its contiguous share of the n_traj trajectories; the packed statistics are
+    all-reduced once per phase.  Returns the dict of utils.evaluate_performance (+ n_failed, kept_bytes)."""
+    from . import utils as U
+    dev = torch.device('cuda', torch.cuda.current_device())
+    d = alg._describe()
+    low = dv.lower(d)
+    dx, N = low.dx, int(n_steps)
+    if isinstance(alg, StudentianInference):
+        raise NotImplementedError('monte_carlo_scores: Gaussian-family filters')
+    if truth is None:
+        truth = {'m0': d['m0'], 'P0': d['P0'], 'q_cov': d['q_cov'], 'r_cov': d['r_cov']}
+    off, cnt_loc = (0, int(n_traj)) if comm is None else comm.shard(int(n_traj))
+    a, b = off, off + cnt_loc
+    kw = dict(dtype=torch.float64, device=dev)
+    W = dv.lib.ssm_scores_width(dx)
+    stats = torch.zeros((N, W), **kw)
+    rm = torch.zeros((dx,), **kw)
+    kept, n_failed = [], 0
+    scratch = {}
+    chunk = max(128, int(chunk))
+    for c0 in range(a, b, chunk):
+        mc = min(chunk, b - c0)
+        x, y = dv.simulate(low, mc, N, rng=dv.make_rng(truth, seed=seed, traj_offset=c0), mode=sim, dt=dt, sub=sub, device=dev)
+        if scratch.get('m') != mc:
+            scratch = {'m': mc, 'fwd': {}}
+        sc = {}
+        if smooth:
+            fwd = dv.filter_forward(low, y, store_pred=True, out=scratch['fwd'])
+            dv.smooth_scores(dx, fwd, x, out=sc)
+        else:
+            try:
+                dv.filter_scored(low, y, x, out=sc)
+            except NotImplementedError:   # no scoring instantiation of this filter: score the stored moments of the chunk
+                fwd = dv.filter_forward(low, y, store_pred=False, out=scratch['fwd'])
+                sc['quad'] = torch.empty((N, mc), **kw)
+                sc['stats'], sc['rmse_acc'] = dv.scores_phase1(x, fwd['fi_mean'], fwd['fi_cov'], fwd['status'], quad=sc['quad'])
+                sc['dres'] = x - fwd['fi_mean']
+                sc['status'] = fwd['status'].clone()
+        st = sc['status']
+        stats += sc['stats']
+        ok = (st == 0)
+        rm += torch.where(ok[None, :], torch.sqrt(sc['rmse_acc'] / N), torch.zeros_like(sc['rmse_acc'])).sum(dim=1)
+        kept.append((sc['dres'], sc['quad'], st))
+        del x, y
+    pack = torch.cat([stats.reshape(-1), rm])
+    if comm is not None:
+        pack = comm.allreduce_sum(pack)
+    st_g, rm_g = pack[:N * W].reshape(N, W), pack[N * W:]
+    cnt = st_g[:, -1]
+    mse = (st_g[:, dx:dx + dx * dx] / cnt[:, None]).T.reshape(dx, dx, N).contiguous()
+    lcr = torch.zeros((N, 2), **kw)
+    for dres, quad, st in kept:
+        lcr += dv.scores_phase2_res(dres, quad, mse, st)
+    nf = torch.stack([(st != 0).sum() for _, _, st in kept]).sum().to(torch.float64).reshape(1) if kept else torch.zeros(1, **kw)
+    if comm is not None:
+        lcr = comm.allreduce_sum(lcr)
+        nf = comm.allreduce_sum(nf)
+    out = finalize_scores(st_g, rm_g, lcr, dx, N)
+    out['n_failed'] = nf[0]
+    if to_host:
+        out = {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}
+    out['kept_bytes'] = int(sum(t[0].numel() + t[1].numel() for t in kept) * 8)
+    return out

@@ -224,19 +224,29 @@ def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, pha
     else:   # the first pass keeps d' P^-1 d per unit, so the second one does not read the covariances again
         quad = torch.empty((N, M), dtype=torch.float64, device=xd.device)
         stats, acc = dv.scores_phase1(xd, md, Pd, status, quad=quad)
-    ok = torch.ones(M, dtype=torch.bool, device=xd.device) if status is None else (status == 0)
+    return finish_scores(stats, acc, status, lambda mse: dv.scores_phase2(xd, md, Pd, mse, status, quad=quad),
+                         comm=comm, to_host=to_host)
+
+
+def finish_scores(stats, acc, status, second_phase, comm=None, to_host=True):
+    """Scores from the first-phase statistics of this rank: stats (N, W) packed rows, acc (dx, M) per-trajectory
+    time-sums of the squared error, status (M,) or None.  second_phase(mse (dx, dx, N)) -> (N, 2) sums of the log
+    credibility ratio, called once the GLOBAL per-step MSE matrix is known (research/gpq/icinco_demo.py:34-40).
+    One all-reduce per phase when comm is given."""
+    N, W = stats.shape
+    dx, M = acc.shape
+    ok = torch.ones(M, dtype=torch.bool, device=stats.device) if status is None else (status == 0)
     # per-trajectory sqrt(time-mean SE), summed over the trajectories that completed
     rm = torch.where(ok[None, :], torch.sqrt(acc / N), torch.zeros_like(acc)).sum(dim=1)
     pack = torch.cat([stats.reshape(-1), rm])
     if comm is not None:
         pack = comm.allreduce_sum(pack)
-    W = stats.shape[1]
     st = pack[:N * W].reshape(N, W)
     rm = pack[N * W:]
     cnt = st[:, -1]
     n_ok = cnt[0]
     mse = (st[:, dx:dx + dx * dx] / cnt[:, None]).T.reshape(dx, dx, N).contiguous()
-    lcr = dv.scores_phase2(xd, md, Pd, mse, status, quad=quad)
+    lcr = second_phase(mse)
     if comm is not None:
         lcr = comm.allreduce_sum(lcr)
     out = dict(rmse=(rm / n_ok), nll=st[1:, dx + dx * dx].sum() / (N * n_ok), inc=lcr[1:, 0].sum() / (N * n_ok),
@@ -245,3 +255,11 @@ def evaluate_performance(x, mean, cov, status=None, comm=None, to_host=True, pha
     if not to_host:
         return out
     return {k: (v.cpu().numpy() if v.ndim else float(v)) for k, v in out.items()}
+
+
+def evaluate_scored(sc, comm=None, to_host=True):
+    """Scores from the outputs of a scoring pass that kept no moment arrays (device.smooth_scores / filter_scored):
+    sc = dict(stats, rmse_acc, quad (N, M), dres (dx, N, M), status).  Same result as evaluate_performance on the
+    arrays that pass did not store."""
+    return finish_scores(sc['stats'], sc['rmse_acc'], sc['status'],
+                         lambda mse: dv.scores_phase2_res(sc['dres'], sc['quad'], mse, sc['status']), comm=comm, to_host=to_host)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_lib.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), 'symbol {} declared in include/ssm_b200.h is not exported'.format(s)
-    assert _lib.lib.ssm_abi_version() == 4
+    assert _lib.lib.ssm_abi_version() == 5
 
 
 def test_struct_layout_matches_header(tmp_path):

@@ -535,3 +535,33 @@ def test_math_probe():
     assert ulps(probe(2, a), 1.0 / np.sqrt(a)).max() <= 1.0
     assert ulps(probe(3, b, a), b / a).max() == 0
     assert ulps(probe(4, b, a - 5e7), np.arctan2(b, a - 5e7)).max() <= 2.0
+
+
+@pytest.mark.parametrize('name', ['c3_reentry_gpq', 'c4_ct_gpq', 'c4_ct_tpq', 'c4_ct_bsq'])
+def test_warp_pair_forward_pass_matches_single_thread_kernel(name, monkeypatch):
+    """The opt-in warp-pair mapping of the forward pass (SSM_PAIR=1, csrc/ssm_filter_pair.cuh; measured slower than the
+    one-thread-per-trajectory kernel) computes the same filter: equal failure status, means to 1e-9, the
+    un-centred BQ covariances to their float64 noise floor (the two kernels associate the double sum differently)."""
+    from ssmtoybox_b200 import device as dv
+    g = golden(name)
+    low = dv.lower(g)
+    M, N = 3000, 60
+    if 'reentry' in name:
+        rng = dv.make_rng({'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+                           'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}, seed=5)
+        x, y = dv.simulate(low, M, N, rng=rng, mode='continuous', dt=0.05, sub=2)
+    else:
+        x, y = dv.simulate(low, M, N, rng=dv.make_rng(g, seed=5))
+    y[:, 7, 11] = float('nan')
+    monkeypatch.setenv('SSM_PAIR', '0')
+    a = dv.filter_forward(low, y, store_pred=True, want_last=True)
+    monkeypatch.setenv('SSM_PAIR', '1')
+    b = dv.filter_forward(low, y, store_pred=True, want_last=True)
+    assert torch.equal(a['status'], b['status']) and int((a['status'] != 0).sum()) >= 1
+    ok = (a['status'] == 0).cpu().numpy()
+    # c4_ct_bsq: unit kernel parameters -> noise-dominated weights, the recursion amplifies rounding (FULL_TOL None)
+    tm, tc = (1e-6, 1e-4) if name == 'c4_ct_bsq' else (1e-9, 2e-6)
+    for k, tol in (('fi_mean', tm), ('pr_mean', tm), ('fi_cov', tc), ('pr_cov', tc), ('pr_xx_cov', tc)):
+        u, v = a[k].cpu().numpy()[..., ok], b[k].cpu().numpy()[..., ok]
+        assert relstep(u, v) < tol, (k, relstep(u, v))
+        assert np.array_equal(np.isnan(a[k].cpu().numpy()), np.isnan(b[k].cpu().numpy())), k

@@ -145,3 +145,55 @@ def test_time_streaming_driver_with_failures_falls_back_to_exact_scores():
     assert (r1['status'] != 0).sum() == 2 and r1['n_ok'] == M - 2
     assert rel(r1['rmse'], r2['rmse']) < 1e-12 and abs(r1['nci'] - r2['nci']) < 1e-10 * abs(r2['nci']) + 1e-12
     assert abs(r1['nll'] - r2['nll']) < 1e-11 * abs(r2['nll'])
+
+
+@pytest.mark.parametrize('M,N,wins', [
+    (300, 40, None),
+    (300, 40, [(0, 13), (13, 30), (30, 40)]),
+    (300, 7, [(0, 1), (1, 2), (2, 6), (6, 7)]),        # windows touching slots N-1, N-2 (filtered values)
+    (5000, 50, [(0, 25), (25, 50)]),
+    (70000, 60, None),
+    (70000, 110, [(0, 55), (55, 110)]),
+])
+@pytest.mark.parametrize('ticket', ['0', '1'])          # 1: opt-in ticket scheduler over (block, time chunk) items
+def test_score_only_smoother_equals_stored_smoother(M, N, wins, ticket, monkeypatch):
+    """ssm_smooth_scores (no smoothed arrays stored, errors d = x - m_s kept for the second score phase) gives bitwise
+    the statistics, quadratic forms and scores of ssm_smooth_quad + evaluate_performance on the stored arrays."""
+    from ssmtoybox_b200 import device as dv, utils as U
+    if ticket == '1' and M < 60000:
+        pytest.skip('the ticket scheduler only engages for multi-wave launches')
+    monkeypatch.setenv('SSM_SMOOTH_TICKET', ticket)
+    g = golden('c3_reentry_gpq')
+    low, x, y = _sim(g, M, N)
+    y[:, 3, 5] = float('nan')                                       # one failed trajectory
+    fwd = dv.filter_forward(low, y, store_pred=True)
+    ref = dv.smooth_backward(low.dx, fwd, x_truth=x, want_quad=True)
+    want = U.evaluate_performance(x, ref['sm_mean'], ref['sm_cov'], status=ref['status'], to_host=False,
+                                  phase1=(ref['stats'], ref['rmse_acc']), quad=ref['quad'])
+    sc = {}
+    for (a, b) in (reversed(wins) if wins else [(0, N)]):
+        dv.smooth_scores(low.dx, fwd, x, out=sc, window=None if wins is None else (a, b))
+    assert 'sm_mean' not in sc and 'sm_cov' not in sc
+    assert torch.equal(sc['status'], ref['status'])
+    ok = (ref['status'] == 0)
+    assert eq(sc['stats'], ref['stats']) and eq(sc['rmse_acc'], ref['rmse_acc'])
+    assert eq(sc['quad'][:, ok], ref['quad'][:, ok])          # rows of failed trajectories are never written
+    assert eq(sc['dres'][:, :, ok], (x - ref['sm_mean'])[:, :, ok])
+    got = U.evaluate_scored(sc, to_host=False)
+    for k in ('rmse', 'nci', 'nll', 'abs_nci', 'mse', 'rmse_vs_time', 'n_ok'):
+        assert eq(got[k], want[k]), k
+
+
+def test_streaming_driver_score_only_equals_keep():
+    """mc.filter_scores(keep=False) -- score-only smoother, statistics rows of several windows all-reduced together --
+    returns the scores of the keep=True pipeline."""
+    from ssmtoybox_b200 import mc
+    import bench
+    alg, g = bench.build_filter()
+    _, x, y = _sim(g, 4000, 60)
+    a = mc.filter_scores(alg, y.cpu().numpy(), x.cpu().numpy(), smooth=True, n_windows=6, keep=True)
+    for every in (1, 4):
+        b = mc.filter_scores(alg, y.cpu().numpy(), x.cpu().numpy(), smooth=True, n_windows=6, keep=False, reduce_every=every)
+        for k in ('rmse', 'nci', 'nll', 'mse'):
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+        assert np.array_equal(a['status'], b['status'])
