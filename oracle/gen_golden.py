@@ -775,9 +775,36 @@ def gen_weight_envelope(n_var=16, mc=32, steps=100):
           ' |base Wc_obs|max', np.abs(base['Wc_obs']).max())
 
 
+def gen_public_attrs():
+    """Public attributes the research code reads after forward_pass (research/bsq/bsq_tracking.py:1004-1013):
+    x_mean_pr, x_cov_pr, xx_cov and the predictive MEASUREMENT moments y_mean_pr, y_cov_pr, xy_cov of the last step
+    (ssinf.py:281-294), for an additive 5-D model (UKF and GPQ) and a model with non-additive noise."""
+    d = {}
+    np.random.seed(0)
+    dyn, obs, x, y = reentry(60, 2)
+    hdyn = np.array([[1.0, 25, 25, 25, 25, 25]])
+    hobs = np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
+    cases = [('reentry_ukf', ssinf.UnscentedKalman(dyn, obs), y), ('reentry_gpq', ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs), y)]
+    np.random.seed(5)
+    x0, q, r = GaussRV(1, mean=np.array([1.0]), cov=np.atleast_2d(5.0)), GaussRV(1, cov=np.atleast_2d(10.0)), GaussRV(1)
+    dna, ona = ssmod.UNGMNATransition(x0, q), ssmod.UNGMNAMeasurement(r, 1)
+    xna = dna.simulate_discrete(40, mc_sims=2)
+    yna = ona.simulate_measurements(xna)
+    cases.append(('ungmna_ukf', ssinf.UnscentedKalman(dna, ona), yna))
+    for name, alg, yy in cases:
+        alg.forward_pass(yy[..., 0])
+        d[name + '_y'] = yy
+        for a in ('x_mean_pr', 'x_cov_pr', 'xx_cov', 'y_mean_pr', 'y_cov_pr', 'xy_cov', 'x_mean_fi', 'x_cov_fi'):
+            d[name + '_' + a] = np.asarray(getattr(alg, a))
+        if name == 'reentry_gpq':
+            d.update(transform_dict(alg.tf_dyn, 'reentry_gpq_dyn_'))
+            d.update(transform_dict(alg.tf_obs, 'reentry_gpq_obs_'))
+    save('public_attrs', **d)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'large_pointsets': gen_large_pointsets, 'weights': gen_weights, 'simulation': gen_simulation,
-            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope}
+            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope, 'public_attrs': gen_public_attrs}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

@@ -20,7 +20,19 @@ import numpy as np
 import scipy
 import scipy.special
 
-REFERENCE_PATH = '/root/reference'
+import os
+
+# /root/reference in the build container; on the GPU box the pip-installed copy under baseline/_ref (git-ignored, ships
+# with the gpurun snapshot: `pip install --no-index --no-deps --target baseline/_ref <copy of /root/reference>`), which
+# holds the ssmtoybox package only (no research/ scripts)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = ('/root/reference', os.path.join(os.path.dirname(_HERE), 'baseline', '_ref'))
+REFERENCE_PATH = next((p for p in _CANDIDATES if os.path.isdir(os.path.join(p, 'ssmtoybox'))), _CANDIDATES[0])
+
+
+def available():
+    """Path of an importable copy of the unmodified reference, or None."""
+    return REFERENCE_PATH if os.path.isdir(os.path.join(REFERENCE_PATH, 'ssmtoybox')) else None
 
 
 def install():

@@ -211,6 +211,42 @@ class StateSpaceInference(metaclass=ABCMeta):
                       lambda self, v: None)
     pr_xx_cov = property(lambda self: None if self._fwd is None else self._with_slot0('pr_xx_cov', 'pr_xx_cov', True),
                          lambda self, v: None)
+    def _obs_pred(self, idx):
+        """y_mean_pr / y_cov_pr / xy_cov of the LAST time step (ssinf.py:281-294): the measurement transform of the
+        last predictive state moments, evaluated on first access (ssm_transform_apply; the fused forward pass keeps
+        them in registers).  Gaussian family, additive or non-additive measurement noise."""
+        if self._fwd is None or isinstance(self, StudentianInference):
+            return None
+        if 'obs_pred' not in self._lazy:
+            from scipy.linalg import block_diag
+            fwd = self._fwd
+            m = fwd['pr_mean'][:, -1].cpu().numpy()           # (dx, M)
+            P = fwd['pr_cov'][:, :, -1].cpu().numpy()         # (dx, dx, M)
+            ok = (fwd['status'] == 0).cpu().numpy()
+            dx, M = m.shape
+            if not self.mod_obs.noise_additive:               # ssinf.py:282-283
+                m = np.vstack((m, np.repeat(np.asarray(self.r_mean, dtype=np.float64).reshape(-1, 1), M, axis=1)))
+                P = np.stack([block_diag(P[..., i], self.r_cov) for i in range(M)], axis=-1)
+            mm, PP = m.copy(), P.copy()
+            mm[:, ~ok] = 0.0                                  # failed trajectories: NaN moments, not transformed
+            PP[:, :, ~ok] = np.eye(PP.shape[0])[:, :, None]
+            time = np.atleast_1d(float(self.N - 1))           # both transforms of step k get time k - 1 (ssinf.py:104)
+            ym, yc, xy = self.tf_obs.apply(self.mod_obs.meas_eval, mm, PP, time)
+            if self.mod_obs.noise_additive:
+                yc = yc + np.asarray(self.r_cov, dtype=np.float64)[:, :, None]      # ssinf.py:290-291
+            xy = xy[:, :dx]                                   # ssinf.py:293
+            for a in (ym, yc, xy):
+                a[..., ~ok] = np.nan
+            outs = []
+            for a in (ym, yc, xy):
+                t = torch.as_tensor(np.ascontiguousarray(a), device=fwd['fi_mean'].device)
+                outs.append(self._out(t))
+            self._lazy['obs_pred'] = outs
+        return self._lazy['obs_pred'][idx]
+
+    y_mean_pr = property(lambda self: self._obs_pred(0), lambda self, v: None)
+    y_cov_pr = property(lambda self: self._obs_pred(1), lambda self, v: None)
+    xy_cov = property(lambda self: self._obs_pred(2), lambda self, v: None)
     sm_mean = property(lambda self: None if getattr(self, '_sm', None) is None else
                        self._with_slot0('sm_mean', 'sm_mean', False, src=self._sm), lambda self, v: None)
     sm_cov = property(lambda self: None if getattr(self, '_sm', None) is None else

@@ -734,3 +734,64 @@ def test_every_filter_on_every_model_like_the_reference_tests():
     assert len(ran) >= 24                   # the classical filters run everywhere; BQ filters with all-one kernel parameters may stop
     for lab in ('ungm:ukf', 'pend:ukf', 'rer:ukf', 'ctb:ukf', 'ungm:ghkf', 'pend:ghkf', 'rer:ghkf', 'ctb:ghkf', 'ungm:fss', 'cv:fss', 'ungm:tpqs', 'cv:tpqs'):
         assert lab in ran, lab
+
+
+def test_public_predictive_measurement_attributes():
+    """y_mean_pr / y_cov_pr / xy_cov (ssinf.py:281-294), read by research/bsq/bsq_tracking.py:1004-1013 after
+    forward_pass, next to x_mean_pr / x_cov_pr / xx_cov: values of the reference for an additive 5-D model (UKF, GPQ
+    with the reference's weights assigned) and a model with non-additive noise; batched calls give (.., M) arrays."""
+    from ssmtoybox_b200.ssinf import UnscentedKalman, GaussianProcessKalman
+    from ssmtoybox_b200.ssmod import UNGMNATransition, UNGMNAMeasurement
+    from ssmtoybox_b200.utils import GaussRV
+    g = golden('public_attrs')
+    dyn, obs = reentry()
+    # the golden run used the fixture of oracle/gen_golden.py reentry(): same filter model as reentry() here
+    cases = [('reentry_ukf', UnscentedKalman(dyn, obs), 1e-9)]
+    alg = GaussianProcessKalman(dyn, obs, np.array([[1.0, 25, 25, 25, 25, 25]]), np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]]))
+    for tf, p in ((alg.tf_dyn, 'reentry_gpq_dyn_'), (alg.tf_obs, 'reentry_gpq_obs_')):
+        tf.wm, tf.Wc, tf.Wcc = g[p + 'wm'], g[p + 'Wc'], g[p + 'Wcc']
+        tf.model.model_var = float(g[p + 'model_var'])
+    cases.append(('reentry_gpq', alg, 1e-5))      # un-centred BQ covariances: the reference's own noise floor after 60 steps
+    x0, q, r = GaussRV(1, mean=np.array([1.0]), cov=np.atleast_2d(5.0)), GaussRV(1, cov=np.atleast_2d(10.0)), GaussRV(1)
+    cases.append(('ungmna_ukf', UnscentedKalman(UNGMNATransition(x0, q), UNGMNAMeasurement(r, 1)), 1e-8))
+    for name, alg, tol in cases:
+        y = g[name + '_y']
+        assert alg.y_mean_pr is None and alg.xy_cov is None
+        alg.forward_pass(y[..., 0])
+        for a in ('x_mean_pr', 'x_cov_pr', 'xx_cov', 'y_mean_pr', 'y_cov_pr', 'xy_cov'):
+            got, want = np.asarray(getattr(alg, a)), g[name + '_' + a]
+            assert got.shape == want.shape, (name, a, got.shape, want.shape)
+            assert rel(got, want) < tol, (name, a, rel(got, want))
+        alg.reset()
+        assert alg.y_mean_pr is None
+        alg.forward_pass(y)                                   # batched: trajectory axis last
+        assert alg.y_mean_pr.shape == want.shape[:0] + (g[name + '_y_mean_pr'].shape[0], y.shape[2])
+        assert rel(alg.y_cov_pr[..., 0], g[name + '_y_cov_pr']) < tol and rel(alg.xy_cov[..., 0], g[name + '_xy_cov']) < tol
+        alg.reset()
+
+
+def test_student_models_simulate_heavy_tails():
+    """TransitionModel.simulate_discrete / MeasurementModel.simulate_measurements draw multivariate-t noise for StudentRV
+    models like init_rv.sample() / noise_rv.sample() of the reference (utils.py:349-382, ssmod.py:193, 1033): the
+    excess kurtosis of the measurement noise is that of a t distribution (6 / (nu - 4)), not 0; a Gaussian model of
+    the same scale stays Gaussian; a non-zero noise mean shifts the draws (replayed through sample())."""
+    from ssmtoybox_b200.utils import GaussRV, StudentRV
+    from ssmtoybox_b200.ssmod import UNGMTransition, UNGMMeasurement
+    nu = 6.0
+    M = 400000
+    x = np.zeros((1, 1, M))
+
+    def kurt(obs):
+        r = obs.simulate_measurements(x)[0, 0]        # h(0) = 0 -> pure noise
+        c = r - r.mean()
+        return r.mean(), c.var(), (c ** 4).mean() / c.var() ** 2 - 3.0
+    m, v, k = kurt(UNGMMeasurement(StudentRV(1, scale=np.atleast_2d(2.0), dof=nu), 1))
+    assert abs(v - 2.0 * nu / (nu - 2)) < 0.05 * 3.0 and 1.5 < k < 6.0            # t_6: variance 3, excess kurtosis 3
+    m, v, k = kurt(UNGMMeasurement(GaussRV(1, cov=np.atleast_2d(2.0)), 1))
+    assert abs(v - 2.0) < 0.03 and abs(k) < 0.1
+    m, v, k = kurt(UNGMMeasurement(GaussRV(1, mean=np.array([0.7]), cov=np.atleast_2d(2.0)), 1))
+    assert abs(m - 0.7) < 0.02 and abs(v - 2.0) < 0.03
+    dyn = UNGMTransition(StudentRV(1, scale=np.atleast_2d(1.0), dof=nu), StudentRV(1, scale=np.atleast_2d(1.0), dof=nu))
+    x0 = dyn.simulate_discrete(2, mc_sims=M)[0, 0]
+    c = x0 - x0.mean()
+    assert (c ** 4).mean() / c.var() ** 2 - 3.0 > 1.5

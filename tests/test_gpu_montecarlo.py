@@ -124,8 +124,8 @@ def test_c5_bsq_scores_match_reference_driver_on_injected_data(name):
     got = U.evaluate_scored(sc)
     assert rel(got['rmse'], g['rmse'][0]) < 1e-8
     assert rel(got['mse'], g['mse']) < 1e-8
-    assert abs(got['nll'] - float(g['nll'])) < 1e-7 * max(1.0, abs(float(g['nll'])))
-    assert abs(got['nci'] - float(g['nci'])) < 1e-7 * max(1.0, abs(float(g['nci'])))
+    assert abs(got['nll'] - float(g['nll'].item())) < 1e-7 * max(1.0, abs(float(g['nll'].item())))
+    assert abs(got['nci'] - float(g['nci'].item())) < 1e-7 * max(1.0, abs(float(g['nci'].item())))
 
 
 def test_bsq_nci_sweep_driver_runs_and_is_shard_invariant():
