@@ -169,7 +169,7 @@ def run_reference_arm(args):
         return
     vals = []
     sample, kind, cores = '', 'port', 1
-    per_core = 4
+    per_core = 16
     for i in range(args.warmup + args.steps):
         v, cores, kind, sample = cpu_rate(n_traj_per_core=per_core, seed=i)
         if i >= args.warmup:
@@ -461,7 +461,7 @@ def run_gpu_arm(args):
     cpu = None
     if comm.world_size == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0))
-        per_core = 8 if reference_kind() == 'reference' else 32
+        per_core = 48 if reference_kind() == 'reference' else 32
         v, cores, kind, sample = cpu_rate(n_traj_per_core=per_core, cores=cores, y=yh[:, :, :cores * per_core].numpy())
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,
                'sample': sample + '; measurements = the first trajectories of this benchmark run (Philox)'}

@@ -55,12 +55,12 @@ def _block_scores(x, m, P, status, idx):
     return (r['stats'][:, d + d * d + 1] / cnt).cpu().numpy(), (r['lcr'][:, 0] / cnt).cpu().numpy()
 
 
-def reentry_demo(dur=200, mc_sims=100, x=None, y=None, keep_arrays=False):
+def reentry_demo(dur=200, mc_sims=100, x=None, y=None, keep_arrays=False, weights=None):
     """bsq_tracking.py:223-349 without the file output and the plots.  x (5, steps, mc), y (2, steps, mc): optional
     data (already sub-sampled); by default the truth is simulated on the device (Euler-Maruyama, dt = 0.05, every
     second point kept).  Returns the reference's result dict: 'alg_str' and, for 'state', 'position', 'velocity',
     'parameter', the arrays 'rmse' and 'inc' of shape (steps, n_alg); with keep_arrays also 'x', 'mean', 'cov'
-    (lists of device tensors per algorithm)."""
+    (lists of device tensors per algorithm).  weights: see below."""
     tau, disc_tau = 0.05, 0.1
     sys, obs, dyn = reentry_models()
     if x is None:
@@ -69,6 +69,13 @@ def reentry_demo(dur=200, mc_sims=100, x=None, y=None, keep_arrays=False):
         x, y = x[:, ::2, :].contiguous(), y[:, ::2, :].contiguous()
     xd, yd = scoring.to_device(x), scoring.to_device(y)
     alg = reentry_algorithms(dyn, obs)
+    if weights is not None:
+        # quadrature weights assigned from outside (the pattern of research/tpq/tpq_ungm.py:114-124), e.g. the values of a
+        # particular reference run: weights = {'dyn': (wm, Wc, Wcc), 'obs': (wm, Wc, Wcc)} for the three BSQ filters
+        for name, a in alg.items():
+            if name.startswith('bsqkf'):
+                a.tf_dyn.wm, a.tf_dyn.Wc, a.tf_dyn.Wcc = weights['dyn']
+                a.tf_obs.wm, a.tf_obs.Wc, a.tf_obs.Wcc = weights['obs']
     res = scoring.run_all(list(alg.values()), yd, smooth=False)
     parts = {'state': [0, 1, 2, 3, 4], 'position': [0, 1], 'velocity': [2, 3], 'parameter': [4]}
     out = {'duration': dur, 'disc_tau': disc_tau, 'alg_str': list(alg.keys())}

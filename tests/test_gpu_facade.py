@@ -761,12 +761,14 @@ def test_public_predictive_measurement_attributes():
         for a in ('x_mean_pr', 'x_cov_pr', 'xx_cov', 'y_mean_pr', 'y_cov_pr', 'xy_cov'):
             got, want = np.asarray(getattr(alg, a)), g[name + '_' + a]
             assert got.shape == want.shape, (name, a, got.shape, want.shape)
-            assert rel(got, want) < tol, (name, a, rel(got, want))
+            # exact zeros of the device's cancellation-exact sums against the reference's 1e-17 residues (UNGMNA)
+            assert rel(got, want) < tol or np.abs(got - want).max() < 1e-12, (name, a, rel(got, want))
         alg.reset()
         assert alg.y_mean_pr is None
         alg.forward_pass(y)                                   # batched: trajectory axis last
         assert alg.y_mean_pr.shape == want.shape[:0] + (g[name + '_y_mean_pr'].shape[0], y.shape[2])
-        assert rel(alg.y_cov_pr[..., 0], g[name + '_y_cov_pr']) < tol and rel(alg.xy_cov[..., 0], g[name + '_xy_cov']) < tol
+        assert rel(alg.y_cov_pr[..., 0], g[name + '_y_cov_pr']) < tol
+        assert rel(alg.xy_cov[..., 0], g[name + '_xy_cov']) < tol or np.abs(alg.xy_cov[..., 0] - g[name + '_xy_cov']).max() < 1e-12
         alg.reset()
 
 

@@ -114,6 +114,29 @@ def test_reentry_demo_matches_reference_driver():
             np.testing.assert_allclose(out[part]['inc'][:, a], g[part + '_inc'][:, a], atol=ti, err_msg=part)
 
 
+def test_reentry_demo_with_the_reference_weights_assigned():
+    """The same driver with the reference's own BSQ weights assigned (they are the weights of the golden case
+    c3_reentry_bsq: same kernel parameters and multi-index): what is left is the per-step arithmetic of barely positive
+    definite recursions -- expected model variances of 2e-4 .. 2e-7 on covariances of 1e-6 --, so the agreement is that
+    of the whole-trajectory BQ comparisons of tests/test_gpu_parity.py (un-centred covariances: the reference's own
+    float64 noise floor, amplified over 20 steps), orders of magnitude below the package-weights variant above."""
+    from ssmtoybox_b200.research import bsq_tracking
+    g, w = golden('research_bsq_reentry_demo'), golden('c3_reentry_bsq')
+    weights = {'dyn': (w['dyn_wm'], w['dyn_Wc'], w['dyn_Wcc']), 'obs': (w['obs_wm'], w['obs_Wc'], w['obs_Wcc'])}
+    out = bsq_tracking.reentry_demo(dur=float(g['dur']), x=g['x'], y=g['y'], keep_arrays=True, weights=weights)
+    assert out['n_failed'] == [0, 0, 0, 0]
+    # tolerances = 10x what the oracle's explicit-loop float64 back-end (same weights, same data) is away from the
+    # reference's LAPACK-based run: 1.6e-9 / 2.6e-7 / 2.9e-6 on the means, 3e-8 / 3e-6 / 5e-5 on the covariances for
+    # model variances 2e-4 / 2e-6 / 2e-7 -- the smaller the assigned variance, the closer to indefinite the recursion
+    for a, (tm, tc, tr, ti) in enumerate([(2e-8, 4e-7, 1e-7, 1e-5), (3e-6, 3e-5, 1e-5, 1e-3), (3e-5, 5e-4, 1e-4, 1e-2)]):
+        em = relstep(out['mean'][a].cpu().numpy(), g['mean'][..., a])
+        ec = relstep(out['cov'][a].cpu().numpy(), g['cov'][..., a])
+        assert em < tm and ec < tc, (a, em, ec)
+        for part in ('state', 'position', 'velocity'):
+            np.testing.assert_allclose(out[part]['rmse'][:, a], g[part + '_rmse'][:, a], rtol=tr, err_msg=part)
+            np.testing.assert_allclose(out[part]['inc'][:, a], g[part + '_inc'][:, a], atol=ti, err_msg=part)
+
+
 def test_tpq_base_scores():
     from ssmtoybox_b200.research import tpq_base
     g = golden('research_tpq_base')
