@@ -606,19 +606,28 @@ def test_noise_dominated_filters_against_the_longdouble_arbiter(name):
     assert rel(rm_g, rm_r) <= 10.0 * worst['fi_mean'] + 1e-12, (rel(rm_g, rm_r), worst)
 
 
-def test_ctrs_fixture_against_the_float64_spread():
+def test_ctrs_fixture_invariants():
     """c10_ctrs_fixture_ukf, the reference's own CTRS test fixture (zero initial mean: the object starts on top of the
-    radar and the sign of a 1e-18 rounding residue decides the bearing of the central sigma point).  A longdouble run
-    takes the other branch at the first step, so the arbiter here is the spread among float64 implementations of the
-    same recursion: the device stays within 10x the distance between the oracle's two float64 back-ends (LAPACK calls
-    like the reference / explicit loops), measured against the reference, while that distance is below 1e-2."""
+    radar and the sign of 1e-18 rounding residues of the predicted position decides the bearing of the sigma points).
+    The recursion is chaotic at that level: moving the initial mean by 1e-13 changes the ORACLE's filtered means by
+    O(1) relative from the first step on (asserted below), so no implementation -- LAPACK-based, explicit loops,
+    longdouble, or this kernel with its fused multiply-adds -- can be compared with another over the trajectory.  What
+    every correct implementation shares is asserted: the failure status, the first predictive moments, per-step
+    parity when restarted from the reference's own filtered moments (test_one_step_parity_1e9 covers this case), and
+    finite, symmetric positive definite covariances throughout."""
     name = 'c10_ctrs_fixture_ukf'
     g = golden(name)
-    a = so.forward_pass(g, g['y'], backend='loops')
+    d = dict(g)
+    d['m0'] = np.asarray(g['m0'], dtype=float) + np.array([1e-13, 1e-13, 0, 0, 0])
+    a, b = so.forward_pass(g, g['y'], backend='loops'), so.forward_pass(d, g['y'], backend='loops')
+    assert relstep(a['fi_mean'][:, :5], b['fi_mean'][:, :5]) > 1e-2          # 1e-13 in, O(1) out: nothing to compare against
     low, o = run_filter(g, g['y'])
     assert np.array_equal(N_(o['status']) >> 8, g['status'])
-    assert relstep(N_(o['pr_mean'])[:, :1], g['pr_mean'][:, 1:2]) < 1e-9           # the first predictive moments are exact
-    for key in ('fi_mean', 'fi_cov'):
-        spread, eg = _cum_step_err(a[key], g[key]), _cum_step_err(N_(o[key]), g[key])
-        valid = spread < 1e-2
-        assert np.all(eg[valid] <= 10.0 * spread[valid] + 1e-9), (key, float(eg[valid].max()), float(spread[valid].max()))
+    assert np.abs(N_(o['pr_mean'])[:, :1] - g['pr_mean'][:, 1:2]).max() < 1e-15   # rounding residues of an exact zero
+    assert relstep(N_(o['pr_cov'])[:, :, :1], g['pr_cov'][:, :, 1:2]) < 1e-9
+    P = N_(o['fi_cov'])
+    assert np.isfinite(N_(o['fi_mean'])).all() and np.isfinite(P).all()
+    assert np.abs(P - P.transpose(1, 0, 2, 3)).max() == 0.0
+    for k in range(P.shape[2]):
+        for i in range(P.shape[3]):
+            np.linalg.cholesky(P[:, :, k, i])
