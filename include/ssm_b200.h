@@ -360,6 +360,17 @@ int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_state, int32_t
                         const double *par, const ssm_transform *tf, double time,
                         const double *mean, const double *cov, double *mean_f, double *cov_f, double *cov_fx,
                         int32_t *status, int64_t n, int64_t ld, void *stream);
+
+/* The same transform (GPQ / BSQ kind: un-centred form, dense Wc, + model_var I) with one weight set PER COLUMN, all on
+ * the device in the layout ssm_bq_weights writes: wm (n, N), Wc (n, N, N), Wcc (n, D, N), model_var (n) (nullable = 0).
+ * points (D, N) on the host.  Replaces BQTransform.apply(f, mean, cov, fcn_par, kern_par) (bq/bqmtran.py:60-109 with
+ * kern_par given: weights recomputed per call) for the batches of (trajectory, parameter vector) pairs that
+ * MarginalInference evaluates (ssinf.py:1107-1185).  Additive models (the dispatch of ssm_model_eval). */
+int ssm_transform_apply_batched(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,
+                                const double *par, int32_t n_pts, const double *points, const double *wm,
+                                const double *Wc, const double *Wcc, const double *model_var, double time,
+                                const double *mean, const double *cov, double *mean_f, double *cov_f, double *cov_fx,
+                                int32_t *status, int64_t n, int64_t ld, void *stream);
 int ssm_model_eval(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,
                    const double *par, double time, const double *x, const double *noise, double *out,
                    int64_t n, int64_t ld, void *stream);

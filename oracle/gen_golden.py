@@ -802,9 +802,41 @@ def gen_public_attrs():
     save('public_attrs', **d)
 
 
+def gen_marginal(steps=15, mc=2):
+    """MarginalizedGaussianProcessKalman (ssinf.py:1034-1296) on the UNGM of tests/test_ssinf.py:267-316 (spherical-radial
+    points): per step a BFGS Laplace approximation over the kernel log-parameters and a spherical-radial mixture of the
+    conditional state posteriors.  Filtered moments and the parameter posterior after every step of every trajectory."""
+    np.random.seed(31)
+    x0 = GaussRV(1, cov=np.atleast_2d(1.0))
+    q = GaussRV(1, cov=np.atleast_2d(10.0))
+    dyn = ssmod.UNGMTransition(x0, q)
+    obs = ssmod.UNGMMeasurement(GaussRV(1, cov=np.atleast_2d(1.0)), 1)
+    x = dyn.simulate_discrete(steps, mc_sims=mc)
+    y = obs.simulate_measurements(x)
+    fm, fc = np.zeros((1, steps, mc)), np.zeros((1, 1, steps, mc))
+    pm, pc = np.zeros((4, steps, mc)), np.zeros((4, 4, steps, mc))
+    for i in range(mc):
+        alg = ssinf.MarginalizedGaussianProcessKalman(dyn, obs, 'rbf', 'sr')
+        # step by step, to record the parameter posterior of every step (forward_pass: ssinf.py:101-111)
+        for k in range(1, steps + 1):
+            alg._time_update(k - 1)
+            alg._measurement_update(y[:, k - 1, i], k)
+            fm[:, k - 1, i], fc[:, :, k - 1, i] = alg.x_mean_fi, alg.x_cov_fi
+            pm[:, k - 1, i], pc[:, :, k - 1, i] = alg.param_mean, alg.param_cov
+    # the two building blocks at fixed parameter vectors (first step of trajectory 0): un-normalised negative log
+    # posterior (ssinf.py:1225-1245) and conditional state posterior moments (:1118-1143)
+    alg = ssinf.MarginalizedGaussianProcessKalman(dyn, obs, 'rbf', 'sr')
+    rs = np.random.RandomState(3)
+    thetas = 0.7 * rs.randn(6, 4)
+    obj = np.array([alg._param_neg_log_posterior(th, y[:, 0, 0], 1) for th in thetas])
+    cm = np.array([alg._state_posterior_moments(th, y[:, 0, 0], 1)[0] for th in thetas])
+    cc = np.array([alg._state_posterior_moments(th, y[:, 0, 0], 1)[1] for th in thetas])
+    save('marginal_ungm', x=x, y=y, fi_mean=fm, fi_cov=fc, param_mean=pm, param_cov=pc, thetas=thetas, obj=obj, cond_mean=cm, cond_cov=cc)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'large_pointsets': gen_large_pointsets, 'weights': gen_weights, 'simulation': gen_simulation,
-            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope, 'public_attrs': gen_public_attrs}
+            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope, 'public_attrs': gen_public_attrs, 'marginal': gen_marginal}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

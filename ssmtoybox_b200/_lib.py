@@ -117,6 +117,9 @@ def _load():
     lib.ssm_transform_apply.restype = C.c_int
     lib.ssm_transform_apply.argtypes = [i32, i32, i32, i32, i32, c_double_p, C.POINTER(SsmTransform), dbl, vp, vp, vp, vp,
                                         vp, vp, i64, i64, vp]
+    lib.ssm_transform_apply_batched.restype = C.c_int
+    lib.ssm_transform_apply_batched.argtypes = [i32, i32, i32, i32, i32, c_double_p, i32, c_double_p, vp, vp, vp, vp, dbl, vp, vp, vp, vp,
+                                                vp, vp, i64, i64, vp]
     lib.ssm_model_eval.restype = C.c_int
     lib.ssm_model_eval.argtypes = [i32, i32, i32, i32, i32, c_double_p, dbl, vp, vp, vp, i64, i64, vp]
     lib.ssm_rbf_eval.restype = C.c_int

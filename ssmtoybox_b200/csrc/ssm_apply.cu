@@ -41,6 +41,10 @@ struct ApplyPar {
     double *mean_f, *cov_f, *cov_fx;
     int32_t *status;
     long long n, ld;
+    // per-column weight sets (ssm_transform_apply_batched): column t reads wm + t N, Wc + t N^2, Wcc + t D N and adds
+    // model_var[t] I to the covariance; batched = 0: one weight set for all columns
+    int batched;
+    const double *mv_col;
 };
 
 template <class Fn, int KIND>
@@ -48,6 +52,19 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
     constexpr int D = Fn::D, E = Fn::E;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.n) return;
+    TfGlobal<D, E> tf = p.tf;
+    if (p.batched) {
+        const long long N = tf.n;
+        tf.wm_ += t * N;
+        tf.Wc_ += t * N * N;
+        tf.Wcc_ += t * D * N;
+        if (p.mv_col) {
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b < E; ++b) tf.mv_[a][b] = (a == b) ? p.mv_col[t] : 0.0;
+        }
+    }
     double m[D], P[TriSize<D>::value], mf[E], Cf[TriSize<E>::value], Cfx[E][D];
 #pragma unroll
     for (int a = 0; a < D; ++a) m[a] = p.mean[(long long)a * p.ld + t];
@@ -56,7 +73,7 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
 #pragma unroll
         for (int c = 0; c <= r; ++c) P[tri(r, c)] = p.cov[(long long)(r * D + c) * p.ld + t];
     const bool ok = moment_transform<D, E, PTS_GENERIC, 0, KIND, 0, Fn::EXACT>(
-        p.tf, m, P,
+        tf, m, P,
         [&](const double (&x)[D], double (&o)[E]) {
             const double z[Fn::NQ] = {};
             Fn::template ev<false>(p.par, x, z, p.time, o);
@@ -105,6 +122,33 @@ static int launch_apply(const ssm_transform &tf, const double *par, double time,
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(dev, s);
     free(host);
+    return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
+}
+
+// BQ transform with one weight set PER COLUMN, all of them already on the device (the (n, N) / (n, N, N) / (n, D, N) outputs
+// of ssm_bq_weights): the moment transforms of MarginalInference, where every (trajectory, parameter vector) pair has
+// its own kernel parameters (ssinf.py:1107-1185)
+template <class Fn>
+static int launch_apply_batched(int n_pts, const double *points, const double *wm, const double *Wc, const double *Wcc,
+                                const double *mv_col, const double *par, double time, const double *mean, const double *cov,
+                                double *mean_f, double *cov_f, double *cov_fx, int32_t *status, long long n, long long ld, cudaStream_t s) {
+    constexpr int D = Fn::D, E = Fn::E;
+    if (n_pts < 1 || n_pts > GEN_CAP) { set_error("ssm_transform_apply_batched: 1 .. %d points, got %d", GEN_CAP, n_pts); return SSM_E_UNSUPPORTED; }
+    double *dev = nullptr;
+    if (scratch_alloc((void **)&dev, (size_t)D * n_pts * sizeof(double), s) != cudaSuccess) return SSM_E_CUDA;
+    cudaMemcpyAsync(dev, points, (size_t)D * n_pts * sizeof(double), cudaMemcpyHostToDevice, s);   // pageable source: staged before return
+    ApplyPar<D, E> p;
+    memset(&p, 0, sizeof(p));
+    p.tf.n = n_pts;
+    p.tf.wm_ = wm; p.tf.wc_ = wm; p.tf.Wc_ = Wc; p.tf.Wcc_ = Wcc; p.tf.iK_ = Wc; p.tf.U_ = dev;
+    p.batched = 1;
+    p.mv_col = mv_col;
+    for (int i = 0; i < 8; ++i) p.par[i] = par ? par[i] : 0.0;
+    p.time = time; p.mean = mean; p.cov = cov; p.mean_f = mean_f; p.cov_f = cov_f; p.cov_fx = cov_fx; p.status = status;
+    p.n = n; p.ld = ld;
+    apply_kernel<Fn, SSM_TF_BQ><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dev, s);
     return e == cudaSuccess ? SSM_OK : SSM_E_CUDA;
 }
 
@@ -176,6 +220,25 @@ extern "C" int ssm_transform_apply(int32_t which, int32_t model, int32_t dim_sta
     else SSM_FN_DISPATCH(CALL)
 #undef CALL
     if (rc == SSM_E_CUDA) set_error("ssm_transform_apply: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    return rc;
+}
+
+extern "C" int ssm_transform_apply_batched(int32_t which, int32_t model, int32_t dim_state, int32_t si0, int32_t si1,
+                                           const double *par, int32_t n_pts, const double *points, const double *wm,
+                                           const double *Wc, const double *Wcc, const double *model_var, double time,
+                                           const double *mean, const double *cov, double *mean_f, double *cov_f,
+                                           double *cov_fx, int32_t *status, int64_t n, int64_t ld, void *stream) {
+    if (!points || !wm || !Wc || !Wcc || !mean || !cov || !mean_f || !cov_f || !cov_fx || !status) {
+        set_error("ssm_transform_apply_batched: NULL argument");
+        return SSM_E_INVALID;
+    }
+    if (n <= 0) return SSM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = SSM_OK;
+#define CALL(FN) rc = launch_apply_batched<FN>(n_pts, points, wm, Wc, Wcc, model_var, par, time, mean, cov, mean_f, cov_f, cov_fx, status, n, ld, s);
+    SSM_FN_DISPATCH(CALL)
+#undef CALL
+    if (rc == SSM_E_CUDA) set_error("ssm_transform_apply_batched: CUDA error: %s", cudaGetErrorString(cudaPeekAtLastError()));
     return rc;
 }
 

@@ -411,7 +411,7 @@ def simulate_measurements(low, x, rng=None, r=None):
 # ------------------------------------------------------------------------------------------------
 # K5: Bayesian-quadrature weights
 # ------------------------------------------------------------------------------------------------
-def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
+def bq_weights(par, points, mulind=None, device='cuda', precision='dd', to_host=True):
     """Batched BQ weights (ssm_bq_weights).  par (n_par, D+1), points (D, N), mulind (D, Q) or None.
     Returns dict of numpy arrays: wm (n_par, N), Wc (n_par, N, N), Wcc (n_par, D, N), iK (n_par, N, N),
     model_var (n_par,), integral_var (n_par,), info (n_par,).
@@ -439,9 +439,32 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd'):
                             _p(wm), _p(Wc), _p(Wcc), _p(iK), _p(scal), _p(info), 0 if precision == 'float64' else 1,
                             _stream())
     _lib.check(rc, 'ssm_bq_weights')
+    if to_host is False:   # device tensors in the layout ssm_transform_apply_batched reads
+        return dict(wm=wm, Wc=Wc, Wcc=Wcc, iK=iK, model_var=scal[:, 0].contiguous(), integral_var=scal[:, 1].contiguous(), info=info)
     sc = scal.cpu().numpy()
     return dict(wm=wm.cpu().numpy(), Wc=Wc.cpu().numpy(), Wcc=Wcc.cpu().numpy(), iK=iK.cpu().numpy(),
                 model_var=sc[:, 0].copy(), integral_var=sc[:, 1].copy(), info=info.cpu().numpy())
+
+
+def transform_apply_batched(which, model_id, dim_state, si, par, points, w, time, mean, cov):
+    """GPQ / BSQ moment transform of n (mean, cov) columns with one weight set per column (ssm_transform_apply_batched).
+    w: dict of device tensors from bq_weights(..., to_host=False) with n parameter vectors; mean (D, n), cov (D, D, n)
+    device tensors.  Returns mean_f (E, n), cov_f (E, E, n), cov_fx (E, D, n), status (n,) on the device."""
+    points = _c(points)
+    D, N = points.shape
+    n = mean.shape[1]
+    E = {0: dim_state}.get(which)
+    if which == 1:
+        E = int(w['_dim_out'])
+    kw = dict(dtype=torch.float64, device=mean.device)
+    mf, cf, cfx = torch.empty((E, n), **kw), torch.empty((E, E, n), **kw), torch.empty((E, D, n), **kw)
+    status = torch.empty((n,), dtype=torch.int32, device=mean.device)
+    p8 = (C.c_double * 8)(*(list(par) + [0.0] * (8 - len(par))))
+    rc = lib.ssm_transform_apply_batched(which, model_id, dim_state, si[0], si[1], p8, N, _ptr(points), _p(w['wm']), _p(w['Wc']),
+                                         _p(w['Wcc']), _p(w['model_var']), float(time), _p(mean.contiguous()), _p(cov.contiguous()),
+                                         _p(mf), _p(cf), _p(cfx), _p(status), n, n, _stream())
+    _lib.check(rc, 'ssm_transform_apply_batched')
+    return mf, cf, cfx, status
 
 
 # ------------------------------------------------------------------------------------------------

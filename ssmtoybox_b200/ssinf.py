@@ -432,3 +432,277 @@ class FullySymmetricStudent(StudentianInference):
         t_dyn = FullySymmetricStudentTransform(dyn.dim_in, degree, kappa, dyn_dof)
         t_obs = FullySymmetricStudentTransform(obs.dim_in, degree, kappa, obs_dof)
         super(FullySymmetricStudent, self).__init__(dyn, obs, t_dyn, t_obs, dof, fixed_dof)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# marginalised moment-transform parameters (ssinf.py:1034-1273; "purely for experimental purposes" in the reference)
+# ------------------------------------------------------------------------------------------------------------------
+class _Rendezvous(object):
+    """Batches the objective evaluations of many scipy optimisers running in parallel threads: every optimiser blocks in
+    request(theta) until ALL optimisers that are still running have asked for a point; the main thread then evaluates
+    the whole batch in one device pass and releases them.  The optimiser itself is scipy's own BFGS -- the algorithm,
+    line search and finite-difference gradient of the reference (ssinf.py:1271) -- so the search path is the
+    reference's; only the objective values come from the device."""
+
+    def __init__(self, n):
+        import threading
+        self.cv = threading.Condition()
+        self.n_running = n
+        self.pending = {}
+        self.results = {}
+
+    def request(self, tid, theta):
+        with self.cv:
+            self.pending[tid] = np.array(theta, dtype=np.float64)
+            self.cv.notify_all()
+            while tid not in self.results:
+                self.cv.wait()
+            return self.results.pop(tid)
+
+    def finish(self, tid):
+        with self.cv:
+            self.n_running -= 1
+            self.cv.notify_all()
+
+    def serve(self, evaluate):
+        """main thread: evaluate(ids, thetas (n, P)) -> values (n,) until every optimiser has finished"""
+        while True:
+            with self.cv:
+                while self.n_running > 0 and len(self.pending) < self.n_running:
+                    self.cv.wait()
+                if self.n_running == 0:
+                    return
+                ids = sorted(self.pending)
+                thetas = np.stack([self.pending.pop(i) for i in ids])
+            vals = evaluate(ids, thetas)
+            with self.cv:
+                for i, v in zip(ids, vals):
+                    self.results[i] = float(v)
+                self.cv.notify_all()
+
+
+class MarginalInference(GaussianInference):
+    """Gaussian filter with the moment-transform (kernel) parameters marginalised out (ssinf.py:1034-1273): per time
+    step a Laplace approximation of the posterior over the log-parameters (BFGS on the un-normalised negative log
+    posterior, its inverse-Hessian estimate as covariance, :1247-1273), then a spherical-radial rule over that posterior
+    mixes the conditional state posteriors (:1089-1116).
+
+    Device mapping: every objective evaluation of every trajectory, and the 2 P conditional state posteriors per
+    trajectory, are (trajectory, parameter vector) PAIRS evaluated in batches -- quadrature weights per pair
+    (ssm_bq_weights, one CTA per parameter vector) and both moment transforms with one weight set per column
+    (ssm_transform_apply_batched).  The optimiser is scipy's BFGS, one instance per trajectory, run in lock step
+    (_Rendezvous).  Batched extension: forward_pass(data (dy, N, M)).  Additive models; no smoother in the reference.
+
+    Reference quirks kept: the measurement update evaluates both transforms with time = k where the plain time update
+    uses k - 1 (:66-118 vs :1089-1116); pr_mean / pr_cov / pr_xx_cov come from a time update with whatever weights the
+    previous step's last parameter point left in the transform objects (:104-107)."""
+
+    def __init__(self, dyn, obs, tf_dyn, tf_obs, par_mean=None, par_cov=None):
+        super(MarginalInference, self).__init__(dyn, obs, tf_dyn, tf_obs)
+        if not (dyn.noise_additive and obs.noise_additive):
+            raise NotImplementedError('MarginalInference on the device: additive noise models')
+        self.param_dyn_dim = self.mod_dyn.dim_in + 1
+        self.param_obs_dim = self.mod_obs.dim_state + 1
+        self.param_dim = self.param_dyn_dim + self.param_obs_dim
+        self.param_prior_mean = np.zeros(self.param_dim, ) if par_mean is None else np.asarray(par_mean, dtype=np.float64)
+        self.param_prior_cov = np.eye(self.param_dim) if par_cov is None else np.asarray(par_cov, dtype=np.float64)
+        self.param_mean = self.param_prior_mean
+        self.param_cov = self.param_prior_cov
+        self.param_jitter = 1e-8 * np.eye(self.param_dim)
+        self.param_upts = SphericalRadialTransform.unit_sigma_points(self.param_dim)
+        self.param_wts = SphericalRadialTransform.weights(self.param_dim)
+        self.param_pts_num = self.param_upts.shape[1]
+        self.max_threads = 256          # optimisers in flight (one thread each); larger batches run in groups
+
+    def reset(self):
+        super(MarginalInference, self).reset()
+        self.param_mean = self.param_prior_mean
+        self.param_cov = self.param_prior_cov
+
+    # -- batched pair evaluation --------------------------------------------------------------------------------
+    def _pairs(self, theta, mean, cov, time):
+        """Time update with per-column parameters (ssinf.py:1137-1168): theta (n, P) log-parameters, mean (dx, n),
+        cov (dx, dx, n) device tensors -> x_mean_pr, x_cov_pr, xx_cov, y_mean_pr, y_cov_pr, xy_cov (device), ok (n,)."""
+        from .bq import bqmod
+        prec = bqmod.get_weight_precision()
+        dyn, obs = self.mod_dyn, self.mod_obs
+        td, to = np.exp(theta[:, :self.param_dyn_dim]), np.exp(theta[:, self.param_dyn_dim:])
+        wd = dv.bq_weights(td, self.tf_dyn.model.points, precision=prec, to_host=False)
+        wo = dv.bq_weights(to, self.tf_obs.model.points, precision=prec, to_host=False)
+        wo['_dim_out'] = obs.dim_out
+        dev = mean.device
+        mp, Pp, Pxx, s1 = dv.transform_apply_batched(0, dyn._device_id, dyn.dim_state, (0, 0), dyn._par(), self.tf_dyn.model.points,
+                                                     wd, time, mean, cov)
+        GQG = torch.as_tensor(np.asarray(self.G.dot(self.q_cov).dot(self.G.T), dtype=np.float64), device=dev)
+        Pp = Pp + GQG[:, :, None]                                                          # ssinf.py:278-279
+        my, Py, Pxy, s2 = dv.transform_apply_batched(1, obs._device_id, obs.dim_state, obs._si(), obs._par(), self.tf_obs.model.points,
+                                                     wo, time, mp, Pp)
+        Py = Py + torch.as_tensor(np.asarray(self.r_cov, dtype=np.float64), device=dev)[:, :, None]      # ssinf.py:290-291
+        ok = (wd['info'] == 0) & (wo['info'] == 0) & (s1 == 0) & (s2 == 0)
+        return mp, Pp, Pxx, my, Py, Pxy, ok, (wd, wo)
+
+    @staticmethod
+    def _logpdf(y, mean, cov):
+        """log N(y | mean, cov) per column (scipy.stats.multivariate_normal.logpdf, ssinf.py:1185): y, mean (dy, n),
+        cov (dy, dy, n) numpy."""
+        dy, n = mean.shape
+        d = (y - mean).T[:, :, None]                       # (n, dy, 1)
+        S = np.moveaxis(cov, -1, 0)                        # (n, dy, dy)
+        with np.errstate(all='ignore'):
+            try:
+                L = np.linalg.cholesky(S)
+            except np.linalg.LinAlgError:
+                L = np.full_like(S, np.nan)
+                for i in range(n):
+                    try:
+                        L[i] = np.linalg.cholesky(S[i])
+                    except np.linalg.LinAlgError:
+                        pass
+            z = np.linalg.solve(L, d)[:, :, 0] if np.isfinite(L).all() else np.stack(
+                [np.linalg.solve(L[i], d[i])[:, 0] if np.isfinite(L[i]).all() else np.full(dy, np.nan) for i in range(n)])
+            logdet = 2.0 * np.log(np.diagonal(L, axis1=1, axis2=2)).sum(axis=1)
+            return -0.5 * (dy * np.log(2.0 * np.pi) + logdet + (z * z).sum(axis=1))
+
+    def forward_pass(self, data):
+        """data (dy, N) or (dy, N, M) -> (dx, N[, M]), (dx, dx, N[, M]) (ssinf.py:66-118 with the measurement update of
+        :1089-1116).  Also fills param_mean (P[, M]) / param_cov (P, P[, M]) with the last parameter posterior."""
+        import threading
+        from scipy.optimize import minimize
+        is_torch = isinstance(data, torch.Tensor)
+        y_all = data.detach().cpu().numpy() if is_torch else np.asarray(data, dtype=np.float64)
+        single = y_all.ndim == 2
+        if single:
+            y_all = y_all[:, :, None]
+        dy, N, M = y_all.shape
+        dx, P = self.mod_dyn.dim_state, self.param_dim
+        self.D, self.N = dy, N
+        dev = torch.device('cuda', torch.cuda.current_device())
+        kw = dict(dtype=torch.float64, device=dev)
+        carry = self._carry
+        m = torch.as_tensor(np.repeat(np.asarray(self.x_mean_fi, dtype=np.float64).reshape(dx, 1), M, axis=1), **kw) \
+            if carry is None else carry[0].clone()
+        Pc = torch.as_tensor(np.repeat(np.asarray(self.x_cov_fi, dtype=np.float64).reshape(dx, dx, 1), M, axis=2), **kw) \
+            if carry is None else carry[1].clone()
+        mu = np.repeat(np.asarray(self.param_mean, dtype=np.float64).reshape(P, -1)[:, :1], M, axis=1) if np.ndim(self.param_mean) == 1 \
+            else np.array(self.param_mean, dtype=np.float64)
+        Pi = np.repeat(np.asarray(self.param_cov, dtype=np.float64).reshape(P, P, -1)[:, :, :1], M, axis=2) if np.ndim(self.param_cov) == 2 \
+            else np.array(self.param_cov, dtype=np.float64)
+        fi_mean, fi_cov = torch.full((dx, N, M), float('nan'), **kw), torch.full((dx, dx, N, M), float('nan'), **kw)
+        pr_mean, pr_cov, pr_xx = torch.full((dx, N, M), float('nan'), **kw), torch.full((dx, dx, N, M), float('nan'), **kw), \
+            torch.full((dx, dx, N, M), float('nan'), **kw)
+        status = np.zeros(M, dtype=np.int32)
+        # weights left in the transform objects (dummy unit parameters before the first step), as log-parameters
+        last_theta = np.repeat(np.log(np.concatenate([np.asarray(self.tf_dyn.model.kernel.par, dtype=np.float64).reshape(-1),
+                                                      np.asarray(self.tf_obs.model.kernel.par, dtype=np.float64).reshape(-1)]))[None], M, axis=0)
+        for k in range(1, N + 1):
+            alive = np.nonzero(status == 0)[0]
+            if alive.size == 0:
+                break
+            yk = y_all[:, k - 1, :]
+            # plain time update of forward_pass (time k - 1) with the weights of the previous step's last parameter point
+            mp, Pp, Pxx, _, _, _, _, _ = self._pairs(last_theta[alive], m[:, alive], Pc[:, :, alive], k - 1)
+            pr_mean[:, k - 1, alive], pr_cov[:, :, k - 1, alive], pr_xx[:, :, k - 1, alive] = mp, Pp, Pxx
+            # ---- Laplace approximation of the parameter posterior (ssinf.py:1247-1273): one BFGS per trajectory --------
+            for g0 in range(0, alive.size, self.max_threads):
+                grp = alive[g0:g0 + self.max_threads]
+                rv = _Rendezvous(len(grp))
+                res = {}
+                Pi_inv = {int(i): np.linalg.inv(Pi[:, :, i]) for i in grp}
+                ldet = {int(i): np.linalg.slogdet(Pi[:, :, i])[1] for i in grp}
+
+                def evaluate(ids, thetas):
+                    idx = np.asarray(ids)
+                    _, _, _, my, Py, _, ok, _ = self._pairs(thetas, m[:, idx], Pc[:, :, idx], k)
+                    ll = self._logpdf(yk[:, idx], my.cpu().numpy(), Py.cpu().numpy())
+                    out = np.empty(len(ids))
+                    okh = ok.cpu().numpy()
+                    for j, i in enumerate(ids):
+                        d = thetas[j] - mu[:, i]
+                        lp = -0.5 * (P * np.log(2.0 * np.pi) + ldet[i] + d.dot(Pi_inv[i]).dot(d))   # log N(theta | mu, Pi), :1204-1223
+                        out[j] = -ll[j] - lp if okh[j] and np.isfinite(ll[j]) else np.inf
+                    return out
+
+                def worker(i):
+                    try:
+                        res[i] = minimize(lambda th: rv.request(i, th), mu[:, i].copy(), method='BFGS')
+                    except Exception as e:      # noqa: BLE001
+                        res[i] = e
+                    finally:
+                        rv.finish(i)
+                threads = [threading.Thread(target=worker, args=(int(i),), daemon=True) for i in grp]
+                for t in threads:
+                    t.start()
+                rv.serve(evaluate)
+                for t in threads:
+                    t.join()
+                for i in grp:
+                    r = res[int(i)]
+                    if isinstance(r, Exception) or not np.all(np.isfinite(r.x)) or not np.all(np.isfinite(r.hess_inv)):
+                        status[i] = (k << 8) | _lib.FAIL_CHOL_GAIN
+                        continue
+                    mu[:, i], Pi[:, :, i] = r.x, r.hess_inv + self.param_jitter
+            alive = np.nonzero(status == 0)[0]
+            if alive.size == 0:
+                break
+            # ---- marginalisation over the parameter posterior (ssinf.py:1096-1116) ---------------------------------
+            pts = np.empty((alive.size, self.param_pts_num, P))
+            for a, i in enumerate(alive):
+                try:
+                    Lp = np.linalg.cholesky(Pi[:, :, i])
+                except np.linalg.LinAlgError:
+                    status[i] = (k << 8) | _lib.FAIL_CHOL_GAIN
+                    Lp = np.eye(P)
+                pts[a] = (mu[:, i][:, None] + Lp.dot(self.param_upts)).T
+            J = self.param_pts_num
+            idx = np.repeat(alive, J)
+            mp, Pp, _, my, Py, Pxy, ok, _ = self._pairs(pts.reshape(-1, P), m[:, idx], Pc[:, :, idx], k)
+            # conditional posteriors N(x_k | y_1:k, theta) (:1137-1143): tiny dy x dy solves, on the host
+            mpn, Ppn = mp.cpu().numpy(), Pp.cpu().numpy()
+            myn, Pyn, Pxyn = my.cpu().numpy(), Py.cpu().numpy(), Pxy.cpu().numpy()
+            okn = ok.cpu().numpy().reshape(alive.size, J)
+            yy = yk[:, idx]
+            S = np.moveaxis(Pyn, -1, 0)
+            C_ = np.moveaxis(Pxyn, -1, 0)                          # (n, dy, dx) = Cov(y, x)
+            with np.errstate(all='ignore'):
+                try:
+                    gain = np.swapaxes(np.linalg.solve(S, C_), 1, 2)   # (n, dx, dy) = (S^-1 Pyx)^T
+                except np.linalg.LinAlgError:
+                    gain = np.full((S.shape[0], dx, dy), np.nan)
+                mean_ij = mpn.T + np.einsum('nij,nj->ni', gain, (yy - myn).T)
+                cov_ij = np.moveaxis(Ppn, -1, 0) - np.einsum('nij,njk,nlk->nil', gain, S, gain)
+            mean_i = np.einsum('ajd,j->ad', mean_ij.reshape(alive.size, J, dx), self.param_wts)
+            cov_i = np.einsum('ajde,j->ade', cov_ij.reshape(alive.size, J, dx, dx), self.param_wts)
+            bad = ~okn.all(axis=1) | ~np.isfinite(mean_i).all(axis=1) | (status[alive] != 0)
+            status[alive[bad]] = np.where(status[alive[bad]] != 0, status[alive[bad]], (k << 8) | _lib.FAIL_CHOL_OBS)
+            good = alive[~bad]
+            m[:, good] = torch.as_tensor(np.ascontiguousarray(mean_i[~bad].T), **kw)
+            Pc[:, :, good] = torch.as_tensor(np.ascontiguousarray(np.moveaxis(cov_i[~bad], 0, -1)), **kw)
+            fi_mean[:, k - 1, good], fi_cov[:, :, k - 1, good] = m[:, good], Pc[:, :, good]
+            last_theta[alive] = pts[:, -1, :]
+        st = torch.as_tensor(status, device=dev)
+        fwd = {'fi_mean': fi_mean, 'fi_cov': fi_cov, 'pr_mean': pr_mean, 'pr_cov': pr_cov, 'pr_xx_cov': pr_xx, 'status': st,
+               'last_mean': m, 'last_cov': Pc,
+               'init_mean': torch.as_tensor(np.asarray(self.x0_mean, dtype=np.float64), **kw)[:, None].expand(-1, M),
+               'init_cov': torch.as_tensor(np.asarray(self.x0_cov, dtype=np.float64), **kw)[:, :, None].expand(-1, -1, M)}
+        self._fwd, self._sm, self._carry, self._single, self.status = fwd, None, (m, Pc), single, st
+        if single and int(status[0]) != 0:
+            self._raise_for_status(int(status[0]))
+        self._publish_forward(fwd, single, is_torch)
+        self.param_mean, self.param_cov = (mu[:, 0], Pi[:, :, 0]) if single else (mu, Pi)
+        self.set_flag('filtered', True)
+        return self._out(fwd['fi_mean']), self._out(fwd['fi_cov'])
+
+    def backward_pass(self):
+        raise NotImplementedError('MarginalInference has no smoother (the reference defines none that marginalises the parameters)')
+
+
+class MarginalizedGaussianProcessKalman(MarginalInference):
+    """GPQ Kalman filter with marginalised kernel parameters (ssinf.py:1276-1296; "for experimental purposes only")."""
+
+    def __init__(self, dyn, obs, kernel='rbf', points='ut', point_hyp=None, par_mean=None, par_cov=None):
+        # arbitrary dummy kernel parameters, because transforms wouldn't initialize (ssinf.py:1287-1289)
+        kpar_dyn = np.ones((1, dyn.dim_in + 1))
+        kpar_obs = np.ones((1, obs.dim_state + 1))
+        t_dyn = GaussianProcessTransform(dyn.dim_in, 1, kpar_dyn, kernel, points, point_hyp)
+        t_obs = GaussianProcessTransform(obs.dim_state, 1, kpar_obs, kernel, points, point_hyp)
+        super(MarginalizedGaussianProcessKalman, self).__init__(dyn, obs, t_dyn, t_obs, par_mean, par_cov)
