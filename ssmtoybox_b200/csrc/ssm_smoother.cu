@@ -224,8 +224,11 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
     if (fail && in_range) status[t] = ((kfail + 1) << 8) | fail;
 }
 
+#ifndef SSM_SMOOTH_SCORE_MINB
+#define SSM_SMOOTH_SCORE_MINB 1   // resident CTAs per SM the score-only kernel is compiled for (developer A/B)
+#endif
 template <int DX, bool SCORE, bool KEEP>
-__global__ void __launch_bounds__(SC_THREADS) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
+__global__ void __launch_bounds__(SC_THREADS, KEEP ? 1 : SSM_SMOOTH_SCORE_MINB) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
                                                               const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
                                                               const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
                                                               double *__restrict__ sm_cov, int32_t *__restrict__ status,

@@ -13,7 +13,11 @@ if 'reentry' in name and 'reentry1d' not in name:
 else:   # the other models: discrete simulation from the golden descriptor
     x, y = dv.simulate(low, M, N, rng=dv.make_rng(g, seed=1))
 o = {}
+scored = len(sys.argv) > 4 and sys.argv[4] == 'scored'     # scoring forward pass (ssm_filter_scores): no moment arrays
 for _ in range(3):
-    dv.filter_forward(low, y, store_pred=sp, out=o)
+    if scored:
+        dv.filter_scored(low, y, x, out=o)
+    else:
+        dv.filter_forward(low, y, store_pred=sp, out=o)
 torch.cuda.synchronize()
 print('ok', int((o['status'] != 0).sum()))
