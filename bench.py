@@ -430,6 +430,23 @@ def run_gpu_arm(args):
     e2e_value = comm.world_size * M * N / (max(e2e_ms, e2e_wall_ms) * 1e-3)
     d2h = 8 * (5 + 4 + 25 * N + N + 1) + 4 * M
 
+    h2d_bytes = int(yh.numel() + xh.numel()) * 8
+    y_cpu = yh[:, :, :64 * 48].clone().numpy() if (comm.world_size == 1 and not args.no_cpu) else None
+    # ---- configuration C5 next to the headline: one BSQ NCI sweep point per model, 10^6 x 100 per GPU, nothing
+    # materialised (simulate -> filter with in-kernel scoring -> second score phase); `python bench.py --config c5` times
+    # it as the workload of its own line
+    c5 = None
+    if not args.no_c5:
+        del yh, xh
+        torch.cuda.empty_cache()
+        from ssmtoybox_b200.research import bsq_nci_sweep as sw
+        c5 = {}
+        for model, flop in (('pendulum', 510.0), ('coordturn', 5668.0)):
+            Mc = 10 ** 6 * comm.world_size
+            sw.bsq_nci_sweep(model, mc_sims=(Mc,), model_var=(1e-2,), comm=comm, chunk=1 << 19)
+            r = sw.bsq_nci_sweep(model, mc_sims=(Mc,), model_var=(1e-2,), comm=comm, chunk=1 << 19)[0]
+            c5[model] = {'n_traj': Mc, 'n_steps': sw.N_STEPS, 'ms': 1e3 * r['seconds'], 'value': r['traj_steps_per_s'], 'unit': UNIT,
+                         'nci': r['nci'], 'n_failed': r['n_failed'], 'flop_per_unit': flop}
     if comm.rank != 0:
         return
     # ---- roofline of the dominant kernel -----------------------------------------------------------
@@ -440,6 +457,9 @@ def run_gpu_arm(args):
     except (OSError, ValueError):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    if c5:
+        for v in c5.values():
+            v['fp64_frac'] = v['value'] * v['flop_per_unit'] / fp64_peak / comm.world_size
     ach_tf = M * N * FLOP_FILTER / (k_filter * 1e-3) / 1e12
     prof = {}
     try:
@@ -462,14 +482,15 @@ def run_gpu_arm(args):
     if comm.world_size == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0))
         per_core = 48 if reference_kind() == 'reference' else 32
-        v, cores, kind, sample = cpu_rate(n_traj_per_core=per_core, cores=cores, y=yh[:, :, :cores * per_core].numpy())
+        cores = min(cores, 64)
+        v, cores, kind, sample = cpu_rate(n_traj_per_core=per_core, cores=cores, y=y_cpu[:, :, :cores * per_core])
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind,
                'sample': sample + '; measurements = the first trajectories of this benchmark run (Philox)'}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': comm.world_size, 'steps': args.steps, 'warmup': n_warm,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic (Philox Euler-Maruyama truth + radar measurements, seed 2026, keyed by global trajectory index)',
             'config': dict(CONFIG, n_traj_per_gpu=M),
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(yh.numel() + xh.numel()) * 8,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': max(e2e_ms, e2e_wall_ms),
                     'api': 'ssmtoybox_b200.mc.filter_scores(GaussianProcessKalman, y, x, smooth=True) on pinned host y, x: '
                            'time-windowed H2D (y forward in time, x backward) overlapped with forward pass + RTS smoother + '
@@ -480,6 +501,7 @@ def run_gpu_arm(args):
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
             'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,
             'clocks': clk, 'n_failed_trajectories': n_failed, 'scores': scores,
+            'c5': c5,
             'weights': 'reference-injected (tests/golden/c3_reentry_gpq.npz)' if args.weights == 'reference' else 'own (double-double ssm_bq_weights)',
             'warmup_steps_until_stable': n_warm,
             'parity': 'means 1e-9 per step; un-centred BQ covariances on this model to the reference\'s own float64 noise floor '
@@ -508,6 +530,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--traj', type=int, default=TRAJ_PER_GPU, help='trajectories per GPU (default: the C3 share)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--no-c5', action='store_true', help='skip the configuration-C5 sweep points reported next to the headline')
     ap.add_argument('--windows', type=int, default=20, help='time windows of the host-streaming (e2e) pipeline')
     ap.add_argument('--weights', default='reference', choices=['reference', 'own'],
                     help="quadrature weights of the C3 filter: the reference's own values (headline) or the package's")

@@ -10,7 +10,7 @@ set -x
 mkdir -p gpurun_out
 OUT=gpurun_out
 TAG=${TAG:-r2}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-c5"
 $CMD > $OUT/plain_launches.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches.log 2>&1
 echo "launch list rc=$?"
@@ -18,7 +18,7 @@ CMD2="python tools/one_launch.py 125000 100 c3_reentry_gpq pred"
 $CMD2 > $OUT/plain_filter.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:filter_kernel -s 2 -c 1 -o $OUT/prof_${TAG}_filter $CMD2 > $OUT/ncu_filter.log 2>&1
 echo "filter capture rc=$?"
-CMD3="python bench.py --steps 1 --warmup 3 --no-cpu --traj 37888"
+CMD3="python bench.py --steps 1 --warmup 3 --no-cpu --no-c5 --traj 37888"
 $CMD3 > $OUT/plain_smoother.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:smoother_kernel -s 3 -c 1 -o $OUT/prof_${TAG}_smoother $CMD3 > $OUT/ncu_smoother.log 2>&1
 echo "smoother capture rc=$?"
