@@ -70,10 +70,30 @@ SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 // own 2^k exp(r) with the coefficients in a constant-bank table (37 instructions per call, -430 per step) 16.14 / 20.45;
 // own Estrin-scheme evaluation with immediates (5-deep instead of 14-deep DFMA chain) 15.92 / 20.31.  Neither the issue
 // slots nor the chain latency of exp are what bounds the kernel; both were within 1 ulp of numpy.
+// Round 2: sqrt / rsqrt (17-21 instructions each, 31 calls per reentry step) are inlined again while exp / atan2 /
+// division stay out of line: a call costs ~10 marshalling instructions plus CALL / RET (28 % of the samples on these two
+// routines were `branch_resolving`), which is more than half of such a small body, and 31 x 20 instructions do not hurt the
+// instruction cache the way the 144 KB all-inline body did.  Measured on the reentry forward pass, 125 000 x 500:
+// 15.64 -> 14.66 ms filter only, 20.11 -> 19.50 ms with predictive moments (SSM_INLINE_SMALL_MATH=0 restores the calls).
+#ifndef SSM_INLINE_SMALL_MATH
+#define SSM_INLINE_SMALL_MATH 1
+#endif
+#ifndef SSM_INLINE_EXP
+#define SSM_INLINE_EXP 0
+#endif
+#if SSM_INLINE_SMALL_MATH
+#define SSM_SMALL_MATH_FN static __device__ __forceinline__
+#else
+#define SSM_SMALL_MATH_FN SSM_MATH_FN
+#endif
+#if SSM_INLINE_EXP
+static __device__ __forceinline__ double m_exp(double x) { return exp(x); }
+#else
 SSM_MATH_FN double m_exp(double x) { return exp(x); }
-SSM_MATH_FN double m_sqrt(double x) { return sqrt(x); }
+#endif
+SSM_SMALL_MATH_FN double m_sqrt(double x) { return sqrt(x); }
 SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
-SSM_MATH_FN double m_rsqrt(double x) { return rsqrt(x); }
+SSM_SMALL_MATH_FN double m_rsqrt(double x) { return rsqrt(x); }
 SSM_MATH_FN double m_div(double a, double b) { return a / b; }
 SSM_MATH_FN double m_atan2(double y, double x) { return atan2(y, x); }
 

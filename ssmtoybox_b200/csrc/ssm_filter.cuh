@@ -629,11 +629,11 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             if (b.pr_cov) {
                 double Cp[TX];
 #pragma unroll
-                for (int a = 0; a < TX; ++a) Cp[a] = Pp[a] + p.GQG[a];  // x_cov_pr, ssinf.py:675
+                for (int a = 0; a < TX; ++a) Cp[a] = Dyn::ADDITIVE ? Pp[a] + p.GQG[a] : Pp[a];  // x_cov_pr, ssinf.py:674-675 (additive noise only)
                 store_sym<DX>(b.pr_cov, cs, rk, Cp);
             }
 #pragma unroll
-            for (int a = 0; a < TX; ++a) Pp[a] = fma(scale, Pp[a], p.s0 * p.GQG[a]);  // x_smat_pr, ssinf.py:672, 676
+            for (int a = 0; a < TX; ++a) Pp[a] = Dyn::ADDITIVE ? fma(scale, Pp[a], p.s0 * p.GQG[a]) : scale * Pp[a];  // x_smat_pr, ssinf.py:672, 674-676
         } else {
             if (Dyn::ADDITIVE) {
 #pragma unroll
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         if (!ok) { fail = SSM_FAIL_CHOL_OBS; kfail = k; break; }
         if (FAMILY == SSM_FAMILY_STUDENT) {
 #pragma unroll
-            for (int a = 0; a < TY; ++a) Sy[a] = fma(scale, Sy[a], p.s0 * p.R[a]);
+            for (int a = 0; a < TY; ++a) Sy[a] = Obs::ADDITIVE ? fma(scale, Sy[a], p.s0 * p.R[a]) : scale * Sy[a];  // ssinf.py:687-693
 #pragma unroll
             for (int a = 0; a < DY; ++a)
 #pragma unroll
