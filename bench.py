@@ -18,12 +18,16 @@ of the packed error statistics).  One "step" = one pass of that hot path over th
   roofline : dominant kernel = the fused forward pass (FP64-pipe bound); achieved = algorithmic FLOPs per
           launch / its CUDA-event duration; peak = FP64 FMA rate measured in this run by a DFMA
           micro-kernel (MEASURED_PEAKS.json carries HBM and bf16 only)
-  cpu_baseline : the numpy port of the reference (oracle/, per-trajectory loop like the reference) on all
-          host cores, bounded sample of the same workload
+  cpu_baseline : the UNMODIFIED reference (pip-installed copy under baseline/_ref, imported through oracle/ref_shim.py;
+          per-trajectory forward_pass + backward_pass + reset like research/gpq/icinco_demo.py:120-124) on all host
+          cores, bounded sample of the same workload; the numpy port of oracle/ only if that copy cannot be imported
+          (`kind` says which ran)
+  c5    : BASELINE configuration C5 next to the headline: one BSQ NCI sweep point per model (10^6 x 100 per GPU,
+          simulate -> filter with in-kernel scoring -> second score phase, nothing materialised)
 
---impl reference times the reference's CPU implementation of the path.  The reference is pure Python and
-cannot travel to the GPU box (/root/reference does not exist there), so this arm runs the oracle port --
-the same calls in the same order, pinned to the reference by tests/golden -- on all host cores.
+--impl reference times the reference's own CPU implementation of the path the same way (data from the reference's own
+simulators, not timed); --weights own runs the headline with the package's own quadrature weights; --config c5 makes the
+C5 sweep point the timed workload of the line.
 """
 import argparse
 import json

@@ -117,3 +117,46 @@ def test_two_rank_gloo_reduction_matches_single_process():
     assert abs(out['nll'] - e['nll']) < 1e-12 * abs(e['nll'])
     assert abs(out['nci'] - e['nci']) < 1e-9 * abs(e['nci'])
     assert abs(out['nci'] - gs['c5_pend_gpq_nci_f'].ravel()[0]) < 1e-9 * abs(e['nci'])
+
+
+def test_rendezvous_batches_scipy_optimisers_without_changing_their_path():
+    """MarginalInference runs one scipy BFGS per trajectory in a thread and serves all their objective requests in
+    batches (ssinf._Rendezvous).  Host logic only: with a numpy objective the batched optimisers must return exactly what
+    scipy.optimize.minimize returns when called directly, every request must be served in a batch of all optimisers still
+    running, and optimisers that finish early must not stall the others."""
+    import threading
+    from scipy.optimize import minimize
+    from ssmtoybox_b200.ssinf import _Rendezvous
+    rs = np.random.RandomState(0)
+    n = 7
+    A = [np.diag(rs.uniform(0.5, 5.0, 3)) + 0.1 * np.ones((3, 3)) for _ in range(n)]
+    b = [rs.randn(3) for _ in range(n)]
+
+    def f(i, th):
+        d = th - b[i]
+        return 0.5 * d.dot(A[i]).dot(d) + 0.1 * np.sum(d ** 4) * (i % 3)     # different difficulty -> different iteration counts
+    direct = [minimize(lambda th, i=i: f(i, th), np.zeros(3), method='BFGS') for i in range(n)]
+    rv = _Rendezvous(n)
+    res, batch_sizes = {}, []
+
+    def worker(i):
+        try:
+            res[i] = minimize(lambda th: rv.request(i, th), np.zeros(3), method='BFGS')
+        finally:
+            rv.finish(i)
+
+    def evaluate(ids, thetas):
+        batch_sizes.append(len(ids))
+        return [f(i, th) for i, th in zip(ids, thetas)]
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n)]
+    for t in threads:
+        t.start()
+    rv.serve(evaluate)
+    for t in threads:
+        t.join(timeout=30)
+        assert not t.is_alive()
+    for i in range(n):
+        assert np.array_equal(res[i].x, direct[i].x) and np.array_equal(res[i].hess_inv, direct[i].hess_inv)
+        assert res[i].nfev == direct[i].nfev
+    assert batch_sizes[0] == n and min(batch_sizes) >= 1 and sorted(batch_sizes, reverse=True) == batch_sizes
+    assert len(batch_sizes) == max(r.nfev for r in direct)
