@@ -24,6 +24,9 @@ enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
 #ifndef SSM_WEIGHT_VIEWS
 #define SSM_WEIGHT_VIEWS 0
 #endif
+#ifndef SSM_SYM_WC
+#define SSM_SYM_WC 1  // fast path: half-row form of fx Wc fx^T (symmetric Wc); 0 = dense rows as in round 1
+#endif
 constexpr int GEN_CAP = 64;  // capacity of the runtime-N (generic point set) path with the function values kept per thread
 constexpr int GEN_CAP_STREAM = 4096;  // sigma-point rules beyond GEN_CAP points: two streaming passes, nothing stored
 
@@ -43,6 +46,7 @@ struct TfConst {
     double wm_[NCAP];
     double wc_[NCAP];
     double Wc_[NW][NCAP];
+    double wch_[NW];  // 0.5 * Wc(j, j): diagonal of the half-row form (see SYMW)
     double Wcc_[DC][NCAP];
     double mv_[E][E];
     double iK_[NK][NCAP];
@@ -62,10 +66,15 @@ struct TfConst {
     SSM_DEV double wm(int i) const { return wm_[i]; }
     SSM_DEV double wc(int i) const { return wc_[i]; }
     SSM_DEV double Wc(int i, int j) const { return Wc_[i][j]; }
+    SSM_DEV double Wch(int j) const { return wch_[j]; }
     SSM_DEV double Wcc(int d, int i) const { return Wcc_[d][i]; }
     SSM_DEV double mv(int a, int b) const { return mv_[a][b]; }
     SSM_DEV double iK(int i, int j) const { return iK_[i][j]; }
     SSM_DEV double U(int d, int i) const { return U_[d][i]; }
+    // The fast path is launched for bitwise SYMMETRIC covariance weights only (wc_symmetric(); every weight set the
+    // reference produces is: bq/bqmod.py:519-521, 988-990 average Wc with its transpose), which lets the dense form
+    // fx Wc fx^T run on the upper triangle of Wc: 605 instead of 770 DFMA for the 5-D dynamics transform.
+    static constexpr bool SYMW = SSM_SYM_WC != 0;
 };
 
 // generic path: weights in global memory (uniform addresses -> one broadcast transaction per warp)
@@ -81,6 +90,8 @@ struct TfGlobal {
     SSM_DEV double wm(int i) const { return __ldg(wm_ + i); }
     SSM_DEV double wc(int i) const { return __ldg(wc_ + i); }
     SSM_DEV double Wc(int i, int j) const { return __ldg(Wc_ + i * n + j); }
+    SSM_DEV double Wch(int j) const { return 0.5 * __ldg(Wc_ + j * n + j); }
+    static constexpr bool SYMW = false;  // any Wc, symmetric or not: dense rows
     SSM_DEV double Wcc(int d, int i) const { return __ldg(Wcc_ + d * n + i); }
     SSM_DEV double mv(int a, int b) const { return mv_[a][b]; }
     SSM_DEV double iK(int i, int j) const { return __ldg(iK_ + i * n + j); }
@@ -306,6 +317,37 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 sink(a, crow);
             }
         }
+        if constexpr (Tf::SYMW) {
+            // Symmetric Wc:  fx_a Wc fx_b^T = h_a . fx_b + h_b . fx_a  with the half rows
+            //   h_a[j] = Wc(j, j) / 2 * fx(a, j) + sum_{i < j} fx(a, i) Wc(i, j)
+            // (each off-diagonal weight multiplies fx(a, i) fx(b, j) + fx(a, j) fx(b, i) once instead of twice):
+            // E N (N + 1) / 2 + E^2 N instead of E N^2 + E (E + 1) N / 2 multiply-adds, same products, same weights.
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const Tf &tw = tf.row_view(a);
+                double h[NCAP];
+#pragma unroll
+                for (int j = 0; j < n; ++j) h[j] = fx(a, j) * tw.Wch(j);
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const double v = fx(a, i);
+#pragma unroll
+                    for (int j = i + 1; j < n; ++j) h[j] = fma(v, tw.Wc(i, j), h[j]);
+                }
+#pragma unroll
+                for (int b = 0; b < E; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < n; ++j) s = fma(h[j], fx(b, j), s);
+                    if (b == a) Cf[tri(a, a)] = s + s;
+                    else Cf[sym(a, b)] += s;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(-mf[a], mf[b], Cf[tri(a, b)]);
+        } else {
 #pragma unroll
         for (int a = 0; a < E; ++a) {
             const Tf &tw = tf.row_view(a);
@@ -325,6 +367,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 for (int j = 0; j < n; ++j) s = fma(row[j], fx(b, j), s);
                 Cf[tri(a, b)] = s - mf[a] * mf[b];
             }
+        }
         }
         if (KIND == SSM_TF_TP) {
             // data-dependent model variance  mv (nu - 2 + fx iK fx^T) / (nu - 2 + N)   bqmod.py:1155-1160
@@ -846,6 +889,16 @@ inline HostTfInfo classify_points(const ssm_transform &tf) {
     return r;
 }
 
+// Wc == Wc^T bit for bit (what the half-row form of the fast path needs; the reference's weights always are)
+inline bool wc_symmetric(const ssm_transform &tf) {
+    if (tf.kind == SSM_TF_SP || !SSM_SYM_WC) return true;
+    const int N = tf.n_pts;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < i; ++j)
+            if (!(tf.Wc[i * N + j] == tf.Wc[j * N + i])) return false;
+    return true;
+}
+
 template <int D>
 inline void pack_lower(const double *full, double *packed) {
     for (int r = 0; r < D; ++r)
@@ -880,6 +933,7 @@ inline void fill_tf(TfConst<D, E, NCAP, KIND, PTS> &o, const ssm_transform &tf, 
     if (KIND != SSM_TF_SP) {
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) o.Wc_[i % o.NW][j] = tf.Wc[i * N + j];
+        for (int i = 0; i < N; ++i) o.wch_[i % o.NW] = 0.5 * tf.Wc[i * N + i];
         for (int d = 0; d < D; ++d)
             for (int i = 0; i < N; ++i) o.Wcc_[d % o.DC][i] = tf.Wcc[d * N + i];
     }

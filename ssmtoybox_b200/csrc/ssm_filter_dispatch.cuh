@@ -4,23 +4,19 @@
 #pragma once
 #include <string.h>
 
+#include <vector>
+
 #include "ssm_filter.cuh"
 #ifdef SSM_PAIR_MODEL
 #include "ssm_filter_pair.cuh"
 #endif
 
-#ifndef SSM_TP_MINB
-#define SSM_TP_MINB 2
-#endif
 
 #ifndef SSM_PAIR_TPB
 #define SSM_PAIR_TPB 64      // trajectories per CTA of the warp-pair kernel (CTA = 2 x TPB threads)
 #endif
 #ifndef SSM_PAIR_MINB
 #define SSM_PAIR_MINB 4
-#endif
-#ifndef SSM_PAIR_MINB_TP
-#define SSM_PAIR_MINB_TP 3
 #endif
 #ifndef SSM_PAIR_DEFAULT
 #define SSM_PAIR_DEFAULT 0
@@ -46,6 +42,38 @@ int dispatch_npts(const FilterLaunch &L, const HostTfInfo &id, const HostTfInfo 
 template <class Dyn, class Obs, int THREADS, int MINB>
 int launch_filter_generic(const FilterLaunch &L, int kind, int family);
 
+// TPQ on the fast path is a BQ transform with folded weights.  The reference adds the data-dependent model variance
+//   mv (nu - 2 + fx K^-1 fx^T) / (nu - 2 + N)                       bqmod.py:1155-1160, bqmtran.py:414-415
+// as a FULL E x E matrix whenever the transform object has dim_out = 1 (I_out is 1 x 1 and broadcasts; ssinf.py:550 builds
+// every TPQ filter that way), so the covariance is one quadratic form plus a constant:
+//   fx Wc fx^T - mf mf^T + c (fx K^-1 fx^T) + c (nu - 2) 11^T  =  fx (Wc + c sym(K^-1)) fx^T - mf mf^T + c (nu - 2) 11^T,
+//   c = mv / (nu - 2 + N).
+// The device needs the lower triangle only, and a symmetric form sees the symmetric part of K^-1 (the reference's
+// cho_solve inverse is symmetric up to its own rounding).  One dense sum instead of two: the TPQ forward pass costs what
+// the GPQ one does (coordinated turn, 121 952 x 500: 31.7 -> 15.9 ms).  Diagonal-only variance (dim_out = E > 1) and
+// generic point sets keep the two separate sums on the runtime-N path.
+struct TpFold {
+    std::vector<double> Wc, mv;
+    ssm_transform tf;
+};
+inline bool tp_foldable(const ssm_transform &tf) {
+    return tf.kind == SSM_TF_TP && tf.iK && tf.model_var && tf.Wc && (tf.tp_full_matrix || tf.dim_out == 1);
+}
+inline void tp_fold(const ssm_transform &tf, TpFold &o) {
+    const int N = tf.n_pts, E = tf.dim_out;
+    const double tp_a = tf.nu - 2.0, tp_b = 1.0 / (tf.nu - 2.0 + (double)N), mv0 = tf.model_var[0];
+    const double c = tp_b * mv0;
+    o.Wc.resize((size_t)N * N);
+    o.mv.assign((size_t)E * E, (tp_a * tp_b) * mv0);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) o.Wc[(size_t)i * N + j] = tf.Wc[i * N + j] + c * (0.5 * (tf.iK[i * N + j] + tf.iK[j * N + i]));
+    o.tf = tf;
+    o.tf.kind = SSM_TF_BQ;
+    o.tf.Wc = o.Wc.data();
+    o.tf.model_var = o.mv.data();
+    o.tf.iK = nullptr;
+}
+
 template <class Dyn, class Obs, int THREADS, int MINB>
 int dispatch_filter_model(const FilterLaunch &L) {
     const ssm_desc &d = *L.desc;
@@ -61,18 +89,30 @@ int dispatch_filter_model(const FilterLaunch &L) {
     if (a.kind != b.kind) { set_error("dynamics and measurement transforms must be of the same kind"); return SSM_E_UNSUPPORTED; }
     const HostTfInfo id = classify_points(a), io = classify_points(b);
     const int kind = a.kind, fam = d.family;
+    if constexpr (Dyn::ADDITIVE && Obs::ADDITIVE) {
+        if (kind == SSM_TF_TP && id.pts != PTS_GENERIC && id.pts == io.pts && a.n_pts == b.n_pts && tp_foldable(a) && tp_foldable(b) &&
+            wc_symmetric(a) && wc_symmetric(b) && SSM_SYM_WC) {
+            TpFold fa, fb;
+            tp_fold(a, fa);
+            tp_fold(b, fb);
+            ssm_desc dd = d;
+            dd.tf_dyn = fa.tf;
+            dd.tf_obs = fb.tf;
+            FilterLaunch Lf = L;
+            Lf.desc = &dd;
+            return dispatch_filter_model<Dyn, Obs, THREADS, MINB>(Lf);  // the parameter block is filled before the launch returns
+        }
+    }
     if (L.buf.x_truth) {
         // scoring forward pass (ssm_filter_scores): instantiated for additive models, UT-type point sets ([0 | cI | -cI]),
         // Gaussian family; everything else reports SSM_E_UNSUPPORTED and the caller scores the stored moments instead
         if constexpr (Dyn::ADDITIVE && Obs::ADDITIVE) {
-            if (id.pts == PTS_AXIS_C && io.pts == PTS_AXIS_C && a.n_pts == b.n_pts && fam == SSM_FAMILY_GAUSS) {
-                constexpr int MINB_TPS = (Dyn::DX >= 4 && MINB > SSM_TP_MINB) ? SSM_TP_MINB : MINB;
+            if (id.pts == PTS_AXIS_C && io.pts == PTS_AXIS_C && a.n_pts == b.n_pts && fam == SSM_FAMILY_GAUSS && wc_symmetric(a) && wc_symmetric(b)) {
                 if (kind == SSM_TF_SP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
                 if (kind == SSM_TF_BQ) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
-                if (kind == SSM_TF_TP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_GAUSS, THREADS, MINB_TPS, true>(L, id, io);
             }
         }
-        set_error("ssm_filter_scores: in-kernel scoring is compiled for additive models, [0 | cI | -cI] point sets and the Gaussian family");
+        set_error("ssm_filter_scores: in-kernel scoring is compiled for additive models, [0 | cI | -cI] point sets, symmetric covariance weights and the Gaussian family");
         return SSM_E_UNSUPPORTED;
     }
     if constexpr (!Dyn::ADDITIVE || !Obs::ADDITIVE) {
@@ -83,32 +123,27 @@ int dispatch_filter_model(const FilterLaunch &L) {
         return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
     } else {
     const bool same = id.pts == io.pts && a.n_pts == b.n_pts;
-    if (!same || id.pts == PTS_GENERIC) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
-    // TPQ carries K^-1 and the row products fx K^-1 next to everything a BQ transform holds: at the register budget
-    // of MINB = 3 (168) the 5-D instantiations spill ~3 KB per step; two CTAs per SM (255 registers) are faster
-    constexpr int MINB_TP = (Dyn::DX >= 4 && MINB > SSM_TP_MINB) ? SSM_TP_MINB : MINB;
+    // asymmetric covariance weights (never produced by the reference, bq/bqmod.py:519-521): dense rows of the runtime-N path
+    // TPQ that did not fold (diagonal-only model variance with dim_out > 1): two separate sums, runtime-N path
+    if (!same || id.pts == PTS_GENERIC || !wc_symmetric(a) || !wc_symmetric(b) || kind == SSM_TF_TP) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
 #ifdef SSM_PAIR_MODEL
-    // warp pair per 32 trajectories (ssm_filter_pair.cuh): UT-type point sets, BQ / TP transforms, Gaussian family
-    if (id.pts == PTS_AXIS_C && fam == SSM_FAMILY_GAUSS && (kind == SSM_TF_BQ || kind == SSM_TF_TP) && pair_enabled()) {
-        const int rc = (kind == SSM_TF_BQ) ? launch_filter_pair<Dyn, Obs, SSM_TF_BQ, SSM_PAIR_TPB, SSM_PAIR_MINB>(L, id, io)
-                                           : launch_filter_pair<Dyn, Obs, SSM_TF_TP, SSM_PAIR_TPB, SSM_PAIR_MINB_TP>(L, id, io);
+    // warp pair per 32 trajectories (ssm_filter_pair.cuh): UT-type point sets, BQ transforms, Gaussian family
+    if (id.pts == PTS_AXIS_C && fam == SSM_FAMILY_GAUSS && kind == SSM_TF_BQ && pair_enabled()) {   // folded TPQ arrives as BQ
+        const int rc = launch_filter_pair<Dyn, Obs, SSM_TF_BQ, SSM_PAIR_TPB, SSM_PAIR_MINB>(L, id, io);
         if (rc != SSM_E_UNSUPPORTED) return rc;
     }
 #endif
 #define SSM_CASE(P, K, F)                                                        \
-    if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, (K == SSM_TF_TP ? MINB_TP : MINB)>(L, id, io);
+    if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, MINB>(L, id, io);
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS)
-    SSM_CASE(PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS, SSM_TF_SP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS, SSM_TF_BQ, SSM_FAMILY_GAUSS)
-    SSM_CASE(PTS_AXIS, SSM_TF_TP, SSM_FAMILY_GAUSS)
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_STUDENT)
     SSM_CASE(PTS_AXIS, SSM_TF_SP, SSM_FAMILY_STUDENT)
     // Student filters with BQ transforms on fully-symmetric degree-3 points: GPQStudent (research/tpq/tpq_base.py:41-91),
     // StudentProcessStudent (ssinf.py:778-833); other point sets take the runtime-N path
     SSM_CASE(PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_STUDENT)
-    SSM_CASE(PTS_AXIS_C, SSM_TF_TP, SSM_FAMILY_STUDENT)
     if (fam == SSM_FAMILY_STUDENT) return launch_filter_generic<Dyn, Obs, THREADS, MINB>(L, kind, fam);
 #undef SSM_CASE
     set_error("unsupported transform kind %d / family %d", kind, fam);

@@ -109,7 +109,9 @@ def test_batched_vs_oracle_seeded(name, M, N):
     assert ok.mean() > 0.9
     # UNGM amplifies rounding differences along the trajectory (the two CPU back-ends of the oracle differ
     # by up to 1e-8 over 500 steps as well); per-step parity is test_one_step_parity_1e9
-    tol = {'c1_ungm_ukf': 1e-5, 'c3_reentry_gpq': 2e-6}.get(name, 1e-9)
+    # TPQ runs with folded weights Wc + c sym(K^-1) (one rounding per weight, ssm_filter_dispatch.cuh tp_fold): whole
+    # trajectories to the golden file's FULL_TOL (1e-8), single steps to 1e-9 in test_one_step_parity_1e9
+    tol = {'c1_ungm_ukf': 1e-5, 'c3_reentry_gpq': 2e-6, 'c4_ct_fsstudent_tpq': FULL_TOL['c4_ct_fsstudent_tpq']}.get(name, 1e-9)
     assert relstep(N_(o['fi_mean'])[..., ok], ref['fi_mean'][..., ok]) < tol
     assert relstep(N_(o['fi_cov'])[..., ok], ref['fi_cov'][..., ok]) < tol
     if not student:
@@ -597,13 +599,17 @@ def test_noise_dominated_filters_against_the_longdouble_arbiter(name):
         assert np.all(eg[valid] <= 10.0 * er[valid] + 1e-13), (name, key, float((eg[valid] / np.maximum(er[valid], 1e-16)).max()))
         worst[key] = float(er[valid].max())
         valid_all = valid if valid_all is None else (valid_all & valid)
-    # aggregate over the steps both arrays are valid on: the per-trajectory RMSE agrees with the reference's to 10x the
-    # reference's own worst relative error of the means against the arbiter
+    # aggregate over the steps both arrays are valid on: per state component and trajectory, the device's RMSE is at most
+    # 10x as far from the arbiter's RMSE as the reference's own is (relative, worst component on both sides: the
+    # per-step bound above is relative to the largest state component and says nothing about the small ones)
     x = g['x']
     m = valid_all[None].repeat(x.shape[0], axis=0)
-    rm_g = np.sqrt(np.where(m, (N_(o['fi_mean']) - x) ** 2, 0.0).sum(axis=1) / valid_all.sum(axis=0))
-    rm_r = np.sqrt(np.where(m, (g['fi_mean'] - x) ** 2, 0.0).sum(axis=1) / valid_all.sum(axis=0))
-    assert rel(rm_g, rm_r) <= 10.0 * worst['fi_mean'] + 1e-12, (rel(rm_g, rm_r), worst)
+
+    def rmse(mean):
+        return np.sqrt(np.where(m, (mean - x) ** 2, 0.0).sum(axis=1) / valid_all.sum(axis=0))
+    rm_g, rm_r, rm_t = rmse(N_(o['fi_mean'])), rmse(g['fi_mean']), rmse(np.asarray(ld['fi_mean'], dtype=np.float64))
+    dev_g, dev_r = float(np.max(np.abs(rm_g - rm_t) / rm_t)), float(np.max(np.abs(rm_r - rm_t) / rm_t))
+    assert dev_g <= 10.0 * dev_r + 1e-12, (dev_g, dev_r, worst)
 
 
 def test_ctrs_fixture_invariants():
