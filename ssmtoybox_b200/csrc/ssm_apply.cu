@@ -79,10 +79,7 @@ __global__ void __launch_bounds__(64) apply_kernel(const __grid_constant__ Apply
             Fn::template ev<false>(p.par, x, z, p.time, o);
         },
         mf, Cf, true,
-        [&](int a, const double (&row)[D]) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) Cfx[a][c] = row[c];
-        },
+        [&](int a, int c, double v) { Cfx[a][c] = v; },
         nullptr);
 #pragma unroll
     for (int a = 0; a < E; ++a) p.mean_f[(long long)a * p.ld + t] = ok ? mf[a] : qnan();

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/ssm_b200.h"
+#include "ssm_math.cuh"
 
 #define SSM_DEV __device__ __forceinline__
 
@@ -21,7 +22,11 @@ struct TriSize {
 
 // streaming (evict-first) global accesses: every bulk array is touched exactly once per pass
 SSM_DEV double ld_stream(const double *p) { return __ldcs(p); }
+#ifdef SSM_ST_PLAIN
+SSM_DEV void st_stream(double *p, double v) { *p = v; }
+#else
 SSM_DEV void st_stream(double *p, double v) { __stcs(p, v); }
+#endif
 
 // Row pointer of a bulk array: base + (k * ld + t), computed once per array and step and made opaque to the
 // optimiser, which otherwise re-associates base + (rk + c * cs) into a 64-bit add plus a 64-bit scaled add (LEA
@@ -86,16 +91,36 @@ SSM_DEV double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 #else
 #define SSM_SMALL_MATH_FN SSM_MATH_FN
 #endif
-#if SSM_INLINE_EXP
+// Round 2: exp and atan2 are the lean routines of ssm_math.cuh (SSM_LEAN_MATH: 1 = inline, 2 = one out-of-line copy each,
+// 0 = libm's as before).
+#ifndef SSM_LEAN_MATH
+#define SSM_LEAN_MATH 0
+#endif
+#if SSM_LEAN_MATH == 1
+static __device__ __forceinline__ double m_exp(double x) { return lean_exp(x); }
+#elif SSM_LEAN_MATH == 2
+static __device__ __noinline__ double m_exp(double x) { return lean_exp(x); }
+#elif SSM_INLINE_EXP
 static __device__ __forceinline__ double m_exp(double x) { return exp(x); }
 #else
 SSM_MATH_FN double m_exp(double x) { return exp(x); }
+#endif
+// Developer switch SSM_DUP_{EXP,ATAN2,SQRT,RSQRT}: evaluate the routine a second time on a perturbed argument and fold
+// the result in with weight 0.0 (not removable: 0 * NaN) -- the time added is the marginal cost of that routine's calls.
+#if defined(SSM_DUP_EXP) || defined(SSM_DUP_ATAN2) || defined(SSM_DUP_SQRT) || defined(SSM_DUP_RSQRT)
+#define SSM_DUP(fn, r, ...) ((r) + 0.0 * fn(__VA_ARGS__))
 #endif
 SSM_SMALL_MATH_FN double m_sqrt(double x) { return sqrt(x); }
 SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
 SSM_SMALL_MATH_FN double m_rsqrt(double x) { return rsqrt(x); }
 SSM_MATH_FN double m_div(double a, double b) { return a / b; }
+#if SSM_LEAN_MATH == 1
+static __device__ __forceinline__ double m_atan2(double y, double x) { return lean_atan2(y, x); }
+#elif SSM_LEAN_MATH == 2
+static __device__ __noinline__ double m_atan2(double y, double x) { return lean_atan2(y, x); }
+#else
 SSM_MATH_FN double m_atan2(double y, double x) { return atan2(y, x); }
+#endif
 
 // Lower Cholesky factor of a symmetric matrix given by its packed lower triangle.
 // Mirrors dpotrf('L') as called by numpy.linalg.cholesky (mtran.py:139, bqmtran.py:98): only the

@@ -24,6 +24,12 @@ enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
 #ifndef SSM_WEIGHT_VIEWS
 #define SSM_WEIGHT_VIEWS 0
 #endif
+#ifndef SSM_CROSS_COLS_MIN_E
+#define SSM_CROSS_COLS_MIN_E 99  // output dimension from which the BQ cross-covariance is formed column by column (measured slower)
+#endif
+#ifndef SSM_SYM_COLUMNS
+#define SSM_SYM_COLUMNS 1
+#endif
 #ifndef SSM_SYM_WC
 #define SSM_SYM_WC 1  // fast path: half-row form of fx Wc fx^T (symmetric Wc); 0 = dense rows as in round 1
 #endif
@@ -152,7 +158,7 @@ struct FxStore<E, NCAP, 0> {  // registers
 // (a, i) of this thread at sfx[(a * N + i) * SMT] (sfx already offset by threadIdx.x, conflict-free 8-byte
 // accesses).  The arithmetic and its order are identical in both variants; the shared-memory variant frees
 // ~2 E N registers per thread, which buys a higher occupancy for the 5-D models.
-// The cross-covariance is handed out row by row through `sink(a, row)` (row = Cov(f_a, x), D values) so that the
+// The cross-covariance is handed out element by element through `sink(a, r, Cov(f_a, x_r))` so that the
 // caller decides where it lives: the measurement transform keeps it in registers for the gain, the dynamics
 // transform streams it straight to HBM (no 25-double live array between the transform and the stores).
 // EXACT: mean and centred cross-covariance sums with separately rounded products (no FMA).  The reference's models
@@ -209,7 +215,9 @@ SSM_DEV void sigma_point_transform_streamed(const Tf &tf, const int n, const dou
     }
     if (want_cross) {
 #pragma unroll
-        for (int a = 0; a < E; ++a) sink(a, Cfx[a]);
+        for (int a = 0; a < E; ++a)
+#pragma unroll
+            for (int r = 0; r < D; ++r) sink(a, r, Cfx[a][r]);
     }
 }
 
@@ -239,13 +247,14 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
         for (int a = 0; a < E; ++a) fxs.set(a, i, o[a]);
     }
     // mean_f = fx . wm                                          mtran.py:143, bqmtran.py:175
+    // point-major: one weight, E consecutive uses (same sums, same order over i as a row-major loop)
 #pragma unroll
-    for (int a = 0; a < E; ++a) {
-        const Tf &tw = tf.row_view(a);
-        double s = 0.0;
+    for (int a = 0; a < E; ++a) mf[a] = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) s = EXACT ? __dadd_rn(s, __dmul_rn(fx(a, i), tw.wm(i))) : fma(fx(a, i), tw.wm(i), s);
-        mf[a] = s;
+    for (int i = 0; i < n; ++i) {
+        const double w = tf.wm(i);
+#pragma unroll
+        for (int a = 0; a < E; ++a) mf[a] = EXACT ? __dadd_rn(mf[a], __dmul_rn(fx(a, i), w)) : fma(fx(a, i), w, mf[a]);
     }
 #pragma unroll
     for (int a = 0; a < TriSize<E>::value; ++a) Cf[a] = 0.0;
@@ -289,32 +298,67 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 }
             }
 #pragma unroll
-            for (int a = 0; a < E; ++a) sink(a, Cfx[a]);
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int r = 0; r < D; ++r) sink(a, r, Cfx[a][r]);
         }
     } else {
         // un-centred form with dense weights                    bqmtran.py:198-199, 223
         if (want_cross) {
+            if constexpr (Tf::SYMW && E >= SSM_CROSS_COLS_MIN_E) {
+                // Opt-in, measured slower.  Column r of the cross-covariance at a time:  Cov(f, x_r) = fx (L Wcc)[r, :]^T,
+                // the product re-associated as fx (Wcc^T L^T) (bqmtran.py:223 evaluates (fx Wcc^T) L^T): N D (D + 1) / 2 +
+                // E N D multiply-adds instead of E N D + E D (D + 1) / 2 (440 instead of 350 for the reentry dynamics), every
+                // weight Wcc(d, i) used by ONE instruction right after its load instead of once per unrolled row.  Reentry
+                // forward pass, 125 000 x 500: 13.51 / 18.66 ms against 12.72 / 17.46 ms row by row.
 #pragma unroll
-            for (int a = 0; a < E; ++a) {
-                const Tf &tw = tf.row_view(a);
-                double T[D];
+                for (int r = 0; r < D; ++r) {
+                    double Mr[NCAP];
 #pragma unroll
-                for (int d = 0; d < D; ++d) T[d] = 0.0;
+                    for (int i = 0; i < n; ++i) {
+                        double s = 0.0;
 #pragma unroll
-                for (int i = 0; i < n; ++i) {  // same summation order over i for every T[d]
-                    const double v = fx(a, i);
+                        for (int d = 0; d <= r; ++d) s = fma(L[tri(r, d)], tf.Wcc(d, i), s);
+                        Mr[i] = s;
+                    }
 #pragma unroll
-                    for (int d = 0; d < D; ++d) T[d] = fma(v, tw.Wcc(d, i), T[d]);
+                    for (int a = 0; a < E; ++a) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int i = 0; i < n; ++i) s = fma(fx(a, i), Mr[i], s);
+                        sink(a, r, s);
+                    }
                 }
-                double crow[D];
+            } else {
+                // G rows at a time (same sums, same order over i for every G).  Measured on the reentry forward pass with
+                // predictive moments: G = 1 17.5 ms, G = 2 20.5 ms, G = 5 18.6 ms
+                constexpr int G = 1;
 #pragma unroll
-                for (int r = 0; r < D; ++r) {  // (T L^T)[a][r] = sum_{d<=r} T[d] L[r][d]
-                    double s = 0.0;
+                for (int a0 = 0; a0 < E; a0 += G) {
+                    double T[G][D];
 #pragma unroll
-                    for (int d = 0; d <= r; ++d) s = fma(T[d], L[tri(r, d)], s);
-                    crow[r] = s;
+                    for (int g = 0; g < G; ++g)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) T[g][d] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < n; ++i) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const double w = tf.Wcc(d, i);
+#pragma unroll
+                            for (int g = 0; g < G; ++g) T[g][d] = fma(fx(a0 + g, i), w, T[g][d]);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+#pragma unroll
+                        for (int r = 0; r < D; ++r) {  // (T L^T)[a][r] = sum_{d<=r} T[a][d] L[r][d]
+                            double s = 0.0;
+#pragma unroll
+                            for (int d = 0; d <= r; ++d) s = fma(T[g][d], L[tri(r, d)], s);
+                            sink(a0 + g, r, s);
+                        }
                 }
-                sink(a, crow);
             }
         }
         if constexpr (Tf::SYMW) {
@@ -322,6 +366,34 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
             //   h_a[j] = Wc(j, j) / 2 * fx(a, j) + sum_{i < j} fx(a, i) Wc(i, j)
             // (each off-diagonal weight multiplies fx(a, i) fx(b, j) + fx(a, j) fx(b, i) once instead of twice):
             // E N (N + 1) / 2 + E^2 N instead of E N^2 + E (E + 1) N / 2 multiply-adds, same products, same weights.
+#if SSM_SYM_COLUMNS
+            // Column by column: every weight Wc(i, j) is loaded once and used by the E rows in consecutive instructions,
+            // then it is dead -- with the row-by-row order below the compiler merges the E uses of a weight across the
+            // unrolled rows, keeps ~70 weights live in the 63 uniform registers and spills them (R2UR.FILL + LDL).
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double hc[E];
+                {
+                    const double w = tf.Wch(j);
+#pragma unroll
+                    for (int a = 0; a < E; ++a) hc[a] = fx(a, j) * w;
+                }
+#pragma unroll
+                for (int i = 0; i < j; ++i) {
+                    const double w = tf.Wc(j, i);  // = Wc(i, j), contiguous along the row
+#pragma unroll
+                    for (int a = 0; a < E; ++a) hc[a] = fma(fx(a, i), w, hc[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < E; ++a)
+#pragma unroll
+                    for (int b = 0; b < E; ++b) Cf[sym(a, b)] = fma(hc[a], fx(b, j), Cf[sym(a, b)]);  // diagonal: half of it
+            }
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(-mf[a], mf[b], (a == b) ? Cf[tri(a, b)] + Cf[tri(a, b)] : Cf[tri(a, b)]);
+#else
 #pragma unroll
             for (int a = 0; a < E; ++a) {
                 const Tf &tw = tf.row_view(a);
@@ -347,6 +419,7 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
             for (int a = 0; a < E; ++a)
 #pragma unroll
                 for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(-mf[a], mf[b], Cf[tri(a, b)]);
+#endif
         } else {
 #pragma unroll
         for (int a = 0; a < E; ++a) {
@@ -472,22 +545,47 @@ SSM_DEV void augment(const double (&m)[DX], const double (&P)[TriSize<DX>::value
 
 // Element (c, k, t) of a bulk array = base + rk + c * cs with rk = k * ld + t (per thread, once per step) and the
 // kernel-uniform component stride cs = n_steps * ld: one 64-bit add per access instead of a 64-bit multiply chain.
-template <int C>
-SSM_DEV void store_vec(double *base, long long cs, long long rk, const double (&v)[C]) {
+// The component stride as a 32-bit unsigned value (models with dx > 1: n_steps * ld < 2^32 is checked at launch, and
+// 2^32 doubles per component are 34 GB): the byte offset c * cs * 8 is ONE IMAD.WIDE.U32 with an immediate, against
+// IMAD.WIDE.U32 + IMAD + IADD for a 64-bit stride -- 87 addresses per reentry step.
+#ifndef SSM_NARROW_STRIDE
+#define SSM_NARROW_STRIDE 1
+#endif
+template <bool NARROW>
+struct CompStride {
+    long long v;
+    SSM_DEV explicit CompStride(long long s) : v(s) {}
+    SSM_DEV long long operator()(int c) const { return c * v; }
+};
+template <>
+struct CompStride<true> {
+    unsigned v;
+    SSM_DEV explicit CompStride(long long s) : v((unsigned)s) {}
+    SSM_DEV size_t operator()(int c) const { return (size_t)(unsigned)c * v; }
+};
+template <int C, class CS>
+SSM_DEV void store_vec(double *base, const CS &cs, long long rk, const double (&v)[C]) {
     if (!base) return;
     double *q = row_ptr(base, rk);
 #pragma unroll
-    for (int c = 0; c < C; ++c) st_stream(q + c * cs, v[c]);
+    for (int c = 0; c < C; ++c) st_stream(q + cs(c), v[c]);
 }
-template <int D>
-SSM_DEV void store_sym(double *base, long long cs, long long rk, const double (&P)[TriSize<D>::value]) {
+template <int D, class CS>
+SSM_DEV void store_sym(double *base, const CS &cs, long long rk, const double (&P)[TriSize<D>::value]) {
     if (!base) return;
     double *q = row_ptr(base, rk);
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-        for (int c = 0; c < D; ++c) st_stream(q + (r * D + c) * cs, P[sym(r, c)]);
+        for (int c = 0; c < D; ++c) st_stream(q + cs(r * D + c), P[sym(r, c)]);
 }
+template <int DX>
+struct NarrowStride {
+    static constexpr bool value = SSM_NARROW_STRIDE != 0 && DX > 1;
+};
+// launch-time check of the 32-bit component stride
+template <int DX>
+inline bool stride_fits(long long n_steps, long long ld) { return !NarrowStride<DX>::value || n_steps * ld < (1LL << 32); }
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -518,9 +616,16 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
     constexpr bool NA = !Dyn::ADDITIVE || !Obs::ADDITIVE;  // non-additive noise somewhere: exact-cancellation sums
     const FilterBuffers &b = p.b;
+    // model parameters as values: a load through the parameter block is repeated after every (rare-path) call, and the
+    // re-loaded value is a new one to common-subexpression elimination
+    double dpar[4], opar[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dpar[i] = p.dyn_par[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) opar[i] = p.obs_par[i];
     const int N = b.n_steps;
     const long long ld = b.ld;
-    const long long cs = (long long)N * ld;  // component stride of the [component][step][trajectory] arrays
+    const CompStride<NarrowStride<DX>::value> cs((long long)N * ld);  // component stride of the [component][step][trajectory] arrays
     constexpr int NSTATE = DX + TX + 2;
     constexpr int WS = ScoreRow<DX>::WP;
     static_assert(!SCORE || THREADS == SC_THREADS, "the CTA reduction of the scores is laid out for SC_THREADS threads");
@@ -589,7 +694,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 
     double ynext[DY];
 #pragma unroll
-    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + ((long long)k_begin * ld + t));
+    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + cs(a) + ((long long)k_begin * ld + t));
     double se_acc[SCORE ? DX : 1];
     if (SCORE) {   // per-trajectory time-sum of the squared error: continued across time chunks and windows
 #pragma unroll
@@ -615,7 +720,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
         for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
         if (k + 1 < k_end) {
 #pragma unroll
-            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + (rk + ld));
+            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + cs(a) + (rk + ld));
         }
         const double time = tbase + (double)k;  // the reference passes time = k - 1, k 1-based (ssinf.py:104)
 
@@ -636,13 +741,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 p.tf_dyn, m, P,
                 [&](const double (&x)[DX], double (&o)[DX]) {
                     const double q0[Dyn::DQ] = {};
-                    Dyn::template f<false>(p.dyn_par, x, q0, time, o);
+                    Dyn::template f<false>(dpar, x, q0, time, o);
                 },
                 mp, Pp, want_xx,
-                [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
-#pragma unroll
-                    for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
-                },
+                [&](int a, int c, double v) { st_stream(q_xx + cs(a * DX + c), v); },  // Cov(x_k, x_{k-1})[a][c] -> pr_xx_cov[a][c][k][t]
                 sfx);
         } else {
             // non-additive process noise: transform of the augmented vector [x; q], cross-covariance trimmed to its
@@ -658,12 +760,11 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                     for (int i = 0; i < DX; ++i) x[i] = xq[i];
 #pragma unroll
                     for (int i = 0; i < Dyn::DQ; ++i) q[i] = xq[DX + i];
-                    Dyn::template f<true>(p.dyn_par, x, q, time, o);
+                    Dyn::template f<true>(dpar, x, q, time, o);
                 },
                 mp, Pp, want_xx,
-                [&](int a, const double (&row)[DD]) {
-#pragma unroll
-                    for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
+                [&](int a, int c, double v) {
+                    if (c < DX) st_stream(q_xx + cs(a * DX + c), v);
                 },
                 sfx);
         }
@@ -693,13 +794,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 p.tf_obs, mp, Pp,
                 [&](const double (&x)[DX], double (&o)[DY]) {
                     const double r0[DY] = {};
-                    Obs::template h<false>(p.obs_par, x, r0, time, o);
+                    Obs::template h<false>(opar, x, r0, time, o);
                 },
                 my, Sy, true,
-                [&](int a, const double (&row)[DX]) {
-#pragma unroll
-                    for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
-                },
+                [&](int a, int c, double v) { Syx[a][c] = v; },
                 sfx);
         } else {
             // non-additive measurement noise: [x; r] (ssinf.py:282-283), cross-covariance trimmed (:293)
@@ -714,12 +812,11 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                     for (int i = 0; i < DX; ++i) x[i] = xr[i];
 #pragma unroll
                     for (int i = 0; i < DY; ++i) r[i] = xr[DX + i];
-                    Obs::template h<true>(p.obs_par, x, r, time, o);
+                    Obs::template h<true>(opar, x, r, time, o);
                 },
                 my, Sy, true,
-                [&](int a, const double (&row)[DO]) {
-#pragma unroll
-                    for (int c = 0; c < DX; ++c) Syx[a][c] = row[c];
+                [&](int a, int c, double v) {
+                    if (c < DX) Syx[a][c] = v;
                 },
                 sfx);
         }
@@ -801,13 +898,13 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 double d[DX], se[DX], qf;
                 const double *qx = row_ptr(b.x_truth, rk);
 #pragma unroll
-                for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + a * cs) - m[a];
+                for (int a = 0; a < DX; ++a) d[a] = ld_stream(qx + cs(a)) - m[a];
                 score_step<DX>(d, P, sv, se, &qf);
                 if (b.quad) st_stream(b.quad + rk, qf);
                 if (b.dres) {
                     double *qd = row_ptr(b.dres, rk);
 #pragma unroll
-                    for (int a = 0; a < DX; ++a) st_stream(qd + a * cs, d[a]);
+                    for (int a = 0; a < DX; ++a) st_stream(qd + cs(a), d[a]);
                 }
 #pragma unroll
                 for (int a = 0; a < DX; ++a) se_acc[a] += se[a];
@@ -978,6 +1075,11 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
     p.s0 = (d.family == SSM_FAMILY_STUDENT) ? (d.dof - 2.0) / d.dof : 1.0;
     p.fixed_dof = d.fixed_dof;
     p.b = L.buf;
+    if (!stride_fits<DX>(L.buf.n_steps, L.buf.ld)) {
+        delete pp;
+        set_error("n_steps * ld = %lld elements per component: this model addresses components with a 32-bit stride (< 2^32); run the trajectories in chunks", (long long)L.buf.n_steps * L.buf.ld);
+        return SSM_E_UNSUPPORTED;
+    }
     const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
     constexpr bool SMEM_FX = (DX >= SSM_SMEM_FX_MIN_DX);
     auto kern = filter_kernel<Dyn, Obs, PTS, NPTS, KIND, FAMILY, Par, THREADS, MINB, SMEM_FX, SCORE>;

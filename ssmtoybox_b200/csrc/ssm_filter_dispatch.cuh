@@ -205,6 +205,10 @@ int launch_filter_global(const FilterLaunch &L) {
         set_error("generic point sets support at most %d points (sigma-point rules: %d); got %d / %d", GEN_CAP, GEN_CAP_STREAM, Na, Nb);
         return SSM_E_UNSUPPORTED;
     }
+    if (!stride_fits<DX>(L.buf.n_steps, L.buf.ld)) {
+        set_error("n_steps * ld = %lld elements per component: this model addresses components with a 32-bit stride (< 2^32); run the trajectories in chunks", (long long)L.buf.n_steps * L.buf.ld);
+        return SSM_E_UNSUPPORTED;
+    }
     const size_t cnt = tf_global_count(d.tf_dyn, DD) + tf_global_count(d.tf_obs, DO);
     double *host = (double *)malloc(cnt * sizeof(double));
     double *dev = nullptr;

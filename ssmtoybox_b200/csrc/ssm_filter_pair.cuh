@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(2 * TPB, MINB) filter_pair_kernel(const __grid
     const FilterBuffers &b = p.b;
     const int N = b.n_steps;
     const long long ld = b.ld;
-    const long long cs = (long long)N * ld;
+    const CompStride<false> cs((long long)N * ld);
     constexpr int NSTATE = DX + TX + 2;
     const int role = threadIdx.x / TPB;  // 0 = main, 1 = helper; uniform within a warp (TPB is a multiple of 32)
     const int lane = threadIdx.x - role * TPB;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(2 * TPB, MINB) filter_pair_kernel(const __grid
             if (kc == 0 && b.resume && active && b.status[t] != 0) { fail = b.status[t] & 0xff; kfail = b.k_lo; }
             double ynext[DY];
 #pragma unroll
-            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + ((long long)k_begin * ld + t));
+            for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + cs(a) + ((long long)k_begin * ld + t));
 
             for (int k = k_begin; k < k_end; ++k) {
                 if (SSM_PAIR_SYNC_STEPS) __syncthreads();
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(2 * TPB, MINB) filter_pair_kernel(const __grid
                 for (int a = 0; a < DY; ++a) yk[a] = ynext[a];
                 if (k + 1 < k_end) {
 #pragma unroll
-                    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + a * cs + (rk + ld));
+                    for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + cs(a) + (rk + ld));
                 }
                 const double time = tbase + (double)k;
                 // ---- time update (ssinf.py:276-279) ----
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(2 * TPB, MINB) filter_pair_kernel(const __grid
                     [&](int a, const double (&row)[DX]) {  // Cov(x_k, x_{k-1}) row a -> pr_xx_cov[a][:][k][t]
                         if (active) {
 #pragma unroll
-                            for (int c = 0; c < DX; ++c) st_stream(q_xx + (a * DX + c) * cs, row[c]);
+                            for (int c = 0; c < DX; ++c) st_stream(q_xx + cs(a * DX + c), row[c]);
                         }
                     },
                     xs, bar_id, p.zero);

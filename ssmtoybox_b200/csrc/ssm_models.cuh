@@ -57,11 +57,19 @@ struct DynReentry {
     static constexpr bool HAS_CONT = true;
     SSM_DEV static void forces(const double (&x)[5], double &D, double &G) {
         const double R0 = 6374.0, H0 = 13.406, Gm0 = 3.9860e5, b0 = -0.59783;
+#ifdef SSM_DUP_EXP
+        const double b = b0 * SSM_DUP(m_exp, m_exp(x[4]), x[4] * 1.0000001);
+#else
         const double b = b0 * m_exp(x[4]);
+#endif
         // R = sqrt(r2) and 1/R^3 from ONE out-of-line call: ir = 1/sqrt(r2), R = r2 ir, R^-3 = ir^3 (a few ulp
         // from the reference's sqrt + pow + divide, far below the parity tolerance; r2 = 0 gives NaN/inf in both)
         const double r2 = x[0] * x[0] + x[1] * x[1];
+#ifdef SSM_DUP_RSQRT
+        const double ir = SSM_DUP(m_rsqrt, m_rsqrt(r2), r2 * 1.0000001);
+#else
         const double ir = m_rsqrt(r2);
+#endif
         const double R = r2 * ir;
         const double V = m_sqrt(x[2] * x[2] + x[3] * x[3]);
         D = b * m_exp((R0 - R) * (1.0 / H0)) * V;  // (R0 - R) / H0 up to 1 ulp: no division call
@@ -272,9 +280,17 @@ struct ObsRadar {
     template <bool NOISE>
     SSM_DEV static void h(const double *par, const double (&x)[DXS], const double (&r)[2], double, double (&o)[2]) {
         const double ex = x[I0] - par[0], ey = x[I1] - par[1];
+#ifdef SSM_DUP_SQRT
+        o[0] = SSM_DUP(m_sqrt, m_sqrt(ex * ex + ey * ey), ex * ex + ey * ey * 1.0000001);
+#else
         o[0] = m_sqrt(ex * ex + ey * ey);
+#endif
         if (NOISE) o[0] += r[0];
+#ifdef SSM_DUP_ATAN2
+        o[1] = SSM_DUP(m_atan2, m_atan2(ey, ex), ey * 1.0000001, ex);
+#else
         o[1] = m_atan2(ey, ex);
+#endif
         if (NOISE) o[1] += r[1];
     }
 };
