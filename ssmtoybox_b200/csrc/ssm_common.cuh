@@ -38,6 +38,32 @@ SSM_DEV T *row_ptr(T *base, long long rk) {
     return q;
 }
 
+// The component stride as a 32-bit unsigned value (models with dx > 1: n_steps * ld < 2^32 is checked at launch, and
+// 2^32 doubles per component are 34 GB): the byte offset c * cs * 8 is ONE IMAD.WIDE.U32 with an immediate, against
+// IMAD.WIDE.U32 + IMAD + IADD for a 64-bit stride -- 87 addresses per reentry step.
+#ifndef SSM_NARROW_STRIDE
+#define SSM_NARROW_STRIDE 1
+#endif
+template <bool NARROW>
+struct CompStride {
+    long long v;
+    SSM_DEV explicit CompStride(long long s) : v(s) {}
+    SSM_DEV long long operator()(int c) const { return c * v; }
+};
+template <>
+struct CompStride<true> {
+    unsigned v;
+    SSM_DEV explicit CompStride(long long s) : v((unsigned)s) {}
+    SSM_DEV size_t operator()(int c) const { return (size_t)(unsigned)c * v; }
+};
+template <int DX>
+struct NarrowStride {
+    static constexpr bool value = SSM_NARROW_STRIDE != 0 && DX > 1;
+};
+// launch-time check of the 32-bit component stride
+template <int DX>
+inline bool stride_fits(long long n_steps, long long ld) { return !NarrowStride<DX>::value || n_steps * ld < (1LL << 32); }
+
 // Stream-ordered scratch memory (scheduler workspace, partial statistics rows).  The default memory pool returns
 // freed blocks to the driver at the next synchronisation (release threshold 0), so a caller that synchronises between
 // calls pays a driver allocation of tens of MB in front of every launch (measured as +-20 % run-to-run noise of the

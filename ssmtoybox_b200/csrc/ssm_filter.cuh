@@ -545,24 +545,6 @@ SSM_DEV void augment(const double (&m)[DX], const double (&P)[TriSize<DX>::value
 
 // Element (c, k, t) of a bulk array = base + rk + c * cs with rk = k * ld + t (per thread, once per step) and the
 // kernel-uniform component stride cs = n_steps * ld: one 64-bit add per access instead of a 64-bit multiply chain.
-// The component stride as a 32-bit unsigned value (models with dx > 1: n_steps * ld < 2^32 is checked at launch, and
-// 2^32 doubles per component are 34 GB): the byte offset c * cs * 8 is ONE IMAD.WIDE.U32 with an immediate, against
-// IMAD.WIDE.U32 + IMAD + IADD for a 64-bit stride -- 87 addresses per reentry step.
-#ifndef SSM_NARROW_STRIDE
-#define SSM_NARROW_STRIDE 1
-#endif
-template <bool NARROW>
-struct CompStride {
-    long long v;
-    SSM_DEV explicit CompStride(long long s) : v(s) {}
-    SSM_DEV long long operator()(int c) const { return c * v; }
-};
-template <>
-struct CompStride<true> {
-    unsigned v;
-    SSM_DEV explicit CompStride(long long s) : v((unsigned)s) {}
-    SSM_DEV size_t operator()(int c) const { return (size_t)(unsigned)c * v; }
-};
 template <int C, class CS>
 SSM_DEV void store_vec(double *base, const CS &cs, long long rk, const double (&v)[C]) {
     if (!base) return;
@@ -579,13 +561,7 @@ SSM_DEV void store_sym(double *base, const CS &cs, long long rk, const double (&
 #pragma unroll
         for (int c = 0; c < D; ++c) st_stream(q + cs(r * D + c), P[sym(r, c)]);
 }
-template <int DX>
-struct NarrowStride {
-    static constexpr bool value = SSM_NARROW_STRIDE != 0 && DX > 1;
-};
-// launch-time check of the 32-bit component stride
-template <int DX>
-inline bool stride_fits(long long n_steps, long long ld) { return !NarrowStride<DX>::value || n_steps * ld < (1LL << 32); }
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------

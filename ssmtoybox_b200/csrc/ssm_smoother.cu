@@ -40,9 +40,9 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
     const long long t = in_range ? t_raw : n_traj - 1;   // idle lanes of the last CTA only take part in the reductions
     // element (c, k, t) = row(k) + c * cs: per-thread row offset + kernel-uniform component stride, so an access
     // costs one 64-bit add instead of the 64-bit multiply chain of ((c * N + k) * ld + t)
-    const long long cs = (long long)N * ld;
+    const CompStride<NarrowStride<DX>::value> cs((long long)N * ld);   // 32-bit for dx > 1 (checked at launch)
     auto row = [&](int k) { return (long long)k * ld + t; };
-    auto at = [&](int c, int k) { return c * cs + row(k); };
+    auto at = [&](int c, int k) { return (long long)cs(c) + row(k); };
     double se_acc[DX];
 #pragma unroll
     for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? __ldcg(rmse_acc + (long long)a * ld + t) : 0.0;
@@ -140,17 +140,17 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         const double *q_fm = row_ptr(fi_mean, rk), *q_fc = row_ptr(fi_cov, rk);
 #pragma unroll
         for (int a = 0; a < DX; ++a) {
-            mp[a] = ld_stream(q_pm + a * cs);
-            mf[a] = ld_stream(q_fm + a * cs);
+            mp[a] = ld_stream(q_pm + cs(a));
+            mf[a] = ld_stream(q_fm + cs(a));
         }
 #pragma unroll
         for (int r = 0; r < DX; ++r)
 #pragma unroll
             for (int c = 0; c < DX; ++c) {
-                Pxx[r][c] = ld_stream(q_px + (r * DX + c) * cs);
+                Pxx[r][c] = ld_stream(q_px + cs(r * DX + c));
                 if (c <= r) {
-                    Pp[tri(r, c)] = ld_stream(q_pc + (r * DX + c) * cs);
-                    Pf[tri(r, c)] = ld_stream(q_fc + (r * DX + c) * cs);
+                    Pp[tri(r, c)] = ld_stream(q_pc + cs(r * DX + c));
+                    Pf[tri(r, c)] = ld_stream(q_fc + cs(r * DX + c));
                 }
             }
         // scipy's cho_factor / cho_solve reject non-finite input (ValueError)        ssinf.py:342
@@ -201,11 +201,11 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         if (KEEP) {
             double *q_sm = row_ptr(sm_mean, rk), *q_sc = row_ptr(sm_cov, rk);
 #pragma unroll
-            for (int a = 0; a < DX; ++a) st_stream(q_sm + a * cs, ms[a]);
+            for (int a = 0; a < DX; ++a) st_stream(q_sm + cs(a), ms[a]);
 #pragma unroll
             for (int r = 0; r < DX; ++r)
 #pragma unroll
-                for (int c = 0; c < DX; ++c) st_stream(q_sc + (r * DX + c) * cs, Ps[sym(r, c)]);
+                for (int c = 0; c < DX; ++c) st_stream(q_sc + cs(r * DX + c), Ps[sym(r, c)]);
         }
       } while (0);
         if (!alive && in_range) nan_row(k);
@@ -313,6 +313,10 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
                            double *stats, double *rmse_acc, double *quad, long long n_traj, int N, int k_lo, int k_hi, long long ld, cudaStream_t s,
                            bool keep = true, double *dres = nullptr, double *carry = nullptr) {
     const int WLEN = k_hi - k_lo;
+    if (!stride_fits<DX>(N, ld)) {
+        set_error("n_steps * ld = %lld elements per component: the smoother addresses components with a 32-bit stride (< 2^32); run the trajectories in chunks", (long long)N * ld);
+        return SSM_E_UNSUPPORTED;
+    }
     SmootherArgs a{fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, nullptr, rmse_acc, ld, N, k_lo, k_hi, quad};
     // TMA path: warp-CTAs over the full blocks of 32 trajectories; the ragged tail (and unaligned problems) take the
     // per-thread ld/st kernel.  Both write partial statistics rows that one finalise kernel sums in block order.

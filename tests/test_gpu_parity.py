@@ -121,6 +121,56 @@ def test_batched_vs_oracle_seeded(name, M, N):
         assert relstep(N_(sm['sm_cov'])[..., ok], bw['sm_cov'][..., ok]) < 10 * tol
 
 
+def test_asymmetric_covariance_weights_take_the_dense_path():
+    """The fast path evaluates fx Wc fx^T on the upper triangle of Wc and is launched for symmetric Wc only (every
+    weight set of the reference is: bq/bqmod.py:519-521).  An asymmetric Wc -- only a caller that assigns its own
+    weights can produce one -- must not be symmetrised silently: it takes the runtime-N path with dense rows, whose
+    lower triangle  fx_a Wc fx_b^T, b <= a,  is what the oracle's explicit loops compute."""
+    g = dict(golden('c4_ct_gpq'))
+    rs = np.random.RandomState(3)
+    for pfx in ('dyn_', 'obs_'):
+        W = g[pfx + 'Wc'].copy()
+        W += 1e-4 * np.abs(W).max() * np.triu(rs.randn(*W.shape), 1)
+        assert not np.array_equal(W, W.T)
+        g[pfx + 'Wc'] = W
+    y = np.ascontiguousarray(g['y'][:, :25])
+    ref = so.forward_pass(g, y, backend='loops')
+    low, o = run_filter(g, y)
+    assert np.array_equal(N_(o['status']) != 0, ref['status'] != 0)
+    ok = N_(o['status']) == 0
+    assert ok.any()
+    # (not to 1e-9: an asymmetric Wc makes the transformed COVARIANCES asymmetric, numpy carries both triangles through
+    # the update while the device keeps packed lower triangles -- a difference of the order of the asymmetry, 1e-4 here,
+    # times the gain.  The reference itself never produces such weights.)
+    assert relstep(N_(o['fi_mean'])[..., ok], ref['fi_mean'][..., ok]) < 1e-5
+    assert relstep(N_(o['fi_cov'])[..., ok], ref['fi_cov'][..., ok]) < 1e-3
+    # and the symmetric part alone gives a different filter: the asymmetry was not dropped
+    g2 = dict(g)
+    for pfx in ('dyn_', 'obs_'):
+        g2[pfx + 'Wc'] = 0.5 * (g[pfx + 'Wc'] + g[pfx + 'Wc'].T)
+    _, o2 = run_filter(g2, y)
+    assert relstep(N_(o2['fi_cov'])[..., ok], N_(o['fi_cov'])[..., ok]) > 1e-7
+
+
+def test_component_stride_beyond_32_bits_is_refused():
+    """Models with dx > 1 address the components of the [component][step][trajectory] arrays with a 32-bit stride
+    n_steps * ld (one IMAD.WIDE per address): a larger stride is refused before anything is launched."""
+    from ssmtoybox_b200 import _lib
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_ukf')
+    low = dv.lower(g)
+    y = torch.zeros(2, 4, 8, dtype=torch.float64, device='cuda')
+    fm = torch.zeros(5, 4, 8, dtype=torch.float64, device='cuda')
+    fc = torch.zeros(5, 5, 4, 8, dtype=torch.float64, device='cuda')
+    st = torch.zeros(8, dtype=torch.int32, device='cuda')
+    import ctypes as C
+    P = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib.ssm_filter(C.byref(low.desc), P(y), P(fm), P(fc), None, None, None, None, None, None, None, None, 0,
+                             P(st), 8, 4, 1 << 31, None)
+    assert rc == _lib.SSM_E_UNSUPPORTED
+    assert b'32-bit stride' in _lib.lib.ssm_last_error()
+
+
 # ------------------------------------------------------------------------------------------------
 # failure semantics and edge cases
 # ------------------------------------------------------------------------------------------------
