@@ -502,7 +502,26 @@ struct FilterBuffers {
     // squared error (dx, ld), and per scored unit d' P^-1 d (n_steps, ld) and d = x - m (dx, n_steps, ld), nullable
     const double *x_truth;
     double *partial, *rmse_acc, *quad, *dres;
+    // Dyn::time_term(k0 + k) per time slot k (models with HasTimeTerm, launches without per-trajectory time offsets), or NULL
+    const double *time_tab;
 };
+
+template <class Dyn>
+__global__ void time_tab_kernel(double *tab, int k0, int k_lo, int k_hi) {
+    const int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (HasTimeTerm<Dyn>::value) {
+        if (k < k_hi) tab[k] = Dyn::time_term((double)(k0 + k));
+    }
+}
+// fills the table behind the launch's stream; returns NULL (in-line evaluation) when it does not apply
+template <class Dyn>
+inline double *make_time_tab(const FilterBuffers &b, cudaStream_t s) {
+    if (!HasTimeTerm<Dyn>::value || b.t_offset || b.k_hi <= b.k_lo) return nullptr;
+    double *tab = nullptr;
+    if (scratch_alloc((void **)&tab, (size_t)b.n_steps * sizeof(double), s) != cudaSuccess) return nullptr;
+    time_tab_kernel<Dyn><<<(b.k_hi - b.k_lo + 127) / 128, 128, 0, s>>>(tab, b.k0, b.k_lo, b.k_hi);
+    return tab;
+}
 
 // NaN-fill of the outputs of failed trajectories from their failing step on, launched behind every forward-pass
 // kernel (ssm_abi.cu).  All lanes of a warp walk the time steps together, so the failed lanes of a warp write the same
@@ -699,6 +718,9 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
             for (int a = 0; a < DY; ++a) ynext[a] = ld_stream(b.y + cs(a) + (rk + ld));
         }
         const double time = tbase + (double)k;  // the reference passes time = k - 1, k 1-based (ssinf.py:104)
+        constexpr bool TT = HasTimeTerm<Dyn>::value;
+        double tt = 0.0;
+        if constexpr (TT) tt = b.time_tab ? __ldg(b.time_tab + k) : Dyn::time_term(time);
 
         double scale = 1.0;
         if (FAMILY == SSM_FAMILY_STUDENT) {  // ssinf.py:650-660
@@ -717,7 +739,8 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 p.tf_dyn, m, P,
                 [&](const double (&x)[DX], double (&o)[DX]) {
                     const double q0[Dyn::DQ] = {};
-                    Dyn::template f<false>(dpar, x, q0, time, o);
+                    if constexpr (TT) Dyn::template f_tt<false>(dpar, x, q0, tt, o);
+                    else Dyn::template f<false>(dpar, x, q0, time, o);
                 },
                 mp, Pp, want_xx,
                 [&](int a, int c, double v) { st_stream(q_xx + cs(a * DX + c), v); },  // Cov(x_k, x_{k-1})[a][c] -> pr_xx_cov[a][c][k][t]
@@ -736,7 +759,8 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                     for (int i = 0; i < DX; ++i) x[i] = xq[i];
 #pragma unroll
                     for (int i = 0; i < Dyn::DQ; ++i) q[i] = xq[DX + i];
-                    Dyn::template f<true>(dpar, x, q, time, o);
+                    if constexpr (TT) Dyn::template f_tt<true>(dpar, x, q, tt, o);
+                    else Dyn::template f<true>(dpar, x, q, time, o);
                 },
                 mp, Pp, want_xx,
                 [&](int a, int c, double v) {
@@ -1102,8 +1126,11 @@ int launch_filter_const(const FilterLaunch &L, const HostTfInfo &id, const HostT
         p.b.n_blocks = (int)blocks;
         grid = cap;
     }
+    double *ttab = make_time_tab<Dyn>(L.buf, L.stream);
+    p.b.time_tab = ttab;
     kern<<<(unsigned)grid, THREADS, smem, L.stream>>>(p);
     cudaError_t err = cudaGetLastError();
+    if (ttab) cudaFreeAsync(ttab, L.stream);
     if (err == cudaSuccess && filter_nan_fill(L.buf, DX, L.stream) != SSM_OK) err = cudaErrorUnknown;
     if (SCORE) {
         const long long row = (long long)WLEN * ScoreRow<DX>::WP;

@@ -238,8 +238,11 @@ int launch_filter_global(const FilterLaunch &L) {
     p.fixed_dof = d.fixed_dof;
     p.b = L.buf;
     const long long blocks = (L.buf.n_traj + THREADS - 1) / THREADS;
+    double *ttab = make_time_tab<Dyn>(L.buf, L.stream);
+    p.b.time_tab = ttab;
     filter_kernel<Dyn, Obs, PTS_GENERIC, 0, KIND, FAMILY, Par, THREADS, MINB, false><<<(unsigned)blocks, THREADS, 0, L.stream>>>(p);
     cudaError_t e = cudaGetLastError();
+    if (ttab) cudaFreeAsync(ttab, L.stream);
     if (e == cudaSuccess && filter_nan_fill(L.buf, DX, L.stream) != SSM_OK) e = cudaErrorUnknown;
     cudaFreeAsync(dev, L.stream);
     free(host);

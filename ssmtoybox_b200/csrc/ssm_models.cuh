@@ -3,19 +3,41 @@
 // serves the filter (zero noise, TransitionModel.dyn_eval ssmod.py:129-166,
 // MeasurementModel.meas_eval ssmod.py:960-1009) and the simulators (ssmod.py:168-244, 1011-1039).
 #pragma once
+#include <type_traits>
+
 #include "ssm_common.cuh"
 
 namespace ssm {
+
+// Dyn::TIME_TERM (optional member): the dynamics have an additive / multiplicative term that depends on time only
+template <class D, class = void>
+struct HasTimeTerm {
+    static constexpr bool value = false;
+};
+template <class D>
+struct HasTimeTerm<D, std::void_t<decltype(D::TIME_TERM)>> {
+    static constexpr bool value = D::TIME_TERM;
+};
 
 // ---- UNGMTransition.dyn_fcn, ssmod.py:268-269 -------------------------------------------------
 struct DynUngm {
     static constexpr int DX = 1, DQ = 1, ID = SSM_DYN_UNGM;
     static constexpr bool ADDITIVE = true;
     static constexpr bool HAS_CONT = false;
+    // The forcing term depends on the time step only.  It is the same for every sigma point and -- unless trajectories
+    // carry their own time offsets -- for every trajectory, so the forward pass reads it from a per-step table filled by
+    // one tiny launch (time_tab_kernel) instead of evaluating an fp64 cosine per trajectory-step (a fifth of the
+    // instructions of a UNGM UKF step).  The product is rounded on its own: table and in-line evaluation agree bit for bit.
+    static constexpr bool TIME_TERM = true;
+    SSM_DEV static double time_term(double t) { return __dmul_rn(8.0, cos(1.2 * t)); }
+    template <bool NOISE>
+    SSM_DEV static void f_tt(const double *, const double (&x)[1], const double (&q)[1], double tt, double (&o)[1]) {
+        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + tt;
+        if (NOISE) o[0] += q[0];
+    }
     template <bool NOISE>
     SSM_DEV static void f(const double *par, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
-        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + 8.0 * cos(1.2 * t);
-        if (NOISE) o[0] += q[0];
+        f_tt<NOISE>(par, x, q, time_term(t), o);
     }
     SSM_DEV static void fc(const double *, const double (&)[1], const double (&)[1], double, double (&o)[1]) { o[0] = 0.0; }
 };
@@ -26,9 +48,15 @@ struct DynUngmNA {
     static constexpr int DX = 1, DQ = 1, ID = SSM_DYN_UNGMNA;
     static constexpr bool ADDITIVE = false;
     static constexpr bool HAS_CONT = false;
+    static constexpr bool TIME_TERM = true;   // see DynUngm
+    SSM_DEV static double time_term(double t) { return cos(1.2 * t); }
     template <bool NOISE>
-    SSM_DEV static void f(const double *, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
-        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + 8.0 * (NOISE ? q[0] : 0.0) * cos(1.2 * t);
+    SSM_DEV static void f_tt(const double *, const double (&x)[1], const double (&q)[1], double tt, double (&o)[1]) {
+        o[0] = 0.5 * x[0] + 25.0 * (x[0] / (1.0 + x[0] * x[0])) + 8.0 * (NOISE ? q[0] : 0.0) * tt;
+    }
+    template <bool NOISE>
+    SSM_DEV static void f(const double *par, const double (&x)[1], const double (&q)[1], double t, double (&o)[1]) {
+        f_tt<NOISE>(par, x, q, time_term(t), o);
     }
     SSM_DEV static void fc(const double *, const double (&)[1], const double (&)[1], double, double (&o)[1]) { o[0] = 0.0; }
 };
