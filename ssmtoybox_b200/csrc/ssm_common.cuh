@@ -140,6 +140,23 @@ SSM_SMALL_MATH_FN double m_sqrt(double x) { return sqrt(x); }
 SSM_MATH_FN double m_rcp(double x) { return 1.0 / x; }
 SSM_SMALL_MATH_FN double m_rsqrt(double x) { return rsqrt(x); }
 SSM_MATH_FN double m_div(double a, double b) { return a / b; }
+// Two results per call (16-byte struct: returned in registers).  sincos: 84 instructions inline, 28 of them UMOV halves of
+// immediates, 11 copies per coordinated-turn step = 15 % of that loop body -- one shared copy instead.  div2: a / b and
+// c / b by the same denominator share the reciprocal seed and its Newton steps; both quotients are the IEEE ones.
+struct Pair2 {
+    double u, v;
+};
+SSM_MATH_FN Pair2 m_sincos(double x) {
+    Pair2 r;
+    sincos(x, &r.u, &r.v);
+    return r;
+}
+SSM_MATH_FN Pair2 m_div2(double a, double c, double b) {
+    Pair2 r;
+    r.u = a / b;
+    r.v = c / b;
+    return r;
+}
 #if SSM_LEAN_MATH == 1
 static __device__ __forceinline__ double m_atan2(double y, double x) { return lean_atan2(y, x); }
 #elif SSM_LEAN_MATH == 2

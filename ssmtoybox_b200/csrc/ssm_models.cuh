@@ -142,10 +142,10 @@ struct DynCoordTurn {
     SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[5], double, double (&o)[5]) {
         const double dt = par[0];
         const double om = x[4];
-        double a, b;
-        sincos(om * dt, &a, &b);
-        const double c = m_div(a, om);
-        const double d = m_div(1.0 - b, om);
+        const Pair2 sc = m_sincos(om * dt);
+        const double a = sc.u, b = sc.v;
+        const Pair2 cd = m_div2(a, 1.0 - b, om);
+        const double c = cd.u, d = cd.v;
         o[0] = x[0] + c * x[1] - d * x[3];
         if (NOISE) o[0] += q[0];
         o[1] = b * x[1] - a * x[3];
@@ -225,16 +225,16 @@ struct DynCtrs {
     SSM_DEV static void f(const double *par, const double (&x)[5], const double (&q)[2], double, double (&o)[5]) {
         const double dt = par[0], h = 0.5 * dt * dt;
         const double q0 = NOISE ? q[0] : 0.0, q1 = NOISE ? q[1] : 0.0;
-        double s3, c3;
-        sincos(x[3], &s3, &c3);
+        const Pair2 sc3 = m_sincos(x[3]);
+        const double s3 = sc3.u, c3 = sc3.v;
         double f0, f1;
         if (x[4] == 0.0) {
             f0 = dt * x[2] * c3;
             f1 = dt * x[2] * s3;
         } else {
             const double c = m_div(x[2], x[4]);
-            double s34, c34;
-            sincos(x[3] + x[4] * dt, &s34, &c34);
+            const Pair2 sc34 = m_sincos(x[3] + x[4] * dt);
+            const double s34 = sc34.u, c34 = sc34.v;
             f0 = c * (s34 - s3) + h * c3 * q0;
             f1 = c * (-c34 + c3) + h * s3 * q0;
         }
