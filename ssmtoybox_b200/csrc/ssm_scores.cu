@@ -10,6 +10,9 @@
 // The log credibility ratio needs the GLOBAL per-step MSE matrix first (two-phase reduction).
 #include "ssm_scores.cuh"
 
+#ifndef SSM_P2_GROUP
+#define SSM_P2_GROUP 4   // measured on 125 000 x 500: 1 / 2 / 4 / 8 steps per reduction 1.37 / 1.26 / 1.12 / 2.01 ms (8: 33 KB of shared memory per CTA)
+#endif
 namespace ssm {
 
 void set_error(const char *fmt, ...);
@@ -135,16 +138,25 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
                                                                    double *__restrict__ lcr_acc,
                                                                    long long n_traj, int N, int k_lo, int k_hi, long long ld) {
     constexpr int TX = TriSize<DX>::value, TW = TX + DX + 1;
+    // G time steps per CTA reduction.  The stored-error form reads 6 doubles per step and has next to no arithmetic: one
+    // step at a time it is a chain of (6 loads -> wait -> reduce -> barrier); four steps at a time 24 loads are in flight
+    // per thread and there is one barrier per four steps.  Same per-step sums in the same order: bitwise equal results.
+    constexpr int G = (QUAD && RES) ? SSM_P2_GROUP : 1;
     const int WLEN = k_hi - k_lo;
-    __shared__ double smem[BlockReduce<2>::SIZE];
+    __shared__ double smem[BlockReduce<2 * G>::SIZE];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_traj && (status == nullptr || status[t] == 0);
     const long long cs = (long long)N * ld;
     // per-trajectory time-sum of the log credibility ratio (nciData of research/gpq/icinco_demo.py:36-47)
     double lcr_sum = (lcr_acc && k_lo > 0 && t < n_traj) ? lcr_acc[t] : 0.0;
-    for (int k = k_lo; k < k_hi; ++k) {
-        double v[2] = {0.0, 0.0};
-        if (live) {
+    for (int kg = k_lo; kg < k_hi; kg += G) {
+        double v[2 * G];
+#pragma unroll
+        for (int i = 0; i < 2 * G; ++i) v[i] = 0.0;
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        const int k = kg + gi;
+        if (live && k < k_hi) {
             double d[DX], P[TX], L[TX], inv[DX];
             const long long rk = (long long)k * ld + t;
             const double *qx = row_ptr(x, rk), *qm = RES ? nullptr : row_ptr(mean, rk), *qc = row_ptr(cov, rk);
@@ -182,11 +194,12 @@ __global__ void __launch_bounds__(SC_THREADS) scores_phase2_kernel(const double 
             }
             if (QUAD) qa = q_given;   // NaN where the covariance was not positive definite
             const double g = ok ? 10.0 * (log10(qa) - log10(qb)) : qnan();
-            v[0] = g;
-            v[1] = fabs(g);
+            v[2 * gi] = g;
+            v[2 * gi + 1] = fabs(g);
             lcr_sum += g;
         }
-        block_reduce_store<2>(v, smem, k, partial + ((long long)blockIdx.x * WLEN + (k - k_lo)) * 2);
+      }
+        block_reduce_store<2 * G>(v, smem, (kg - k_lo) / G, partial + ((long long)blockIdx.x * WLEN + (kg - k_lo)) * 2, 2 * min(G, k_hi - kg));
     }
     if (lcr_acc && t < n_traj) lcr_acc[t] = live ? lcr_sum : qnan();
 }

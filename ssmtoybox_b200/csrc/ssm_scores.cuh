@@ -73,7 +73,7 @@ struct BlockReduce {
     static_assert(4 * W <= SC_THREADS, "four threads per row");
 };
 template <int W>
-SSM_DEV void block_reduce_store(const double (&v)[W], double *smem /* [BlockReduce<W>::SIZE] */, int parity, double *dst) {
+SSM_DEV void block_reduce_store(const double (&v)[W], double *smem /* [BlockReduce<W>::SIZE] */, int parity, double *dst, int n_rows = W) {
     constexpr int LD = BlockReduce<W>::LD;
     double *buf = smem + (parity & 1) * (W * LD);
     const int tid = threadIdx.x;
@@ -94,7 +94,7 @@ SSM_DEV void block_reduce_store(const double (&v)[W], double *smem /* [BlockRedu
         double s = (s0 + s1) + (s2 + s3);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (seg == 0 && row < W) dst[row] = s;
+        if (seg == 0 && row < n_rows) dst[row] = s;   // n_rows < W: the last, partial group of a multi-step reduction
     }
 }
 
