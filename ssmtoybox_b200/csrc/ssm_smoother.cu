@@ -2,6 +2,7 @@
 // stored by the forward pass.  Pure small-matrix algebra on five streamed arrays: HBM-bound.
 // Replaces StateSpaceInference.backward_pass (ssinf.py:120-147) and
 // GaussianInference._smoothing_update (ssinf.py:325-344).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "ssm_smoother_tma.cuh"
@@ -17,7 +18,23 @@ void set_error(const char *fmt, ...);
 // never stored -- nothing downstream reads them when only the scores are wanted (200 of the 808 bytes per unit for
 // dx = 5).  The second score phase gets the error d = x - m_s itself (dres) next to d' P_s^-1 d (quad), and the
 // recursion crosses time windows through a (dx + dx (dx + 1) / 2, ld) carry buffer instead of the sm arrays.
-template <int DX, bool SCORE, bool KEEP>
+// STAGE (score-only mode): the inputs of iteration k - 1 (predictive mean / covariance / cross-covariance and the filtered
+// covariance, 60 of the 70 doubles of a dx = 5 step) are copied global -> shared with cp.async while iteration k computes.
+// Each thread copies into and later reads from its OWN column of the staging area, so no barrier is involved: shared
+// memory is just the landing zone that a register prefetch has no room for (the kernel sits at 244 registers).  The
+// filtered mean and the truth, needed late in a step, stay plain loads.
+SSM_DEV void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+SSM_DEV void cp_async16(double *smem_dst, const double *gsrc) {   // L2 -> shared memory, no L1 allocation
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+SSM_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SSM_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int DX, bool SCORE, bool KEEP, int STAGE_MODE = 0>
 SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
                            const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
                            const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
@@ -26,13 +43,16 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
                            double *__restrict__ rmse_acc, double *__restrict__ quad,
                            double *__restrict__ dres, double *__restrict__ carry, long long n_traj, int N,
                            const int k_lo0, const int k_hi0, long long ld, const long long blk, const int k_lo, const int k_hi,
-                           double *smem) {
+                           double *smem, double *stage = nullptr) {
     // Time window [k_lo, k_hi) of the N slots (ssm_smooth_window): a window with k_hi < N continues the recursion
     // from the smoothed moments the later window left in sm_mean / sm_cov (same stream => ordered), so walking the
     // windows from the last to the first reproduces the one-pass result bit for bit.  [k_lo0, k_hi0) is the window of
     // the whole launch (row index of the partial statistics); they differ when the ticket kernel below runs one of
     // its time chunks.
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
+    constexpr bool STAGE = (STAGE_MODE & 1) != 0;    // the inputs of the recursion, one iteration ahead
+    constexpr bool XSTAGE = (STAGE_MODE & 2) != 0;   // the truth of the current iteration, issued at its start
+    constexpr int XS0 = STAGE ? DX + DX * DX + 2 * TX : 0;   // first staging column of the truth
     const int WLEN = k_hi0 - k_lo0;
     const long long t_raw = blk * blockDim.x + threadIdx.x;
     const bool in_range = t_raw < n_traj;
@@ -47,14 +67,20 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
 #pragma unroll
     for (int a = 0; a < DX; ++a) se_acc[a] = (SCORE && rmse_acc && k_hi < N) ? __ldcg(rmse_acc + (long long)a * ld + t) : 0.0;
     // score the smoothed moments (ms, Ps) of step k; every thread of the CTA calls this once per step
-    auto score = [&](int k, bool live, const double (&ms_)[DX], const double (&Ps_)[TX]) {
+    auto score = [&](int k, bool live, const double (&ms_)[DX], const double (&Ps_)[TX], const double *xs = nullptr) {
         double v[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = 0.0;
         if (live) {
             double d[DX], se[DX];
+            if (xs) {   // truth staged in shared memory by this thread at the start of the iteration
+                cp_async_wait_all();
 #pragma unroll
-            for (int a = 0; a < DX; ++a) d[a] = ld_stream(x_truth + at(a, k)) - ms_[a];
+                for (int a = 0; a < DX; ++a) d[a] = xs[a * SC_THREADS] - ms_[a];
+            } else {
+#pragma unroll
+                for (int a = 0; a < DX; ++a) d[a] = ld_stream(x_truth + at(a, k)) - ms_[a];
+            }
             double qf;
             score_step<DX>(d, Ps_, v, se, &qf);
             if (quad) st_stream(quad + row(k), qf);
@@ -129,15 +155,87 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         if (SCORE) score(k, alive, mk, Pk);
     }
     int fail = 0, kfail = 0;
+    // Staging area: component j of trajectory column c at stage[j * SC_THREADS + c]; order [mp | Pxx | Pp (packed) | Pf
+    // (packed) | truth].  Inputs (STAGE): lane pairs copy 16 bytes = the same component of BOTH trajectories of the pair
+    // (even lane: even components, odd lane: odd components) with cp.async.cg, which goes L2 -> shared memory without an
+    // L1 allocation -- the 8-byte form allocates in L1, and with 228 KB of the SM's array carved out as shared memory the
+    // remaining L1 cannot hold the lines in flight (measured 11.3 ms against 9.2 ms without staging).
+    double *sg = (STAGE || XSTAGE) ? stage + threadIdx.x : nullptr;
+    const int par = threadIdx.x & 1;
+    double *sgp = (STAGE || XSTAGE) ? stage + (threadIdx.x & ~1) : nullptr;
+    const bool pair_in = (t_raw | 1) < n_traj;   // both trajectories of the lane pair exist (n_traj is even in this mode)
+    auto stage_truth16 = [&](int k) {   // truth of iteration k, columns [XS0, XS0 + DX)
+        const double *q_x = row_ptr(x_truth, (long long)k * ld + (t_raw - par));
+#pragma unroll
+        for (int a = 0; a < DX; ++a)
+            if (((XS0 + a) & 1) == par) cp_async16(sgp + (XS0 + a) * SC_THREADS, q_x + cs(a));
+    };
+    auto stage_issue = [&](int k) {     // inputs of iteration k
+        const long long rkp = (long long)k * ld + (t_raw - par);
+        const double *q_pm = row_ptr(pr_mean, rkp + ld), *q_pc = row_ptr(pr_cov, rkp + ld), *q_px = row_ptr(pr_xx, rkp + ld);
+        const double *q_fc = row_ptr(fi_cov, rkp);
+#pragma unroll
+        for (int a = 0; a < DX; ++a)
+            if ((a & 1) == par) cp_async16(sgp + a * SC_THREADS, q_pm + cs(a));
+#pragma unroll
+        for (int c = 0; c < DX * DX; ++c)
+            if (((DX + c) & 1) == par) cp_async16(sgp + (DX + c) * SC_THREADS, q_px + cs(c));
+#pragma unroll
+        for (int r = 0; r < DX; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+                if (((DX + DX * DX + tri(r, c)) & 1) == par) cp_async16(sgp + (DX + DX * DX + tri(r, c)) * SC_THREADS, q_pc + cs(r * DX + c));
+                if (((DX + DX * DX + TX + tri(r, c)) & 1) == par) cp_async16(sgp + (DX + DX * DX + TX + tri(r, c)) * SC_THREADS, q_fc + cs(r * DX + c));
+            }
+    };
+    if (STAGE && pair_in && min(k_hi - 1, N - 3) >= k_lo) {
+        stage_issue(min(k_hi - 1, N - 3));
+        cp_async_commit();
+    }
     for (int k = min(k_hi - 1, N - 3); k >= k_lo; --k) {
       // ONE score() call site per iteration: its warp shuffles and CTA barriers must be reached by every thread
       // through the same instruction, so failures leave the step body with `break`, never `continue`.
+      double mp[DX], Pp[TX], Pxx[DX][DX], mf[DX], Pf[TX];
+      if constexpr (STAGE) {
+          // the copies issued during the previous iteration have landed; every lane of the warp passes here (dead
+          // trajectories keep copying for their pair partner), the two warp barriers order partner copies and own reads
+          cp_async_wait_all();
+          __syncwarp();
+          if (alive) {
+#pragma unroll
+              for (int a = 0; a < DX; ++a) mp[a] = sg[a * SC_THREADS];
+#pragma unroll
+              for (int r = 0; r < DX; ++r)
+#pragma unroll
+                  for (int c = 0; c < DX; ++c) Pxx[r][c] = sg[(DX + r * DX + c) * SC_THREADS];
+#pragma unroll
+              for (int a = 0; a < TX; ++a) {
+                  Pp[a] = sg[(DX + DX * DX + a) * SC_THREADS];
+                  Pf[a] = sg[(DX + DX * DX + TX + a) * SC_THREADS];
+              }
+          }
+          __syncwarp();
+          if (pair_in) {
+              if (XSTAGE) stage_truth16(k);        // scored at the end of this iteration
+              if (k > k_lo) stage_issue(k - 1);    // into the columns just read
+              cp_async_commit();
+          }
+      }
       do {
         if (!alive) break;
-        double mp[DX], Pp[TX], Pxx[DX][DX], mf[DX], Pf[TX];
         const long long rk = row(k);
         const double *q_pm = row_ptr(pr_mean, rk + ld), *q_pc = row_ptr(pr_cov, rk + ld), *q_px = row_ptr(pr_xx, rk + ld);
         const double *q_fm = row_ptr(fi_mean, rk), *q_fc = row_ptr(fi_cov, rk);
+        if constexpr (XSTAGE && !STAGE) {   // the truth is scored ~1 500 instructions further down: fetch it now
+            const double *q_x = row_ptr(x_truth, rk);
+#pragma unroll
+            for (int a = 0; a < DX; ++a) cp_async8(sg + (XS0 + a) * SC_THREADS, q_x + cs(a));
+            cp_async_commit();
+        }
+        if constexpr (STAGE) {
+#pragma unroll
+            for (int a = 0; a < DX; ++a) mf[a] = ld_stream(q_fm + cs(a));
+        } else {
 #pragma unroll
         for (int a = 0; a < DX; ++a) {
             mp[a] = ld_stream(q_pm + cs(a));
@@ -153,6 +251,7 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
                     Pf[tri(r, c)] = ld_stream(q_fc + cs(r * DX + c));
                 }
             }
+        }
         // scipy's cho_factor / cho_solve reject non-finite input (ValueError)        ssinf.py:342
         bool fin = true;
 #pragma unroll
@@ -209,7 +308,7 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         }
       } while (0);
         if (!alive && in_range) nan_row(k);
-        if (SCORE) score(k, alive, ms, Ps);
+        if (SCORE) score(k, alive, ms, Ps, XSTAGE ? sg + XS0 * SC_THREADS : nullptr);
     }
     if (SCORE && rmse_acc && in_range) {
 #pragma unroll
@@ -222,12 +321,21 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         for (int a = 0; a < TX; ++a) carry[(long long)(DX + a) * ld + t] = Ps[a];
     }
     if (fail && in_range) status[t] = ((kfail + 1) << 8) | fail;
+    if (STAGE || XSTAGE) cp_async_wait_all();   // a trajectory that failed on the way may still have copies in flight
 }
 
+#ifndef SSM_SMOOTH_STAGE_DEFAULT
+#define SSM_SMOOTH_STAGE_DEFAULT 3
+#endif
 #ifndef SSM_SMOOTH_SCORE_MINB
 #define SSM_SMOOTH_SCORE_MINB 1   // resident CTAs per SM the score-only kernel is compiled for (developer A/B)
 #endif
-template <int DX, bool SCORE, bool KEEP>
+template <int DX, int STAGE_MODE>
+struct StageBytes {
+    static constexpr int COMPS = ((STAGE_MODE & 1) ? DX + DX * DX + 2 * TriSize<DX>::value : 0) + ((STAGE_MODE & 2) ? DX : 0);
+    static constexpr size_t value = (size_t)COMPS * SC_THREADS * sizeof(double);
+};
+template <int DX, bool SCORE, bool KEEP, int STAGE = 0>
 __global__ void __launch_bounds__(SC_THREADS, KEEP ? 1 : SSM_SMOOTH_SCORE_MINB) smoother_kernel(const double *__restrict__ fi_mean, const double *__restrict__ fi_cov,
                                                               const double *__restrict__ pr_mean, const double *__restrict__ pr_cov,
                                                               const double *__restrict__ pr_xx, double *__restrict__ sm_mean,
@@ -237,8 +345,9 @@ __global__ void __launch_bounds__(SC_THREADS, KEEP ? 1 : SSM_SMOOTH_SCORE_MINB) 
                                                               double *__restrict__ dres, double *__restrict__ carry, long long n_traj, int N,
                                                               int k_lo, int k_hi, long long ld) {
     __shared__ double smem[SCORE ? BlockReduce<ScoreRow<DX>::WP>::SIZE : 1];
-    smoother_body<DX, SCORE, KEEP>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, partial, rmse_acc, quad,
-                                   dres, carry, n_traj, N, k_lo, k_hi, ld, blockIdx.x, k_lo, k_hi, smem);
+    extern __shared__ __align__(16) double ssm_stage_smem[];
+    smoother_body<DX, SCORE, KEEP, STAGE>(fi_mean, fi_cov, pr_mean, pr_cov, pr_xx, sm_mean, sm_cov, status, x_truth, partial, rmse_acc, quad,
+                                          dres, carry, n_traj, N, k_lo, k_hi, ld, blockIdx.x, k_lo, k_hi, smem, STAGE ? ssm_stage_smem : nullptr);
 }
 
 // Ticket scheduling of the score-only smoother (opt-in, see launch_smoother: measured and rejected).  A trajectory is a serial recursion, so a plain launch is quantised in
@@ -358,6 +467,31 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
                     (int *)work, CHUNK, (int)tail_blocks);
                 cudaFreeAsync(work, s);
             } else {
+                // staged inputs (cp.async into shared memory one iteration ahead) unless SSM_SMOOTH_STAGE=0
+                // SSM_SMOOTH_STAGE (developer switch): 0 plain loads, 1 inputs staged one iteration ahead, 2 truth staged, 3 both
+                const char *env_stage = getenv("SSM_SMOOTH_STAGE");
+                int mode = env_stage ? atoi(env_stage) : SSM_SMOOTH_STAGE_DEFAULT;
+                {   // the 16-byte pair copies need even trajectory counts / leading dimensions and 16-byte aligned rows
+                    auto al = [&](const void *q) { return ((uintptr_t)q & 15) == 0; };
+                    if ((mode & 1) && ((rem & 1) || (ld & 1) || (t_tail & 1) || !al(off(fi_cov)) || !al(off(pr_mean)) || !al(off(pr_cov)) || !al(off(pr_xx)) || !al(off(x_truth))))
+                        mode &= 2;
+                }
+                auto launch_staged = [&](auto kst, size_t bytes) {
+                    cudaFuncSetAttribute(kst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                    if (getenv("SSM_SMOOTH_CARVEOUT")) cudaFuncSetAttribute(kst, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("SSM_SMOOTH_CARVEOUT")));
+                    if (getenv("SSM_SMOOTH_DEBUG")) {
+                        int occ = 0;
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kst, SC_THREADS, bytes);
+                        fprintf(stderr, "[ssm smoother] staging mode %d: %zu bytes dynamic shared memory, %d CTAs per SM\n", mode, bytes, occ);
+                    }
+                    kst<<<(unsigned)tail_blocks, SC_THREADS, bytes, s>>>(
+                        off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), nullptr, nullptr, status + t_tail,
+                        off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), offw(dres), offw(carry), rem, N, k_lo, k_hi, ld);
+                };
+                if (mode == 1) launch_staged(smoother_kernel<DX, true, false, 1>, StageBytes<DX, 1>::value);
+                else if (mode == 2) launch_staged(smoother_kernel<DX, true, false, 2>, StageBytes<DX, 2>::value);
+                else if (mode == 3) launch_staged(smoother_kernel<DX, true, false, 3>, StageBytes<DX, 3>::value);
+                else
                 smoother_kernel<DX, true, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                     off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), nullptr, nullptr, status + t_tail,
                     off(x_truth), partial + (size_t)n_full * WLEN * W, offw(rmse_acc), offw(quad), offw(dres), offw(carry), rem, N, k_lo, k_hi, ld);
