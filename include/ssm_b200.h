@@ -130,6 +130,14 @@ typedef struct ssm_desc {
 int ssm_abi_version(void);
 const char *ssm_last_error(void);
 
+/* 1 when the forward pass (ssm_filter*) will evaluate this BQ transform with the compact sums of the
+ * reflection-symmetric form, 0 when it takes the dense sums of bqmtran.py:175-223 as they stand.  The compact form
+ * applies to point sets [0 | cI | -cI] whose weights are invariant, bit for bit, under every coordinate reflection
+ * x_j -> -x_j (wm(j+) == wm(j-), Wc equal within each class of reflected index pairs, Wcc(d, .) zero except for
+ * Wcc(d, d+) == -Wcc(d, d-)): what the formulas of bq/bqmod.py:495-523, 893-992 give in exact arithmetic.  Host-side
+ * check, no CUDA call.  Environment SSM_REFL=0 switches the compact form off. */
+int ssm_weights_reflective(const ssm_transform *tf);
+
 /* ---- K2: fused forward pass -----------------------------------------------------------------
  * Replaces StateSpaceInference.forward_pass (ssinf.py:66-118) with _time_update (:254-295 /
  * :634-698), _measurement_update (:297-323 / :700-736), MomentTransform.apply and the model

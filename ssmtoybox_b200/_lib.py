@@ -67,6 +67,8 @@ def _load():
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.ssm_abi_version.restype = C.c_int
     lib.ssm_last_error.restype = C.c_char_p
+    lib.ssm_weights_reflective.restype = C.c_int
+    lib.ssm_weights_reflective.argtypes = [C.POINTER(SsmTransform)]
     lib.ssm_filter.restype = C.c_int
     lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
     lib.ssm_filter_window.restype = C.c_int

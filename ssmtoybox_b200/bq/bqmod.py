@@ -55,6 +55,82 @@ class weight_precision(object):
         return False
 
 
+# structure of the quadrature weights
+# ------------------------------------------------------------------------------------------------
+# Point sets of the form [0 | c I | -c I] (UT, fully-symmetric degree 3) are mapped onto themselves by every coordinate
+# reflection x_j -> -x_j, and so are the RBF kernel, the polynomial bases closed under x_j -> -x_j and the integration
+# density: in exact arithmetic wm(j+) = wm(j-), Wc and K^-1 commute with every reflection, and Wcc(d, .) vanishes
+# except for Wcc(d, d+) = -Wcc(d, d-).  Computed weights have this structure up to rounding only (the reference's float64
+# weights for its reentry hyper-parameters: 1e-12 ... 1e-9 where zeros belong, next to entries of 0.22).  With the switch
+# on (default, 'dd' precision only) the computed weights are projected onto the invariant subspace -- averaged over each
+# class of entries that are equal in exact arithmetic, exact zeros where they belong -- which removes rounding noise,
+# never adds any, and lets the forward pass use the compact sums of the reflection-symmetric form (ssm_filter.cuh,
+# SSM_TF_BQR: ~45 % fewer multiply-adds per moment transform).  'float64' precision keeps the reference's arithmetic as is.
+_SYMMETRY = [__import__('os').environ.get('SSM_BQ_SYMMETRIZE', '1') != '0']
+
+
+def set_weight_symmetry(on):
+    """Package-level switch: project 'dd' weights on axis-symmetric point sets onto their exact reflection structure."""
+    old, _SYMMETRY[0] = _SYMMETRY[0], bool(on)
+    return old
+
+
+def get_weight_symmetry():
+    return _SYMMETRY[0]
+
+
+def reflective_axis_set(points):
+    """c > 0 when points (D, N) are [0 | c I | -c I] bit for bit (the layout the forward pass calls PTS_AXIS_C), else None."""
+    pts = np.asarray(points, dtype=np.float64)
+    D, N = pts.shape
+    if N != 2 * D + 1 or not pts[0, 1] > 0.0:
+        return None
+    c = pts[0, 1]
+    want = np.hstack([np.zeros((D, 1)), c * np.eye(D), -c * np.eye(D)])
+    return float(c) if np.array_equal(pts, want) else None
+
+
+def symmetrize_reflective(points, w, rtol=1e-6):
+    """Project one weight set (dict with wm (N,), Wc (N, N), Wcc (D, N), optionally iK (N, N)) onto the reflection-invariant
+    structure of an axis-symmetric point set.  Returns a new dict, or `w` itself when the point set is not of that form
+    or the weights are further than rtol (relative to the largest entry of each array) from the structure -- a kernel
+    or basis without the symmetry is left alone."""
+    if reflective_axis_set(points) is None:
+        return w
+    D = np.asarray(points).shape[0]
+    N = 2 * D + 1
+    mirror = np.r_[0, np.arange(1, D + 1) + D, np.arange(1, D + 1)]
+
+    def average(A):
+        # (A + P_j A P_j^T) / 2 for every axis j in turn: the reflections commute, so the product of these projectors is
+        # the average over the whole group; (x + y) / 2 is the same bits for both members of a pair, and a pair made
+        # equal by axis j stays equal through the steps of the other axes
+        A = 0.5 * (A + A.T)
+        for j in range(D):
+            perm = np.arange(N)
+            perm[[1 + j, 1 + D + j]] = perm[[1 + D + j, 1 + j]]
+            A = 0.5 * (A + A[np.ix_(perm, perm)])
+        return A
+
+    out = dict(w)
+    wm = np.asarray(w['wm'], dtype=np.float64)
+    out['wm'] = 0.5 * (wm + wm[mirror])
+    out['Wc'] = average(np.asarray(w['Wc'], dtype=np.float64))
+    Wcc = np.asarray(w['Wcc'], dtype=np.float64)
+    S = np.zeros_like(Wcc)
+    for d in range(D):
+        v = 0.5 * (Wcc[d, 1 + d] - Wcc[d, 1 + D + d])
+        S[d, 1 + d], S[d, 1 + D + d] = v, -v
+    out['Wcc'] = S
+    if w.get('iK') is not None:
+        out['iK'] = average(np.asarray(w['iK'], dtype=np.float64))
+    for k in ('wm', 'Wc', 'Wcc') + (('iK',) if w.get('iK') is not None else ()):
+        a, b = np.asarray(w[k], dtype=np.float64), out[k]
+        if not np.all(np.isfinite(a)) or np.abs(a - b).max() > rtol * np.abs(a).max():
+            return w
+    return out
+
+
 def n_sum_k(n, k):
     """All n-tuples of non-negative integers summing to k, in the reference's column order (utils.py:459-475)."""
     assert k >= 0
@@ -123,6 +199,10 @@ class Model(object):
         w = dv.bq_weights(par[:1], self.points, mulind, precision=get_weight_precision())
         if int(w['info'][0]) != 0:
             raise np.linalg.LinAlgError('kernel matrix is not positive definite (info = {})'.format(int(w['info'][0])))
+        if get_weight_symmetry() and get_weight_precision() == 'dd':
+            w1 = symmetrize_reflective(self.points, {k: w[k][0] for k in ('wm', 'Wc', 'Wcc', 'iK')})
+            for k in ('wm', 'Wc', 'Wcc', 'iK'):
+                w[k] = w1[k][None]
         return w
 
 

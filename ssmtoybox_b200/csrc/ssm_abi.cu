@@ -69,6 +69,11 @@ using namespace ssm;
 extern "C" int ssm_abi_version(void) { return SSM_ABI_VERSION; }
 extern "C" const char *ssm_last_error(void) { return g_err; }
 
+extern "C" int ssm_weights_reflective(const ssm_transform *tf) {
+    if (!tf || !tf->points || tf->dim_in < 1 || tf->n_pts != 2 * tf->dim_in + 1) return 0;
+    return weights_reflective(*tf, classify_points(*tf)) ? 1 : 0;
+}
+
 struct ScoreOut {
     const double *x_truth;
     double *stats, *rmse_acc, *quad, *dres;

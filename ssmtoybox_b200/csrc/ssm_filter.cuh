@@ -21,6 +21,10 @@
 namespace ssm {
 
 enum { PTS_AXIS_C = 0, PTS_AXIS = 1, PTS_GENERIC = 2 };
+// Internal transform kind of the fast path (never part of the C ABI): a BQ transform on a [0 | cI | -cI] point set whose
+// weights are bitwise invariant under the coordinate reflections x_j -> -x_j (weights_reflective()).  See the BQR branch of
+// moment_transform for what that buys.
+#define SSM_TF_BQR 1001
 #ifndef SSM_WEIGHT_VIEWS
 #define SSM_WEIGHT_VIEWS 0
 #endif
@@ -41,7 +45,7 @@ constexpr int GEN_CAP_STREAM = 4096;  // sigma-point rules beyond GEN_CAP points
 // ------------------------------------------------------------------------------------------------
 template <int D, int E, int NCAP, int KIND, int PTS>
 struct TfConst {
-    static constexpr int NW = (KIND == SSM_TF_SP) ? 1 : NCAP;
+    static constexpr int NW = (KIND == SSM_TF_SP) ? 1 : (KIND == SSM_TF_BQR ? D + 1 : NCAP);
     static constexpr int NK = (KIND == SSM_TF_TP) ? NCAP : 1;
     static constexpr int DU = (PTS == PTS_GENERIC) ? D : 1;
     static constexpr int DC = (KIND == SSM_TF_SP) ? 1 : D;
@@ -246,6 +250,98 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
 #pragma unroll
         for (int a = 0; a < E; ++a) fxs.set(a, i, o[a]);
     }
+    if constexpr (KIND == SSM_TF_BQR) {
+        // Reflection-symmetric weights.  The point set [0 | c e_j | -c e_j] is mapped onto itself by each coordinate
+        // reflection x_j -> -x_j, and so is everything the weights are made of (a kernel that depends on x_j - x'_j
+        // through its square, a symmetric integration density): in exact arithmetic
+        //   wm(j+) = wm(j-),   Wc = P Wc P^T for every reflection P,   Wcc(d, .) is odd under reflection d and even under
+        //   all others, i.e. zero except for  Wcc(d, d+) = -Wcc(d, d-).
+        // With  g = [f_0, f_1+ + f_1-, ..., f_D+ + f_D-]  and  a_j = f_j+ - f_j-  the three sums of bqmtran.py:175-223 are
+        //   mean  = wm_0 g_0 + sum_j wm_j g_j                                              (D + 1 instead of 2 D + 1 terms)
+        //   fx Wc fx^T = g S g^T + sum_j alpha_j a_j a_j^T,   S (D+1 x D+1), alpha_j = (Wc(j+,j+) - Wc(j+,j-)) / 2
+        //   fx Wcc^T = [Wcc(d, d+) a_d]_d                                                   (E D instead of E N D terms)
+        // -- for the 5-D reentry dynamics ~565 instead of ~1 040 multiply-adds per transform and 37 instead of 132
+        // weights.  The host launches this instantiation only for weight sets that HAVE the invariance bit for bit
+        // (weights_reflective(): the package's own weights, which are symmetrised when they are built; weights assigned
+        // from a reference run carry its rounding noise in the entries that are zero here and take the dense path).
+        static_assert(PTS == PTS_AXIS_C && NPTS == 2 * D + 1 && SMT == 0, "reflection-symmetric path: [0 | cI | -cI] points, registers");
+        constexpr int M = D + 1;
+        double g[E][M], av[E][D];
+#pragma unroll
+        for (int a = 0; a < E; ++a) {
+            g[a][0] = fx(a, 0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                g[a][1 + j] = fx(a, 1 + j) + fx(a, 1 + D + j);
+                av[a][j] = fx(a, 1 + j) - fx(a, 1 + D + j);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < E; ++a) mf[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const double w = tf.wm(i);
+#pragma unroll
+            for (int a = 0; a < E; ++a) mf[a] = fma(g[a][i], w, mf[a]);
+        }
+        if (want_cross) {
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                double T[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) T[d] = av[a][d] * tf.Wcc(d, 0);
+#pragma unroll
+                for (int r = 0; r < D; ++r) {  // (T L^T)[a][r] = sum_{d<=r} T[a][d] L[r][d]                bqmtran.py:223
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d <= r; ++d) s = fma(T[d], L[tri(r, d)], s);
+                    sink(a, r, s);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < TriSize<E>::value; ++a) Cf[a] = 0.0;
+        // g S g^T column by column on half rows (as the SYMW branch below, over D + 1 columns)
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            double hc[E];
+            {
+                const double w = tf.Wch(j);
+#pragma unroll
+                for (int a = 0; a < E; ++a) hc[a] = g[a][j] * w;
+            }
+#pragma unroll
+            for (int i = 0; i < j; ++i) {
+                const double w = tf.Wc(j, i);
+#pragma unroll
+                for (int a = 0; a < E; ++a) hc[a] = fma(g[a][i], w, hc[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b < E; ++b) Cf[sym(a, b)] = fma(hc[a], g[b][j], Cf[sym(a, b)]);
+        }
+#pragma unroll
+        for (int a = 0; a < E; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(-mf[a], mf[b], (a == b) ? Cf[tri(a, b)] + Cf[tri(a, b)] : Cf[tri(a, b)]);
+        // the odd parts are differences of neighbouring function values: small, and added after the cancellation
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double w = tf.wc(j);
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const double t = av[a][j] * w;
+#pragma unroll
+                for (int b = 0; b <= a; ++b) Cf[tri(a, b)] = fma(t, av[b][j], Cf[tri(a, b)]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < E; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) Cf[tri(a, b)] += tf.mv(a, b);
+        return ok;
+    } else {
     // mean_f = fx . wm                                          mtran.py:143, bqmtran.py:175
     // point-major: one weight, E consecutive uses (same sums, same order over i as a row-major loop)
 #pragma unroll
@@ -473,8 +569,9 @@ SSM_DEV bool moment_transform(const Tf &tf, const double (&m)[D], const double (
                 for (int b = 0; b <= a; ++b) Cf[tri(a, b)] += tf.mv(a, b);
         }
     }
-#undef fx
     return ok;
+    }   // KIND != SSM_TF_BQR
+#undef fx
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -996,6 +1093,35 @@ inline bool wc_symmetric(const ssm_transform &tf) {
     return true;
 }
 
+// Weights of a BQ transform on [0 | cI | -cI] points that are invariant under every coordinate reflection, bit for bit
+// (the BQR instantiation reads one representative of each class of equal weights).  SSM_REFL=0 forces the dense path.
+inline bool weights_reflective(const ssm_transform &tf, const HostTfInfo &info) {
+    const char *env = getenv("SSM_REFL");
+    if (env && atoi(env) == 0) return false;
+    if (tf.kind != SSM_TF_BQ || info.pts != PTS_AXIS_C || !tf.wm || !tf.Wc || !tf.Wcc) return false;
+    const int D = tf.dim_in, N = tf.n_pts;
+    if (N != 2 * D + 1) return false;
+    auto W = [&](int i, int j) { return tf.Wc[i * N + j]; };
+    auto mirror = [&](int i) { return i == 0 ? 0 : (i <= D ? i + D : i - D); };
+    auto axis = [&](int i) { return i == 0 ? -1 : (i - 1) % D; };
+    for (int i = 0; i < N; ++i) {
+        if (!(tf.wm[i] == tf.wm[mirror(i)])) return false;
+        for (int j = 0; j < N; ++j) {
+            if (!(W(i, j) == W(j, i))) return false;
+            // reflecting the axis of point i alone, the axis of point j alone, or (same axis) both
+            if (axis(i) != axis(j)) { if (!(W(i, j) == W(mirror(i), j)) || !(W(i, j) == W(i, mirror(j)))) return false; }
+            else if (!(W(i, j) == W(mirror(i), mirror(j)))) return false;
+        }
+    }
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < N; ++i) {
+            const double w = tf.Wcc[d * N + i];
+            if (axis(i) != d) { if (!(w == 0.0)) return false; }
+            else if (!(w == -tf.Wcc[d * N + mirror(i)])) return false;
+        }
+    return true;
+}
+
 template <int D>
 inline void pack_lower(const double *full, double *packed) {
     for (int r = 0; r < D; ++r)
@@ -1026,6 +1152,20 @@ inline void fill_tf(TfConst<D, E, NCAP, KIND, PTS> &o, const ssm_transform &tf, 
     for (int i = 0; i < N; ++i) {
         o.wm_[i] = tf.wm[i];
         o.wc_[i] = tf.Wc[i * N + i];
+    }
+    if constexpr (KIND == SSM_TF_BQR) {
+        // compact tables of the reflection-symmetric form (moment_transform): S in Wc_ / wch_, alpha in wc_, the one
+        // cross-covariance weight per axis in Wcc_[d][0]; wm_[0 .. D] already are the weights of g
+        auto W = [&](int i, int j) { return tf.Wc[i * N + j]; };
+        for (int i = 0; i <= D; ++i)
+            for (int j = 0; j <= D; ++j) o.Wc_[i][j] = W(i, j);
+        for (int j = 0; j < D; ++j) {
+            o.Wc_[1 + j][1 + j] = 0.5 * (W(1 + j, 1 + j) + W(1 + j, 1 + D + j));
+            o.wc_[j] = 0.5 * (W(1 + j, 1 + j) - W(1 + j, 1 + D + j));
+            o.Wcc_[j][0] = tf.Wcc[j * N + 1 + j];
+        }
+        for (int i = 0; i <= D; ++i) o.wch_[i] = 0.5 * o.Wc_[i][i];
+        return;
     }
     if (KIND != SSM_TF_SP) {
         for (int i = 0; i < N; ++i)

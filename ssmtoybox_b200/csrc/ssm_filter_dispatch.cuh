@@ -109,6 +109,8 @@ int dispatch_filter_model(const FilterLaunch &L) {
         if constexpr (Dyn::ADDITIVE && Obs::ADDITIVE) {
             if (id.pts == PTS_AXIS_C && io.pts == PTS_AXIS_C && a.n_pts == b.n_pts && fam == SSM_FAMILY_GAUSS && wc_symmetric(a) && wc_symmetric(b)) {
                 if (kind == SSM_TF_SP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
+                if (kind == SSM_TF_BQ && weights_reflective(a, id) && weights_reflective(b, io))
+                    return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQR, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
                 if (kind == SSM_TF_BQ) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
             }
         }
@@ -133,6 +135,9 @@ int dispatch_filter_model(const FilterLaunch &L) {
         if (rc != SSM_E_UNSUPPORTED) return rc;
     }
 #endif
+    // reflection-invariant BQ weights (the package's own, symmetrised when built): compact sums, see moment_transform
+    if (id.pts == PTS_AXIS_C && kind == SSM_TF_BQ && fam == SSM_FAMILY_GAUSS && weights_reflective(a, id) && weights_reflective(b, io))
+        return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQR, SSM_FAMILY_GAUSS, THREADS, MINB>(L, id, io);
 #define SSM_CASE(P, K, F)                                                        \
     if (id.pts == P && kind == K && fam == F) return dispatch_npts<Dyn, Obs, P, K, F, THREADS, MINB>(L, id, io);
     SSM_CASE(PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS)

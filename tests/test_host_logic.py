@@ -160,3 +160,45 @@ def test_rendezvous_batches_scipy_optimisers_without_changing_their_path():
         assert res[i].nfev == direct[i].nfev
     assert batch_sizes[0] == n and min(batch_sizes) >= 1 and sorted(batch_sizes, reverse=True) == batch_sizes
     assert len(batch_sizes) == max(r.nfev for r in direct)
+
+
+def test_reflection_symmetric_weights_projection_and_predicate():
+    """symmetrize_reflective projects a weight set on [0 | cI | -cI] points onto the structure the formulas have in exact
+    arithmetic (bq/bqmod.py:495-523): afterwards ssm_weights_reflective (the host check that selects the compact sums of
+    the forward pass) accepts it; weights that carry rounding noise, or no structure at all, are refused / left alone."""
+    import ctypes as C
+    from conftest import golden, rel
+    from ssmtoybox_b200 import device as dv, _lib
+    from ssmtoybox_b200.bq import bqmod
+    g = golden('c3_reentry_gpq')
+    pred = lambda low: (_lib.lib.ssm_weights_reflective(C.byref(low.desc.tf_dyn)), _lib.lib.ssm_weights_reflective(C.byref(low.desc.tf_obs)))  # noqa: E731
+    assert pred(dv.lower(g)) == (0, 0)                     # the reference's weights: 1e-12 ... O(1) noise where zeros belong
+    w = dict(wm=g['dyn_wm'], Wc=g['dyn_Wc'], Wcc=g['dyn_Wcc'], iK=None)
+    s = bqmod.symmetrize_reflective(g['dyn_points'], w)
+    assert s is not w
+    for k in ('wm', 'Wc', 'Wcc'):
+        assert rel(s[k], w[k]) < 2e-7, k                   # the dynamics kernel is well conditioned: structure up to 1e-7
+    s2 = bqmod.symmetrize_reflective(g['dyn_points'], s)
+    assert all(np.array_equal(s2[k], s[k]) for k in ('wm', 'Wc', 'Wcc'))          # a projection
+    D = 5
+    assert np.count_nonzero(s['Wcc']) == 2 * D and np.array_equal(s['Wcc'][:, 1:1 + D], -s['Wcc'][:, 1 + D:])
+    # the measurement kernel (cond 1e9): the reference's float64 Wc is O(1) noise, no structure to project onto
+    wo = dict(wm=g['obs_wm'], Wc=g['obs_Wc'], Wcc=g['obs_Wcc'], iK=None)
+    assert bqmod.symmetrize_reflective(g['obs_points'], wo) is wo
+    g2 = dict(g)
+    for k in ('wm', 'Wc', 'Wcc'):
+        g2['dyn_' + k] = s[k]
+        g2['obs_' + k] = s[k]        # any exactly structured set will do for the predicate
+    assert pred(dv.lower(g2)) == (1, 1)
+    g3 = dict(g2)
+    g3['dyn_Wcc'] = s['Wcc'].copy()
+    g3['dyn_Wcc'][0, 3] = 1e-300                           # one entry that should be zero is not
+    assert pred(dv.lower(g3)) == (0, 1)
+    g4 = dict(g2)
+    g4['obs_wm'] = s['wm'].copy()
+    g4['obs_wm'][2] = np.nextafter(s['wm'][2], 1.0)        # one ulp off its mirror image
+    assert pred(dv.lower(g4)) == (1, 0)
+    # other point sets are left alone
+    gh = golden('c3_reentry_ghkf3')
+    wg = dict(wm=gh['dyn_wm'], Wc=np.diag(gh['dyn_Wc']) if gh['dyn_Wc'].ndim == 1 else gh['dyn_Wc'], Wcc=np.zeros((5, gh['dyn_points'].shape[1])), iK=None)
+    assert bqmod.symmetrize_reflective(gh['dyn_points'], wg) is wg
