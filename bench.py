@@ -50,6 +50,10 @@ FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filte
 FLOP_SMOOTH = 902.0
 BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
 BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 1)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write d = x - m_s, quad (score-only mode)
+WEIGHTS_DESC = {'own': "own: ssm_bq_weights in double-double, projected onto the reflection structure the formulas have in exact "
+                       "arithmetic (what GaussianProcessKalman(...) builds by default)",
+                'reference': "reference-injected: wm / Wc / Wcc of the reference's own run assigned from tests/golden/c3_reentry_gpq.npz "
+                             "(float64 rounding noise included)"}
 METRIC = 'filtered trajectory-steps/sec (fp64)'
 UNIT = 'trajectory-steps/s'
 CONFIG = {'workload': 'C3: reentry 5-D + radar, GPQ (RBF, UT) filter + RTS smoother + scores, '
@@ -349,7 +353,7 @@ def run_gpu_arm(args):
     fwd, sm = {}, {}
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def hot_path(timers=None):
+    def hot_path(timers=None, low=low):
         """forward pass (stores predictive moments) -> RTS smoother with in-kernel score accumulation ->
         all-reduce of the packed statistics -> second score phase (log credibility ratio) -> all-reduce."""
         e = [ev() for _ in range(4)] if timers is not None else None
@@ -402,6 +406,35 @@ def run_gpu_arm(args):
     k_smooth = float(np.mean([e[1].elapsed_time(e[2]) for e in timers]))
     k_scores = float(np.mean([e[2].elapsed_time(e[3]) for e in timers]))
     scores = {k: (v.tolist() if hasattr(v, 'tolist') else v) for k, v in sc.items() if k in ('rmse', 'nci', 'nll', 'n_ok')}
+
+    # ---- the same device-resident step with the OTHER weight set, next to the headline ------------------------------
+    # (own weights carry their exact reflection structure -> compact sums of the forward pass; weights assigned from a
+    # reference run carry its rounding noise instead -> the dense sums of bqmtran.py:175-223 as they stand)
+    other = 'reference' if args.weights == 'own' else 'own'
+    alg_o, _ = build_filter(other)
+    low_o = dv.lower(alg_o._describe())
+    for _ in range(3):
+        hot_path(low=low_o)
+    timers_o = []
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        sc_o = hot_path(timers_o, low=low_o)
+    t1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    ms_other = comm.allreduce_max(t0.elapsed_time(t1)) / args.steps
+    weights_other = {'weights': WEIGHTS_DESC[other], 'compact_sums': list(dv.weights_reflective(low_o)), 'ms_per_step': ms_other,
+                     'value': comm.world_size * M * N / (ms_other * 1e-3),
+                     'kernel_ms': {'filter_forward': float(np.mean([e[0].elapsed_time(e[1]) for e in timers_o])),
+                                   'rts_smoother_with_phase1_scores': float(np.mean([e[1].elapsed_time(e[2]) for e in timers_o])),
+                                   'scores_phase2_incl_allreduce': float(np.mean([e[2].elapsed_time(e[3]) for e in timers_o]))},
+                     'n_failed_trajectories': int((sm['status'] != 0).sum().item()),
+                     'scores': {k: (v.tolist() if hasattr(v, 'tolist') else v) for k, v in sc_o.items() if k in ('rmse', 'nci', 'nll', 'n_ok')}}
+    compact = list(dv.weights_reflective(low))
+    hot_path()   # leave the headline filter's moments in fwd / sm
 
     # ---- e2e: host buffers through the reference-facing API --------------------------------------
     yh = torch.empty(y.shape, dtype=torch.float64, pin_memory=True).copy_(y)
@@ -470,8 +503,15 @@ def run_gpu_arm(args):
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
     except (OSError, ValueError):
         pass
-    roofline = {'kernel': 'filter_kernel<DynReentry, ObsRadar<5,0,1>, AXIS_C, 11, BQ, GAUSS> (fused forward pass)',
+    kname = 'BQR (compact reflection-symmetric sums)' if all(compact) else 'BQ (dense sums)'
+    exe = prof.get('filter_kernel_executed_flop_per_unit_bqr' if all(compact) else 'filter_kernel_executed_flop_per_unit_bq')
+    roofline = {'kernel': 'filter_kernel<DynReentry, ObsRadar<5,0,1>, AXIS_C, 11, %s, GAUSS> (fused forward pass)' % kname,
                 'bound': 'fp64', 'achieved': ach_tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s', 'frac': ach_tf / (fp64_peak / 1e12),
+                # frac counts the ALGORITHMIC flops of the reference's dense sums per unit of time; the kernel
+                # executes fewer (half-row and reflection-symmetric forms of the same sums): FP64 instructions actually executed
+                # per unit from the ncu capture (DFMA = 2), and the share of the FP64 pipe they occupy
+                'executed_flop_per_unit': exe,
+                'frac_executed': (M * N * exe / (k_filter * 1e-3) / fp64_peak) if exe else None,
                 'peak_source': 'measured in this run: DFMA micro-kernel ssm_fp64_peak_kernel (MEASURED_PEAKS.json has no fp64 figure)',
                 'flop_per_unit': FLOP_FILTER, 'units_per_launch': M * N, 'launch_ms': k_filter,
                 'traffic': prof.get('filter_kernel_dram_bytes_per_launch'),
@@ -506,7 +546,7 @@ def run_gpu_arm(args):
             'roofline': roofline, 'roofline_smoother': roofline_smoother, 'cpu_baseline': cpu,
             'clocks': clk, 'n_failed_trajectories': n_failed, 'scores': scores,
             'c5': c5,
-            'weights': 'reference-injected (tests/golden/c3_reentry_gpq.npz)' if args.weights == 'reference' else 'own (double-double ssm_bq_weights)',
+            'weights': WEIGHTS_DESC[args.weights], 'compact_sums': compact, 'weights_other': weights_other,
             'warmup_steps_until_stable': n_warm,
             'parity': 'means 1e-9 per step; un-centred BQ covariances on this model to the reference\'s own float64 noise floor '
                       '(2e-6 whole trajectory, <= 4x the reference\'s error against a longdouble evaluation: tests/test_gpu_parity.py)'}
@@ -536,8 +576,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-c5', action='store_true', help='skip the configuration-C5 sweep points reported next to the headline')
     ap.add_argument('--windows', type=int, default=20, help='time windows of the host-streaming (e2e) pipeline')
-    ap.add_argument('--weights', default='reference', choices=['reference', 'own'],
-                    help="quadrature weights of the C3 filter: the reference's own values (headline) or the package's")
+    ap.add_argument('--weights', default='own', choices=['reference', 'own'],
+                    help="quadrature weights of the C3 filter: the package's own (default: what the public constructor builds) or "
+                         "the reference's values assigned from its golden run; the other set is timed next to it (weights_other)")
     ap.add_argument('--config', default='c3', choices=['c3', 'c5'], help='c3: the headline workload; c5: BSQ NCI sweep point')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -446,6 +446,38 @@ def bq_weights(par, points, mulind=None, device='cuda', precision='dd', to_host=
                 model_var=sc[:, 0].copy(), integral_var=sc[:, 1].copy(), info=info.cpu().numpy())
 
 
+def own_weights(d, symmetric=True):
+    """A description dict (keys of tests/golden/*.npz, see lower()) with its BQ / TPQ weights re-derived from the kernel
+    parameters by ssm_bq_weights ('dd'), and -- symmetric=True, what the facade does by default -- projected onto their
+    exact reflection structure (bq/bqmod.symmetrize_reflective), so that lower() + filter_forward() take the compact sums
+    of the forward pass.  Sigma-point transforms are left as they are."""
+    from .bq import bqmod
+    out = dict(d)
+    for pfx in ('dyn_', 'obs_'):
+        if str(d[pfx + 'kind']) == 'sp':
+            continue
+        mul = d[pfx + 'mulind'] if (pfx + 'mulind') in d else None
+        w = bq_weights(d[pfx + 'kern_par'], d[pfx + 'points'], mul)
+        if int(w['info'][0]) != 0:
+            raise np.linalg.LinAlgError('kernel matrix is not positive definite')
+        w1 = {k: w[k][0] for k in ('wm', 'Wc', 'Wcc', 'iK')}
+        if symmetric:
+            w1 = bqmod.symmetrize_reflective(d[pfx + 'points'], w1)
+        for k in ('wm', 'Wc', 'Wcc'):
+            out[pfx + k] = w1[k]
+        if (pfx + 'iK') in d:
+            out[pfx + 'iK'] = w1['iK']
+        if str(d[pfx + 'kind']) != 'tp':
+            out[pfx + 'model_var'] = w['model_var'][0]
+    return out
+
+
+def weights_reflective(low):
+    """(dynamics, measurement): does the forward pass take the compact reflection-symmetric sums for this transform?
+    (ssm_weights_reflective; host-side check)"""
+    return (bool(lib.ssm_weights_reflective(C.byref(low.desc.tf_dyn))), bool(lib.ssm_weights_reflective(C.byref(low.desc.tf_obs))))
+
+
 def transform_apply_batched(which, model_id, dim_state, si, par, points, w, time, mean, cov):
     """GPQ / BSQ moment transform of n (mean, cov) columns with one weight set per column (ssm_transform_apply_batched).
     w: dict of device tensors from bq_weights(..., to_host=False) with n parameter vectors; mean (D, n), cov (D, D, n)

@@ -24,3 +24,6 @@ for row in src[2:]:
     n = int(row[ei]); ops[op] += n; tot += n; static += 1
 print('static SASS lines', static, ' dynamic warp-inst', tot, (' per unit %.0f' % (tot / units)) if units else '')
 print(', '.join('%s %.1f%%' % (k, 100 * v / tot) for k, v in ops.most_common(16)))
+if units:
+    f = {k: ops.get(k, 0) / units for k in ('DFMA', 'DMUL', 'DADD')}
+    print('FP64 arithmetic per unit: DFMA %.0f, DMUL %.0f, DADD %.0f -> executed FLOP per trajectory-step (DFMA = 2) %.0f' % (f['DFMA'], f['DMUL'], f['DADD'], 2 * f['DFMA'] + f['DMUL'] + f['DADD']))

@@ -7,8 +7,13 @@ from ssmtoybox_b200 import device as dv
 def main():
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 125000
     name = sys.argv[2] if len(sys.argv) > 2 else 'c3_reentry_gpq'
+    own = name.endswith(':own')     # <case>:own = the package's own (structured) weights instead of the golden run's
+    name = name.split(':')[0]
     g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', name + '.npz')))
+    if own:
+        g = dv.own_weights(g)
     low = dv.lower(g)
+    print('compact sums (dyn, obs):', dv.weights_reflective(low))
     N = 500
     if 'reentry' in name:
         truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]), 'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}
