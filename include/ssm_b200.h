@@ -135,7 +135,8 @@ const char *ssm_last_error(void);
  * applies to point sets [0 | cI | -cI] whose weights are invariant, bit for bit, under every coordinate reflection
  * x_j -> -x_j (wm(j+) == wm(j-), Wc equal within each class of reflected index pairs, Wcc(d, .) zero except for
  * Wcc(d, d+) == -Wcc(d, d-)): what the formulas of bq/bqmod.py:495-523, 893-992 give in exact arithmetic.  Host-side
- * check, no CUDA call.  Environment SSM_REFL=0 switches the compact form off. */
+ * check, no CUDA call; a TPQ transform is judged by the folded BQ weights it runs with.  Environment SSM_REFL=0
+ * switches the compact form off. */
 int ssm_weights_reflective(const ssm_transform *tf);
 
 /* ---- K2: fused forward pass -----------------------------------------------------------------

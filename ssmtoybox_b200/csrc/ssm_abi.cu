@@ -2,7 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
-#include "ssm_filter.cuh"
+#include "ssm_filter_dispatch.cuh"
 
 namespace ssm {
 
@@ -71,6 +71,12 @@ extern "C" const char *ssm_last_error(void) { return g_err; }
 
 extern "C" int ssm_weights_reflective(const ssm_transform *tf) {
     if (!tf || !tf->points || tf->dim_in < 1 || tf->n_pts != 2 * tf->dim_in + 1) return 0;
+    if (tf->kind == SSM_TF_TP) {   // a TPQ transform runs as a BQ one with folded weights (tp_fold): the check sees those
+        if (!tp_foldable(*tf) || !wc_symmetric(*tf)) return 0;
+        TpFold f;
+        tp_fold(*tf, f);
+        return weights_reflective(f.tf, classify_points(f.tf)) ? 1 : 0;
+    }
     return weights_reflective(*tf, classify_points(*tf)) ? 1 : 0;
 }
 

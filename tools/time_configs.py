@@ -3,7 +3,8 @@ roofline fractions (algorithmic FLOP and bytes per trajectory-step from SURVEY.m
 measured by ssm_fp64_peak_kernel, HBM peak from MEASURED_PEAKS.json).  Data are simulated on the device from the
 golden descriptors; the filters are the golden files' own (reference weights).
 
-    python tools/time_configs.py [M]
+    python tools/time_configs.py [M] [--own]     --own: the package's own structured weights for the BQ / TPQ filters
+                                                 (compact reflection-symmetric sums of the forward pass)
 """
 import json
 import os
@@ -47,11 +48,18 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     hbm = float(peaks.get('hbm_gbs', 6556.8))
     fp64 = 36.5
-    M_arg = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    own = '--own' in sys.argv
+    args = [a for a in sys.argv[1:] if a != '--own']
+    M_arg = int(args[0]) if args else 0
     print('| configuration | M x N | filter only ms | traj-steps/s | FP64 frac | HBM frac | + predictive moments + RTS smoother ms | traj-steps/s | failed |')
     print('|---|---|---:|---:|---:|---:|---:|---:|---:|')
     for label, name, N, flop, bts, smooth in CONFIGS:
         g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', name + '.npz')))
+        if own:
+            if str(g['dyn_kind']) == 'sp':
+                continue
+            g = dv.own_weights(g)
+            label += ' (own weights, compact sums: %s)' % (dv.weights_reflective(dv.lower(g)),)
         low = dv.lower(g)
         dx = low.dx
         # outputs with predictive moments: 8 (2 dx + 3 dx^2) bytes per step, + smoothed 8 (dx + dx^2): stay below ~60 GB
