@@ -148,3 +148,24 @@ def test_facade_filters_take_the_compact_form():
         assert _lib.lib.ssm_weights_reflective(C.byref(low2.desc.tf_obs)) == 0
     finally:
         bqmod.set_weight_symmetry(old)
+
+
+def test_compact_sums_at_the_benchmark_size(monkeypatch):
+    """125 000 trajectories (the C3 share of one GPU, ticket-scheduled persistent grid) x 100 steps: the compact and the
+    dense sums on the same structured weights fail nowhere and give the same aggregate scores."""
+    from ssmtoybox_b200 import device as dv, utils as U
+    g2 = own_weights(golden('c3_reentry_gpq'))
+    low = dv.lower(g2)
+    truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+             'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g2['r_cov']}
+    x, ys = dv.simulate(low, 125000, 100, rng=dv.make_rng(truth, seed=11), mode='continuous', dt=0.05, sub=2)
+    out = []
+    for refl in ('1', '0'):
+        monkeypatch.setenv('SSM_REFL', refl)
+        f = dv.filter_forward(low, ys, store_pred=True)
+        assert int((f['status'] != 0).sum()) == 0
+        out.append((U.evaluate_scored(dv.smooth_scores(low.dx, f, x)), f['fi_mean'][:, -1].cpu().numpy()))
+        del f
+    (a, ma), (b, mb) = out
+    assert np.allclose(a['rmse'], b['rmse'], rtol=1e-6) and abs(a['nci'] - b['nci']) < 1e-5 and abs(a['nll'] - b['nll']) < 1e-5 * abs(b['nll'])
+    assert np.abs(ma - mb).max() / np.abs(mb).max() < 1e-8
