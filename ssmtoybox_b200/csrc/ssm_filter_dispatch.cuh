@@ -109,8 +109,11 @@ int dispatch_filter_model(const FilterLaunch &L) {
         if constexpr (Dyn::ADDITIVE && Obs::ADDITIVE) {
             if (id.pts == PTS_AXIS_C && io.pts == PTS_AXIS_C && a.n_pts == b.n_pts && fam == SSM_FAMILY_GAUSS && wc_symmetric(a) && wc_symmetric(b)) {
                 if (kind == SSM_TF_SP) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_SP, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
+                // compact sums + scoring, no predictive-moment stores: four CTAs per SM at 128 registers beat three at 168
+                // (coordinated-turn BSQ sweep point, 10^6 x 100: 33.7 against 35.2 ms; with predictive moments it is
+                // the other way round)
                 if (kind == SSM_TF_BQ && weights_reflective(a, id) && weights_reflective(b, io))
-                    return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQR, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
+                    return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQR, SSM_FAMILY_GAUSS, THREADS, (MINB == 3 ? 4 : MINB), true>(L, id, io);
                 if (kind == SSM_TF_BQ) return dispatch_npts<Dyn, Obs, PTS_AXIS_C, SSM_TF_BQ, SSM_FAMILY_GAUSS, THREADS, MINB, true>(L, id, io);
             }
         }
