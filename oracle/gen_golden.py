@@ -834,9 +834,47 @@ def gen_marginal(steps=15, mc=2):
     save('marginal_ungm', x=x, y=y, fi_mean=fm, fi_cov=fc, param_mean=pm, param_cov=pc, thetas=thetas, obj=obj, cond_mean=cm, cond_cov=cc)
 
 
+def gen_structured():
+    """The REFERENCE's GPQ filters run with structured weights assigned (the pattern of research/tpq/tpq_ungm.py:114-124):
+    the exact values of its own formulas (oracle/exact_weights.py: mpmath, 60 digits, rounded once) projected onto the
+    reflection structure they have in exact arithmetic (ssmtoybox_b200.bq.bqmod.symmetrize_reflective, pure numpy) --
+    i.e. what the package's double-double weights kernel + projection produce, up to 1e-12.  These weight sets pass
+    ssm_weights_reflective, so the golden parity tests run the COMPACT sums of the forward pass against the reference's
+    dense numpy sums on identical inputs."""
+    from exact_weights import exact_gp_weights
+    sys.path.insert(0, os.path.dirname(HERE))
+    from ssmtoybox_b200.bq.bqmod import symmetrize_reflective
+
+    def assign(alg):
+        for tf in (alg.tf_dyn, alg.tf_obs):
+            par, pts = tf.model.kernel.par, tf.model.points
+            w = exact_gp_weights(par, pts)
+            s = symmetrize_reflective(pts, {k: w[k] for k in ('wm', 'Wc', 'Wcc', 'iK')})
+            assert s is not w and all(np.abs(s[k] - w[k]).max() <= 1e-12 * np.abs(w[k]).max() for k in ('wm', 'Wc', 'Wcc'))
+            tf.wm, tf.Wc, tf.Wcc = s['wm'], s['Wc'], s['Wcc']
+            tf.model.model_var = w['model_var']
+            tf.model.integral_var = w['integral_var']
+        return alg
+
+    np.random.seed(0)
+    dyn, obs, x, y = reentry(500, 3)      # the data of c3_reentry_gpq
+    hdyn = np.array([[1.0, 25, 25, 25, 25, 25]])
+    hobs = np.array([[1.0, 25, 25, 1e4, 1e4, 1e4]])
+    filter_case('c3_reentry_gpq_structured', assign(ssinf.GaussianProcessKalman(dyn, obs, hdyn, hobs, kernel='rbf', points='ut')), x, y)
+    np.random.seed(3)
+    dyn, obs, x, y = coordinated_turn(200, 4)      # the data of c4_ct_gpq
+    par_dyn = np.array([[1.0, 1, 1, 1, 1, 1]])
+    par_obs = np.array([[1.0, 1, 1e2, 1, 1e2, 1e2]])
+    filter_case('c4_ct_gpq_structured', assign(ssinf.GaussianProcessKalman(dyn, obs, par_dyn, par_obs)), x[..., :2], y[..., :2])
+    np.random.seed(7)
+    dyn, obs, x, y = pendulum(300, 3)      # the data of c5_pend_gpq
+    kp = np.array([[1.0, 1.0, 1.0]])
+    filter_case('c5_pend_gpq_structured', assign(ssinf.GaussianProcessKalman(dyn, obs, kp, kp)), x, y)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     sets = {'filters': gen_filters, 'reentry1d': gen_reentry1d, 'ungmna': gen_ungmna, 'student_bq': gen_student_bq, 'more_models': gen_more_models, 'nlml': gen_nlml, 'large_pointsets': gen_large_pointsets, 'weights': gen_weights, 'simulation': gen_simulation,
-            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope, 'public_attrs': gen_public_attrs, 'marginal': gen_marginal}
+            'scores': gen_scores, 'c5_sweep': gen_c5_sweep, 'weight_envelope': gen_weight_envelope, 'public_attrs': gen_public_attrs, 'marginal': gen_marginal, 'structured': gen_structured}
     for name in (sys.argv[1:] or list(sets)):   # optional: only the named sets
         sets[name]()

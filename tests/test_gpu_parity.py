@@ -37,6 +37,11 @@ def test_forward_and_smoother_vs_reference_golden(name):
     from ssmtoybox_b200 import device as dv
     g = golden(name)
     low, o = run_filter(g, g['y'])
+    # reference runs with structured weights assigned are compared with the COMPACT sums of the forward pass
+    # (some of the reference's own weight sets have the structure bit for bit too -- UNGM with 3 points: c1_ungm_bsq_ut,
+    # c2_ungm_gpq_el00..02 -- and run the compact sums against their goldens as well)
+    if name.endswith('_structured'):
+        assert dv.weights_reflective(low) == (True, True)
     st = N_(o['status'])
     assert np.array_equal(st >> 8, g['status']), 'failure steps differ from the reference'
     tol = FULL_TOL[name]
@@ -69,7 +74,7 @@ def test_one_step_parity_1e9(name):
     assert relstep(N_(o['pr_cov']), p['pr_cov']) < ONE_STEP_COV_TOL.get(name, 1e-9)
 
 
-@pytest.mark.parametrize('name', ['c3_reentry_gpq', 'c3_reentry_bsq', 'c4_ct_bsq', 'c4_ct_tpq'])
+@pytest.mark.parametrize('name', ['c3_reentry_gpq', 'c3_reentry_bsq', 'c4_ct_bsq', 'c4_ct_tpq', 'c3_reentry_gpq_structured'])
 def test_bq_noise_floor(name):
     """Un-centred BQ covariances (fx Wc fx' - m m') on the tracking models cancel ~1e7 against ~1e-6: the
     REFERENCE's float64 result is itself only reproducible to ~1e-8..1e-4.  Arbiter: the
@@ -486,34 +491,10 @@ def test_scores_vs_reference(name):
 
 
 def _exact_gp_weights(par, x, digits=60):
-    """GaussianProcessModel.bq_weights (bqmod.py:495-523) evaluated with mpmath at `digits` digits."""
-    mp = pytest.importorskip('mpmath')
-    mp.mp.dps = digits
-    D, N = x.shape
-    ell = [mp.mpf(float(v)) for v in np.asarray(par).ravel()[1:]]
-    alpha = mp.mpf(float(np.asarray(par).ravel()[0]))
-    X = [[mp.mpf(float(x[d, i])) for i in range(N)] for d in range(D)]
-    K, Qm, qv, Rm = mp.matrix(N, N), mp.matrix(N, N), mp.matrix(1, N), mp.matrix(D, N)
-    cdet = rdet = mp.mpf(1)
-    for d in range(D):
-        cdet *= 1 / ell[d] ** 2 + 1
-        rdet *= 2 / ell[d] ** 2 + 1
-    for i in range(N):
-        s = sum(X[d][i] ** 2 / (ell[d] ** 2 + 1) for d in range(D))
-        qv[i] = mp.exp(-s / 2) / mp.sqrt(cdet)
-        for d in range(D):
-            Rm[d, i] = qv[i] * X[d][i] / (ell[d] ** 2 + 1)
-        for j in range(N):
-            K[i, j] = mp.exp(-sum(((X[d][i] - X[d][j]) / ell[d]) ** 2 for d in range(D)) / 2) + (mp.mpf('1e-8') if i == j else 0)
-            n = -sum((X[d][i] / ell[d]) ** 2 + (X[d][j] / ell[d]) ** 2 for d in range(D)) / 2 + \
-                sum((X[d][i] / ell[d] ** 2 + X[d][j] / ell[d] ** 2) ** 2 / (2 / ell[d] ** 2 + 1) for d in range(D)) / 2
-            Qm[i, j] = mp.exp(n) / mp.sqrt(rdet)
-    iK = K ** -1
-    tof = lambda M: np.array([[float(M[i, j]) for j in range(M.cols)] for i in range(M.rows)])  # noqa: E731
-    QiK = Qm * iK
-    return dict(wm=tof(qv * iK).ravel(), Wc=tof(iK * Qm * iK), Wcc=tof(Rm * iK),
-                model_var=float(alpha ** 2 * (1 - sum(QiK[i, i] for i in range(N)))),
-                integral_var=float(alpha ** 2 / mp.sqrt(rdet) - (qv * iK * qv.T)[0, 0]))
+    """GaussianProcessModel.bq_weights (bqmod.py:495-523) evaluated with mpmath at `digits` digits (oracle/exact_weights.py)."""
+    pytest.importorskip('mpmath')
+    from exact_weights import exact_gp_weights
+    return exact_gp_weights(par, x, digits)
 
 
 def test_bq_weights_double_double_matches_exact_arithmetic():
