@@ -48,7 +48,7 @@ N_STEPS = 500
 TRAJ_PER_GPU = 125000           # 10^6 / 8
 FLOP_FILTER = 5756.0            # algorithmic FLOP per trajectory-step, BQ filter, reentry N=11
 FLOP_SMOOTH = 902.0
-BYTES_FILTER = 8.0 * (2 + 5 + 25 + 5 + 25 + 25)      # read y; write fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov
+BYTES_FILTER = 8.0 * (2 + 5 + 15 + 5 + 15 + 25)      # read y; write fi_mean, tril(fi_cov), pr_mean, tril(pr_cov), pr_xx_cov (ssm_filter_window_lower)
 BYTES_SMOOTH = 8.0 * (5 + 15 + 25 + 5 + 15 + 5 + 5 + 1)  # read pr_mean, tril(pr_cov), pr_xx, fi_mean, tril(fi_cov), x; write d = x - m_s, quad (score-only mode)
 WEIGHTS_DESC = {'own': "own: ssm_bq_weights in double-double, projected onto the reflection structure the formulas have in exact "
                        "arithmetic (what GaussianProcessKalman(...) builds by default)",
@@ -358,7 +358,7 @@ def run_gpu_arm(args):
         all-reduce of the packed statistics -> second score phase (log credibility ratio) -> all-reduce."""
         e = [ev() for _ in range(4)] if timers is not None else None
         if e: e[0].record()
-        dv.filter_forward(low, y, store_pred=True, out=fwd)
+        dv.filter_forward(low, y, store_pred=True, out=fwd, lower_only=True)   # the score-only smoother reads lower triangles only
         if e: e[1].record()
         dv.smooth_scores(low.dx, fwd, x, out=sm)   # RTS smoother, score-only mode: in-kernel phase-1 statistics, no sm_* stores
         if e: e[2].record()

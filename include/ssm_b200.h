@@ -181,6 +181,19 @@ int ssm_filter_window(const ssm_desc *desc, const double *y,
                       int32_t *status, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld,
                       void *stream);
 
+/* ssm_filter_window for consumers that read only the lower triangles of the symmetric outputs (ssm_smooth_scores does:
+ * ssinf.py:342-344 needs P_k and P^-_{k+1} as symmetric matrices): the entries (row, column > row) of fi_cov and pr_cov
+ * are NOT written -- 20 of the 85 stores of a 5-D step, 536 instead of 696 bytes per trajectory-step -- everything else
+ * (layout, the entries that are written, status) is bit for bit what ssm_filter_window produces. */
+int ssm_filter_window_lower(const ssm_desc *desc, const double *y,
+                            double *fi_mean, double *fi_cov,
+                            double *pr_mean, double *pr_cov, double *pr_xx_cov,
+                            const double *init_mean, const double *init_cov,
+                            double *last_mean, double *last_cov,
+                            const int32_t *t_offset, int32_t k0,
+                            int32_t *status, int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld,
+                            void *stream);
+
 /* Scoring forward pass: ssm_filter_window with the error statistics of the FILTERED moments accumulated in-kernel, so a
  * filter-only Monte-Carlo run keeps no per-trajectory moment arrays (the loops of research/gpq/icinco_demo.py:115-125 and
  * research/bsq/bsq_tracking.py:300-337 keep none either): fi_mean / fi_cov may be NULL.  x_truth (dx, n_steps, ld);

@@ -73,6 +73,8 @@ def _load():
     lib.ssm_filter.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, vp]
     lib.ssm_filter_window.restype = C.c_int
     lib.ssm_filter_window.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i64, vp]
+    lib.ssm_filter_window_lower.restype = C.c_int
+    lib.ssm_filter_window_lower.argtypes = lib.ssm_filter_window.argtypes
     lib.ssm_filter_scores.restype = C.c_int
     lib.ssm_filter_scores.argtypes = [C.POINTER(SsmDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, i64, vp]
     lib.ssm_smooth_window.restype = C.c_int

@@ -89,7 +89,7 @@ static int filter_window_impl(const ssm_desc *desc, const double *y, double *fi_
                               double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
                               double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
                               int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream,
-                              const ScoreOut *sc) {
+                              const ScoreOut *sc, bool lower_only = false) {
     if (!desc || !y || !status) { set_error("ssm_filter: desc, y and status must not be NULL"); return SSM_E_INVALID; }
     if (n_traj < 0 || n_steps < 0 || ld < n_traj) { set_error("ssm_filter: bad sizes (n_traj=%lld n_steps=%d ld=%lld)", (long long)n_traj, n_steps, (long long)ld); return SSM_E_INVALID; }
     if (k_lo < 0 || k_hi < k_lo || k_hi > n_steps) { set_error("ssm_filter: bad time window [%d, %d) of %d steps", k_lo, k_hi, n_steps); return SSM_E_INVALID; }
@@ -104,6 +104,7 @@ static int filter_window_impl(const ssm_desc *desc, const double *y, double *fi_
     L.buf = FilterBuffers{y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
                           t_offset, status, (long long)n_traj, (long long)ld, n_steps, k0, nullptr, nullptr, 0, 0,
                           k_lo, k_hi, k_lo > 0 ? 1 : 0};
+    L.buf.lower_only = lower_only ? 1 : 0;
     if (sc) {
         L.buf.x_truth = sc->x_truth; L.buf.rmse_acc = sc->rmse_acc; L.buf.quad = sc->quad; L.buf.dres = sc->dres;
         L.stats = sc->stats;
@@ -144,6 +145,14 @@ extern "C" int ssm_filter_window(const ssm_desc *desc, const double *y, double *
                                  int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
     return filter_window_impl(desc, y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
                               t_offset, k0, status, n_traj, n_steps, k_lo, k_hi, ld, stream, nullptr);
+}
+
+extern "C" int ssm_filter_window_lower(const ssm_desc *desc, const double *y, double *fi_mean, double *fi_cov, double *pr_mean,
+                                       double *pr_cov, double *pr_xx_cov, const double *init_mean, const double *init_cov,
+                                       double *last_mean, double *last_cov, const int32_t *t_offset, int32_t k0, int32_t *status,
+                                       int64_t n_traj, int32_t n_steps, int32_t k_lo, int32_t k_hi, int64_t ld, void *stream) {
+    return filter_window_impl(desc, y, fi_mean, fi_cov, pr_mean, pr_cov, pr_xx_cov, init_mean, init_cov, last_mean, last_cov,
+                              t_offset, k0, status, n_traj, n_steps, k_lo, k_hi, ld, stream, nullptr, true);
 }
 
 extern "C" int ssm_filter_scores(const ssm_desc *desc, const double *y, const double *x_truth, double *fi_mean, double *fi_cov,

@@ -601,6 +601,9 @@ struct FilterBuffers {
     double *partial, *rmse_acc, *quad, *dres;
     // Dyn::time_term(k0 + k) per time slot k (models with HasTimeTerm, launches without per-trajectory time offsets), or NULL
     const double *time_tab;
+    // ssm_filter_window_lower: of the symmetric outputs fi_cov / pr_cov only the lower triangles (column <= row) are
+    // written -- for consumers that read nothing else (the score-only smoother): 20 of the 85 stores of a 5-D step less
+    int lower_only;
 };
 
 template <class Dyn>
@@ -669,13 +672,16 @@ SSM_DEV void store_vec(double *base, const CS &cs, long long rk, const double (&
     for (int c = 0; c < C; ++c) st_stream(q + cs(c), v[c]);
 }
 template <int D, class CS>
-SSM_DEV void store_sym(double *base, const CS &cs, long long rk, const double (&P)[TriSize<D>::value]) {
+SSM_DEV void store_sym(double *base, const CS &cs, long long rk, const double (&P)[TriSize<D>::value], const bool lower_only = false) {
     if (!base) return;
     double *q = row_ptr(base, rk);
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-        for (int c = 0; c < D; ++c) st_stream(q + cs(r * D + c), P[sym(r, c)]);
+        for (int c = 0; c < D; ++c) {
+            if (c > r && lower_only) continue;   // kernel-uniform
+            st_stream(q + cs(r * D + c), P[sym(r, c)]);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -871,7 +877,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 double Cp[TX];
 #pragma unroll
                 for (int a = 0; a < TX; ++a) Cp[a] = Dyn::ADDITIVE ? Pp[a] + p.GQG[a] : Pp[a];  // x_cov_pr, ssinf.py:674-675 (additive noise only)
-                store_sym<DX>(b.pr_cov, cs, rk, Cp);
+                store_sym<DX>(b.pr_cov, cs, rk, Cp, b.lower_only != 0);
             }
 #pragma unroll
             for (int a = 0; a < TX; ++a) Pp[a] = Dyn::ADDITIVE ? fma(scale, Pp[a], p.s0 * p.GQG[a]) : scale * Pp[a];  // x_smat_pr, ssinf.py:672, 674-676
@@ -880,7 +886,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 #pragma unroll
                 for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:278-279
             }
-            store_sym<DX>(b.pr_cov, cs, rk, Pp);
+            store_sym<DX>(b.pr_cov, cs, rk, Pp, b.lower_only != 0);
         }
         store_vec<DX>(b.pr_mean, cs, rk, mp);
 
@@ -974,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 }
         }
         store_vec<DX>(b.fi_mean, cs, rk, m);
-        store_sym<DX>(b.fi_cov, cs, rk, P);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
+        store_sym<DX>(b.fi_cov, cs, rk, P, b.lower_only != 0);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
         if (FAMILY == SSM_FAMILY_STUDENT) {
             // delta = chol(Sy)^-1 e ; x_smat_fi = (dof + delta'delta) / (dof + dy) x_cov_fi   ssinf.py:731-733
             double dd = 0.0, z[DY];

@@ -154,8 +154,10 @@ def bulk_ld(t):
 
 
 def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, init_cov=None, t_offset=None, k0=0,
-                   want_last=False, out=None, window=None):
+                   want_last=False, out=None, window=None, lower_only=False):
     """Run the fused forward pass (ssm_filter) on y (dy, N, M) -> dict of device tensors.
+    lower_only: write only the lower triangles (column <= row) of fi_cov / pr_cov (ssm_filter_window_lower) -- for
+    pipelines whose only consumer is smooth_scores, which reads nothing else; the other entries stay uninitialised.
     window = (k_lo, k_hi): process only those time steps of the N slots (ssm_filter_window); successive windows
     carry the state through out['last_mean'/'last_cov'] -> init_mean / init_cov and the status through out['status']."""
     dy, N, M = y.shape
@@ -189,7 +191,8 @@ def filter_forward(low, y, store_pred=False, store_cov=True, init_mean=None, ini
     if (init_mean is not None or want_last) and ld != M:
         raise ValueError('init / last moments are not supported on trajectory-range views')
     k_lo, k_hi = (0, N) if window is None else (int(window[0]), int(window[1]))
-    rc = lib.ssm_filter_window(C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
+    rc = (lib.ssm_filter_window_lower if lower_only else lib.ssm_filter_window)(
+                               C.byref(low.desc), _p(y), _p(o.get('fi_mean')), _p(o.get('fi_cov')), _p(o.get('pr_mean')),
                                _p(o.get('pr_cov')), _p(o.get('pr_xx_cov')), _p(init_mean), _p(init_cov),
                                _p(o.get('last_mean') if want_last else None), _p(o.get('last_cov') if want_last else None),
                                _p(t_offset), int(k0), _p(o['status']), M, N, k_lo, k_hi, ld, _stream())

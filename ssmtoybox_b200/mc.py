@@ -121,8 +121,10 @@ def filter_scores(alg, y, x, smooth=True, n_windows=20, comm=None, keep=False, n
     for c, (k0, k1) in enumerate(wins):
         if ev_y[c] is not None:
             comp.wait_event(ev_y[c])
+        # (score-only smoother behind it: it reads the lower triangles of the covariances only, so only those are written)
         dv.filter_forward(low, yd, store_pred=do_smooth, out=fwd, window=(k0, k1), want_last=True,
-                          init_mean=fwd['last_mean'] if c else None, init_cov=fwd['last_cov'] if c else None)
+                          init_mean=fwd['last_mean'] if c else None, init_cov=fwd['last_cov'] if c else None,
+                          lower_only=do_smooth and not keep)
         if not do_smooth:
             if ev_x[c] is not None:
                 comp.wait_event(ev_x[c])
@@ -320,7 +322,7 @@ def monte_carlo_scores(alg, n_traj, n_steps, truth=None, sim='discrete', dt=0.0,
             scratch = {'m': mc, 'fwd': {}}
         sc = {}
         if smooth:
-            fwd = dv.filter_forward(low, y, store_pred=True, out=scratch['fwd'])
+            fwd = dv.filter_forward(low, y, store_pred=True, out=scratch['fwd'], lower_only=True)
             dv.smooth_scores(dx, fwd, x, out=sc)
         else:
             try:

@@ -197,3 +197,37 @@ def test_streaming_driver_score_only_equals_keep():
         for k in ('rmse', 'nci', 'nll', 'mse'):
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
         assert np.array_equal(a['status'], b['status'])
+
+
+def test_lower_triangle_only_forward_pass_feeds_the_score_only_smoother():
+    """ssm_filter_window_lower writes only the entries (row, column <= row) of fi_cov / pr_cov: those are bit for bit the
+    entries of the full pass, the others are never touched, and the score-only smoother -- which reads nothing else --
+    gives bitwise the same statistics from either."""
+    from ssmtoybox_b200 import device as dv, utils as U
+    g = golden('c3_reentry_gpq')
+    low = dv.lower(g)
+    truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+             'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}
+    x, y = dv.simulate(low, 1000, 60, rng=dv.make_rng(truth, seed=5), mode='continuous', dt=0.05, sub=2)
+    full = dv.filter_forward(low, y, store_pred=True)
+    sentinel = -12345.0
+    out = {k: torch.full_like(full[k], sentinel) for k in ('fi_cov', 'pr_cov')}
+    low_o = dv.filter_forward(low, y, store_pred=True, out=out, lower_only=True)
+    for k in ('fi_mean', 'pr_mean', 'pr_xx_cov', 'status'):
+        assert torch.equal(low_o[k], full[k]), k
+    for k in ('fi_cov', 'pr_cov'):
+        for r in range(5):
+            for c in range(5):
+                if c <= r:
+                    assert torch.equal(low_o[k][r, c], full[k][r, c]), (k, r, c)
+                else:
+                    assert bool((low_o[k][r, c] == sentinel).all()), (k, r, c)
+    a, b = dv.smooth_scores(low.dx, full, x), dv.smooth_scores(low.dx, low_o, x)
+    for k in ('stats', 'rmse_acc', 'quad', 'dres', 'status'):
+        assert torch.equal(a[k], b[k]), k
+    # windows: the carried state travels through last_mean / last_cov, which stay full matrices
+    w = {}
+    for c, (k0, k1) in enumerate(((0, 25), (25, 60))):
+        dv.filter_forward(low, y, store_pred=True, out=w, window=(k0, k1), want_last=True, lower_only=True,
+                          init_mean=w['last_mean'] if c else None, init_cov=w['last_cov'] if c else None)
+    assert torch.equal(w['fi_mean'], full['fi_mean']) and torch.equal(w['fi_cov'][2, 1], full['fi_cov'][2, 1])
