@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config C3): 5-D reentry vehicle + radar, GaussianProcessKalman (RBF GPQ,
-UT points, the reference's hyper-parameters and weights) forward pass + RTS smoother + error scores,
+UT points, the reference's hyper-parameters; quadrature weights: see --weights) forward pass + RTS smoother + error scores,
 10^6 trajectories x 500 steps on 8 GPUs = 125 000 trajectories x 500 steps PER GPU (weak scaling:
 trajectories are independent, each rank owns a contiguous block, the only collective is the all-reduce
 of the packed error statistics).  One "step" = one pass of that hot path over the rank's batch.
@@ -26,8 +26,9 @@ of the packed error statistics).  One "step" = one pass of that hot path over th
           simulate -> filter with in-kernel scoring -> second score phase, nothing materialised)
 
 --impl reference times the reference's own CPU implementation of the path the same way (data from the reference's own
-simulators, not timed); --weights own runs the headline with the package's own quadrature weights; --config c5 makes the
-C5 sweep point the timed workload of the line.
+simulators, not timed); --weights own (default) runs the headline with the quadrature weights the public constructor builds,
+--weights reference with the golden reference run's weights assigned, and either way the other set is timed next to it in the
+same process (`weights_other`); --config c5 makes the C5 sweep point the timed workload of the line.
 """
 import argparse
 import json
@@ -271,11 +272,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def build_filter(weights='reference'):
     """The C3 filter through the reference-facing API (research/gpq/gpq_tracking.py:41-44 on the model of
-    research/bsq/bsq_tracking.py:230-261).  weights='reference' (default, the headline): the reference's own weights
-    are assigned from outside (the pattern of research/tpq/tpq_ungm.py:114-124): its obs-transform kernel matrix has
-    cond 1e9, so its covariance weights are LAPACK rounding noise that no independent evaluation reproduces
-    (tests/test_gpu_weights_envelope.py).  weights='own': the weights the package computes itself
-    (double-double, the correctly rounded values of the reference's formulas)."""
+    research/bsq/bsq_tracking.py:230-261).  weights='reference': the reference's own weights are assigned from outside
+    (the pattern of research/tpq/tpq_ungm.py:114-124): its obs-transform kernel matrix has cond 1e9, so its covariance
+    weights are LAPACK rounding noise that no independent evaluation reproduces (DESIGN.md,
+    tests/test_gpu_weights_envelope.py).  weights='own' (the bench default): the weights the package computes itself
+    (double-double, the correctly rounded values of the reference's formulas, projected onto their exact reflection
+    structure -> compact sums in the forward pass)."""
     from ssmtoybox_b200.ssinf import GaussianProcessKalman
     from ssmtoybox_b200.ssmod import ReentryVehicle2DTransition, Radar2DMeasurement
     from ssmtoybox_b200.utils import GaussRV
@@ -548,8 +550,11 @@ def run_gpu_arm(args):
             'c5': c5,
             'weights': WEIGHTS_DESC[args.weights], 'compact_sums': compact, 'weights_other': weights_other,
             'warmup_steps_until_stable': n_warm,
-            'parity': 'means 1e-9 per step; un-centred BQ covariances on this model to the reference\'s own float64 noise floor '
-                      '(2e-6 whole trajectory, <= 4x the reference\'s error against a longdouble evaluation: tests/test_gpu_parity.py)'}
+            'parity': 'means 1e-9 per step against the unmodified reference on identical inputs, weights included (golden runs with the '
+                      "reference's own weights -> dense sums; golden runs with structured weights assigned -> the compact sums of this "
+                      "headline: tests/golden/c3_reentry_gpq_structured.npz); un-centred BQ covariances on this model to the reference's own "
+                      'float64 noise floor (<= 4x the reference\'s error against a longdouble evaluation: tests/test_gpu_parity.py, '
+                      'tests/test_gpu_reflective.py)'}
     _emit(line)
 
 

@@ -4,7 +4,8 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ssmtoybox_b200 import device as dv
 M = int(sys.argv[1]); N = int(sys.argv[2]); name = sys.argv[3] if len(sys.argv) > 3 else 'c3_reentry_gpq'
-sp = len(sys.argv) > 4 and sys.argv[4] == 'pred'
+sp = len(sys.argv) > 4 and sys.argv[4] in ('pred', 'predlow')
+low_only = len(sys.argv) > 4 and sys.argv[4] == 'predlow'     # the score pipeline's forward pass: lower triangles only
 own = name.endswith(':own')     # <case>:own = the package's own (structured) weights instead of the golden run's
 name = name.split(':')[0]
 g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', name + '.npz')))
@@ -23,6 +24,6 @@ for _ in range(3):
     if scored:
         dv.filter_scored(low, y, x, out=o)
     else:
-        dv.filter_forward(low, y, store_pred=sp, out=o)
+        dv.filter_forward(low, y, store_pred=sp, out=o, lower_only=low_only)
 torch.cuda.synchronize()
 print('ok', int((o['status'] != 0).sum()))
