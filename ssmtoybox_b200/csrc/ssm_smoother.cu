@@ -263,7 +263,14 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
         if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; alive = false; break; }
         // D = (Pp^-1 Pxx)^T                                                       ssinf.py:342
         double Dg[DX][DX], Ls[TX];
+#ifdef SSM_DIAG_NO_GAIN   // diagnostic build, WRONG results: the cost of the kernel without its factorisation and solves
+#pragma unroll
+        for (int a = 0; a < DX; ++a)
+#pragma unroll
+            for (int c = 0; c < DX; ++c) Dg[a][c] = Pxx[c][a] * 1e-3;
+#else
         if (!spd_gain<DX, DX>(Pp, Pxx, Dg, Ls)) { fail = SSM_FAIL_CHOL_SMOOTH; kfail = k; alive = false; break; }
+#endif
         // m_s = m_f + D (m_s+ - m_p)                                              ssinf.py:343
         double dm[DX];
 #pragma unroll
