@@ -202,3 +202,28 @@ def test_reflection_symmetric_weights_projection_and_predicate():
     gh = golden('c3_reentry_ghkf3')
     wg = dict(wm=gh['dyn_wm'], Wc=np.diag(gh['dyn_Wc']) if gh['dyn_Wc'].ndim == 1 else gh['dyn_Wc'], Wcc=np.zeros((5, gh['dyn_points'].shape[1])), iK=None)
     assert bqmod.symmetrize_reflective(gh['dyn_points'], wg) is wg
+
+
+@pytest.mark.parametrize('dim,kind', [(1, 'gp'), (2, 'gp'), (5, 'gp'), (2, 'bs'), (5, 'bs')])
+def test_weight_formulas_have_the_reflection_structure(dim, kind):
+    """The oracle's float64 restatement of GaussianProcessModel.bq_weights (bq/bqmod.py:495-523) and
+    BayesSardModel.bq_weights (:893-992) on UT points with well-conditioned kernels: the computed weights are within
+    rounding of the reflection structure (so the projection accepts them and moves them by rounding noise only) -- for the
+    polynomial-mean model too, whose basis 1, x_j, x_j^2 is closed under coordinate reflections."""
+    import ssm_oracle as so
+    from ssmtoybox_b200.bq import bqmod
+    from ssmtoybox_b200.mtran import UnscentedTransform
+    pts = UnscentedTransform.unit_sigma_points(dim)
+    assert bqmod.reflective_axis_set(pts) is not None
+    par = np.array([[1.0] + [1.5 + 0.5 * d for d in range(dim)]])       # distinct length-scales: no permutation symmetry
+    if kind == 'gp':
+        w = so.gp_weights(par, pts)
+    else:
+        # the basis of the reference's BSQ set-ups: 1, x_j, x_j^2 (as many functions as UT points; tests/test_ssinf.py:195-203)
+        w = so.bs_weights(par, pts, np.hstack((np.zeros((dim, 1)), np.eye(dim), 2 * np.eye(dim))).astype(int))
+    w = dict(wm=np.asarray(w['wm']), Wc=np.asarray(w['Wc']), Wcc=np.asarray(w['Wcc']), iK=None)
+    s = bqmod.symmetrize_reflective(pts, w)
+    assert s is not w, 'weights further than 1e-6 from the reflection structure'
+    for k in ('wm', 'Wc', 'Wcc'):
+        assert np.abs(s[k] - w[k]).max() <= 1e-10 * max(np.abs(w[k]).max(), 1e-300), (k, np.abs(s[k] - w[k]).max())
+    assert np.count_nonzero(s['Wcc']) <= 2 * dim
