@@ -183,8 +183,10 @@ int ssm_filter_window(const ssm_desc *desc, const double *y,
 
 /* ssm_filter_window for consumers that read only the lower triangles of the symmetric outputs (ssm_smooth_scores does:
  * ssinf.py:342-344 needs P_k and P^-_{k+1} as symmetric matrices): the entries (row, column > row) of fi_cov and pr_cov
- * are NOT written -- 20 of the 85 stores of a 5-D step, 536 instead of 696 bytes per trajectory-step -- everything else
- * (layout, the entries that are written, status) is bit for bit what ssm_filter_window produces. */
+ * NEED NOT be written, and the compact-sum instantiation (ssm_weights_reflective) does not write them -- 20 of the 85
+ * stores of a 5-D step, 536 instead of 696 bytes per trajectory-step; the other instantiations write full matrices as
+ * ssm_filter_window does.  Everything else (layout, the entries that are written, status) is bit for bit what
+ * ssm_filter_window produces. */
 int ssm_filter_window_lower(const ssm_desc *desc, const double *y,
                             double *fi_mean, double *fi_cov,
                             double *pr_mean, double *pr_cov, double *pr_xx_cov,

@@ -671,17 +671,20 @@ SSM_DEV void store_vec(double *base, const CS &cs, long long rk, const double (&
 #pragma unroll
     for (int c = 0; c < C; ++c) st_stream(q + cs(c), v[c]);
 }
+template <int D, bool LOWER, class CS>
+SSM_DEV void store_sym_impl(double *q, const CS &cs, const double (&P)[TriSize<D>::value]) {
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < (LOWER ? r + 1 : D); ++c) st_stream(q + cs(r * D + c), P[sym(r, c)]);
+}
+// lower_only (kernel-uniform): two straight store sequences behind ONE branch
 template <int D, class CS>
 SSM_DEV void store_sym(double *base, const CS &cs, long long rk, const double (&P)[TriSize<D>::value], const bool lower_only = false) {
     if (!base) return;
     double *q = row_ptr(base, rk);
-#pragma unroll
-    for (int r = 0; r < D; ++r)
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            if (c > r && lower_only) continue;   // kernel-uniform
-            st_stream(q + cs(r * D + c), P[sym(r, c)]);
-        }
+    if (lower_only) store_sym_impl<D, true>(q, cs, P);
+    else store_sym_impl<D, false>(q, cs, P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -713,6 +716,10 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
     constexpr int DX = Dyn::DX, DY = Obs::DY;
     constexpr int TX = TriSize<DX>::value, TY = TriSize<DY>::value;
     constexpr bool NA = !Dyn::ADDITIVE || !Obs::ADDITIVE;  // non-additive noise somewhere: exact-cancellation sums
+    // lower-triangle-only stores (ssm_filter_window_lower) are honoured by the compact-sum instantiation; in the others the
+    // extra branch around the stores cost the full-store launches 4 % (dense-sum reentry pass 17.5 -> 18.2 ms) and the
+    // skipped stores bought them nothing, so they always write the full matrices
+    constexpr bool LOWER_OK = (KIND == SSM_TF_BQR);
     const FilterBuffers &b = p.b;
     // model parameters as values: a load through the parameter block is repeated after every (rare-path) call, and the
     // re-loaded value is a new one to common-subexpression elimination
@@ -877,7 +884,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 double Cp[TX];
 #pragma unroll
                 for (int a = 0; a < TX; ++a) Cp[a] = Dyn::ADDITIVE ? Pp[a] + p.GQG[a] : Pp[a];  // x_cov_pr, ssinf.py:674-675 (additive noise only)
-                store_sym<DX>(b.pr_cov, cs, rk, Cp, b.lower_only != 0);
+                store_sym<DX>(b.pr_cov, cs, rk, Cp, LOWER_OK && b.lower_only != 0);
             }
 #pragma unroll
             for (int a = 0; a < TX; ++a) Pp[a] = Dyn::ADDITIVE ? fma(scale, Pp[a], p.s0 * p.GQG[a]) : scale * Pp[a];  // x_smat_pr, ssinf.py:672, 674-676
@@ -886,7 +893,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
 #pragma unroll
                 for (int a = 0; a < TX; ++a) Pp[a] += p.GQG[a];  // ssinf.py:278-279
             }
-            store_sym<DX>(b.pr_cov, cs, rk, Pp, b.lower_only != 0);
+            store_sym<DX>(b.pr_cov, cs, rk, Pp, LOWER_OK && b.lower_only != 0);
         }
         store_vec<DX>(b.pr_mean, cs, rk, mp);
 
@@ -980,7 +987,7 @@ __global__ void __launch_bounds__(THREADS, MINB) filter_kernel(const __grid_cons
                 }
         }
         store_vec<DX>(b.fi_mean, cs, rk, m);
-        store_sym<DX>(b.fi_cov, cs, rk, P, b.lower_only != 0);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
+        store_sym<DX>(b.fi_cov, cs, rk, P, LOWER_OK && b.lower_only != 0);  // Student: x_cov_fi = x_smat_pr - K Sy K^T (ssinf.py:727)
         if (FAMILY == SSM_FAMILY_STUDENT) {
             // delta = chol(Sy)^-1 e ; x_smat_fi = (dof + delta'delta) / (dof + dy) x_cov_fi   ssinf.py:731-733
             double dd = 0.0, z[DY];

@@ -200,12 +200,13 @@ def test_streaming_driver_score_only_equals_keep():
 
 
 def test_lower_triangle_only_forward_pass_feeds_the_score_only_smoother():
-    """ssm_filter_window_lower writes only the entries (row, column <= row) of fi_cov / pr_cov: those are bit for bit the
-    entries of the full pass, the others are never touched, and the score-only smoother -- which reads nothing else --
-    gives bitwise the same statistics from either."""
+    """ssm_filter_window_lower need only write the entries (row, column <= row) of fi_cov / pr_cov: those are bit for bit
+    the entries of the full pass, the compact-sum instantiation (structured weights) never touches the others, and the
+    score-only smoother -- which reads nothing else -- gives bitwise the same statistics from either."""
     from ssmtoybox_b200 import device as dv, utils as U
-    g = golden('c3_reentry_gpq')
+    g = dv.own_weights(golden('c3_reentry_gpq'))
     low = dv.lower(g)
+    assert dv.weights_reflective(low) == (True, True)
     truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
              'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}
     x, y = dv.simulate(low, 1000, 60, rng=dv.make_rng(truth, seed=5), mode='continuous', dt=0.05, sub=2)
@@ -231,3 +232,10 @@ def test_lower_triangle_only_forward_pass_feeds_the_score_only_smoother():
         dv.filter_forward(low, y, store_pred=True, out=w, window=(k0, k1), want_last=True, lower_only=True,
                           init_mean=w['last_mean'] if c else None, init_cov=w['last_cov'] if c else None)
     assert torch.equal(w['fi_mean'], full['fi_mean']) and torch.equal(w['fi_cov'][2, 1], full['fi_cov'][2, 1])
+    # dense-sum instantiation (the reference's weights): same contract, full matrices written
+    gd = golden('c3_reentry_gpq')
+    lowd = dv.lower(gd)
+    fd, ld_ = dv.filter_forward(lowd, y, store_pred=True), dv.filter_forward(lowd, y, store_pred=True, lower_only=True)
+    assert torch.equal(torch.tril(fd['fi_cov'].permute(2, 3, 0, 1)), torch.tril(ld_['fi_cov'].permute(2, 3, 0, 1)))
+    sa, sb = dv.smooth_scores(lowd.dx, fd, x), dv.smooth_scores(lowd.dx, ld_, x)
+    assert torch.equal(sa['stats'], sb['stats'])
