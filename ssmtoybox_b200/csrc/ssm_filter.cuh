@@ -1,8 +1,9 @@
 // K2: fused forward pass.  One thread owns one trajectory for the whole time loop; the filter
 // state (mean, packed covariance), the Cholesky factor, the sigma points and the function
 // evaluations live in registers; quadrature weights are read from the kernel-parameter constant
-// bank (fast path) so every DFMA takes its weight operand straight from c[0][..]; measurements are
-// read and moments written with coalesced streaming accesses over the trajectory axis.
+// bank (fast path): LDCU into uniform registers, which the DFMAs take as their weight operand (sm_100
+// has no constant-bank operand form for fp64); measurements are read and moments written with
+// coalesced streaming accesses over the trajectory axis.
 //
 // Replaces, per trajectory and time step (file:line in /root/reference/ssmtoybox):
 //   StateSpaceInference.forward_pass            ssinf.py:66-118
