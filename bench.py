@@ -454,6 +454,21 @@ def run_gpu_arm(args):
 
     for _ in range(max(1, min(args.warmup, 2))):
         out = e2e_step()
+    # like the device-resident path: keep warming up until three consecutive steps agree to 3 % (at most 8 more; every rank
+    # takes the same number of steps -- the decision is all-reduced).  The pinned host -> device copy, 63 of the step's
+    # ~65 ms, fluctuates from step to step on some boxes (67 / 72 / 102 ms in three consecutive steps of one run; 66 / 82 /
+    # 96 ms per step as the mean of runs on three boxes, same code): the last three warm-up times go into the line
+    # (`warmup_last_ms`) so that a noisy box is visible as such.
+    e2e_warm, recent = max(1, min(args.warmup, 2)), []
+    for _ in range(8):
+        torch.cuda.synchronize()
+        w = time.perf_counter()
+        out = e2e_step()
+        torch.cuda.synchronize()
+        recent = (recent + [comm.allreduce_max((time.perf_counter() - w) * 1e3)])[-3:]
+        e2e_warm += 1
+        if len(recent) == 3 and max(recent) - min(recent) <= 0.03 * min(recent):
+            break
     comm.barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
@@ -541,7 +556,7 @@ def run_gpu_arm(args):
                     'api': 'ssmtoybox_b200.mc.filter_scores(GaussianProcessKalman, y, x, smooth=True) on pinned host y, x: '
                            'time-windowed H2D (y forward in time, x backward) overlapped with forward pass + RTS smoother + '
                            'scores of the windows that have landed; scores and status read back',
-                    'windows': args.windows},
+                    'windows': args.windows, 'warmup_steps': e2e_warm, 'warmup_last_ms': recent},
             'gpu_launches': 7 * args.steps,   # filter, NaN fill of failed trajectories, smoother, finalize, MSE factor table, scores phase 2, finalize
             'kernel_ms': {'filter_forward': k_filter, 'rts_smoother_with_phase1_scores': k_smooth, 'scores_phase2_incl_allreduce': k_scores},
             'filter_only_value': comm.world_size * M * N / (k_filter * 1e-3),
