@@ -253,14 +253,28 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
             }
         }
         // scipy's cho_factor / cho_solve reject non-finite input (ValueError)        ssinf.py:342
-        bool fin = true;
+        // One test on the SUM of the 40 inputs instead of 40 tests (the bit tests were 6 % of the kernel's instructions:
+        // 8.30 -> 7.89 ms without them): any NaN or infinity makes the sum non-finite; a sum of finite values that
+        // overflows only sends the step through the exact element-wise test below, which then finds nothing.
+        {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int a = 0; a < TX; ++a) fin = fin && finite_d(Pp[a]);
+            for (int a = 0; a < TX; ++a) acc[a & 3] += Pp[a];
 #pragma unroll
-        for (int r = 0; r < DX; ++r)
+            for (int r = 0; r < DX; ++r)
 #pragma unroll
-            for (int c = 0; c < DX; ++c) fin = fin && finite_d(Pxx[r][c]);
-        if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; alive = false; break; }
+                for (int c = 0; c < DX; ++c) acc[(r * DX + c + TX) & 3] += Pxx[r][c];
+            if (!finite_d((acc[0] + acc[1]) + (acc[2] + acc[3]))) {
+                bool fin = true;
+#pragma unroll
+                for (int a = 0; a < TX; ++a) fin = fin && finite_d(Pp[a]);
+#pragma unroll
+                for (int r = 0; r < DX; ++r)
+#pragma unroll
+                    for (int c = 0; c < DX; ++c) fin = fin && finite_d(Pxx[r][c]);
+                if (!fin) { fail = SSM_FAIL_NONFINITE_GAIN; kfail = k; alive = false; break; }
+            }
+        }
         // D = (Pp^-1 Pxx)^T                                                       ssinf.py:342
         double Dg[DX][DX], Ls[TX];
 #ifdef SSM_DIAG_NO_GAIN   // diagnostic build, WRONG results: the cost of the kernel without its factorisation and solves

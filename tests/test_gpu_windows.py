@@ -239,3 +239,35 @@ def test_lower_triangle_only_forward_pass_feeds_the_score_only_smoother():
     assert torch.equal(torch.tril(fd['fi_cov'].permute(2, 3, 0, 1)), torch.tril(ld_['fi_cov'].permute(2, 3, 0, 1)))
     sa, sb = dv.smooth_scores(lowd.dx, fd, x), dv.smooth_scores(lowd.dx, ld_, x)
     assert torch.equal(sa['stats'], sb['stats'])
+
+
+def test_smoother_rejects_non_finite_inputs_like_the_reference():
+    """scipy's cho_factor / cho_solve raise ValueError on NaN / infinite input (ssinf.py:342): status = failing step | code 4,
+    in the stored-moments and the score-only smoother alike.  The kernel tests the SUM of a step's inputs and falls back to
+    the element-wise test only when that sum is not finite -- so huge FINITE inputs whose sum overflows must not be flagged
+    (the reference goes on with the infinities they produce)."""
+    import ssm_oracle as so
+    from ssmtoybox_b200 import device as dv
+    g = golden('c3_reentry_gpq')
+    low = dv.lower(g)
+    truth = {'m0': [6500, 350, -1.8, -6.8, 0.7], 'P0': np.diag([1e-6, 1e-6, 1e-6, 1e-6, 0.0]),
+             'q_cov': np.diag([2.4e-5, 2.4e-5, 0.0]), 'r_cov': g['r_cov']}
+    x, y = dv.simulate(low, 256, 40, rng=dv.make_rng(truth, seed=9), mode='continuous', dt=0.05, sub=2)
+    fwd = dv.filter_forward(low, y, store_pred=True)
+    assert int((fwd['status'] != 0).sum()) == 0
+    fwd['pr_xx_cov'][1, 2, 11, 3] = float('nan')
+    fwd['pr_cov'][2, 1, 21, 5] = float('inf')
+    fwd['pr_cov'][0, 0, 30, 6] = float('-inf')
+    fwd['pr_xx_cov'][:, :, 16, 7] = 1e308          # finite, but the 25 of them sum to infinity
+    want = np.zeros(256, dtype=np.int64)
+    want[3], want[5], want[6] = (11 << 8) | so.FAIL_NONFINITE_GAIN, (21 << 8) | so.FAIL_NONFINITE_GAIN, (30 << 8) | so.FAIL_NONFINITE_GAIN
+    for run in (lambda f: dv.smooth_backward(low.dx, f), lambda f: dv.smooth_scores(low.dx, f, x),
+                lambda f: dv.smooth_backward(low.dx, f, x_truth=x)):
+        f = dict(fwd)
+        f['status'] = fwd['status'].clone()
+        st = run(f)['status'].cpu().numpy()
+        assert np.array_equal(st, want), (st[[3, 5, 6, 7]], want[[3, 5, 6, 7]])
+    sm = dv.smooth_backward(low.dx, dict(fwd, status=fwd['status'].clone()))
+    m = sm['sm_mean'].cpu().numpy()
+    assert np.isfinite(m[:, 16:, 7]).all() and not np.isfinite(m[:, :15, 7]).any()     # overflow goes on as inf / NaN, unflagged
+    assert np.isnan(m[:, :11, 3]).all() and np.isfinite(m[:, 11:, 3]).all()            # NaN rows from the failing step down
