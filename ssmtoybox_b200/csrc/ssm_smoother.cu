@@ -52,6 +52,8 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
     constexpr int TX = TriSize<DX>::value, W = ScoreRow<DX>::WP;
     constexpr bool STAGE = (STAGE_MODE & 1) != 0;    // the inputs of the recursion, one iteration ahead
     constexpr bool XSTAGE = (STAGE_MODE & 2) != 0;   // the truth of the current iteration, issued at its start
+    constexpr bool PAIRC = (STAGE_MODE & 4) != 0;    // (with both of the above) lane pairs copy two components per instruction
+    static_assert(!PAIRC || (STAGE && XSTAGE), "paired copies are an option of staging mode 3");
     constexpr int XS0 = STAGE ? DX + DX * DX + 2 * TX : 0;   // first staging column of the truth
     const int WLEN = k_hi0 - k_lo0;
     const long long t_raw = blk * blockDim.x + threadIdx.x;
@@ -164,13 +166,51 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
     const int par = threadIdx.x & 1;
     double *sgp = (STAGE || XSTAGE) ? stage + (threadIdx.x & ~1) : nullptr;
     const bool pair_in = (t_raw | 1) < n_traj;   // both trajectories of the lane pair exist (n_traj is even in this mode)
+    // PAIRC: a run of components that is consecutive both in its source array and in the staging area is copied two at a
+    // time -- the even lane takes component j, the odd lane component j + 1, through a per-lane source offset of one
+    // component stride (par_off) and a per-lane staging base (sgq) -- so every lane takes part in every copy and a step
+    // issues 37 instead of 65 copies (and as many 64-bit address additions less); the odd component of a run is left to
+    // the even lanes.  Rows of the packed triangles are such runs (source r DX + c, staging tri(r, 0) + c).
+    const long long par_off = (PAIRC && par) ? (long long)cs(1) : 0;
+    double *sgq = (STAGE || XSTAGE) ? sgp + (PAIRC ? par * SC_THREADS : 0) : nullptr;
     auto stage_truth16 = [&](int k) {   // truth of iteration k, columns [XS0, XS0 + DX)
+        if constexpr (PAIRC) {
+            const double *q_x = row_ptr(x_truth, (long long)k * ld + (t_raw - par) + par_off);
+#pragma unroll
+            for (int a = 0; a + 1 < DX; a += 2) cp_async16(sgq + (XS0 + a) * SC_THREADS, q_x + cs(a));
+            if ((DX & 1) && par == 0) cp_async16(sgq + (XS0 + DX - 1) * SC_THREADS, q_x + cs(DX - 1));
+            return;
+        }
         const double *q_x = row_ptr(x_truth, (long long)k * ld + (t_raw - par));
 #pragma unroll
         for (int a = 0; a < DX; ++a)
             if (((XS0 + a) & 1) == par) cp_async16(sgp + (XS0 + a) * SC_THREADS, q_x + cs(a));
     };
     auto stage_issue = [&](int k) {     // inputs of iteration k
+        if constexpr (PAIRC) {
+            const long long rkq = (long long)k * ld + (t_raw - par) + par_off;
+            const double *q_pm = row_ptr(pr_mean, rkq + ld), *q_pc = row_ptr(pr_cov, rkq + ld), *q_px = row_ptr(pr_xx, rkq + ld);
+            const double *q_fc = row_ptr(fi_cov, rkq);
+#pragma unroll
+            for (int a = 0; a + 1 < DX; a += 2) cp_async16(sgq + a * SC_THREADS, q_pm + cs(a));
+            if ((DX & 1) && par == 0) cp_async16(sgq + (DX - 1) * SC_THREADS, q_pm + cs(DX - 1));
+#pragma unroll
+            for (int c = 0; c + 1 < DX * DX; c += 2) cp_async16(sgq + (DX + c) * SC_THREADS, q_px + cs(c));
+            if (((DX * DX) & 1) && par == 0) cp_async16(sgq + (DX + DX * DX - 1) * SC_THREADS, q_px + cs(DX * DX - 1));
+#pragma unroll
+            for (int r = 0; r < DX; ++r) {
+#pragma unroll
+                for (int c = 0; c + 1 <= r; c += 2) {
+                    cp_async16(sgq + (DX + DX * DX + tri(r, c)) * SC_THREADS, q_pc + cs(r * DX + c));
+                    cp_async16(sgq + (DX + DX * DX + TX + tri(r, c)) * SC_THREADS, q_fc + cs(r * DX + c));
+                }
+                if (((r + 1) & 1) && par == 0) {   // odd row length: the diagonal element is left over
+                    cp_async16(sgq + (DX + DX * DX + tri(r, r)) * SC_THREADS, q_pc + cs(r * DX + r));
+                    cp_async16(sgq + (DX + DX * DX + TX + tri(r, r)) * SC_THREADS, q_fc + cs(r * DX + r));
+                }
+            }
+            return;
+        }
         const long long rkp = (long long)k * ld + (t_raw - par);
         const double *q_pm = row_ptr(pr_mean, rkp + ld), *q_pc = row_ptr(pr_cov, rkp + ld), *q_px = row_ptr(pr_xx, rkp + ld);
         const double *q_fc = row_ptr(fi_cov, rkp);
@@ -346,7 +386,7 @@ SSM_DEV void smoother_body(const double *__restrict__ fi_mean, const double *__r
 }
 
 #ifndef SSM_SMOOTH_STAGE_DEFAULT
-#define SSM_SMOOTH_STAGE_DEFAULT 3
+#define SSM_SMOOTH_STAGE_DEFAULT 7
 #endif
 #ifndef SSM_SMOOTH_SCORE_MINB
 #define SSM_SMOOTH_SCORE_MINB 1   // resident CTAs per SM the score-only kernel is compiled for (developer A/B)
@@ -489,7 +529,8 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
                 cudaFreeAsync(work, s);
             } else {
                 // staged inputs (cp.async into shared memory one iteration ahead) unless SSM_SMOOTH_STAGE=0
-                // SSM_SMOOTH_STAGE (developer switch): 0 plain loads, 1 inputs staged one iteration ahead, 2 truth staged, 3 both
+                // SSM_SMOOTH_STAGE (developer switch): 0 plain loads, 1 inputs staged one iteration ahead, 2 truth staged, 3 both,
+                // 7 both with two components per copy instruction (PAIRC)
                 const char *env_stage = getenv("SSM_SMOOTH_STAGE");
                 int mode = env_stage ? atoi(env_stage) : SSM_SMOOTH_STAGE_DEFAULT;
                 {   // the 16-byte pair copies need even trajectory counts / leading dimensions and 16-byte aligned rows
@@ -512,6 +553,7 @@ static int launch_smoother(const double *fi_mean, const double *fi_cov, const do
                 if (mode == 1) launch_staged(smoother_kernel<DX, true, false, 1>, StageBytes<DX, 1>::value);
                 else if (mode == 2) launch_staged(smoother_kernel<DX, true, false, 2>, StageBytes<DX, 2>::value);
                 else if (mode == 3) launch_staged(smoother_kernel<DX, true, false, 3>, StageBytes<DX, 3>::value);
+                else if (mode == 7) launch_staged(smoother_kernel<DX, true, false, 7>, StageBytes<DX, 3>::value);
                 else
                 smoother_kernel<DX, true, false><<<(unsigned)tail_blocks, SC_THREADS, 0, s>>>(
                     off(fi_mean), off(fi_cov), off(pr_mean), off(pr_cov), off(pr_xx), nullptr, nullptr, status + t_tail,

@@ -155,14 +155,16 @@ def test_time_streaming_driver_with_failures_falls_back_to_exact_scores():
     (70000, 60, None),
     (70000, 110, [(0, 55), (55, 110)]),
 ])
-@pytest.mark.parametrize('ticket', ['0', '1'])          # 1: opt-in ticket scheduler over (block, time chunk) items
-def test_score_only_smoother_equals_stored_smoother(M, N, wins, ticket, monkeypatch):
+@pytest.mark.parametrize('ticket,stage', [('0', None), ('0', '0'), ('0', '3'), ('0', '7'), ('1', None)])
+def test_score_only_smoother_equals_stored_smoother(M, N, wins, ticket, stage, monkeypatch):
     """ssm_smooth_scores (no smoothed arrays stored, errors d = x - m_s kept for the second score phase) gives bitwise
     the statistics, quadratic forms and scores of ssm_smooth_quad + evaluate_performance on the stored arrays."""
     from ssmtoybox_b200 import device as dv, utils as U
     if ticket == '1' and M < 60000:
         pytest.skip('the ticket scheduler only engages for multi-wave launches')
-    monkeypatch.setenv('SSM_SMOOTH_TICKET', ticket)
+    monkeypatch.setenv('SSM_SMOOTH_TICKET', ticket)   # 1: opt-in ticket scheduler over (block, time chunk) items
+    if stage is not None:   # staging mode of the score-only kernel (None: the library's default; 0 plain loads, 3 inputs and
+        monkeypatch.setenv('SSM_SMOOTH_STAGE', stage)   # truth staged through shared memory, 7 two components per copy)
     g = golden('c3_reentry_gpq')
     low, x, y = _sim(g, M, N)
     y[:, 3, 5] = float('nan')                                       # one failed trajectory
@@ -182,6 +184,36 @@ def test_score_only_smoother_equals_stored_smoother(M, N, wins, ticket, monkeypa
     got = U.evaluate_scored(sc, to_host=False)
     for k in ('rmse', 'nci', 'nll', 'abs_nci', 'mse', 'rmse_vs_time', 'n_ok'):
         assert eq(got[k], want[k]), k
+
+
+@pytest.mark.parametrize('name,M,N', [('c1_ungm_gpq_ut', 4098, 50), ('c5_pend_gpq', 4098, 50), ('c4_ct_gpq', 2050, 40),
+                                      ('c3_reentry_gpq', 130, 30)])
+def test_score_only_smoother_staging_modes_agree_bitwise(name, M, N, monkeypatch):
+    """Every staging mode of the score-only smoother (SSM_SMOOTH_STAGE: 0 plain loads, 1 / 2 / 3 inputs / truth / both
+    staged through shared memory, 7 lane pairs copying two components per instruction) moves the same numbers into the
+    same arithmetic: statistics, quadratic forms and errors are bitwise equal for state dimensions 1, 2 and 5, with a
+    last CTA that is only partly filled and a failed trajectory next to its pair partner."""
+    from ssmtoybox_b200 import device as dv
+    g = golden(name)
+    if name == 'c3_reentry_gpq':
+        low, x, y = _sim(g, M, N)
+    else:
+        low = dv.lower(g)
+        x, y = dv.simulate(low, M, N, rng=dv.make_rng(g, seed=11))
+    y[:, 2, 7] = float('nan')
+    fwd = dv.filter_forward(low, y, store_pred=True)
+    assert int((fwd['status'] == 0).sum()) > M // 2
+    outs = {}
+    for mode in ('0', '1', '2', '3', '7'):
+        monkeypatch.setenv('SSM_SMOOTH_STAGE', mode)
+        outs[mode] = dv.smooth_scores(low.dx, fwd, x)
+    torch.cuda.synchronize()
+    ok = outs['0']['status'] == 0
+    assert int((~ok).sum()) >= 1
+    for mode in ('1', '2', '3', '7'):
+        assert torch.equal(outs[mode]['status'], outs['0']['status']), mode
+        assert eq(outs[mode]['stats'], outs['0']['stats']) and eq(outs[mode]['rmse_acc'], outs['0']['rmse_acc']), mode
+        assert eq(outs[mode]['quad'][:, ok], outs['0']['quad'][:, ok]) and eq(outs[mode]['dres'][:, :, ok], outs['0']['dres'][:, :, ok]), mode
 
 
 def test_streaming_driver_score_only_equals_keep():
