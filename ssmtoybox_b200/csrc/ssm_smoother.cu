@@ -20,9 +20,12 @@ void set_error(const char *fmt, ...);
 // recursion crosses time windows through a (dx + dx (dx + 1) / 2, ld) carry buffer instead of the sm arrays.
 // STAGE (score-only mode): the inputs of iteration k - 1 (predictive mean / covariance / cross-covariance and the filtered
 // covariance, 60 of the 70 doubles of a dx = 5 step) are copied global -> shared with cp.async while iteration k computes.
-// Each thread copies into and later reads from its OWN column of the staging area, so no barrier is involved: shared
-// memory is just the landing zone that a register prefetch has no room for (the kernel sits at 244 registers).  The
-// filtered mean and the truth, needed late in a step, stay plain loads.
+// Shared memory is just the landing zone that a register prefetch has no room for (the kernel sits at 255 registers):
+// every thread reads its OWN column of the staging area; the copies are issued by lane pairs (16 bytes = one component of
+// both trajectories of the pair; since staging mode 7 two consecutive components per instruction), so two warp barriers
+// per step order the partner's copies and the own reads -- no CTA barrier.  The truth is staged at the start of the
+// step that scores it; the filtered mean, needed late in a step, stays a plain load (shared memory is exhausted: 65 KB
+// of staging + 47 KB of score reduction per CTA, two CTAs per SM).
 SSM_DEV void cp_async8(double *smem_dst, const double *gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
